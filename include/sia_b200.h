@@ -1,0 +1,215 @@
+/* sia_b200.h — C ABI of the B200-native SIA fingerprint-and-match path.
+ *
+ * The reference (CarlosArturoMe/shazam) is pure Python and has no FFI; its
+ * plug-in surface is the module-level functions `fingerprint`, `get_2D_peaks`,
+ * `generate_hashes` (__init__.py:116-245), `return_matches`, `align_matches`
+ * (recognizer.py:222-338) and the duck-typed database backend
+ * (mysql_database.py:28-255) selected through `DATABASES`/`get_database`
+ * (__init__.py:24-27,54-67).  This header is what a ctypes stub behind those
+ * names binds; each entry point cites the reference
+ * code it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types cross the boundary;
+ *  - every function returns 0 on success, <0 on error (SIA_E_*), never throws;
+ *    sia_last_error() returns a thread-local message for the last failure;
+ *  - `d_` parameters are DEVICE pointers (cudaMalloc / torch CUDA tensors),
+ *    `h_` parameters are HOST pointers (pinned for best throughput);
+ *  - the caller owns all I/O buffers; the library owns workspaces and index
+ *    storage behind opaque handles; one context per device; calls on one
+ *    handle must be serialised by the caller;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default
+ *    stream).  Device-pointer entry points are stream-ordered and do not
+ *    synchronise unless stated.
+ *
+ * Data formats
+ *  - PCM: int16 mono, tracks concatenated; track b occupies samples
+ *    [track_starts[b], track_starts[b] + track_len[b]).  track_starts[b] must be
+ *    a multiple of 8 samples (16-byte aligned loads); gaps are never read.
+ *  - spectrogram: TIME-major, row g = frame (track-concatenated), SIA_F_STRIDE
+ *    values per row, bins 0..2048 valid (the transpose of the reference's
+ *    [freq][time] array, __init__.py:232-241).
+ *  - hash: the first 10 bytes of sha1("f1|f2|dt") — BINARY(10) in
+ *    mysql_database.py:49; hex(hash) is the reference's 20-char string.
+ */
+#ifndef SIA_B200_H
+#define SIA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIA_NFFT        4096   /* DEFAULT_WINDOW_SIZE, __init__.py:43 */
+#define SIA_HOP         2048   /* NFFT * DEFAULT_OVERLAP_RATIO(0.5), __init__.py:44 */
+#define SIA_NBINS       2049
+#define SIA_F_STRIDE    2080   /* row stride (values) of device spectrograms: 65*32 */
+#define SIA_ROW_WORDS   65     /* 32-bit words per row of the peak bitmap */
+#define SIA_HASH_BYTES  10     /* FINGERPRINT_REDUCTION(20 hex chars)/2, __init__.py:51 */
+#define SIA_MAX_DT      200    /* MAX_HASH_TIME_DELTA, __init__.py:50 */
+#define SIA_MAX_NBHD    16     /* largest PEAK_NEIGHBORHOOD_SIZE supported (reference: 10) */
+
+enum {
+  SIA_OK = 0,
+  SIA_E_INVALID = -1,     /* bad argument */
+  SIA_E_CUDA = -2,        /* CUDA runtime error (message has the detail) */
+  SIA_E_CAPACITY = -3,    /* an output or workspace capacity was exceeded; see message */
+  SIA_E_NOMEM = -4,
+  SIA_E_UNSUPPORTED = -5  /* parameter combination outside the CUDA path (e.g. wsize != 4096) */
+};
+
+enum { SIA_F32 = 0, SIA_F64 = 1 };  /* arithmetic / storage type selectors */
+
+typedef struct sia_ctx sia_ctx;       /* per-device fingerprinting context */
+typedef struct sia_index sia_index;   /* per-device fingerprint index shard */
+
+const char *sia_last_error(void);
+int sia_version(void);
+
+/* ---- parameters of fingerprint(), __init__.py:212-217 and constants :40-51 -------- */
+typedef struct sia_fp_params {
+  double  Fs;            /* sampling rate; enters only as the 1/Fs PSD scale */
+  int32_t wsize;         /* must be 4096 */
+  double  wratio;        /* must be 0.5 */
+  int32_t fan_value;     /* DEFAULT_FAN_VALUE 5; partners per peak = fan_value-1; <= 64 */
+  double  amp_min;       /* DEFAULT_AMP_MIN 10 (dB); negative values enable the erosion term */
+  int32_t connectivity;  /* CONNECTIVITY_MASK: 2 = square (reference default), 1 = diamond */
+  int32_t nbhd;          /* PEAK_NEIGHBORHOOD_SIZE 10; 1..SIA_MAX_NBHD */
+  int32_t compute;       /* SIA_F64 (default; |dB error| << 1e-3 on every bin) or SIA_F32 */
+} sia_fp_params;
+
+void sia_fp_params_default(sia_fp_params *p);
+
+/* ---- context ------------------------------------------------------------------------- */
+/* max_chunk_frames: spectrogram rows the workspace holds at once (0 = default 131072);
+ * the longest single track must fit.  Allocates ~ max_chunk_frames * 8.6 KB. */
+int sia_ctx_create(int device, int64_t max_chunk_frames, sia_ctx **out);
+int sia_ctx_destroy(sia_ctx *ctx);
+
+/* frames mlab.specgram yields for a track of n samples (short input -> 1 padded frame) */
+int64_t sia_num_frames(int64_t n_samples);
+
+/* ---- stage entry points (parity tests drive these one by one) -------------------------- */
+
+/* K1. Replaces mlab.specgram(...)[0] + the dB transform, __init__.py:232-241.
+ * d_spec receives total_frames rows of SIA_F_STRIDE values (float if out_type==SIA_F32,
+ * double if SIA_F64).  h_track_starts/h_track_len: host arrays, n_tracks entries. */
+int sia_stft_db(sia_ctx *ctx, const int16_t *d_pcm, const int64_t *h_track_starts,
+                const int64_t *h_track_len, int32_t n_tracks, const sia_fp_params *p,
+                void *d_spec, int32_t out_type, int64_t *h_total_frames, void *stream);
+
+/* K2. Replaces get_2D_peaks, __init__.py:116-177.  d_spec as produced by K1 (in_type
+ * says float/double).  Peaks are written per track in (t asc, f asc) order — the order
+ * generate_hashes establishes with its stable sort (__init__.py:194-195).
+ * d_peak_t: frame index within the track; d_peak_f: bin.  d_track_peak_starts: n_tracks+1
+ * prefix offsets into the peak arrays.  Counts stay on the device; when the number of
+ * peaks exceeds cap_peaks the excess is dropped and d_status[0] is set to 1. */
+int sia_peaks(sia_ctx *ctx, const void *d_spec, int32_t in_type, const int64_t *h_track_frames,
+              int32_t n_tracks, const sia_fp_params *p, int32_t *d_peak_t, int32_t *d_peak_f,
+              int64_t cap_peaks, int64_t *d_track_peak_starts, int32_t *d_status, void *stream);
+
+/* K3. Replaces generate_hashes, __init__.py:179-210, on peaks already in (t, f) order.
+ * Output order is the reference's list order (i major, j minor).  d_hash: [cap][10] bytes,
+ * d_t1: [cap].  d_track_hash_starts: n_tracks+1 prefix offsets.  Overflow -> d_status[0]=2. */
+int sia_pairs_sha1(sia_ctx *ctx, const int32_t *d_peak_t, const int32_t *d_peak_f,
+                   const int64_t *d_track_peak_starts, int32_t n_tracks, int32_t fan_value,
+                   uint8_t *d_hash, int32_t *d_t1, int64_t cap_hashes,
+                   int64_t *d_track_hash_starts, int32_t *d_status, void *stream);
+
+/* ---- whole path ----------------------------------------------------------------------- */
+
+/* Replaces the per-channel body of fingerprint() (__init__.py:212-245) for a batch of
+ * tracks — the unit _fingerprint_worker/imap_unordered distributes (__init__.py:271,357).
+ * PCM resident on the device.  Tracks are processed in chunks of <= max_chunk_frames.
+ * Outputs on the device; h_track_hash_starts (n_tracks+1, host) and *h_total are filled
+ * after one synchronisation at the end.  Returns SIA_E_CAPACITY if cap_hashes was too
+ * small (h_total then holds the required size). */
+int sia_fingerprint_batch(sia_ctx *ctx, const int16_t *d_pcm, const int64_t *h_track_starts,
+                          const int64_t *h_track_len, int32_t n_tracks, const sia_fp_params *p,
+                          uint8_t *d_hash, int32_t *d_t1, int64_t cap_hashes,
+                          int64_t *h_track_hash_starts, int64_t *h_total, void *stream);
+
+/* Same, end to end from HOST memory: pinned (or pageable) PCM in, digests out to host
+ * memory, H2D / kernels / D2H pipelined over internal streams.  Synchronous. */
+int sia_fingerprint_batch_host(sia_ctx *ctx, const int16_t *h_pcm, const int64_t *h_track_starts,
+                               const int64_t *h_track_len, int32_t n_tracks, const sia_fp_params *p,
+                               uint8_t *h_hash, int32_t *h_t1, int64_t cap_hashes,
+                               int64_t *h_track_hash_starts, int64_t *h_total);
+
+/* per-kernel device time (ms, CUDA events on the launching stream) accumulated since the
+ * last reset; order: stft, peaks(bitmap), peaks(compact), pairs+sha1, scans.  n <= 8. */
+int sia_ctx_timing(sia_ctx *ctx, int enable, double *h_ms_out, int32_t *h_launches_out, int32_t n);
+
+/* ---- index (replaces the fingerprints table + SELECT_MULTIPLE + align_matches) --------- */
+
+/* One shard of the `fingerprints` table (mysql_database.py:46-59): rows
+ * (hash BINARY(10), song_id MEDIUMINT UNSIGNED (< 2^24), offset INT UNSIGNED (< 2^24 here)),
+ * UNIQUE(song_id, offset, hash) -> set semantics (INSERT IGNORE, :62-68). */
+int sia_index_create(int device, int64_t capacity_rows, sia_index **out);
+int sia_index_destroy(sia_index *ix);
+
+/* insert_hashes(song_id, hashes), mysql_database.py:167-181.  Rows are appended to a
+ * pending run; they become visible to queries after sia_index_finalize. */
+int sia_index_insert(sia_index *ix, int32_t song_id, const uint8_t *d_hash, const int32_t *d_off,
+                     int64_t n, void *stream);
+/* rows for many songs at once: d_song[n] gives each row's song id */
+int sia_index_insert_rows(sia_index *ix, const int32_t *d_song, const uint8_t *d_hash,
+                          const int32_t *d_off, int64_t n, void *stream);
+int sia_index_insert_host(sia_index *ix, int32_t song_id, const uint8_t *h_hash, const int32_t *h_off,
+                          int64_t n);
+
+/* sort pending rows into the index, drop duplicates, rebuild the bucket directory.
+ * *h_rows = rows now stored.  Synchronous. */
+int sia_index_finalize(sia_index *ix, int64_t *h_rows);
+int64_t sia_index_rows(const sia_index *ix);
+
+/* SELECT HEX(hash), song_id, offset WHERE hash IN (...) (recognizer.py:60-64, 252-259):
+ * every stored row whose hash is in the list of n DISTINCT hashes.  Row order: by
+ * position in h_hash, then (song_id, offset).  Fills up to cap rows; *h_nrows = total. */
+int sia_index_select_host(sia_index *ix, const uint8_t *h_hash, int64_t n, int32_t *h_row_hashidx,
+                          int32_t *h_row_song, int32_t *h_row_off, int64_t cap, int64_t *h_nrows);
+
+/* return_matches + the vote of align_matches (recognizer.py:222-271, 303-310) for Q
+ * queries at once.  Query q owns (hash, offset) pairs [query_starts[q], query_starts[q+1]);
+ * duplicates of a (hash, offset) pair inside one query are ignored (the callers pass a
+ * set, recognizer.py:378-382).  Per query, up to topn results, best first:
+ *   out_song / out_diff  — song id and winning offset difference (db_offset - query_offset;
+ *                          smallest difference among equal counts),
+ *   out_count            — aligned matches in that bin,
+ *   out_rows             — dedup_hashes[song]: DB rows matched, counted once per row,
+ *   out_nres[q]          — number of valid results (<= topn).
+ * Equal counts order by ascending song id (stable sort, recognizer.py:307-310).
+ * h_stats (optional, 4 x int64): distinct query hashes, DB rows matched, (song,diff)
+ * tuples voted, distinct bins. */
+int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff,
+                          const int64_t *h_query_starts, int32_t n_queries, int32_t topn,
+                          int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
+                          int32_t *d_out_rows, int32_t *d_out_nres, int64_t *h_stats, void *stream);
+
+/* multi-GPU building blocks (hash-prefix sharding; the exchange itself is NCCL, driven by
+ * the host layer).  Partial bins: per shard, the (query, song, diff) -> count histogram
+ * and (query, song) -> rows histogram for the hashes this shard owns; merged by summing
+ * equal keys, then voted with sia_vote_bins. */
+int sia_index_query_partial(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff,
+                            const int32_t *d_qid, int64_t n, uint64_t *d_bin_key, int32_t *d_bin_count,
+                            int64_t cap_bins, int64_t *h_nbins, uint64_t *d_row_key,
+                            int32_t *d_row_count, int64_t cap_rowbins, int64_t *h_nrowbins,
+                            void *stream);
+int sia_vote_bins(int device, const uint64_t *d_bin_key, const int32_t *d_bin_count, int64_t nbins,
+                  const uint64_t *d_row_key, const int32_t *d_row_count, int64_t nrowbins,
+                  int32_t n_queries, int32_t topn, int32_t *d_out_song, int32_t *d_out_diff,
+                  int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres, void *stream);
+
+/* bin key layout: [63:44] query id (20 bits) | [43:20] song id (24 bits) | [19:0]... see
+ * SIA_BINKEY_* — diff is stored biased by 2^24 in 25 bits, so the key is
+ * qid(15) | song(24) | diff+2^24 (25). */
+#define SIA_BINKEY_DIFF_BITS 25
+#define SIA_BINKEY_SONG_BITS 24
+#define SIA_BINKEY_QID_BITS  15
+#define SIA_DIFF_BIAS        (1 << 24)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIA_B200_H */

@@ -1,0 +1,353 @@
+// K1 — batched 4096-point STFT -> dB spectrogram, replacing
+//   mlab.specgram(x, NFFT=4096, Fs, window_hanning, noverlap=2048)[0]   (__init__.py:232-237)
+//   10*log10(P) with P==0 -> 0                                           (__init__.py:241)
+//
+// One CTA (128 threads) transforms one frame at a time and walks a run of consecutive
+// frames.  The real 4096-point FFT is done as a 2048-point complex FFT of the
+// even/odd-packed windowed samples plus a split post-pass; the complex FFT is three
+// register passes (radix 16, 16, 8) through shared memory:
+//
+//   n = 128a + 8b + c      k = ka + 16kb + 256kc
+//   pass A  thread t=8b+c   : FFT16 over a, x W2048^(t*ka)      -> L1[ka*136 + t]
+//   pass B  thread (ka,c)   : FFT16 over b, x W128^(c*kb)       -> L2[c*258 + kb*16 + ka]
+//   pass C  thread u=kb*16+ka (2 per thread): FFT8 over c       -> L3[u + 256kc] = Z[k]
+//   post    pairs (k, 2048-k): E +/- W4096^k O, |.|^2, dB       -> global, coalesced
+//
+// The strides 136 and 258 make every shared-memory access of every pass conflict-free
+// for 8-byte (and 4-byte) elements.  PCM is read straight from global memory as packed
+// int16 pairs (each warp load is one 128-byte line; the 50% overlap re-read hits L2).
+//
+// T = double is the default arithmetic: with 144 dB between the strongest and weakest
+// bins of a frame, float butterflies leave O(1) relative error on the weak bins, which
+// breaks the 1e-3 dB bound against the reference's float64 spectrogram.  T = float is
+// kept as a selectable fast mode.
+#include "sia_common.cuh"
+#include "stft.cuh"
+
+#include <math.h>
+#include <vector>
+
+namespace sia {
+
+namespace {
+
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+constexpr int kL1Stride = 136;
+constexpr int kL2Stride = 258;
+constexpr int kBufElems = 16 * kL1Stride;  // 2176 >= 8*258=2064 >= 2048
+
+template <typename T>
+__device__ __forceinline__ void cmul(T &r, T &i, T wr, T wi) {
+  T nr = r * wr - i * wi;
+  T ni = r * wi + i * wr;
+  r = nr; i = ni;
+}
+
+template <typename T>
+__device__ __forceinline__ void fft4(T &r0, T &i0, T &r1, T &i1, T &r2, T &i2, T &r3, T &i3) {
+  T ar = r0 + r2, ai = i0 + i2;
+  T br = r0 - r2, bi = i0 - i2;
+  T cr = r1 + r3, ci = i1 + i3;
+  T dr = r1 - r3, di = i1 - i3;
+  r0 = ar + cr; i0 = ai + ci;
+  r2 = ar - cr; i2 = ai - ci;
+  r1 = br + di; i1 = bi - dr;   // b - i*d
+  r3 = br - di; i3 = bi + dr;   // b + i*d
+}
+
+// In-place 16-point forward FFT.  Output X[k], k = k1 + 4*k2, lands at position 4*k1 + k2.
+template <typename T>
+__device__ __forceinline__ void fft16(T (&r)[16], T (&i)[16]) {
+  const T C1 = (T)0.92387953251128675613;   // cos(pi/8)
+  const T S1 = (T)0.38268343236508977173;   // sin(pi/8)
+  const T H = (T)0.70710678118654752440;    // sqrt(1/2)
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2)
+    fft4(r[n2], i[n2], r[n2 + 4], i[n2 + 4], r[n2 + 8], i[n2 + 8], r[n2 + 12], i[n2 + 12]);
+  // element (n2 + 4*k1) *= W16^(n2*k1),  W16^m = (cos(m pi/8), -sin(m pi/8))
+  cmul(r[5], i[5], C1, -S1);                                  // m=1
+  { T a = r[6], b = i[6]; r[6] = (a + b) * H; i[6] = (b - a) * H; }   // m=2: (1-i)/sqrt2
+  cmul(r[7], i[7], S1, -C1);                                  // m=3
+  { T a = r[9], b = i[9]; r[9] = (a + b) * H; i[9] = (b - a) * H; }   // m=2
+  { T a = r[10], b = i[10]; r[10] = b; i[10] = -a; }          // m=4: -i
+  { T a = r[11], b = i[11]; r[11] = (b - a) * H; i[11] = -(a + b) * H; }  // m=6: (-1-i)/sqrt2
+  cmul(r[13], i[13], S1, -C1);                                // m=3
+  { T a = r[14], b = i[14]; r[14] = (b - a) * H; i[14] = -(a + b) * H; }  // m=6
+  cmul(r[15], i[15], -C1, S1);                                // m=9 = -W^1
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+    fft4(r[4 * k1], i[4 * k1], r[4 * k1 + 1], i[4 * k1 + 1], r[4 * k1 + 2], i[4 * k1 + 2], r[4 * k1 + 3],
+         i[4 * k1 + 3]);
+}
+__host__ __device__ constexpr int pos16(int k) { return 4 * (k & 3) + (k >> 2); }
+
+// In-place 8-point forward FFT.  Output X[k], k = k1 + 4*k2, lands at position 2*k1 + k2.
+template <typename T>
+__device__ __forceinline__ void fft8(T (&r)[8], T (&i)[8]) {
+  const T H = (T)0.70710678118654752440;
+#pragma unroll
+  for (int n2 = 0; n2 < 2; ++n2)
+    fft4(r[n2], i[n2], r[n2 + 2], i[n2 + 2], r[n2 + 4], i[n2 + 4], r[n2 + 6], i[n2 + 6]);
+  // element (1 + 2*k1) *= W8^k1
+  { T a = r[3], b = i[3]; r[3] = (a + b) * H; i[3] = (b - a) * H; }       // k1=1
+  { T a = r[5], b = i[5]; r[5] = b; i[5] = -a; }                          // k1=2: -i
+  { T a = r[7], b = i[7]; r[7] = (b - a) * H; i[7] = -(a + b) * H; }      // k1=3
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    T ar = r[2 * k1], ai = i[2 * k1], br = r[2 * k1 + 1], bi = i[2 * k1 + 1];
+    r[2 * k1] = ar + br; i[2 * k1] = ai + bi;
+    r[2 * k1 + 1] = ar - br; i[2 * k1 + 1] = ai - bi;
+  }
+}
+__host__ __device__ constexpr int pos8(int k) { return 2 * (k & 3) + (k >> 2); }
+
+// 10*log10(p) + c for p > 0.  The mantissa's log2 is taken in float (MUFU.LG2 on [1,2):
+// absolute error ~2^-22) and recombined with the exponent in double: |error| < 1e-6 dB,
+// below the float32 rounding of the stored value.
+__device__ __forceinline__ double db_from_power(double p, double c) {
+  const int hi = __double2hiint(p), lo = __double2loint(p);
+  const int e = (hi >> 20) - 1023;
+  if (e == -1023 || e == 1024) return 10.0 * log10(p) + c;   // subnormal / inf / nan: exact path
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const float l2 = __log2f((float)m);
+  return ((double)e + (double)l2) * 3.01029995663981195 + c;
+}
+__device__ __forceinline__ float db_from_power(float p, float c) {
+  return __log2f(p) * 3.0102999566f + c;
+}
+
+template <typename T, typename OutT>
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 8)
+stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ track_starts,
+               const int64_t *__restrict__ track_len, const int64_t *__restrict__ frame_starts, int n_tracks,
+               int64_t total_frames, int frames_per_cta, OutT *__restrict__ out, T c_mid, T c_edge,
+               const typename Vec2<T>::type *__restrict__ win2, const typename Vec2<T>::type *__restrict__ twA,
+               const typename Vec2<T>::type *__restrict__ twB, const typename Vec2<T>::type *__restrict__ twP) {
+  using V2 = typename Vec2<T>::type;
+  __shared__ T sre[kBufElems];
+  __shared__ T sim[kBufElems];
+
+  const int t = threadIdx.x;
+  int64_t g = (int64_t)blockIdx.x * frames_per_cta;
+  if (g >= total_frames) return;
+  int64_t g_end = g + frames_per_cta;
+  if (g_end > total_frames) g_end = total_frames;
+  int trk = find_segment(frame_starts, n_tracks, g);
+
+  for (; g < g_end; ++g) {
+    while (g >= frame_starts[trk + 1]) ++trk;
+    const int64_t k = g - frame_starts[trk];
+    const int64_t off = track_starts[trk] + k * SIA_HOP;
+    const int64_t rem = track_len[trk] - k * SIA_HOP;   // >= 4096 except for a short (zero padded) track
+    const uint32_t *__restrict__ p32 = reinterpret_cast<const uint32_t *>(pcm + off);
+
+    T xr[16], xi[16];
+    // ---- pass A: window, pack even/odd samples as complex, FFT16 over a -----------------
+    {
+      uint32_t w[16];
+      if (rem >= SIA_NFFT) {
+#pragma unroll
+        for (int a = 0; a < 16; ++a) w[a] = __ldg(p32 + 128 * a + t);
+      } else {
+#pragma unroll
+        for (int a = 0; a < 16; ++a) {
+          const int s = 2 * (128 * a + t);
+          uint32_t v = 0;
+          if (s + 1 < rem) v = p32[128 * a + t];
+          else if (s < rem) v = (uint32_t)(uint16_t)pcm[off + s];
+          w[a] = v;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 16; ++a) {
+        const V2 wn = __ldg(win2 + 128 * a + t);
+        xr[a] = (T)(int)(short)(w[a] & 0xffffu) * wn.x;
+        xi[a] = (T)(int)(short)(w[a] >> 16) * wn.y;
+      }
+      fft16(xr, xi);
+#pragma unroll
+      for (int ka = 0; ka < 16; ++ka) {
+        T r = xr[pos16(ka)], i = xi[pos16(ka)];
+        if (ka) {
+          const V2 tw = __ldg(twA + ka * 128 + t);
+          cmul(r, i, tw.x, tw.y);
+        }
+        sre[ka * kL1Stride + t] = r;
+        sim[ka * kL1Stride + t] = i;
+      }
+    }
+    __syncthreads();
+    // ---- pass B: FFT16 over b -----------------------------------------------------------
+    {
+      const int ka = t >> 3, c = t & 7;
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        xr[b] = sre[ka * kL1Stride + 8 * b + c];
+        xi[b] = sim[ka * kL1Stride + 8 * b + c];
+      }
+      __syncthreads();
+      fft16(xr, xi);
+#pragma unroll
+      for (int kb = 0; kb < 16; ++kb) {
+        T r = xr[pos16(kb)], i = xi[pos16(kb)];
+        if (kb) {
+          const V2 tw = __ldg(twB + kb * 8 + c);
+          cmul(r, i, tw.x, tw.y);
+        }
+        sre[c * kL2Stride + kb * 16 + ka] = r;
+        sim[c * kL2Stride + kb * 16 + ka] = i;
+      }
+    }
+    __syncthreads();
+    // ---- pass C: two FFT8 over c per thread ------------------------------------------------
+    {
+      T yr[2][8], yi[2][8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          yr[h][c] = sre[c * kL2Stride + t + 128 * h];
+          yi[h][c] = sim[c * kL2Stride + t + 128 * h];
+        }
+      __syncthreads();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        fft8(yr[h], yi[h]);
+#pragma unroll
+        for (int kc = 0; kc < 8; ++kc) {
+          sre[t + 128 * h + 256 * kc] = yr[h][pos8(kc)];
+          sim[t + 128 * h + 256 * kc] = yi[h][pos8(kc)];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- post-pass: bins k and 2048-k from Z[k], Z[2048-k] ------------------------------------
+    {
+      OutT *__restrict__ row = out + g * (int64_t)SIA_F_STRIDE;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int kk = t + 128 * it;            // 0..1023
+        const int kn = (2048 - kk) & 2047;
+        const T ar = sre[kk], ai = sim[kk], br = sre[kn], bi = sim[kn];
+        const V2 tw = __ldg(twP + kk);
+        // 2E = A + conj(B), 2O = -i (A - conj(B))
+        const T er = ar + br, ei = ai - bi;
+        const T orr = ai + bi, oi = br - ar;
+        const T tr = orr * tw.x - oi * tw.y, ti = orr * tw.y + oi * tw.x;
+        const T pr = er + tr, pi = ei + ti;     // 2 X[k]
+        const T qr = er - tr, qi = ei - ti;     // 2 conj(X[2048-k])
+        const T p1 = pr * pr + pi * pi;
+        const T p2 = qr * qr + qi * qi;
+        const T c1 = kk == 0 ? c_edge : c_mid;
+        row[kk] = (OutT)(p1 == (T)0 ? (T)0 : (T)db_from_power(p1, c1));
+        row[2048 - kk] = (OutT)(p2 == (T)0 ? (T)0 : (T)db_from_power(p2, c1));
+      }
+      if (t == 0) {                              // k = 1024 pairs with itself: X = conj(Z[1024])
+        const T ar = sre[1024], ai = sim[1024];
+        const T p1 = (T)4 * (ar * ar + ai * ai);
+        row[1024] = (OutT)(p1 == (T)0 ? (T)0 : (T)db_from_power(p1, c_mid));
+      }
+    }
+    __syncthreads();   // L3 is overwritten by the next frame's pass A
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int upload_tables(StftTables<T> &tb) {
+  using V2 = typename Vec2<T>::type;
+  const long double PI = 3.141592653589793238462643383279502884L;
+  std::vector<V2> win(2048), twA(16 * 128), twB(16 * 8), twP(1025);
+  for (int n = 0; n < 2048; ++n) {
+    // np.hanning(4096): 0.5 - 0.5*cos(2*pi*n/(M-1)), symmetric
+    long double w0 = 0.5L - 0.5L * cosl(2 * PI * (2 * n) / 4095.0L);
+    long double w1 = 0.5L - 0.5L * cosl(2 * PI * (2 * n + 1) / 4095.0L);
+    win[n].x = (T)w0; win[n].y = (T)w1;
+  }
+  for (int ka = 0; ka < 16; ++ka)
+    for (int t = 0; t < 128; ++t) {
+      long double ang = -2 * PI * (long double)(t * ka) / 2048.0L;
+      twA[ka * 128 + t].x = (T)cosl(ang); twA[ka * 128 + t].y = (T)sinl(ang);
+    }
+  for (int kb = 0; kb < 16; ++kb)
+    for (int c = 0; c < 8; ++c) {
+      long double ang = -2 * PI * (long double)(c * kb) / 128.0L;
+      twB[kb * 8 + c].x = (T)cosl(ang); twB[kb * 8 + c].y = (T)sinl(ang);
+    }
+  for (int k = 0; k <= 1024; ++k) {
+    long double ang = -2 * PI * (long double)k / 4096.0L;
+    twP[k].x = (T)cosl(ang); twP[k].y = (T)sinl(ang);
+  }
+  const size_t total = (win.size() + twA.size() + twB.size() + twP.size()) * sizeof(V2);
+  char *d = nullptr;
+  SIA_CUDA(cudaMalloc(&d, total));
+  tb.base = d;
+  size_t o = 0;
+  auto put = [&](const std::vector<V2> &v, const void **dst) -> cudaError_t {
+    *dst = d + o;
+    cudaError_t e = cudaMemcpy(d + o, v.data(), v.size() * sizeof(V2), cudaMemcpyHostToDevice);
+    o += v.size() * sizeof(V2);
+    return e;
+  };
+  SIA_CUDA(put(win, &tb.win2));
+  SIA_CUDA(put(twA, &tb.twA));
+  SIA_CUDA(put(twB, &tb.twB));
+  SIA_CUDA(put(twP, &tb.twP));
+  return SIA_OK;
+}
+
+int stft_tables_create(StftTables<float> &f, StftTables<double> &d) {
+  int rc = upload_tables<float>(f);
+  if (rc) return rc;
+  return upload_tables<double>(d);
+}
+
+void stft_tables_destroy(StftTables<float> &f, StftTables<double> &d) {
+  if (f.base) cudaFree(f.base);
+  if (d.base) cudaFree(d.base);
+  f.base = d.base = nullptr;
+}
+
+double hann_power_sum() {
+  // sum(np.hanning(4096)**2) accumulated like numpy would to double precision
+  const long double PI = 3.141592653589793238462643383279502884L;
+  long double s = 0;
+  for (int n = 0; n < 4096; ++n) {
+    double w = (double)(0.5L - 0.5L * cosl(2 * PI * n / 4095.0L));
+    s += (long double)w * w;
+  }
+  return (double)s;
+}
+
+template <typename T, typename OutT>
+static int launch(const StftLaunch &a, const StftTables<T> &tb, cudaStream_t s) {
+  using V2 = typename Vec2<T>::type;
+  const double scale = 1.0 / (4.0 * a.Fs * hann_power_sum());  // the 1/4: the post-pass keeps 2E, 2O
+  const double c_edge = 10.0 * log10(scale);
+  const double c_mid = 10.0 * log10(2.0 * scale);
+  const int G = a.frames_per_cta;
+  const int64_t blocks = ceil_div(a.total_frames, G);
+  if (blocks == 0) return SIA_OK;
+  stft_db_kernel<T, OutT><<<(unsigned)blocks, 128, 0, s>>>(
+      a.d_pcm, a.d_track_starts, a.d_track_len, a.d_frame_starts, a.n_tracks, a.total_frames, G, (OutT *)a.d_spec,
+      (T)c_mid, (T)c_edge, (const V2 *)tb.win2, (const V2 *)tb.twA, (const V2 *)tb.twB, (const V2 *)tb.twP);
+  SIA_CHECK_LAUNCH();
+  return SIA_OK;
+}
+
+int stft_db_launch(const StftLaunch &a, const StftTables<float> &tf, const StftTables<double> &td,
+                   cudaStream_t s) {
+  if (a.compute == SIA_F64) {
+    return a.out_type == SIA_F64 ? launch<double, double>(a, td, s) : launch<double, float>(a, td, s);
+  }
+  return a.out_type == SIA_F64 ? launch<float, double>(a, tf, s) : launch<float, float>(a, tf, s);
+}
+
+}  // namespace sia

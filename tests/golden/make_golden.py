@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors by EXECUTING THE REFERENCE'S OWN CODE.
+
+Run in the dev container only (``/root/reference`` does not exist on the GPU
+box):  ``python tests/golden/make_golden.py``
+
+How: the reference scripts cannot be imported (they open PortAudio / MySQL at
+import and need matplotlib, pydub, ... which are absent), so the pure functions
+``get_2D_peaks``, ``generate_hashes``, ``fingerprint`` (``__init__.py``) and
+``return_matches``, ``align_matches`` (``recognizer.py``) plus the UPPER_CASE
+module constants are AST-extracted from the reference files and exec'd
+unmodified.  Two stand-ins are injected:
+
+* ``mlab`` — ``mlab.specgram`` is the restated third-party call
+  (``oracle.sia_oracle.specgram_psd``; matplotlib is not installed);
+* ``db``   — an in-memory object answering ``SELECT_MULTIPLE`` /
+  ``get_song_by_id`` (MySQL cannot run here).
+
+Outputs (all under ``tests/golden/``):
+  wav_fixture.npz   PCM of signal_with_noise.wav + reference peaks/hashes
+  synth_cases.npz   seeded short clips (silence gaps, sub-frame input, ...) + reference hashes
+  peaks_cases.npz   small float64 spectrograms (plateaus, zeros, negative amp_min) + reference peaks
+  match_cases.json  reference return_matches + align_matches on small tables
+"""
+import ast
+import hashlib
+import json
+import os
+import sys
+import warnings
+import wave
+from itertools import groupby
+from operator import itemgetter
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from oracle import sia_oracle as O  # noqa: E402
+
+
+def extract(path, func_names):
+    """Compile the named FunctionDefs and every UPPER_CASE constant of `path`."""
+    tree = ast.parse(open(path).read())
+    keep = []
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in func_names:
+            keep.append(node)
+        elif isinstance(node, ast.Assign) and all(
+                isinstance(t, ast.Name) and t.id.isupper() for t in node.targets):
+            # constants only: literals and f-strings, no calls into pyaudio etc.
+            if not any(isinstance(n, (ast.Call, ast.Attribute)) for n in ast.walk(node.value)):
+                keep.append(node)
+    return compile(ast.Module(body=keep, type_ignores=[]), path, "exec")
+
+
+class _Mlab:
+    window_hanning = staticmethod(lambda x: x)
+
+    @staticmethod
+    def specgram(x, NFFT, Fs, window, noverlap):
+        return (O.specgram_psd(x, Fs, NFFT, noverlap), None, None)
+
+
+def ref_namespace():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from scipy.ndimage import (binary_erosion, generate_binary_structure,
+                                   iterate_structure, maximum_filter)
+    ns = dict(np=np, hashlib=hashlib, itemgetter=itemgetter, groupby=groupby, mlab=_Mlab,
+              binary_erosion=binary_erosion, generate_binary_structure=generate_binary_structure,
+              iterate_structure=iterate_structure, maximum_filter=maximum_filter)
+    exec(extract(f"{REF}/__init__.py", {"get_2D_peaks", "generate_hashes", "fingerprint"}), ns)
+    return ns
+
+
+class _Cursor:
+    def __init__(self, table):
+        self.table, self.rows = table, []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def execute(self, query, params=None):
+        assert "SELECT HEX(`hash`), `song_id`, `offset`" in query and "IN (" in query
+        assert query.count("UNHEX(%s)") == len(params)
+        self.rows = list(self.table.select_multiple(list(params)))
+
+    def __iter__(self):
+        return iter(self.rows)
+
+
+class _Db:
+    def __init__(self, table):
+        self.table = table
+
+    def cursor(self, **kw):
+        return _Cursor(self.table)
+
+    def get_song_by_id(self, sid):
+        return self.table.get_song_by_id(sid)
+
+
+def match_namespace(table):
+    ns = dict(np=np, groupby=groupby, db=_Db(table))
+    exec(extract(f"{REF}/recognizer.py", {"return_matches", "align_matches"}), ns)
+    return ns
+
+
+def hashes_to_arrays(hs):
+    if not hs:
+        return np.zeros((0, 10), np.uint8), np.zeros((0,), np.int32)
+    h = np.frombuffer(bytes.fromhex("".join(x[0] for x in hs)), np.uint8).reshape(-1, 10).copy()
+    return h, np.array([int(x[1]) for x in hs], np.int32)
+
+
+def synth_clip(kind, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "tones":          # 3 s of the Config-2 generator
+        return O.synth_track(seed, 3 * 44100)
+    if kind == "gaps":           # music / digital silence / music: exact-zero frames (the 0 dB quirk)
+        a = O.synth_track(seed, 44100 + 300)
+        return np.concatenate([a, np.zeros(5 * 4096 + 123, np.int16), O.synth_track(seed + 1, 50000)])
+    if kind == "noise":          # loud white noise: many peaks, full-scale clipping
+        return np.clip(rng.normal(0, 12000, 60000), -32768, 32767).astype(np.int16)
+    if kind == "short":          # shorter than one window -> zero padded to 4096
+        return O.synth_track(seed, 3000)
+    if kind == "oneframe":       # exactly 4096 samples
+        return O.synth_track(seed, 4096)
+    if kind == "ragged":         # 2 frames + a dropped partial tail
+        return O.synth_track(seed, 4096 + 2048 + 2047)
+    if kind == "silence":
+        return np.zeros(30000, np.int16)
+    if kind == "periodic":       # period divides the hop: identical frames -> plateaus along time
+        base = (8000 * np.sin(2 * np.pi * np.arange(2048) * 37 / 2048) +
+                3000 * np.sin(2 * np.pi * np.arange(2048) * 300 / 2048)).round().astype(np.int16)
+        return np.tile(base, 40)
+    if kind == "longgap":        # two bursts > 200 frames apart -> dt > MAX_HASH_TIME_DELTA rejected
+        a = O.synth_track(seed, 20000)
+        return np.concatenate([a, np.zeros(215 * 2048, np.int16), O.synth_track(seed + 7, 20000)])
+    raise KeyError(kind)
+
+
+def main():
+    ns = ref_namespace()
+    out = {}
+
+    # ---- wav fixture (BASELINE.json configs[0]) ---------------------------------
+    w = wave.open(f"{REF}/signal_with_noise.wav")
+    assert (w.getnchannels(), w.getsampwidth(), w.getframerate()) == (1, 2, 22050)
+    pcm = np.frombuffer(w.readframes(w.getnframes()), np.int16).copy()
+    out["pcm"] = pcm
+    out["fs"] = np.int64(22050)
+    for conn in (2, 1):
+        ns["CONNECTIVITY_MASK"] = conn
+        arr = O.spectrogram_db(pcm, 22050)
+        pk = ns["get_2D_peaks"](arr, amp_min=10)
+        out[f"peaks_c{conn}"] = np.array(pk, np.int32).reshape(-1, 2)      # (f, t) freq-major
+        for fan in (5, 15):
+            for fs in (22050, 44100):
+                h, t = hashes_to_arrays(ns["fingerprint"](pcm, Fs=fs, fan_value=fan, amp_min=10))
+                out[f"hash_c{conn}_fan{fan}_fs{fs}"] = h
+                out[f"t1_c{conn}_fan{fan}_fs{fs}"] = t
+    ns["CONNECTIVITY_MASK"] = 2
+    # list-of-python-ints input, as the recorder passes it (recognizer.py:361-368)
+    h, t = hashes_to_arrays(ns["fingerprint"]([int(v) for v in pcm[:50000]], Fs=44100))
+    out["hash_list50k"], out["t1_list50k"] = h, t
+    np.savez_compressed(f"{HERE}/wav_fixture.npz", **out)
+    print("wav: peaks", len(out["peaks_c2"]), "hashes fan5", len(out["hash_c2_fan5_fs22050"]),
+          "fan15", len(out["hash_c2_fan15_fs22050"]), "diamond peaks", len(out["peaks_c1"]))
+
+    # ---- synthetic clips -----------------------------------------------------------
+    out = {}
+    kinds = ["tones", "gaps", "noise", "short", "oneframe", "ragged", "silence", "periodic", "longgap"]
+    out["kinds"] = np.array(kinds)
+    for i, kind in enumerate(kinds):
+        x = synth_clip(kind, 100 + i)
+        out[f"{kind}_pcm"] = x
+        for fan, amp in ((5, 10), (15, 10), (15, 0), (15, -5)):
+            h, t = hashes_to_arrays(ns["fingerprint"](x, Fs=44100, fan_value=fan, amp_min=amp))
+            out[f"{kind}_hash_fan{fan}_amp{amp}"] = h
+            out[f"{kind}_t1_fan{fan}_amp{amp}"] = t
+        print(kind, len(x), "samples ->", len(out[f"{kind}_hash_fan15_amp10"]), "hashes @fan15")
+    np.savez_compressed(f"{HERE}/synth_cases.npz", **out)
+
+    # ---- raw peak cases: small float64 spectrograms ----------------------------------
+    out = {}
+    rng = np.random.default_rng(7)
+    cases = {
+        "rand": rng.normal(5, 12, (90, 70)),
+        "quant": np.round(rng.normal(8, 8, (64, 120))),                     # many exact ties
+        "zeros": np.where(rng.random((80, 80)) < 0.7, 0.0, rng.normal(0, 15, (80, 80))),
+        "allzero": np.zeros((40, 50)),
+        "const": np.full((30, 45), 12.5),
+        "neg": rng.normal(-30, 5, (50, 50)),
+        "tiny": rng.normal(15, 5, (5, 3)),
+        "onecol": rng.normal(15, 5, (2049, 1)),
+        "fullF": rng.normal(0, 14, (2049, 24)),
+    }
+    block = np.zeros((70, 70))
+    block[:, 35:] = rng.normal(0, 15, (70, 35))                              # zero background next to signal
+    cases["halfzero"] = block
+    out["names"] = np.array(list(cases))
+    for name, arr in cases.items():
+        out[f"{name}_arr"] = arr
+        for conn in (2, 1):
+            ns["CONNECTIVITY_MASK"] = conn
+            for amp in (10, 0, -5, -100):
+                pk = ns["get_2D_peaks"](arr, amp_min=amp)
+                out[f"{name}_c{conn}_amp{amp}"] = np.array(pk, np.int32).reshape(-1, 2)
+    ns["CONNECTIVITY_MASK"] = 2
+    np.savez_compressed(f"{HERE}/peaks_cases.npz", **out)
+
+    # ---- match cases ---------------------------------------------------------------
+    mcases = []
+    rng = np.random.default_rng(11)
+
+    def hx(i):
+        return hashlib.sha1(str(i).encode()).hexdigest()[:20]
+
+    for case_id, (nsongs, per_song, universe, nquery) in enumerate(
+            [(3, 40, 25, 30), (8, 300, 120, 200), (5, 60, 10, 40), (4, 50, 30, 0)]):
+        table = O.FingerprintTable()
+        rows = []
+        for s in range(nsongs):
+            sid = table.insert_song(f"song{s}", hashlib.sha1(f"file{s}".encode()).hexdigest().upper(), per_song)
+            hs = [(hx(int(rng.integers(0, universe))), int(rng.integers(0, 60))) for _ in range(per_song)]
+            hs += hs[:5]                                    # duplicates -> INSERT IGNORE
+            table.insert_hashes(sid, hs)
+            table.set_song_fingerprinted(sid)
+            rows += [[sid, h, o] for h, o in hs]
+        # query = a time-shifted excerpt of song 2 + random hashes (some absent from the table)
+        target = [r for r in rows if r[0] == min(2, nsongs)]
+        q = [(h, max(0, o - 7)) for _, h, o in target[: nquery // 2]]
+        q += [(hx(int(rng.integers(0, universe * 2))), int(rng.integers(0, 20))) for _ in range(nquery - len(q))]
+        q = list(set(q))
+        q.sort()
+        mns = match_namespace(table)
+        matches, dedup = mns["return_matches"](q)
+        by_topn = {}
+        for topn in (1, 2, 3, 50):
+            res = mns["align_matches"](matches, dedup, len(q), topn) if q else []
+            by_topn[str(topn)] = [{k: (v.decode() if isinstance(v, bytes) else v) for k, v in r.items()}
+                                  for r in res]
+        mcases.append({
+            "case": case_id, "rows": rows, "query": q,
+            "songs": {str(k): v for k, v in table.songs.items()},
+            "n_matches": len(matches),
+            "matches_sorted_sha": hashlib.sha256(repr(sorted(matches)).encode()).hexdigest(),
+            "dedup": {str(k): v for k, v in dedup.items()},
+            "results_by_topn": by_topn,
+        })
+    # the KAT of SURVEY.md §8c
+    table = O.FingerprintTable()
+    for s in range(9):
+        table.insert_song(f"s{s + 1}", "AB" * 20, 100)
+    mns = match_namespace(table)
+    kat = mns["align_matches"]([(7, 3), (7, 3), (7, 5), (2, 10), (2, 10), (2, -4), (2, -4), (9, 1)],
+                               {7: 3, 2: 4, 9: 1}, 10, 3)
+    mcases.append({"case": "kat", "results": [{k: (v.decode() if isinstance(v, bytes) else v)
+                                               for k, v in r.items()} for r in kat]})
+    json.dump(mcases, open(f"{HERE}/match_cases.json", "w"), indent=0)
+    print("match cases:", len(mcases))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,291 @@
+"""Parity of the CUDA fingerprint path (through the C ABI) with the oracle and the golden
+vectors.  Bit-exact for peaks and hashes; the spectrogram within 1e-3 dB (the tolerance
+BASELINE.json's north_star states) of the float64 oracle."""
+import numpy as np
+import pytest
+
+from oracle import sia_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DB_TOL = 1e-3   # dB, north_star
+
+
+def _device_spec(fpr, x, fs, compute, out_dtype):
+    import torch
+    from shazam_b200.fingerprinter import pack_tracks
+    pcm, starts, lens = pack_tracks([x])
+    d = torch.from_numpy(pcm).to(fpr.tdev)
+    p = fpr.params(Fs=fs, compute=compute)
+    spec = fpr.stft_db(d, starts, lens, p, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    return spec[:, :2049].cpu().numpy().T      # [F][T] like the reference
+
+
+def _check_spec(got, ref, floor_db, tol=DB_TOL):
+    """|dB error| <= tol on every bin that is above the numerical floor of its own frame
+    (bins more than `floor_db` below the frame maximum are rounding noise in ANY FFT,
+    numpy's included); exact zeros must be reproduced exactly."""
+    assert got.shape == ref.shape
+    fmax = ref.max(axis=0, keepdims=True)
+    live = ref > fmax - floor_db
+    zero_frames = (ref == 0).all(axis=0)
+    assert np.all(got[:, zero_frames] == 0)
+    live &= ~zero_frames[None, :]
+    err = np.abs(got - ref)[live]
+    assert live.mean() > 0.5 or zero_frames.all()
+    return float(err.max()) if err.size else 0.0
+
+
+@pytest.mark.parametrize("fs", [22050, 44100])
+def test_k1_spectrogram_f64_wav(fpr, wav_fixture, fs):
+    import torch
+    x = wav_fixture["pcm"]
+    ref = O.spectrogram_db(x, fs)
+    got = _device_spec(fpr, x, fs, "f64", torch.float64)
+    e = _check_spec(got, ref, floor_db=230.0)
+    assert e < 1e-6, e                      # float64 storage: far inside the tolerance
+    got32 = _device_spec(fpr, x, fs, "f64", torch.float32)
+    assert _check_spec(got32, ref, floor_db=230.0) < 2e-5     # + float32 rounding of the stored dB
+    assert np.abs(got32 - ref).max() < DB_TOL                 # EVERY bin of the fixture, no floor
+
+
+def test_k1_spectrogram_f32_mode_wav(fpr, wav_fixture):
+    import torch
+    x = wav_fixture["pcm"]
+    ref = O.spectrogram_db(x, 22050)
+    got = _device_spec(fpr, x, 22050, "f32", torch.float32)
+    # float butterflies: the tolerance holds on bins within 80 dB of the frame maximum only
+    assert _check_spec(got, ref, floor_db=80.0) < DB_TOL
+
+
+def test_k1_spectrogram_synth_cases(fpr, synth_cases):
+    import torch
+    for kind in synth_cases["kinds"]:
+        x = synth_cases[f"{kind}_pcm"]
+        ref = O.spectrogram_db(x, 44100)
+        got = _device_spec(fpr, x, 44100, "f64", torch.float32)
+        assert got.shape == ref.shape, kind
+        assert _check_spec(got, ref, floor_db=200.0) < 5e-5, kind
+
+
+def test_k1_batch_layout(fpr):
+    """Several ragged tracks in one launch land in track-concatenated rows."""
+    import torch
+    from shazam_b200.fingerprinter import pack_tracks
+    tracks = [O.synth_track(s, n) for s, n in [(1, 30000), (2, 3000), (3, 4096), (4, 8191), (5, 100000), (6, 0)]]
+    pcm, starts, lens = pack_tracks(tracks)
+    d = torch.from_numpy(pcm).to(fpr.tdev)
+    spec = fpr.stft_db(d, starts, lens, fpr.params(), out_dtype=torch.float32).cpu().numpy()
+    row = 0
+    for t in tracks:
+        ref = O.spectrogram_db(t, 44100)
+        got = spec[row:row + ref.shape[1], :2049].T
+        assert _check_spec(got, ref, floor_db=200.0) < 5e-5
+        row += ref.shape[1]
+    assert row == spec.shape[0]
+
+
+def _gpu_peaks(fpr, arr, amp, conn, nbhd=10):
+    """Feed an oracle [F][T] float64 array to K2; returns (f,t) int32 array freq-major."""
+    import torch
+    F, T = arr.shape
+    host = np.full((T, 2080), -np.inf, np.float64)
+    host[:, :F] = arr.T
+    spec = torch.from_numpy(host).to(fpr.tdev)
+    p = fpr.params(amp_min=amp, connectivity=conn, nbhd=nbhd)
+    pt, pf, tps = fpr.peaks(spec, np.array([T], np.int64), p, cap_peaks=max(1024, F * T))
+    t = pt.cpu().numpy(); f = pf.cpu().numpy()
+    # device order must be (t asc, f asc)
+    assert np.all(np.diff(t.astype(np.int64) * 4096 + f) > 0)
+    order = np.lexsort((t, f))
+    return np.stack([f[order], t[order]], 1).astype(np.int32).reshape(-1, 2)
+
+
+def test_k2_peaks_golden_cases(fpr, peaks_cases):
+    g = peaks_cases
+    for name in g["names"]:
+        arr = g[f"{name}_arr"]
+        for conn in (2, 1):
+            for amp in (10, 0, -5, -100):
+                got = _gpu_peaks(fpr, arr, amp, conn)
+                assert np.array_equal(got, g[f"{name}_c{conn}_amp{amp}"]), (name, conn, amp)
+
+
+def test_k2_peaks_wav_bit_exact(fpr, wav_fixture):
+    arr = O.spectrogram_db(wav_fixture["pcm"], 22050)      # the reference's float64 spectrogram
+    for conn in (2, 1):
+        got = _gpu_peaks(fpr, arr, 10, conn)
+        assert np.array_equal(got, wav_fixture[f"peaks_c{conn}"])
+
+
+def test_k2_other_neighbourhoods_and_float32(fpr):
+    import torch
+    rng = np.random.default_rng(3)
+    arr = np.round(rng.normal(8, 9, (300, 150)), 1)
+    for nbhd in (1, 3, 16):
+        for conn in (1, 2):
+            got = _gpu_peaks(fpr, arr, 5, conn, nbhd)
+            want = np.array(O.get_2D_peaks(arr, 5, conn, nbhd), np.int32).reshape(-1, 2)
+            assert np.array_equal(got, want), (nbhd, conn)
+    # float32 input (the production layout) on float32-representable values, multi-track
+    a1 = rng.normal(5, 10, (2049, 90)).astype(np.float32)
+    a2 = rng.normal(5, 10, (2049, 7)).astype(np.float32)
+    host = np.concatenate([a1.T, a2.T]).astype(np.float32)
+    buf = np.zeros((host.shape[0], 2080), np.float32); buf[:, :2049] = host
+    spec = torch.from_numpy(buf).to(fpr.tdev)
+    for amp in (10, -3):
+        p = fpr.params(amp_min=amp)
+        pt, pf, tps = fpr.peaks(spec, np.array([90, 7], np.int64), p)
+        tps = tps.cpu().numpy(); pt = pt.cpu().numpy(); pf = pf.cpu().numpy()
+        for k, a in enumerate((a1, a2)):
+            want = sorted((int(t), int(f)) for f, t in O.get_2D_peaks(a.astype(np.float64), amp))
+            got = list(zip(pt[tps[k]:tps[k + 1]].tolist(), pf[tps[k]:tps[k + 1]].tolist()))
+            assert got == want, (amp, k)
+
+
+def test_k3_hashes_from_reference_peaks(fpr, wav_fixture):
+    import torch
+    from shazam_b200.fingerprinter import digests_to_hex
+    pk = wav_fixture["peaks_c2"]                       # (f, t) freq-major, as get_2D_peaks returns
+    pk = pk[np.argsort(pk[:, 1], kind="stable")]
+    pt = torch.from_numpy(pk[:, 1].copy()).to(fpr.tdev)
+    pf = torch.from_numpy(pk[:, 0].copy()).to(fpr.tdev)
+    tps = torch.tensor([0, len(pk)], dtype=torch.int64, device=fpr.tdev)
+    for fan in (5, 15, 2, 1, 64):
+        h, t1, ths = fpr.pairs_sha1(pt, pf, tps, fan)
+        if fan in (5, 15):
+            assert np.array_equal(h.cpu().numpy(), wav_fixture[f"hash_c2_fan{fan}_fs22050"])
+            assert np.array_equal(t1.cpu().numpy(), wav_fixture[f"t1_c2_fan{fan}_fs22050"])
+        else:
+            want = O.generate_hashes([(int(f), int(t)) for f, t in pk], fan)
+            assert digests_to_hex(h) == [w[0] for w in want]
+            assert t1.cpu().numpy().tolist() == [int(w[1]) for w in want]
+
+
+def test_k3_sha1_known_answers_and_digit_widths(fpr):
+    import torch
+    from shazam_b200.fingerprinter import digests_to_hex
+    import hashlib
+    # every digit-count combination of f1, f2, dt, incl. the KATs of SURVEY §8 a-5
+    fs = [0, 7, 10, 99, 100, 253, 999, 1000, 2048]
+    peaks = []
+    t = 0
+    for i, f in enumerate(fs * 3):
+        peaks.append((f, t))
+        t += [0, 1, 9, 10, 99, 100, 200, 0, 3][i % 9]
+    peaks = sorted(peaks, key=lambda p: p[1])
+    pt = torch.tensor([p[1] for p in peaks], dtype=torch.int32, device=fpr.tdev)
+    pf = torch.tensor([p[0] for p in peaks], dtype=torch.int32, device=fpr.tdev)
+    tps = torch.tensor([0, len(peaks)], dtype=torch.int64, device=fpr.tdev)
+    h, t1, _ = fpr.pairs_sha1(pt, pf, tps, 15)
+    want = O.generate_hashes(peaks, 15)
+    assert digests_to_hex(h) == [w[0] for w in want] and len(want) > 200
+    assert hashlib.sha1(b"2048|0|200").hexdigest()[:20] == "a8b1bf935e7453ba6aef"
+    pt = torch.tensor([0, 0, 200], dtype=torch.int32, device=fpr.tdev)
+    pf = torch.tensor([253, 422, 0], dtype=torch.int32, device=fpr.tdev)
+    h, t1, _ = fpr.pairs_sha1(pt, pf, torch.tensor([0, 3], dtype=torch.int64, device=fpr.tdev), 5)
+    assert digests_to_hex(h) == ["987a1bcc49e707cb9e6a", hashlib.sha1(b"253|0|200").hexdigest()[:20],
+                                 hashlib.sha1(b"422|0|200").hexdigest()[:20]]
+
+
+@pytest.mark.parametrize("conn", [2, 1])
+@pytest.mark.parametrize("fan", [5, 15])
+def test_config0_wav_end_to_end_bit_exact(fpr, wav_fixture, fan, conn):
+    """BASELINE.json configs[0]: signal_with_noise.wav, wsize 4096, overlap 0.5, amp_min 10."""
+    for fs in (22050, 44100):
+        b = fpr.fingerprint_tracks([wav_fixture["pcm"]], Fs=fs, fan_value=fan, amp_min=10, connectivity=conn)
+        assert np.array_equal(b.hash, wav_fixture[f"hash_c{conn}_fan{fan}_fs{fs}"])
+        assert np.array_equal(b.t1, wav_fixture[f"t1_c{conn}_fan{fan}_fs{fs}"])
+
+
+def test_synth_cases_end_to_end(fpr, synth_cases):
+    g = synth_cases
+    for fan, amp in ((5, 10), (15, 10), (15, 0)):
+        tracks = [g[f"{k}_pcm"] for k in g["kinds"]]
+        b = fpr.fingerprint_tracks(tracks, Fs=44100, fan_value=fan, amp_min=amp)   # one ragged batch
+        for i, kind in enumerate(g["kinds"]):
+            h, t = b.track(i)
+            assert np.array_equal(h, g[f"{kind}_hash_fan{fan}_amp{amp}"]), (kind, fan, amp)
+            assert np.array_equal(t, g[f"{kind}_t1_fan{fan}_amp{amp}"]), (kind, fan, amp)
+
+
+def test_compat_functions(fpr, wav_fixture, peaks_cases):
+    from shazam_b200 import compat
+    compat.set_fingerprinter(fpr)
+    x = wav_fixture["pcm"]
+    hs = compat.fingerprint(x, Fs=22050)
+    assert hs[:3] == [("987a1bcc49e707cb9e6a", 0), ("0f34024f21634bf6fbb0", 0), ("6d959a973dd5f6209f9c", 0)]
+    assert len(hs) == 1626 and len(set(hs)) == 1626
+    # a Python list of ints, as the recorder passes it (recognizer.py:361-368)
+    hs2, secs = compat.generate_fingerprints([int(v) for v in x[:50000]], Fs=44100)
+    h = np.frombuffer(bytes.fromhex("".join(a for a, _ in hs2)), np.uint8).reshape(-1, 10)
+    assert np.array_equal(h, wav_fixture["hash_list50k"]) and secs > 0
+    arr = peaks_cases["rand_arr"]
+    got = compat.get_2D_peaks(arr, amp_min=10)
+    assert [(int(f), int(t)) for f, t in got] == [tuple(r) for r in peaks_cases["rand_c2_amp10"].tolist()]
+    pk = [(int(f), int(t)) for f, t in wav_fixture["peaks_c2"]]
+    want = O.generate_hashes(list(pk), 5)
+    assert compat.generate_hashes(list(pk), 5) == [(a, int(b)) for a, b in want]
+    with pytest.raises(Exception):
+        compat.fingerprint(x, wsize=2048)
+    with pytest.raises(TypeError):
+        compat.fingerprint(x.astype(np.float64) / 3.0)
+    compat.set_fingerprinter(None)
+
+
+def test_chunking_and_device_path_agree(wav_fixture, native_lib):
+    """A batch split over many small chunks (host pipeline) equals the one-chunk device path."""
+    import torch
+    from shazam_b200.fingerprinter import Fingerprinter, pack_tracks
+    tracks = [O.synth_track(40 + i, n) for i, n in enumerate([90000, 30000, 5000, 250000, 44100, 3000, 120000, 66000])]
+    small = Fingerprinter(0, max_chunk_frames=128)          # forces 6+ chunks
+    big = Fingerprinter(0, max_chunk_frames=4096)
+    try:
+        a = small.fingerprint_tracks(tracks, fan_value=15)
+        pcm, starts, lens = pack_tracks(tracks)
+        d = torch.from_numpy(pcm).to(big.tdev)
+        b = big.fingerprint_device(d, starts, lens, big.params(fan_value=15))
+        c = small.fingerprint_device(d, starts, lens, small.params(fan_value=15))
+        for other in (b, c):
+            assert np.array_equal(a.starts, other.starts)
+            assert np.array_equal(a.hash, other.hash.cpu().numpy())
+            assert np.array_equal(a.t1, other.t1.cpu().numpy())
+        for i, t in enumerate(tracks):
+            h, t1 = O.fingerprint_arrays(t, 44100, 15)
+            gh, gt = a.track(i)
+            assert np.array_equal(gh, h) and np.array_equal(gt, t1), i
+        with pytest.raises(Exception, match="frames"):
+            small.fingerprint_tracks([O.synth_track(1, 2048 * 200)])
+    finally:
+        small.close(); big.close()
+
+
+def test_capacity_error_is_reported(fpr):
+    from shazam_b200 import _native as N
+    from shazam_b200.fingerprinter import pack_tracks
+    pcm, starts, lens = pack_tracks([O.synth_track(9, 100000)])
+    with pytest.raises(N.CapacityError):
+        fpr.fingerprint_host(pcm, starts, lens, fpr.params(fan_value=15), cap_hashes=10)
+
+
+def test_full_size_track_properties(fpr):
+    """BASELINE configs[1] size (3-min tracks): size-independent properties + oracle on one track."""
+    import torch
+    n = 7_938_000
+    t0 = O.synth_track(1000, n)
+    b = fpr.fingerprint_tracks([t0, t0[: n // 2], t0], fan_value=15)
+    h0, t10 = b.track(0)
+    h2, t12 = b.track(2)
+    assert np.array_equal(h0, h2) and np.array_equal(t10, t12)          # deterministic, batch-position independent
+    assert np.all(np.diff(t10) >= 0) and t10.max() < 3874                # anchors time-ordered, inside the track
+    h1, t11 = b.track(1)
+    # a prefix of the audio gives a prefix of the fingerprints (frames far from the cut are unaffected)
+    keep = t11 < (n // 2 - 2048) // 2048 - 1 - 10 - 200
+    m = keep.sum()
+    assert m > 1000 and np.array_equal(h1[:m], h0[:m]) and np.array_equal(t11[:m], t10[:m])
+    oh, ot = O.fingerprint_arrays(t0, 44100, 15)
+    sa = set(zip(map(bytes, h0), t10.tolist())); sb = set(zip(map(bytes, oh), ot.tolist()))
+    jacc = len(sa & sb) / len(sa | sb)
+    assert jacc >= 0.99, jacc
+    assert len(h0) == len(oh) or jacc < 1.0
