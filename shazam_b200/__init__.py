@@ -17,7 +17,7 @@ def __getattr__(name):
                 "as_pcm_int16"):
         from . import fingerprinter
         return getattr(fingerprinter, name)
-    if name == "compat":
-        from . import compat
-        return compat
+    if name in ("compat", "fingerprinter", "database", "recognize", "distributed"):
+        import importlib
+        return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -271,6 +271,8 @@ class Fingerprinter:
         for _ in range(6):
             try:
                 return self.fingerprint_host(pcm, starts, lens, p, cap_hashes=cap)
-            except N.CapacityError:
+            except N.CapacityError as e:
+                if "hash output capacity" not in str(e):
+                    raise
                 cap *= 4
         raise N.CapacityError(N.E_CAPACITY, "hash output keeps overflowing")
