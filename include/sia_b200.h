@@ -164,6 +164,10 @@ int sia_index_insert_host(sia_index *ix, int32_t song_id, const uint8_t *h_hash,
 int sia_index_finalize(sia_index *ix, int64_t *h_rows);
 int64_t sia_index_rows(const sia_index *ix);
 
+/* DELETE FROM songs WHERE ... with ON DELETE CASCADE on fingerprints (mysql_database.py:56-57,
+ * 132-139): remove every stored row of the listed songs.  *h_rows = rows left.  Synchronous. */
+int sia_index_delete_songs(sia_index *ix, const int32_t *h_song_ids, int32_t n, int64_t *h_rows);
+
 /* SELECT HEX(hash), song_id, offset WHERE hash IN (...) (recognizer.py:60-64, 252-259):
  * every stored row whose hash is in the list of n DISTINCT hashes.  Row order: by
  * position in h_hash, then (song_id, offset).  Fills up to cap rows; *h_nrows = total. */
@@ -180,8 +184,8 @@ int sia_index_select_host(sia_index *ix, const uint8_t *h_hash, int64_t n, int32
  *   out_rows             — dedup_hashes[song]: DB rows matched, counted once per row,
  *   out_nres[q]          — number of valid results (<= topn).
  * Equal counts order by ascending song id (stable sort, recognizer.py:307-310).
- * h_stats (optional, 4 x int64): distinct query hashes, DB rows matched, (song,diff)
- * tuples voted, distinct bins. */
+ * h_stats (optional, 4 x int64): query (hash, offset) pairs, DB rows matched (the total of
+ * dedup_hashes), (song, diff) tuples voted (len(results) of return_matches), distinct bins. */
 int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff,
                           const int64_t *h_query_starts, int32_t n_queries, int32_t topn,
                           int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
@@ -201,9 +205,9 @@ int sia_vote_bins(int device, const uint64_t *d_bin_key, const int32_t *d_bin_co
                   int32_t n_queries, int32_t topn, int32_t *d_out_song, int32_t *d_out_diff,
                   int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres, void *stream);
 
-/* bin key layout: [63:44] query id (20 bits) | [43:20] song id (24 bits) | [19:0]... see
- * SIA_BINKEY_* — diff is stored biased by 2^24 in 25 bits, so the key is
- * qid(15) | song(24) | diff+2^24 (25). */
+/* bin key layout (64 bits): query id (15 bits) | song id (24 bits) | offset difference + 2^24
+ * (25 bits); row keys use the same layout with a zero difference field.  At most 32768 queries
+ * per sia_index_query_partial / sia_vote_bins call (sia_index_query_batch splits internally). */
 #define SIA_BINKEY_DIFF_BITS 25
 #define SIA_BINKEY_SONG_BITS 24
 #define SIA_BINKEY_QID_BITS  15

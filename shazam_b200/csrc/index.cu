@@ -1,20 +1,941 @@
-// K4 placeholder — replaced by the real index in the next milestone.
+// K4 — the fingerprint index: replaces the MySQL `fingerprints` table
+// (mysql_database.py:46-59), its INSERT IGNORE (:62-68,167-181), the
+// SELECT ... WHERE hash IN (...) lookup (recognizer.py:60-64,252-259) and the vote inside
+// align_matches (recognizer.py:303-310).
+//
+// Storage: one 16-byte row per fingerprint, sorted by (hash, song_id, offset):
+//     .y = digest bytes 0..7 (big-endian, so integer order = byte order)
+//     .x = digest bytes 8..9 (16 bits) | song_id (24 bits) | offset (24 bits)
+// plus a bucket directory on the top `dir_bits` bits of the digest (SHA-1 output is
+// uniform, so buckets are balanced; a heavy key is one long run inside its bucket).
+// Equal rows are adjacent after the sort, which is how UNIQUE(song_id, offset, hash)
+// (INSERT IGNORE set semantics) is enforced.
+//
+// Query: the (hash, offset) pairs of a batch of queries are sorted by (query, hash,
+// offset) — duplicates drop out, equal hashes of one query become adjacent — each is
+// looked up (directory + binary search), the posting runs are expanded into
+// (query, song, db_offset - query_offset) keys, sorted, run-length counted into bins,
+// and voted: per (query, song) the bin with the largest count (smallest difference on
+// ties), per query the top-n songs by that count (ascending song id on ties).
 #include "sia_common.cuh"
+#include "sort.cuh"
+
+#include <algorithm>
+#include <vector>
+
 using namespace sia;
-#define NOTYET() do { set_error("index: not implemented yet"); return SIA_E_UNSUPPORTED; } while (0)
-extern "C" {
-int sia_index_create(int, int64_t, sia_index **) { NOTYET(); }
-int sia_index_destroy(sia_index *) { return SIA_OK; }
-int sia_index_insert(sia_index *, int32_t, const uint8_t *, const int32_t *, int64_t, void *) { NOTYET(); }
-int sia_index_insert_rows(sia_index *, const int32_t *, const uint8_t *, const int32_t *, int64_t, void *) { NOTYET(); }
-int sia_index_insert_host(sia_index *, int32_t, const uint8_t *, const int32_t *, int64_t) { NOTYET(); }
-int sia_index_finalize(sia_index *, int64_t *) { NOTYET(); }
-int64_t sia_index_rows(const sia_index *) { return 0; }
-int sia_index_select_host(sia_index *, const uint8_t *, int64_t, int32_t *, int32_t *, int32_t *, int64_t, int64_t *) { NOTYET(); }
-int sia_index_query_batch(sia_index *, const uint8_t *, const int32_t *, const int64_t *, int32_t, int32_t, int32_t *,
-                          int32_t *, int32_t *, int32_t *, int32_t *, int64_t *, void *) { NOTYET(); }
-int sia_index_query_partial(sia_index *, const uint8_t *, const int32_t *, const int32_t *, int64_t, uint64_t *, int32_t *,
-                            int64_t, int64_t *, uint64_t *, int32_t *, int64_t, int64_t *, void *) { NOTYET(); }
-int sia_vote_bins(int, const uint64_t *, const int32_t *, int64_t, const uint64_t *, const int32_t *, int64_t, int32_t,
-                  int32_t, int32_t *, int32_t *, int32_t *, int32_t *, int32_t *, void *) { NOTYET(); }
+
+namespace {
+
+constexpr int kQidBits = SIA_BINKEY_QID_BITS, kSongBits = SIA_BINKEY_SONG_BITS, kDiffBits = SIA_BINKEY_DIFF_BITS;
+constexpr int64_t kMaxQueriesPerPass = 1ll << kQidBits;
+constexpr uint64_t kM24 = 0xffffffull;
+
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, used = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) { used = 0; return SIA_OK; }
+    if (base) cudaFree(base);
+    base = nullptr; cap = 0; used = 0;
+    size_t want = bytes + (bytes >> 3) + (1 << 20);
+    SIA_CUDA(cudaMalloc(&base, want));
+    cap = want;
+    return SIA_OK;
+  }
+  template <typename T> T *take(size_t n) {
+    used = (used + 255) & ~(size_t)255;
+    T *p = reinterpret_cast<T *>(base + used);
+    used += n * sizeof(T);
+    return used <= cap ? p : nullptr;
+  }
+  void release() { if (base) cudaFree(base); base = nullptr; cap = used = 0; }
+};
+
+}  // namespace
+
+struct sia_index {
+  int device = 0;
+  int64_t capacity = 0;
+  ulonglong2 *rows = nullptr;   // [capacity]: sorted rows [0, n_rows), then pending rows
+  int64_t n_rows = 0, n_pending = 0;
+  uint32_t *dir = nullptr;      // [2^dir_bits + 1]
+  int dir_bits = 0;
+  int32_t *status = nullptr;    // device flag: 1 = song/offset out of range on insert, 2 = query offset out of range
+  Arena arena;                  // build / lookup scratch
+  Arena arena2;                 // per-group vote scratch
+};
+
+namespace {
+
+__device__ __forceinline__ void load_digest(const uint8_t *__restrict__ h, uint64_t &hi, uint32_t &lo16) {
+  const uint16_t *p = reinterpret_cast<const uint16_t *>(h);   // 10*i is 2-byte aligned
+  uint32_t w[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { const uint32_t v = p[k]; w[k] = ((v & 0xff) << 8) | (v >> 8); }   // big-endian pairs
+  hi = ((uint64_t)w[0] << 48) | ((uint64_t)w[1] << 32) | ((uint64_t)w[2] << 16) | (uint64_t)w[3];
+  lo16 = w[4];
 }
+
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const uint8_t *__restrict__ hash, const int32_t *__restrict__ off, const int32_t *__restrict__ song_arr,
+                 int32_t song_const, int64_t n, ulonglong2 *__restrict__ out, int32_t *__restrict__ status) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t hi; uint32_t lo16;
+    load_digest(hash + i * SIA_HASH_BYTES, hi, lo16);
+    const int32_t song = song_arr ? song_arr[i] : song_const;
+    const int32_t o = off[i];
+    if (song < 0 || song > (int32_t)kM24 || o < 0 || o > (int32_t)kM24) atomicOr(status, 1);
+    out[i] = make_ulonglong2(((uint64_t)lo16 << 48) | (((uint64_t)song & kM24) << 24) | ((uint64_t)o & kM24), hi);
+  }
+}
+
+__device__ __forceinline__ bool rec_eq(const ulonglong2 &a, const ulonglong2 &b) { return a.x == b.x && a.y == b.y; }
+
+__global__ void __launch_bounds__(256)
+uniq_flag_kernel(const ulonglong2 *__restrict__ r, int64_t n, uint32_t *__restrict__ flag) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    flag[i] = (i == 0 || !rec_eq(r[i], r[i - 1])) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+keep_flag_kernel(const ulonglong2 *__restrict__ r, int64_t n, const uint32_t *__restrict__ dead_bitmap,
+                 uint32_t *__restrict__ flag) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t song = (uint32_t)(r[i].x >> 24) & 0xffffffu;
+    flag[i] = (dead_bitmap[song >> 5] >> (song & 31)) & 1u ? 0u : 1u;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+uniq_compact_kernel(const ulonglong2 *__restrict__ r, int64_t n, const uint32_t *__restrict__ flag,
+                    const int64_t *__restrict__ pos, ulonglong2 *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (flag[i]) out[pos[i]] = r[i];
+}
+
+__global__ void __launch_bounds__(256)
+build_dir_kernel(const ulonglong2 *__restrict__ r, int64_t n, int bits, uint32_t *__restrict__ dir) {
+  const int64_t nb = 1ll << bits;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b_prev = i == 0 ? -1 : (int64_t)(r[i - 1].y >> (64 - bits));
+    const int64_t b = i == n ? nb : (int64_t)(r[i].y >> (64 - bits));
+    for (int64_t k = b_prev + 1; k <= b; ++k) dir[k] = (uint32_t)i;
+  }
+}
+
+// first row index in [lo, hi) whose (digest) >= (khi, klo16)
+__device__ __forceinline__ uint32_t lower_bound_key(const ulonglong2 *__restrict__ r, uint32_t lo, uint32_t hi, uint64_t khi,
+                                                    uint32_t klo16) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    const ulonglong2 v = r[mid];
+    const bool less = v.y < khi || (v.y == khi && (uint32_t)(v.x >> 48) < klo16);
+    if (less) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void posting_range(const ulonglong2 *__restrict__ rows, const uint32_t *__restrict__ dir, int bits,
+                                              uint64_t khi, uint32_t klo16, uint32_t &first, uint32_t &count) {
+  const uint64_t b = khi >> (64 - bits);
+  const uint32_t lo = dir[b], hi = dir[b + 1];
+  first = lower_bound_key(rows, lo, hi, khi, klo16);
+  uint32_t e = first;
+  auto match = [&](uint32_t i) { const ulonglong2 v = rows[i]; return v.y == khi && (uint32_t)(v.x >> 48) == klo16; };
+  if (e < hi && match(e)) {
+    // runs are short: gallop to bracket the end of the equal run, then binary search it
+    uint32_t good = e, bad = hi, step = 1;       // rows[good] matches; rows[bad] does not (or bad == hi)
+    for (;;) {
+      const uint32_t nxt = good + step;
+      if (nxt >= hi) break;
+      if (!match(nxt)) { bad = nxt; break; }
+      good = nxt;
+      step <<= 1;
+    }
+    uint32_t a = good + 1, c = bad;
+    while (a < c) {
+      const uint32_t mid = a + ((c - a) >> 1);
+      if (match(mid)) a = mid + 1; else c = mid;
+    }
+    e = a;
+  }
+  count = e - first;
+}
+
+// query entry record, sorted by all 16 bytes = (qid, digest, qoff):
+//   .y = qid (24) | digest bits 79..40 (40)      .x = digest bits 39..16 (24) | digest lo16 (16) | qoff (24)
+__global__ void __launch_bounds__(256)
+pack_queries_kernel(const uint8_t *__restrict__ hash, const int32_t *__restrict__ qoff, const int32_t *__restrict__ qid_arr,
+                    const int64_t *__restrict__ query_starts, int n_queries, int qid_base, int64_t i0, int64_t n,
+                    ulonglong2 *__restrict__ out, int32_t *__restrict__ status) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + k;
+    uint64_t hi; uint32_t lo16;
+    load_digest(hash + i * SIA_HASH_BYTES, hi, lo16);
+    const int32_t q = qid_arr ? qid_arr[i] - qid_base : find_segment(query_starts, n_queries, i) - qid_base;
+    const int32_t o = qoff[i];
+    if (o < 0 || o > (int32_t)kM24 || q < 0 || q >= (1 << kQidBits)) atomicOr(status, 2);
+    out[k] = make_ulonglong2(((hi & kM24) << 40) | ((uint64_t)lo16 << 24) | ((uint64_t)o & kM24),
+                             ((uint64_t)q << 40) | (hi >> 24));
+  }
+}
+
+__device__ __forceinline__ void entry_key(const ulonglong2 &e, uint64_t &khi, uint32_t &klo16, uint32_t &qid, uint32_t &qoff) {
+  qid = (uint32_t)(e.y >> 40);
+  khi = (e.y << 24) | (e.x >> 40);
+  klo16 = (uint32_t)(e.x >> 24) & 0xffffu;
+  qoff = (uint32_t)(e.x & kM24);
+}
+
+__global__ void __launch_bounds__(256)
+lookup_kernel(const ulonglong2 *__restrict__ ent, int64_t n, const ulonglong2 *__restrict__ rows,
+              const uint32_t *__restrict__ dir, int bits, int64_t n_rows, uint32_t *__restrict__ first,
+              uint32_t *__restrict__ cnt_all, uint32_t *__restrict__ cnt_head) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const ulonglong2 e = ent[i];
+    bool dup = false, head = true;
+    if (i > 0) {
+      const ulonglong2 p = ent[i - 1];
+      dup = rec_eq(e, p);
+      head = !(p.y == e.y && (p.x >> 24) == (e.x >> 24));   // same (qid, digest) as the previous entry?
+    }
+    uint32_t f = 0, c = 0;
+    if (!dup && n_rows > 0) {
+      uint64_t khi; uint32_t klo16, qid, qoff;
+      entry_key(e, khi, klo16, qid, qoff);
+      posting_range(rows, dir, bits, khi, klo16, f, c);
+    }
+    first[i] = f;
+    cnt_all[i] = c;
+    cnt_head[i] = head ? c : 0u;
+  }
+}
+
+// Expand posting runs into vote keys.  One block handles 256 consecutive entries and spreads
+// their postings evenly over its threads (binary search over the block-local offsets).
+template <bool HEADS>
+__global__ void __launch_bounds__(256)
+expand_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, const uint32_t *__restrict__ first,
+              const int64_t *__restrict__ off, const ulonglong2 *__restrict__ rows, uint64_t *__restrict__ out,
+              int64_t out_base) {
+  __shared__ int64_t s_off[257];
+  const int64_t b0 = e0 + (int64_t)blockIdx.x * 256;
+  const int64_t i = b0 + threadIdx.x;
+  const int nloc = (int)min((int64_t)256, e0 + n - b0);
+  if (threadIdx.x < nloc) s_off[threadIdx.x] = off[i];
+  if (threadIdx.x == 0) s_off[nloc] = off[b0 + nloc];
+  __syncthreads();
+  const int64_t base = s_off[0], total = s_off[nloc] - base;
+  for (int64_t j = threadIdx.x; j < total; j += 256) {
+    int lo = 0, hi = nloc;               // largest e with s_off[e] - base <= j
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] - base <= j) lo = mid; else hi = mid; }
+    const int64_t ei = b0 + lo;
+    const uint32_t k = (uint32_t)(j - (s_off[lo] - base));
+    const ulonglong2 e = ent[ei];
+    const ulonglong2 r = rows[first[ei] + k];
+    const uint64_t qid = e.y >> 40;
+    const uint64_t song = (r.x >> 24) & kM24;
+    uint64_t key = (qid << (kSongBits + kDiffBits)) | (song << kDiffBits);
+    if (!HEADS) {
+      const int32_t diff = (int32_t)(r.x & kM24) - (int32_t)(e.x & kM24);   // db offset - query offset
+      key |= (uint64_t)(uint32_t)(diff + SIA_DIFF_BIAS);
+    }
+    out[base - out_base + j] = key;
+  }
+}
+
+// run-length / weighted-run reduction of sorted keys: flag run heads, scan, then accumulate
+__global__ void __launch_bounds__(256)
+run_flag_kernel(const uint64_t *__restrict__ key, int64_t n, int shift, uint32_t *__restrict__ flag) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    flag[i] = (i == 0 || (key[i] >> shift) != (key[i - 1] >> shift)) ? 1u : 0u;
+}
+
+// pos[] is the exclusive scan of flag[]: element i belongs to run pos[i+1]-1
+__global__ void __launch_bounds__(256)
+run_reduce_kernel(const uint64_t *__restrict__ key, const int32_t *__restrict__ weight, int64_t n,
+                  const uint32_t *__restrict__ flag, const int64_t *__restrict__ pos, uint64_t *__restrict__ bin_key,
+                  int32_t *__restrict__ bin_count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = pos[i + 1] - 1;
+    if (flag[i]) bin_key[b] = key[i];
+    atomicAdd(&bin_count[b], weight ? weight[i] : 1);
+  }
+}
+
+// per (query, song) segment: best = max over its bins of (count << 25 | inverted diff) -> largest count,
+// smallest offset difference on ties (Python's max() keeps the first maximum, recognizer.py:308)
+__global__ void __launch_bounds__(256)
+seg_best_kernel(const uint64_t *__restrict__ bin_key, const int32_t *__restrict__ bin_count, int64_t nbins,
+                const uint32_t *__restrict__ flag, const int64_t *__restrict__ pos, uint64_t *__restrict__ seg_key,
+                unsigned long long *__restrict__ seg_best) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbins; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = pos[i + 1] - 1;
+    const uint64_t k = bin_key[i];
+    if (flag[i]) seg_key[s] = k >> kDiffBits;
+    const uint64_t inv = ((1ull << kDiffBits) - 1) - (k & ((1ull << kDiffBits) - 1));
+    atomicMax(&seg_best[s], ((unsigned long long)(uint32_t)bin_count[i] << kDiffBits) | inv);
+  }
+}
+
+__device__ __forceinline__ int64_t lower_bound_u64(const uint64_t *__restrict__ a, int64_t n, uint64_t v) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if (a[mid] < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// one block per query: top-n segments by (count desc, song asc)
+__global__ void __launch_bounds__(256)
+topn_kernel(const uint64_t *__restrict__ seg_key, const unsigned long long *__restrict__ seg_best, int64_t nseg,
+            const uint64_t *__restrict__ row_key, const int32_t *__restrict__ row_count, int64_t nrowbins, int q_lo,
+            int qid_base, int topn, int32_t *__restrict__ out_song, int32_t *__restrict__ out_diff, int32_t *__restrict__ out_count,
+            int32_t *__restrict__ out_rows, int32_t *__restrict__ out_nres) {
+  __shared__ unsigned long long s_best[256];
+  __shared__ int64_t s_idx[256];
+  __shared__ unsigned long long s_prev;
+  const uint64_t q = (uint64_t)blockIdx.x + q_lo;
+  const int64_t s0 = lower_bound_u64(seg_key, nseg, q << kSongBits);
+  const int64_t s1 = lower_bound_u64(seg_key, nseg, (q + 1) << kSongBits);
+  if (threadIdx.x == 0) s_prev = ~0ull;
+  __syncthreads();
+  int nres = 0;
+  for (int r = 0; r < topn; ++r) {
+    const unsigned long long prev = s_prev;
+    unsigned long long best = 0;
+    int64_t bi = -1;
+    for (int64_t s = s0 + threadIdx.x; s < s1; s += 256) {
+      // rank key: count (high) then inverted song id, so equal counts order by ascending song id
+      const unsigned long long c = seg_best[s] >> kDiffBits;
+      const unsigned long long k = (c << kSongBits) | (kM24 - (seg_key[s] & kM24));
+      if (k < prev && (bi < 0 || k > best)) { best = k; bi = s; }
+    }
+    s_best[threadIdx.x] = best; s_idx[threadIdx.x] = bi;
+    __syncthreads();
+    for (int d = 128; d; d >>= 1) {
+      if (threadIdx.x < d) {
+        const int64_t oi = s_idx[threadIdx.x + d];
+        if (oi >= 0 && (s_idx[threadIdx.x] < 0 || s_best[threadIdx.x + d] > s_best[threadIdx.x])) {
+          s_best[threadIdx.x] = s_best[threadIdx.x + d]; s_idx[threadIdx.x] = oi;
+        }
+      }
+      __syncthreads();
+    }
+    const int64_t w = s_idx[0];
+    if (w < 0) break;                       // uniform: every thread reads the same shared value
+    if (threadIdx.x == 0) {
+      const uint64_t sk = seg_key[w];
+      const unsigned long long v = seg_best[w];
+      const int64_t o = ((int64_t)q + qid_base) * topn + r;
+      out_song[o] = (int32_t)(sk & kM24);
+      out_count[o] = (int32_t)(v >> kDiffBits);
+      out_diff[o] = (int32_t)(((1ull << kDiffBits) - 1) - (v & ((1ull << kDiffBits) - 1))) - SIA_DIFF_BIAS;
+      const int64_t rb = lower_bound_u64(row_key, nrowbins, sk << kDiffBits);
+      out_rows[o] = (rb < nrowbins && row_key[rb] == (sk << kDiffBits)) ? row_count[rb] : 0;
+      s_prev = s_best[0];
+    }
+    ++nres;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out_nres[q + qid_base] = nres;
+}
+
+__global__ void split_bins_kernel(const ulonglong2 *__restrict__ rec, int64_t n, uint64_t *__restrict__ key,
+                                  int32_t *__restrict__ w) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    key[i] = rec[i].y; w[i] = (int32_t)rec[i].x;
+  }
+}
+__global__ void join_bins_kernel(const uint64_t *__restrict__ key, const int32_t *__restrict__ w, int64_t n,
+                                 ulonglong2 *__restrict__ rec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    rec[i] = make_ulonglong2((uint64_t)(uint32_t)w[i], key[i]);
+}
+
+__global__ void select_rows_kernel(const ulonglong2 *__restrict__ ent, int64_t n, const uint32_t *__restrict__ first,
+                                   const int64_t *__restrict__ off, const ulonglong2 *__restrict__ rows,
+                                   int32_t *__restrict__ o_idx, int32_t *__restrict__ o_song, int32_t *__restrict__ o_off,
+                                   int64_t cap) {
+  // entries here are packed with qid = position of the hash in the caller's list
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = off[i], c = off[i + 1] - b;
+    for (int64_t k = 0; k < c; ++k) {
+      if (b + k >= cap) break;
+      const ulonglong2 r = rows[first[i] + k];
+      o_idx[b + k] = (int32_t)(ent[i].x & kM24);
+      o_song[b + k] = (int32_t)((r.x >> 24) & kM24);
+      o_off[b + k] = (int32_t)(r.x & kM24);
+    }
+  }
+}
+
+__global__ void gather_offsets_kernel(const int64_t *__restrict__ off_all, const int64_t *__restrict__ off_head,
+                                      const int64_t *__restrict__ query_starts, int64_t i0, int nq,
+                                      int64_t *__restrict__ out) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q <= nq; q += gridDim.x * blockDim.x) {
+    const int64_t e = query_starts[q] - i0;
+    out[q] = off_all[e];
+    out[nq + 1 + q] = off_head[e];
+  }
+}
+
+inline unsigned grid_for(int64_t n, int threads = 256) {
+  int64_t b = ceil_div(n > 0 ? n : 1, threads);
+  return (unsigned)std::min<int64_t>(b, kNumSMs * 32);
+}
+
+int set_device(const sia_index *ix) {
+  SIA_CUDA(cudaSetDevice(ix->device));
+  return SIA_OK;
+}
+
+// sorted unique keys + counts from a sorted key array (optionally weighted).  Returns bins on the device.
+int reduce_runs(Arena &ar, const uint64_t *d_key, const int32_t *d_weight, int64_t n, uint64_t **bin_key,
+                int32_t **bin_count, int64_t *nbins, cudaStream_t s) {
+  *nbins = 0; *bin_key = nullptr; *bin_count = nullptr;
+  if (n == 0) return SIA_OK;
+  uint32_t *flag = ar.take<uint32_t>(n);
+  int64_t *pos = ar.take<int64_t>(n + 1);
+  void *stmp = ar.take<char>(scan_tmp_bytes(n));
+  SIA_REQUIRE(flag && pos && stmp, SIA_E_NOMEM, "index scratch arena too small (reduce_runs)");
+  run_flag_kernel<<<grid_for(n), 256, 0, s>>>(d_key, n, 0, flag);
+  SIA_CHECK_LAUNCH();
+  int rc = exclusive_scan_u32(flag, pos, n, stmp, s);
+  if (rc) return rc;
+  int64_t nb = 0;
+  SIA_CUDA(cudaMemcpyAsync(&nb, pos + n, sizeof nb, cudaMemcpyDeviceToHost, s));
+  SIA_CUDA(cudaStreamSynchronize(s));
+  uint64_t *bk = ar.take<uint64_t>(nb);
+  int32_t *bc = ar.take<int32_t>(nb);
+  SIA_REQUIRE(bk && bc, SIA_E_NOMEM, "index scratch arena too small (bins)");
+  SIA_CUDA(cudaMemsetAsync(bc, 0, sizeof(int32_t) * nb, s));
+  run_reduce_kernel<<<grid_for(n), 256, 0, s>>>(d_key, d_weight, n, flag, pos, bk, bc);
+  SIA_CHECK_LAUNCH();
+  *bin_key = bk; *bin_count = bc; *nbins = nb;
+  return SIA_OK;
+}
+
+size_t reduce_runs_bytes(int64_t n) { return (size_t)n * (4 + 8 + 8 + 4) + scan_tmp_bytes(n) + 4096; }
+
+// vote over sorted unique bins (+ sorted unique row bins) for the pass-local queries [q_lo, q_hi)
+int vote_sorted(Arena &ar, const uint64_t *bin_key, const int32_t *bin_count, int64_t nbins, const uint64_t *row_key,
+                const int32_t *row_count, int64_t nrowbins, int q_lo, int q_hi, int qid_base, int topn, int32_t *o_song,
+                int32_t *o_diff, int32_t *o_count, int32_t *o_rows, int32_t *o_nres, cudaStream_t s) {
+  if (q_hi <= q_lo) return SIA_OK;
+  uint64_t *seg_key = nullptr;
+  unsigned long long *seg_best = nullptr;
+  int64_t nseg = 0;
+  if (nbins > 0) {
+    uint32_t *flag = ar.take<uint32_t>(nbins);
+    int64_t *pos = ar.take<int64_t>(nbins + 1);
+    void *stmp = ar.take<char>(scan_tmp_bytes(nbins));
+    SIA_REQUIRE(flag && pos && stmp, SIA_E_NOMEM, "index scratch arena too small (vote)");
+    run_flag_kernel<<<grid_for(nbins), 256, 0, s>>>(bin_key, nbins, kDiffBits, flag);
+    SIA_CHECK_LAUNCH();
+    int rc = exclusive_scan_u32(flag, pos, nbins, stmp, s);
+    if (rc) return rc;
+    SIA_CUDA(cudaMemcpyAsync(&nseg, pos + nbins, sizeof nseg, cudaMemcpyDeviceToHost, s));
+    SIA_CUDA(cudaStreamSynchronize(s));
+    seg_key = ar.take<uint64_t>(nseg);
+    seg_best = ar.take<unsigned long long>(nseg);
+    SIA_REQUIRE(seg_key && seg_best, SIA_E_NOMEM, "index scratch arena too small (segments)");
+    SIA_CUDA(cudaMemsetAsync(seg_best, 0, sizeof(unsigned long long) * nseg, s));
+    seg_best_kernel<<<grid_for(nbins), 256, 0, s>>>(bin_key, bin_count, nbins, flag, pos, seg_key, seg_best);
+    SIA_CHECK_LAUNCH();
+  }
+  topn_kernel<<<q_hi - q_lo, 256, 0, s>>>(seg_key, seg_best, nseg, row_key, row_count, nrowbins, q_lo, qid_base, topn,
+                                          o_song, o_diff, o_count, o_rows, o_nres);
+  SIA_CHECK_LAUNCH();
+  return SIA_OK;
+}
+
+size_t vote_bytes(int64_t nbins) { return (size_t)nbins * (4 + 8 + 8 + 8) + scan_tmp_bytes(nbins) + 4096; }
+
+// Sorted, de-duplicated query entries for queries [q0, q1) (entries [i0, i1) of the caller's arrays).
+struct Lookup {
+  ulonglong2 *ent = nullptr;
+  uint32_t *first = nullptr;
+  int64_t *off_all = nullptr, *off_head = nullptr;
+  int64_t n = 0, tuples = 0, head_rows = 0, distinct = 0;
+};
+
+int lookup_pass(sia_index *ix, Arena &ar, const uint8_t *d_hash, const int32_t *d_qoff, const int32_t *d_qid,
+                const int64_t *d_query_starts, int n_queries, int qid_base, int64_t i0, int64_t n, Lookup &L,
+                cudaStream_t s) {
+  L = Lookup();
+  L.n = n;
+  if (n == 0) return SIA_OK;
+  ulonglong2 *a = ar.take<ulonglong2>(n), *b = ar.take<ulonglong2>(n);
+  void *stmp = ar.take<char>(radix_sort_tmp_bytes(n));
+  uint32_t *first = ar.take<uint32_t>(n), *c_all = ar.take<uint32_t>(n), *c_head = ar.take<uint32_t>(n);
+  int64_t *off_all = ar.take<int64_t>(n + 1), *off_head = ar.take<int64_t>(n + 1);
+  SIA_REQUIRE(a && b && stmp && first && c_all && c_head && off_all && off_head, SIA_E_NOMEM,
+              "index scratch arena too small (lookup)");
+  pack_queries_kernel<<<grid_for(n), 256, 0, s>>>(d_hash, d_qoff, d_qid, d_query_starts, n_queries, qid_base, i0, n, a,
+                                                 ix->status);
+  SIA_CHECK_LAUNCH();
+  bool in_b = false;
+  int rc = radix_sort(a, b, n, 16, 0, 16, stmp, s, &in_b);
+  if (rc) return rc;
+  L.ent = in_b ? b : a;
+  lookup_kernel<<<grid_for(n), 256, 0, s>>>(L.ent, n, ix->rows, ix->dir, ix->dir_bits, ix->n_rows, first, c_all, c_head);
+  SIA_CHECK_LAUNCH();
+  if ((rc = exclusive_scan_u32(c_all, off_all, n, stmp, s))) return rc;
+  if ((rc = exclusive_scan_u32(c_head, off_head, n, stmp, s))) return rc;
+  int64_t tot[2];
+  SIA_CUDA(cudaMemcpyAsync(&tot[0], off_all + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  SIA_CUDA(cudaMemcpyAsync(&tot[1], off_head + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  SIA_CUDA(cudaStreamSynchronize(s));
+  L.first = first; L.off_all = off_all; L.off_head = off_head; L.tuples = tot[0]; L.head_rows = tot[1];
+  return SIA_OK;
+}
+
+size_t lookup_bytes(int64_t n) { return (size_t)n * (16 * 2 + 4 * 3) + (size_t)(n + 1) * 16 + radix_sort_tmp_bytes(n) + 8192; }
+
+// entries [e0, e0+ne) of a Lookup -> sorted unique vote bins and row bins
+int bins_from_entries(sia_index *ix, Arena &ar, const Lookup &L, int64_t e0, int64_t ne, int64_t tuples, int64_t tuple_base,
+                      int64_t head_rows, int64_t head_base, uint64_t **bin_key, int32_t **bin_count, int64_t *nbins,
+                      uint64_t **row_key, int32_t **row_count, int64_t *nrowbins, cudaStream_t s) {
+  int rc;
+  *nbins = *nrowbins = 0;
+  *bin_key = *row_key = nullptr; *bin_count = *row_count = nullptr;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int64_t m = pass == 0 ? tuples : head_rows;
+    if (m == 0) continue;
+    uint64_t *ka = ar.take<uint64_t>(m), *kb = ar.take<uint64_t>(m);
+    void *stmp = ar.take<char>(radix_sort_tmp_bytes(m));
+    SIA_REQUIRE(ka && kb && stmp, SIA_E_NOMEM, "index scratch arena too small (tuples)");
+    const unsigned blocks = (unsigned)ceil_div(ne, 256);
+    if (pass == 0)
+      expand_kernel<false><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, ix->rows, ka, tuple_base);
+    else
+      expand_kernel<true><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_head, ix->rows, ka, head_base);
+    SIA_CHECK_LAUNCH();
+    bool in_b = false;
+    if ((rc = radix_sort(ka, kb, m, 8, 0, 8, stmp, s, &in_b))) return rc;
+    uint64_t *sorted = in_b ? kb : ka;
+    if (pass == 0) rc = reduce_runs(ar, sorted, nullptr, m, bin_key, bin_count, nbins, s);
+    else rc = reduce_runs(ar, sorted, nullptr, m, row_key, row_count, nrowbins, s);
+    if (rc) return rc;
+  }
+  return SIA_OK;
+}
+
+size_t bins_bytes(int64_t tuples, int64_t head_rows) {
+  return (size_t)tuples * 16 + radix_sort_tmp_bytes(tuples) + reduce_runs_bytes(tuples) + (size_t)head_rows * 16 +
+         radix_sort_tmp_bytes(head_rows) + reduce_runs_bytes(head_rows) + 8192;
+}
+
+int check_status(sia_index *ix, cudaStream_t s, int mask, const char *msg) {
+  int32_t st = 0;
+  SIA_CUDA(cudaMemcpyAsync(&st, ix->status, sizeof st, cudaMemcpyDeviceToHost, s));
+  SIA_CUDA(cudaStreamSynchronize(s));
+  if (st & mask) {
+    SIA_CUDA(cudaMemsetAsync(ix->status, 0, sizeof(int32_t), s));
+    set_error(msg);
+    return SIA_E_INVALID;
+  }
+  return SIA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sia_index_create(int device, int64_t capacity_rows, sia_index **out) {
+  SIA_REQUIRE(out != nullptr, SIA_E_INVALID, "out is NULL");
+  *out = nullptr;
+  SIA_REQUIRE(capacity_rows > 0 && capacity_rows < 0xfffffff0ll, SIA_E_INVALID,
+              "capacity_rows must be in 1 .. 2^32-17 (row ids are 32 bit)");
+  int ndev = 0;
+  SIA_CUDA(cudaGetDeviceCount(&ndev));
+  SIA_REQUIRE(device >= 0 && device < ndev, SIA_E_INVALID, "no such CUDA device");
+  SIA_CUDA(cudaSetDevice(device));
+  sia_index *ix = new (std::nothrow) sia_index();
+  SIA_REQUIRE(ix != nullptr, SIA_E_NOMEM, "out of host memory");
+  ix->device = device;
+  ix->capacity = capacity_rows;
+  cudaError_t e = cudaMalloc(&ix->rows, (size_t)capacity_rows * sizeof(ulonglong2));
+  if (e == cudaSuccess) e = cudaMalloc(&ix->status, sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemset(ix->status, 0, sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&ix->dir, 2 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(ix->dir, 0, 2 * sizeof(uint32_t));
+  if (e != cudaSuccess) {
+    int rc = cuda_fail(e, "index allocation", __FILE__, __LINE__);
+    sia_index_destroy(ix);
+    return rc;
+  }
+  ix->dir_bits = 0;
+  *out = ix;
+  return SIA_OK;
+}
+
+int sia_index_destroy(sia_index *ix) {
+  if (!ix) return SIA_OK;
+  cudaSetDevice(ix->device);
+  cudaDeviceSynchronize();
+  if (ix->rows) cudaFree(ix->rows);
+  if (ix->dir) cudaFree(ix->dir);
+  if (ix->status) cudaFree(ix->status);
+  ix->arena.release();
+  ix->arena2.release();
+  delete ix;
+  return SIA_OK;
+}
+
+int64_t sia_index_rows(const sia_index *ix) { return ix ? ix->n_rows : 0; }
+
+static int insert_common(sia_index *ix, const int32_t *d_song, int32_t song_const, const uint8_t *d_hash,
+                         const int32_t *d_off, int64_t n, cudaStream_t s) {
+  SIA_REQUIRE(ix != nullptr, SIA_E_INVALID, "index is NULL");
+  SIA_REQUIRE(n >= 0, SIA_E_INVALID, "n < 0");
+  if (n == 0) return SIA_OK;
+  SIA_REQUIRE(d_hash && d_off, SIA_E_INVALID, "NULL argument");
+  int rc = set_device(ix);
+  if (rc) return rc;
+  if (ix->n_rows + ix->n_pending + n > ix->capacity) {
+    set_error("index capacity exceeded (capacity_rows counts stored + pending rows)");
+    return SIA_E_CAPACITY;
+  }
+  pack_rows_kernel<<<grid_for(n), 256, 0, s>>>(d_hash, d_off, d_song, song_const, n,
+                                              ix->rows + ix->n_rows + ix->n_pending, ix->status);
+  SIA_CHECK_LAUNCH();
+  ix->n_pending += n;
+  return SIA_OK;
+}
+
+int sia_index_insert(sia_index *ix, int32_t song_id, const uint8_t *d_hash, const int32_t *d_off, int64_t n, void *stream) {
+  SIA_REQUIRE(song_id >= 0 && song_id <= (int32_t)kM24, SIA_E_INVALID, "song_id outside MEDIUMINT UNSIGNED (0..2^24-1)");
+  return insert_common(ix, nullptr, song_id, d_hash, d_off, n, (cudaStream_t)stream);
+}
+
+int sia_index_insert_rows(sia_index *ix, const int32_t *d_song, const uint8_t *d_hash, const int32_t *d_off, int64_t n,
+                          void *stream) {
+  SIA_REQUIRE(d_song != nullptr || n == 0, SIA_E_INVALID, "NULL argument");
+  return insert_common(ix, d_song, 0, d_hash, d_off, n, (cudaStream_t)stream);
+}
+
+int sia_index_insert_host(sia_index *ix, int32_t song_id, const uint8_t *h_hash, const int32_t *h_off, int64_t n) {
+  SIA_REQUIRE(ix != nullptr, SIA_E_INVALID, "index is NULL");
+  if (n == 0) return SIA_OK;
+  SIA_REQUIRE(h_hash && h_off && n > 0, SIA_E_INVALID, "bad argument");
+  int rc = set_device(ix);
+  if (rc) return rc;
+  if ((rc = ix->arena.reserve((size_t)n * (SIA_HASH_BYTES + 4) + 4096))) return rc;
+  uint8_t *dh = ix->arena.take<uint8_t>((size_t)n * SIA_HASH_BYTES);
+  int32_t *dof = ix->arena.take<int32_t>(n);
+  SIA_CUDA(cudaMemcpy(dh, h_hash, (size_t)n * SIA_HASH_BYTES, cudaMemcpyHostToDevice));
+  SIA_CUDA(cudaMemcpy(dof, h_off, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  rc = sia_index_insert(ix, song_id, dh, dof, n, nullptr);
+  if (rc) return rc;
+  SIA_CUDA(cudaDeviceSynchronize());
+  return SIA_OK;
+}
+
+int sia_index_finalize(sia_index *ix, int64_t *h_rows) {
+  SIA_REQUIRE(ix != nullptr, SIA_E_INVALID, "index is NULL");
+  int rc = set_device(ix);
+  if (rc) return rc;
+  cudaStream_t s = nullptr;
+  if ((rc = check_status(ix, s, 1, "insert: song_id or offset outside 0..2^24-1"))) {
+    ix->n_pending = 0;   // drop the offending batch
+    return rc;
+  }
+  const int64_t n = ix->n_rows + ix->n_pending;
+  if (ix->n_pending > 0 && n > 0) {
+    ulonglong2 *alt = nullptr;
+    SIA_CUDA(cudaMalloc(&alt, (size_t)n * sizeof(ulonglong2)));
+    auto fail = [&](int code) { cudaFree(alt); return code; };
+    if ((rc = ix->arena.reserve(radix_sort_tmp_bytes(n) + (size_t)n * 12 + scan_tmp_bytes(n) + 8192))) return fail(rc);
+    void *stmp = ix->arena.take<char>(radix_sort_tmp_bytes(n));
+    bool in_b = false;
+    if ((rc = radix_sort(ix->rows, alt, n, 16, 0, 16, stmp, s, &in_b))) return fail(rc);
+    ulonglong2 *sorted = in_b ? alt : ix->rows, *other = in_b ? ix->rows : alt;
+    // UNIQUE(song_id, offset, hash): drop adjacent duplicates
+    uint32_t *flag = ix->arena.take<uint32_t>(n);
+    int64_t *pos = ix->arena.take<int64_t>(n + 1);
+    void *sc = ix->arena.take<char>(scan_tmp_bytes(n));
+    if (!flag || !pos || !sc) { set_error("index scratch arena too small (finalize)"); return fail(SIA_E_NOMEM); }
+    uniq_flag_kernel<<<grid_for(n), 256, 0, s>>>(sorted, n, flag);
+    if ((rc = exclusive_scan_u32(flag, pos, n, sc, s))) return fail(rc);
+    int64_t nu = 0;
+    cudaError_t e = cudaMemcpy(&nu, pos + n, sizeof nu, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "finalize readback", __FILE__, __LINE__));
+    if (nu != n) {
+      uniq_compact_kernel<<<grid_for(n), 256, 0, s>>>(sorted, n, flag, pos, other);
+      std::swap(sorted, other);
+    }
+    if (sorted != ix->rows) {
+      e = cudaMemcpyAsync(ix->rows, sorted, (size_t)nu * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return fail(cuda_fail(e, "finalize copy", __FILE__, __LINE__));
+    }
+    e = cudaDeviceSynchronize();
+    cudaFree(alt);
+    if (e != cudaSuccess) return cuda_fail(e, "finalize", __FILE__, __LINE__);
+    ix->n_rows = nu;
+    ix->n_pending = 0;
+  }
+  // directory: ~8 rows per bucket
+  int bits = 10;
+  while (bits < 28 && (ix->n_rows >> bits) > 8) ++bits;
+  if (bits != ix->dir_bits) {
+    if (ix->dir) cudaFree(ix->dir);
+    ix->dir = nullptr;
+    SIA_CUDA(cudaMalloc(&ix->dir, ((size_t)(1ull << bits) + 1) * sizeof(uint32_t)));
+    ix->dir_bits = bits;
+  }
+  build_dir_kernel<<<grid_for(ix->n_rows + 1), 256, 0, s>>>(ix->rows, ix->n_rows, bits, ix->dir);
+  SIA_CHECK_LAUNCH();
+  SIA_CUDA(cudaDeviceSynchronize());
+  if (h_rows) *h_rows = ix->n_rows;
+  return SIA_OK;
+}
+
+int sia_index_delete_songs(sia_index *ix, const int32_t *h_song_ids, int32_t n, int64_t *h_rows) {
+  SIA_REQUIRE(ix != nullptr, SIA_E_INVALID, "index is NULL");
+  SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
+  if (h_rows) *h_rows = ix->n_rows;
+  if (n <= 0 || ix->n_rows == 0) return SIA_OK;
+  SIA_REQUIRE(h_song_ids != nullptr, SIA_E_INVALID, "NULL argument");
+  int rc = set_device(ix);
+  if (rc) return rc;
+  cudaStream_t s = nullptr;
+  std::vector<uint32_t> bitmap((1u << 24) / 32, 0u);
+  for (int i = 0; i < n; ++i) {
+    SIA_REQUIRE(h_song_ids[i] >= 0 && h_song_ids[i] <= (int32_t)kM24, SIA_E_INVALID, "song id out of range");
+    bitmap[h_song_ids[i] >> 5] |= 1u << (h_song_ids[i] & 31);
+  }
+  const int64_t nr = ix->n_rows;
+  if ((rc = ix->arena.reserve(bitmap.size() * 4 + (size_t)nr * 12 + scan_tmp_bytes(nr) + 8192))) return rc;
+  uint32_t *d_bm = ix->arena.take<uint32_t>(bitmap.size());
+  uint32_t *flag = ix->arena.take<uint32_t>(nr);
+  int64_t *pos = ix->arena.take<int64_t>(nr + 1);
+  void *sc = ix->arena.take<char>(scan_tmp_bytes(nr));
+  SIA_REQUIRE(d_bm && flag && pos && sc, SIA_E_NOMEM, "index scratch arena too small (delete)");
+  SIA_CUDA(cudaMemcpyAsync(d_bm, bitmap.data(), bitmap.size() * 4, cudaMemcpyHostToDevice, s));
+  keep_flag_kernel<<<grid_for(nr), 256, 0, s>>>(ix->rows, nr, d_bm, flag);
+  SIA_CHECK_LAUNCH();
+  if ((rc = exclusive_scan_u32(flag, pos, nr, sc, s))) return rc;
+  int64_t keep = 0;
+  SIA_CUDA(cudaMemcpy(&keep, pos + nr, sizeof keep, cudaMemcpyDeviceToHost));
+  if (keep != nr) {
+    ulonglong2 *alt = nullptr;
+    SIA_CUDA(cudaMalloc(&alt, (size_t)std::max<int64_t>(keep, 1) * sizeof(ulonglong2)));
+    uniq_compact_kernel<<<grid_for(nr), 256, 0, s>>>(ix->rows, nr, flag, pos, alt);
+    cudaError_t e = cudaMemcpyAsync(ix->rows, alt, (size_t)keep * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(alt);
+    if (e != cudaSuccess) return cuda_fail(e, "delete_songs", __FILE__, __LINE__);
+    ix->n_rows = keep;
+    build_dir_kernel<<<grid_for(ix->n_rows + 1), 256, 0, s>>>(ix->rows, ix->n_rows, ix->dir_bits, ix->dir);
+    SIA_CHECK_LAUNCH();
+    SIA_CUDA(cudaDeviceSynchronize());
+  }
+  if (h_rows) *h_rows = ix->n_rows;
+  return SIA_OK;
+}
+
+int sia_index_select_host(sia_index *ix, const uint8_t *h_hash, int64_t n, int32_t *h_row_hashidx, int32_t *h_row_song,
+                          int32_t *h_row_off, int64_t cap, int64_t *h_nrows) {
+  SIA_REQUIRE(ix && h_nrows, SIA_E_INVALID, "NULL argument");
+  SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
+  *h_nrows = 0;
+  if (n == 0) return SIA_OK;
+  SIA_REQUIRE(h_hash && n > 0 && n <= (int64_t)kM24, SIA_E_INVALID, "select: 1..2^24-1 hashes per call");
+  int rc = set_device(ix);
+  if (rc) return rc;
+  cudaStream_t s = nullptr;
+  // position of each hash rides in the qoff field, qid = 0 -> sorted by (digest, position)
+  std::vector<int32_t> pos(n);
+  for (int64_t i = 0; i < n; ++i) pos[i] = (int32_t)i;
+  const size_t in_bytes = (size_t)n * (SIA_HASH_BYTES + 4 + 4) + 4096;
+  if ((rc = ix->arena.reserve(in_bytes + lookup_bytes(n) + (size_t)cap * 12 + 4096))) return rc;
+  uint8_t *dh = ix->arena.take<uint8_t>((size_t)n * SIA_HASH_BYTES);
+  int32_t *dpos = ix->arena.take<int32_t>(n), *dq = ix->arena.take<int32_t>(n);
+  SIA_CUDA(cudaMemcpyAsync(dh, h_hash, (size_t)n * SIA_HASH_BYTES, cudaMemcpyHostToDevice, s));
+  SIA_CUDA(cudaMemcpyAsync(dpos, pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  SIA_CUDA(cudaMemsetAsync(dq, 0, (size_t)n * 4, s));
+  Lookup L;
+  if ((rc = lookup_pass(ix, ix->arena, dh, dpos, dq, nullptr, 1, 0, 0, n, L, s))) return rc;
+  *h_nrows = L.tuples;
+  const int64_t m = std::min(L.tuples, cap);
+  if (m > 0) {
+    SIA_REQUIRE(h_row_hashidx && h_row_song && h_row_off, SIA_E_INVALID, "NULL output");
+    int32_t *o1 = ix->arena.take<int32_t>(m), *o2 = ix->arena.take<int32_t>(m), *o3 = ix->arena.take<int32_t>(m);
+    SIA_REQUIRE(o1 && o2 && o3, SIA_E_NOMEM, "index scratch arena too small (select)");
+    select_rows_kernel<<<grid_for(n), 256, 0, s>>>(L.ent, n, L.first, L.off_all, ix->rows, o1, o2, o3, m);
+    SIA_CHECK_LAUNCH();
+    SIA_CUDA(cudaMemcpyAsync(h_row_hashidx, o1, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    SIA_CUDA(cudaMemcpyAsync(h_row_song, o2, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    SIA_CUDA(cudaMemcpyAsync(h_row_off, o3, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+  }
+  SIA_CUDA(cudaStreamSynchronize(s));
+  return SIA_OK;
+}
+
+int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff, const int64_t *h_query_starts,
+                          int32_t n_queries, int32_t topn, int32_t *d_out_song, int32_t *d_out_diff,
+                          int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres, int64_t *h_stats, void *stream) {
+  SIA_REQUIRE(ix && h_query_starts, SIA_E_INVALID, "NULL argument");
+  SIA_REQUIRE(n_queries >= 0 && topn >= 1, SIA_E_INVALID, "n_queries >= 0 and topn >= 1 required");
+  SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
+  if (h_stats) h_stats[0] = h_stats[1] = h_stats[2] = h_stats[3] = 0;
+  if (n_queries == 0) return SIA_OK;
+  SIA_REQUIRE(d_out_song && d_out_diff && d_out_count && d_out_rows && d_out_nres, SIA_E_INVALID, "NULL output");
+  int rc = set_device(ix);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int q = 0; q < n_queries; ++q)
+    SIA_REQUIRE(h_query_starts[q] <= h_query_starts[q + 1], SIA_E_INVALID, "query_starts must be non-decreasing");
+  SIA_REQUIRE(h_query_starts[n_queries] == h_query_starts[0] || (d_hash && d_qoff), SIA_E_INVALID, "NULL input");
+  SIA_CUDA(cudaMemsetAsync(d_out_nres, 0, sizeof(int32_t) * n_queries, s));
+
+  const int64_t tuple_budget = 96ll << 20;   // vote keys expanded at once (x ~70 B of scratch each)
+  for (int64_t q0 = 0; q0 < n_queries; q0 += kMaxQueriesPerPass) {
+    const int nq = (int)std::min<int64_t>(kMaxQueriesPerPass, n_queries - q0);
+    const int64_t i0 = h_query_starts[q0], n = h_query_starts[q0 + nq] - i0;
+    if (h_stats) h_stats[0] += n;
+    if (n == 0) continue;    // out_nres is already 0 for these queries
+    if ((rc = ix->arena.reserve((size_t)(nq + 1) * 8 * 3 + lookup_bytes(n) + (1 << 20)))) return rc;
+    int64_t *d_qs = ix->arena.take<int64_t>(nq + 1);
+    int64_t *d_goff = ix->arena.take<int64_t>(2 * (size_t)(nq + 1));
+    SIA_CUDA(cudaMemcpyAsync(d_qs, h_query_starts + q0, sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, s));
+    Lookup L;
+    if ((rc = lookup_pass(ix, ix->arena, d_hash, d_qoff, nullptr, d_qs, nq, 0, i0, n, L, s))) return rc;
+    if ((rc = check_status(ix, s, 2, "query: offset outside 0..2^24-1"))) return rc;
+    if (h_stats) { h_stats[1] += L.head_rows; h_stats[2] += L.tuples; }
+    // After the sort query q still owns entries [starts[q]-i0, starts[q+1]-i0) (duplicates stay, with no
+    // postings), so the scanned offsets at those positions split the pass into groups that fit the budget.
+    std::vector<int64_t> h_goff(2 * (size_t)(nq + 1));
+    gather_offsets_kernel<<<grid_for(nq + 1), 256, 0, s>>>(L.off_all, L.off_head, d_qs, i0, nq, d_goff);
+    SIA_CHECK_LAUNCH();
+    SIA_CUDA(cudaMemcpyAsync(h_goff.data(), d_goff, h_goff.size() * 8, cudaMemcpyDeviceToHost, s));
+    SIA_CUDA(cudaStreamSynchronize(s));
+    const int64_t *h_off_all = h_goff.data(), *h_off_head = h_goff.data() + nq + 1;
+    struct Group { int qa, qb; };
+    std::vector<Group> groups;
+    size_t need = 0;
+    for (int qa = 0; qa < nq;) {
+      int qb = qa + 1;
+      while (qb < nq && h_off_all[qb + 1] - h_off_all[qa] <= tuple_budget) ++qb;
+      groups.push_back({qa, qb});
+      const int64_t t = h_off_all[qb] - h_off_all[qa], h = h_off_head[qb] - h_off_head[qa];
+      need = std::max(need, bins_bytes(t, h) + vote_bytes(t) + (1 << 20));
+      qa = qb;
+    }
+    if ((rc = ix->arena2.reserve(need))) return rc;
+    for (const Group &g : groups) {
+      const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
+      const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa], heads = h_off_head[g.qb] - h_off_head[g.qa];
+      ix->arena2.used = 0;
+      uint64_t *bk = nullptr, *rk = nullptr;
+      int32_t *bc = nullptr, *rcnt = nullptr;
+      int64_t nbins = 0, nrowbins = 0;
+      if (ne > 0 && (rc = bins_from_entries(ix, ix->arena2, L, e0, ne, tuples, h_off_all[g.qa], heads, h_off_head[g.qa],
+                                            &bk, &bc, &nbins, &rk, &rcnt, &nrowbins, s)))
+        return rc;
+      if (h_stats) h_stats[3] += nbins;
+      // keys carry the pass-local query id; outputs are indexed by q0 + q
+      if ((rc = vote_sorted(ix->arena2, bk, bc, nbins, rk, rcnt, nrowbins, g.qa, g.qb, (int)q0, topn, d_out_song,
+                            d_out_diff, d_out_count, d_out_rows, d_out_nres, s)))
+        return rc;
+      SIA_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  return SIA_OK;
+}
+
+int sia_index_query_partial(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff, const int32_t *d_qid, int64_t n,
+                            uint64_t *d_bin_key, int32_t *d_bin_count, int64_t cap_bins, int64_t *h_nbins,
+                            uint64_t *d_row_key, int32_t *d_row_count, int64_t cap_rowbins, int64_t *h_nrowbins,
+                            void *stream) {
+  SIA_REQUIRE(ix && h_nbins && h_nrowbins, SIA_E_INVALID, "NULL argument");
+  SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
+  *h_nbins = *h_nrowbins = 0;
+  if (n == 0) return SIA_OK;
+  SIA_REQUIRE(d_hash && d_qoff && d_qid && n > 0, SIA_E_INVALID, "bad argument");
+  int rc = set_device(ix);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = ix->arena.reserve(lookup_bytes(n) + (1 << 20)))) return rc;
+  Lookup L;
+  if ((rc = lookup_pass(ix, ix->arena, d_hash, d_qoff, d_qid, nullptr, 0, 0, 0, n, L, s))) return rc;
+  if ((rc = check_status(ix, s, 2, "query: offset outside 0..2^24-1 or query id outside 0..32767"))) return rc;
+  // grow the arena for the expansion without losing the lookup results: allocate a second arena
+  Arena ar2;
+  if ((rc = ar2.reserve(bins_bytes(L.tuples, L.head_rows) + (1 << 20)))) return rc;
+  uint64_t *bk = nullptr, *rk = nullptr;
+  int32_t *bc = nullptr, *rcnt = nullptr;
+  int64_t nbins = 0, nrowbins = 0;
+  rc = bins_from_entries(ix, ar2, L, 0, n, L.tuples, 0, L.head_rows, 0, &bk, &bc, &nbins, &rk, &rcnt, &nrowbins, s);
+  if (!rc) {
+    *h_nbins = nbins; *h_nrowbins = nrowbins;
+    if (nbins > cap_bins || nrowbins > cap_rowbins) {
+      set_error("query_partial: bin output capacity exceeded; *h_nbins / *h_nrowbins hold the required sizes");
+      rc = SIA_E_CAPACITY;
+    } else {
+      cudaError_t e = cudaSuccess;
+      if (nbins) {
+        e = cudaMemcpyAsync(d_bin_key, bk, nbins * 8, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_bin_count, bc, nbins * 4, cudaMemcpyDeviceToDevice, s);
+      }
+      if (e == cudaSuccess && nrowbins) {
+        e = cudaMemcpyAsync(d_row_key, rk, nrowbins * 8, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_row_count, rcnt, nrowbins * 4, cudaMemcpyDeviceToDevice, s);
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) rc = cuda_fail(e, "query_partial copy", __FILE__, __LINE__);
+    }
+  }
+  cudaStreamSynchronize(s);
+  ar2.release();
+  return rc;
+}
+
+int sia_vote_bins(int device, const uint64_t *d_bin_key, const int32_t *d_bin_count, int64_t nbins,
+                  const uint64_t *d_row_key, const int32_t *d_row_count, int64_t nrowbins, int32_t n_queries,
+                  int32_t topn, int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count, int32_t *d_out_rows,
+                  int32_t *d_out_nres, void *stream) {
+  SIA_REQUIRE(n_queries >= 0 && n_queries <= kMaxQueriesPerPass && topn >= 1, SIA_E_INVALID,
+              "vote_bins: 0..32768 queries, topn >= 1");
+  SIA_REQUIRE(nbins >= 0 && nrowbins >= 0, SIA_E_INVALID, "negative size");
+  if (n_queries == 0) return SIA_OK;
+  SIA_REQUIRE(d_out_song && d_out_diff && d_out_count && d_out_rows && d_out_nres, SIA_E_INVALID, "NULL output");
+  SIA_CUDA(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar;
+  int rc = ar.reserve((size_t)(nbins + nrowbins) * (16 * 2 + 12) + radix_sort_tmp_bytes(nbins) +
+                      radix_sort_tmp_bytes(nrowbins) + reduce_runs_bytes(nbins) + reduce_runs_bytes(nrowbins) +
+                      vote_bytes(nbins) + (1 << 20));
+  if (rc) return rc;
+  // partial bins from several shards: equal keys must be summed -> sort (key, count) records, then weighted runs
+  uint64_t *mk[2] = {nullptr, nullptr};
+  int32_t *mc[2] = {nullptr, nullptr};
+  int64_t mn[2] = {0, 0};
+  for (int pass = 0; pass < 2 && !rc; ++pass) {
+    const int64_t m = pass == 0 ? nbins : nrowbins;
+    const uint64_t *k = pass == 0 ? d_bin_key : d_row_key;
+    const int32_t *c = pass == 0 ? d_bin_count : d_row_count;
+    if (m == 0) continue;
+    ulonglong2 *ra = ar.take<ulonglong2>(m), *rb = ar.take<ulonglong2>(m);
+    uint64_t *sk = ar.take<uint64_t>(m);
+    int32_t *sw = ar.take<int32_t>(m);
+    void *stmp = ar.take<char>(radix_sort_tmp_bytes(m));
+    if (!ra || !rb || !sk || !sw || !stmp) { set_error("vote_bins: scratch"); rc = SIA_E_NOMEM; break; }
+    join_bins_kernel<<<grid_for(m), 256, 0, s>>>(k, c, m, ra);
+    bool in_b = false;
+    if ((rc = radix_sort(ra, rb, m, 16, 8, 16, stmp, s, &in_b))) break;
+    split_bins_kernel<<<grid_for(m), 256, 0, s>>>(in_b ? rb : ra, m, sk, sw);
+    rc = reduce_runs(ar, sk, sw, m, &mk[pass], &mc[pass], &mn[pass], s);
+  }
+  if (!rc) {
+    cudaMemsetAsync(d_out_nres, 0, sizeof(int32_t) * n_queries, s);
+    rc = vote_sorted(ar, mk[0], mc[0], mn[0], mk[1], mc[1], mn[1], 0, n_queries, 0, topn, d_out_song, d_out_diff,
+                     d_out_count, d_out_rows, d_out_nres, s);
+  }
+  cudaStreamSynchronize(s);
+  ar.release();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,346 @@
+"""``GPUDatabase`` — the reference's database-backend interface on an HBM-resident index.
+
+Registered as ``DATABASES['gpu'] = ("shazam_b200.database", "GPUDatabase")`` it slots into
+``get_database`` (``__init__.py:24-27,54-67``).  The method set, argument meaning and
+return shapes follow ``MySQLDatabase`` (``mysql_database.py:28-255``); ``find_matches``
+follows ``ElasticDatabase`` (``elastic_database.py:195-226``).  The songs table lives on
+the host (it is a few rows per track); the fingerprints table is ``sia_index`` on the GPU.
+
+``cursor()`` understands exactly the statements the reference drivers issue through it:
+the two CREATEs and DELETE_UNFINGERPRINTED (``__init__.py:421-424``) and SELECT_MULTIPLE
+with ``UNHEX(%s)`` parameters (``recognizer.py:251-259``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import datetime
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .fingerprinter import digests_to_hex, hex_to_digests
+
+FIELD_SONG_ID = "song_id"
+FIELD_SONGNAME = "song_name"
+FIELD_FINGERPRINTED = "fingerprinted"
+FIELD_FILE_SHA1 = "file_sha1"
+FIELD_TOTAL_HASHES = "total_hashes"
+FIELD_HASH = "hash"
+FIELD_OFFSET = "offset"
+SONGS_TABLENAME = "songs"
+FINGERPRINTS_TABLENAME = "fingerprints"
+
+
+class FingerprintIndex:
+    """Thin owner of one ``sia_index`` (one shard of the fingerprints table on one GPU)."""
+
+    def __init__(self, device: int = 0, capacity_rows: int = 1 << 24):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sia_b200 needs a CUDA device (B200); there is no CPU fallback")
+        self.lib = N.lib()
+        self.device = int(device)
+        self.tdev = torch.device("cuda", self.device)
+        self.capacity = int(capacity_rows)
+        h = C.c_void_p()
+        N.check(self.lib.sia_index_create(self.device, self.capacity, C.byref(h)))
+        self._h = h
+        self._dirty = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.sia_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    @property
+    def rows(self) -> int:
+        self.finalize()
+        return int(self.lib.sia_index_rows(self._h))
+
+    # ---- build -------------------------------------------------------------------------
+    def insert(self, song_id: int, digests, offsets) -> None:
+        """Append rows (pending until ``finalize``).  Host arrays or CUDA tensors."""
+        n = len(offsets)
+        if n == 0:
+            return
+        if isinstance(digests, torch.Tensor) and digests.is_cuda:
+            d = digests.contiguous()
+            o = offsets.to(torch.int32).contiguous()
+            assert d.dtype == torch.uint8 and d.shape == (n, N.HASH_BYTES)
+            N.check(self.lib.sia_index_insert(self._h, int(song_id), C.c_void_p(d.data_ptr()),
+                                              C.c_void_p(o.data_ptr()), n, self._stream()))
+            torch.cuda.current_stream(self.tdev).synchronize()   # d/o may be temporaries
+        else:
+            d = np.ascontiguousarray(digests, np.uint8).reshape(n, N.HASH_BYTES)
+            o = np.ascontiguousarray(offsets, np.int32)
+            N.check(self.lib.sia_index_insert_host(self._h, int(song_id), C.c_void_p(d.ctypes.data),
+                                                   C.c_void_p(o.ctypes.data), n))
+        self._dirty = True
+
+    def insert_rows(self, songs: torch.Tensor, digests: torch.Tensor, offsets: torch.Tensor) -> None:
+        """Rows of many songs at once (CUDA tensors; ``songs[i]`` is row i's song id)."""
+        n = offsets.numel()
+        if n == 0:
+            return
+        s = songs.to(torch.int32).contiguous()
+        d = digests.contiguous()
+        o = offsets.to(torch.int32).contiguous()
+        N.check(self.lib.sia_index_insert_rows(self._h, C.c_void_p(s.data_ptr()), C.c_void_p(d.data_ptr()),
+                                               C.c_void_p(o.data_ptr()), n, self._stream()))
+        torch.cuda.current_stream(self.tdev).synchronize()
+        self._dirty = True
+
+    def finalize(self) -> int:
+        if self._dirty:
+            r = C.c_int64()
+            N.check(self.lib.sia_index_finalize(self._h, C.byref(r)))
+            self._dirty = False
+        return int(self.lib.sia_index_rows(self._h))
+
+    def delete_songs(self, song_ids: Sequence[int]) -> int:
+        self.finalize()
+        ids = np.ascontiguousarray(list(song_ids), np.int32)
+        r = C.c_int64()
+        N.check(self.lib.sia_index_delete_songs(self._h, ids.ctypes.data_as(C.POINTER(C.c_int32)), len(ids), C.byref(r)))
+        return int(r.value)
+
+    # ---- lookup ------------------------------------------------------------------------
+    def select(self, digests: np.ndarray):
+        """SELECT_MULTIPLE: every stored row whose hash is in ``digests`` (distinct).
+        Returns (hash_index, song_id, offset) int32 arrays."""
+        self.finalize()
+        d = np.ascontiguousarray(digests, np.uint8).reshape(-1, N.HASH_BYTES)
+        n = len(d)
+        cap = max(1024, 8 * n)
+        while True:
+            idx = np.empty(cap, np.int32); sid = np.empty(cap, np.int32); off = np.empty(cap, np.int32)
+            nr = C.c_int64()
+            N.check(self.lib.sia_index_select_host(self._h, C.c_void_p(d.ctypes.data), n, C.c_void_p(idx.ctypes.data),
+                                                   C.c_void_p(sid.ctypes.data), C.c_void_p(off.ctypes.data), cap,
+                                                   C.byref(nr)))
+            if nr.value <= cap:
+                m = nr.value
+                return idx[:m], sid[:m], off[:m]
+            cap = int(nr.value)
+
+    def query_batch(self, digests: torch.Tensor, qoffsets: torch.Tensor, query_starts: np.ndarray, topn: int,
+                    want_stats: bool = False):
+        """return_matches + the align_matches vote for Q queries.  Returns CUDA int32 tensors
+        (song[Q,topn], diff[Q,topn], count[Q,topn], rows[Q,topn], nres[Q]) (+ stats)."""
+        self.finalize()
+        qs = np.ascontiguousarray(query_starts, np.int64)
+        Q = len(qs) - 1
+        d = digests.contiguous()
+        o = qoffsets.to(torch.int32).contiguous()
+        assert d.is_cuda and o.is_cuda and d.dtype == torch.uint8
+        outs = [torch.zeros((Q, topn), dtype=torch.int32, device=self.tdev) for _ in range(4)]
+        nres = torch.zeros(Q, dtype=torch.int32, device=self.tdev)
+        stats = (C.c_int64 * 4)()
+        N.check(self.lib.sia_index_query_batch(self._h, C.c_void_p(d.data_ptr()), C.c_void_p(o.data_ptr()),
+                                               qs.ctypes.data_as(C.POINTER(C.c_int64)), Q, int(topn),
+                                               C.c_void_p(outs[0].data_ptr()), C.c_void_p(outs[1].data_ptr()),
+                                               C.c_void_p(outs[2].data_ptr()), C.c_void_p(outs[3].data_ptr()),
+                                               C.c_void_p(nres.data_ptr()), stats, self._stream()))
+        if want_stats:
+            return (*outs, nres, list(stats))
+        return (*outs, nres)
+
+    def query_partial(self, digests: torch.Tensor, qoffsets: torch.Tensor, qids: torch.Tensor):
+        """Partial vote histograms of this shard for routed query hashes (multi-GPU path).
+        Returns (bin_key u64, bin_count i32, row_key u64, row_count i32) CUDA tensors."""
+        self.finalize()
+        n = qoffsets.numel()
+        d = digests.contiguous(); o = qoffsets.to(torch.int32).contiguous(); q = qids.to(torch.int32).contiguous()
+        cap = max(1024, 4 * n)
+        while True:
+            bk = torch.empty(cap, dtype=torch.int64, device=self.tdev); bc = torch.empty(cap, dtype=torch.int32, device=self.tdev)
+            rk = torch.empty(cap, dtype=torch.int64, device=self.tdev); rc_ = torch.empty(cap, dtype=torch.int32, device=self.tdev)
+            nb = C.c_int64(); nr = C.c_int64()
+            rc = self.lib.sia_index_query_partial(self._h, C.c_void_p(d.data_ptr()), C.c_void_p(o.data_ptr()),
+                                                  C.c_void_p(q.data_ptr()), n, C.c_void_p(bk.data_ptr()),
+                                                  C.c_void_p(bc.data_ptr()), cap, C.byref(nb), C.c_void_p(rk.data_ptr()),
+                                                  C.c_void_p(rc_.data_ptr()), cap, C.byref(nr), self._stream())
+            if rc == N.E_CAPACITY and max(nb.value, nr.value) > cap:
+                cap = int(max(nb.value, nr.value))
+                continue
+            N.check(rc)
+            return bk[:nb.value], bc[:nb.value], rk[:nr.value], rc_[:nr.value]
+
+
+def vote_bins(device: int, bin_key: torch.Tensor, bin_count: torch.Tensor, row_key: torch.Tensor,
+              row_count: torch.Tensor, n_queries: int, topn: int):
+    """Sum equal keys of (possibly several shards') partial bins and vote.  CUDA tensors in and out."""
+    lib = N.lib()
+    tdev = torch.device("cuda", device)
+    outs = [torch.zeros((n_queries, topn), dtype=torch.int32, device=tdev) for _ in range(4)]
+    nres = torch.zeros(n_queries, dtype=torch.int32, device=tdev)
+    bk = bin_key.contiguous(); bc = bin_count.to(torch.int32).contiguous()
+    rk = row_key.contiguous(); rc_ = row_count.to(torch.int32).contiguous()
+    N.check(lib.sia_vote_bins(device, C.c_void_p(bk.data_ptr()), C.c_void_p(bc.data_ptr()), bk.numel(),
+                              C.c_void_p(rk.data_ptr()), C.c_void_p(rc_.data_ptr()), rk.numel(), n_queries, int(topn),
+                              C.c_void_p(outs[0].data_ptr()), C.c_void_p(outs[1].data_ptr()),
+                              C.c_void_p(outs[2].data_ptr()), C.c_void_p(outs[3].data_ptr()),
+                              C.c_void_p(nres.data_ptr()), C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)))
+    return (*outs, nres)
+
+
+class _Cursor:
+    """What ``db.cursor()`` yields: ``execute(sql, params)`` + row iteration for the statements
+    the reference issues through a raw cursor."""
+
+    def __init__(self, db: "GPUDatabase", dictionary: bool = False):
+        self.db = db
+        self.rows = []
+        self.lastrowid = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, extype, exvalue, tb):
+        return False
+
+    def execute(self, query: str, params=None):
+        q = " ".join(query.split())
+        db = self.db
+        if q.startswith("CREATE TABLE"):
+            self.rows = []
+        elif q.startswith("DELETE FROM") and FIELD_FINGERPRINTED in q:
+            db.delete_unfingerprinted()
+            self.rows = []
+        elif q.startswith("SELECT HEX(") and " IN (" in q:
+            values = list(params or [])
+            if q.count("UNHEX(%s)") != len(values):
+                raise ValueError("SELECT_MULTIPLE: parameter count does not match the IN list")
+            self.rows = db.select_multiple(values)
+        else:
+            raise N.SiaError(N.E_UNSUPPORTED, f"GPUDatabase cursor does not implement: {q[:80]}")
+        return len(self.rows)
+
+    def __iter__(self):
+        return iter(self.rows)
+
+    def fetchone(self):
+        return self.rows[0] if self.rows else None
+
+    def fetchall(self):
+        return list(self.rows)
+
+    def close(self):
+        pass
+
+
+class GPUDatabase:
+    type = "gpu"
+
+    # statements the drivers pass to cursor.execute (same attribute names as MySQLDatabase)
+    CREATE_SONGS_TABLE = f"CREATE TABLE IF NOT EXISTS `{SONGS_TABLENAME}` (host-side table)"
+    CREATE_FINGERPRINTS_TABLE = f"CREATE TABLE IF NOT EXISTS `{FINGERPRINTS_TABLENAME}` (sia_index in HBM)"
+    DELETE_UNFINGERPRINTED = f"DELETE FROM `{SONGS_TABLENAME}` WHERE `{FIELD_FINGERPRINTED}` = 0;"
+    SELECT_MULTIPLE = (f"SELECT HEX(`{FIELD_HASH}`), `{FIELD_SONG_ID}`, `{FIELD_OFFSET}` "
+                       f"FROM `{FINGERPRINTS_TABLENAME}` WHERE `{FIELD_HASH}` IN (%s);")
+    IN_MATCH = "UNHEX(%s)"
+
+    def __init__(self, device: Optional[int] = None, capacity_rows: int = 1 << 24, metadata: Optional[dict] = None,
+                 **options):
+        # host/user/password/database of config["database"] (__init__.py:29-37) are accepted and ignored
+        self._options = dict(options, device=device, capacity_rows=capacity_rows)
+        dev = torch.cuda.current_device() if device is None and torch.cuda.is_available() else (device or 0)
+        self.index = FingerprintIndex(dev, capacity_rows)
+        self.songs = {}           # song_id -> dict(song_name, file_sha1, total_hashes, fingerprinted, date_created)
+        self._next_id = 1         # MEDIUMINT UNSIGNED AUTO_INCREMENT
+        self._metadata = metadata or {}
+
+    # ---- MySQLDatabase surface ------------------------------------------------------------
+    def setup(self) -> None:
+        with self.cursor() as cur:
+            cur.execute(self.CREATE_SONGS_TABLE)
+            cur.execute(self.CREATE_FINGERPRINTS_TABLE)
+            cur.execute(self.DELETE_UNFINGERPRINTED)
+
+    def cursor(self, **options):
+        return _Cursor(self, **options)
+
+    def after_fork(self) -> None:
+        pass
+
+    def insert_song(self, song_name: str, file_hash: str, total_hashes: int) -> int:
+        sid = self._next_id
+        if sid >= 1 << 24:
+            raise N.SiaError(N.E_CAPACITY, "song_id exceeds MEDIUMINT UNSIGNED")
+        self._next_id += 1
+        self.songs[sid] = {FIELD_SONGNAME: song_name, FIELD_FILE_SHA1: str(file_hash).upper(),
+                           FIELD_TOTAL_HASHES: int(total_hashes), FIELD_FINGERPRINTED: 0,
+                           "date_created": datetime.datetime.now()}
+        return sid
+
+    def insert_hashes(self, song_id: int, hashes, batch_size: int = 1000) -> None:
+        """``hashes``: iterable of ``(hex20, offset)`` (a set in the ingest flow, ``__init__.py:265,383``)."""
+        hashes = list(hashes)
+        if not hashes:
+            return
+        d = hex_to_digests([h for h, _ in hashes])
+        o = np.array([int(t) for _, t in hashes], np.int64)
+        if o.min() < 0 or o.max() >= 1 << 24:
+            raise N.SiaError(N.E_INVALID, "offset outside 0..2^24-1")
+        self.index.insert(song_id, d, o.astype(np.int32))
+
+    def insert_hashes_array(self, song_id: int, digests, offsets) -> None:
+        """Array fast path: uint8[N,10] digests + int32 offsets (host arrays or CUDA tensors)."""
+        self.index.insert(song_id, digests, offsets)
+
+    def set_song_fingerprinted(self, song_id: int) -> None:
+        self.songs[song_id][FIELD_FINGERPRINTED] = 1
+
+    def delete_unfingerprinted(self) -> None:
+        dead = [sid for sid, s in self.songs.items() if not s[FIELD_FINGERPRINTED]]
+        if dead:
+            self.index.delete_songs(dead)      # ON DELETE CASCADE
+            for sid in dead:
+                del self.songs[sid]
+
+    def get_songs(self):
+        """Rows ``(song_id, song_name, file_sha1, total_hashes, date_created)`` of fingerprinted songs
+        — ``row[2]`` is the upper-hex file SHA-1 (``FIELD_FILE_SHA1 = 2``, ``__init__.py:40,413``)."""
+        return [(sid, s[FIELD_SONGNAME], s[FIELD_FILE_SHA1], s[FIELD_TOTAL_HASHES], s["date_created"])
+                for sid, s in sorted(self.songs.items()) if s[FIELD_FINGERPRINTED]]
+
+    def get_song_by_id(self, song_id: int):
+        s = self.songs[int(song_id)]
+        return {"song_name": s[FIELD_SONGNAME], "total_hashes": s[FIELD_TOTAL_HASHES], "file_sha1": s[FIELD_FILE_SHA1]}
+
+    def get_metadata(self, song_id: int):
+        return self._metadata.get(int(song_id))
+
+    def get_num_fingerprints(self) -> int:
+        return self.index.rows
+
+    # ---- lookups ----------------------------------------------------------------------------
+    def select_multiple(self, hex_values: Sequence[str]):
+        """Rows ``(HEXUPPER, song_id, offset)`` for ``WHERE hash IN (...)``."""
+        if not hex_values:
+            return []
+        uniq = list(dict.fromkeys(v.upper() for v in hex_values))      # SQL IN is a set
+        idx, sid, off = self.index.select(hex_to_digests(uniq))
+        return [(uniq[i], int(s), int(o)) for i, s, o in zip(idx.tolist(), sid.tolist(), off.tolist())]
+
+    def find_matches(self, hashes: Iterable[str]):
+        """ES-style lookup (``elastic_database.py:195-226``): docs ``{'_source': {...}}``."""
+        hx = list(dict.fromkeys(hashes))
+        if not hx:
+            return
+        idx, sid, off = self.index.select(hex_to_digests(hx))
+        for i, s, o in zip(idx.tolist(), sid.tolist(), off.tolist()):
+            yield {"_source": {FIELD_HASH: hx[i], FIELD_SONG_ID: int(s), FIELD_OFFSET: int(o)}}
+
+    def __getstate__(self):
+        return (self._options,)
