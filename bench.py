@@ -315,7 +315,10 @@ def main():
     prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            per_frame = json.load(open(prof)).get("dram_bytes_per_frame")
+            frames = B * frames_per_track * args.steps / k1_launches
+            roofline["traffic"] = per_frame * frames if per_frame else None
+            roofline["traffic_source"] = "profiles/k1_traffic.json (ncu --set full, dram read+write per frame) x frames per launch"
         except Exception:
             pass
 

@@ -33,6 +33,24 @@ SONGS_TABLENAME = "songs"
 FINGERPRINTS_TABLENAME = "fingerprints"
 
 
+# the reference's backend registry (__init__.py:24-27) with this backend added
+DATABASES = {
+    "mysql": ("mysql_database", "MySQLDatabase"),
+    "postgres": ("dejavu.database_handler.postgres_database", "PostgreSQLDatabase"),
+    "gpu": ("shazam_b200.database", "GPUDatabase"),
+}
+
+
+def get_database(database_type: str = "gpu"):
+    """``__init__.py:54-67``: resolve a backend CLASS by name; unknown names raise TypeError."""
+    import importlib
+    try:
+        path, db_class_name = DATABASES[database_type]
+        return getattr(importlib.import_module(path), db_class_name)
+    except (ImportError, KeyError):
+        raise TypeError("Unsupported database type supplied.")
+
+
 class FingerprintIndex:
     """Thin owner of one ``sia_index`` (one shard of the fingerprints table on one GPU)."""
 

@@ -281,3 +281,55 @@ def test_recognition_end_to_end_noisy_clips(gpudb, fpr):
         assert _strip(got[i]) == _strip(want), i
         correct += bool(got[i]) and got[i][0]["song_id"] == truth[i]
     assert correct >= 14, correct          # 16 clips; the 0 dB ones may miss, identically in both paths
+
+
+def test_ingest_directory_flow(tmp_path, fpr):
+    """The ingest main flow (__init__.py:417-432) against the 'gpu' backend: registry, start-up sweep,
+    stereo set-union, resume by file SHA-1; then a clip is recognised through the compat functions."""
+    import wave
+    from shazam_b200 import compat, ingest, recognize
+    from shazam_b200.database import get_database
+    compat.set_fingerprinter(fpr)
+    fs = 44100
+    mono = O.synth_track(900, 6 * fs)
+    left, right = O.synth_track(901, 5 * fs), O.synth_track(902, 5 * fs)
+    same = O.synth_track(903, 4 * fs)
+    files = {"mono.wav": [mono], "stereo.wav": [left, right], "dual.wav": [same, same]}
+    for name, chans in files.items():
+        with wave.open(str(tmp_path / name), "wb") as w:
+            w.setnchannels(len(chans)); w.setsampwidth(2); w.setframerate(fs)
+            w.writeframes(np.stack(chans, 1).astype("<i2").tobytes())
+    (tmp_path / "broken.wav").write_bytes(b"not a wav")
+    with pytest.raises(TypeError):
+        get_database("oracle")
+    db = get_database("gpu")(host="127.0.0.1", user="root", password="x", database="music_recognition",
+                             capacity_rows=1 << 20)
+    try:
+        ingest.set_database(db); recognize.set_database(db)
+        with db.cursor() as cur:
+            cur.execute(db.CREATE_SONGS_TABLE); cur.execute(db.CREATE_FINGERPRINTS_TABLE); cur.execute(db.DELETE_UNFINGERPRINTED)
+        known = ingest.load_fingerprinted_audio_hashes(set())
+        assert ingest.fingerprint_directory(str(tmp_path), [".wav"], 4, known) == 3
+        songs = {r[1]: r for r in db.get_songs()}
+        assert set(songs) == {"mono", "stereo", "dual"}
+        for name, chans in files.items():
+            want = set()
+            for c in chans:
+                want |= set(O.fingerprint(c, Fs=fs))
+            row = songs[name[:-4]]
+            assert row[3] == len(want)                                   # total_hashes = len(set), __init__.py:381
+            assert row[2] == ingest.unique_hash(str(tmp_path / name))
+            fset, fh = ingest.get_file_fingerprints(str(tmp_path / name))
+            assert fset == want and fh == row[2]
+        assert db.get_num_fingerprints() == sum(r[3] for r in songs.values())
+        assert ingest.fingerprint_directory(str(tmp_path), ["wav"], None, ingest.load_fingerprinted_audio_hashes(set())) == 0
+        # recognise 3 s of the stereo file's left channel (recognizer.py:379-397 flow)
+        clip = left[fs:4 * fs]
+        hashes = set(compat.generate_fingerprints(clip, Fs=fs)[0])
+        matches, dedup, _ = recognize.find_matches(hashes)
+        res = recognize.align_matches(matches, dedup, len(hashes))
+        assert res[0]["song_name"] == b"stereo" and res[0]["offset"] == round(fs / 2048)
+        assert res[0]["offset_seconds"] == round(float(res[0]["offset"]) / 44100 * 4096 * 0.5, 5)
+    finally:
+        compat.set_fingerprinter(None)
+        db.index.close()
