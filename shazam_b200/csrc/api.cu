@@ -222,17 +222,18 @@ int run_peaks(sia_ctx *c, const void *d_spec, int in_type, const MetaView &m, in
               const sia_fp_params *p, int32_t *d_peak_t, int32_t *d_peak_f, int64_t cap_peaks,
               int64_t *d_track_peak_starts, int32_t *d_status, cudaStream_t s) {
   int rc;
+  bool striped = false;
   {
     PeaksLaunch a;
     a.d_spec = d_spec; a.in_type = in_type; a.d_frame_starts = m.frame_starts; a.d_ttile_starts = m.ttile_starts;
     a.n_tracks = nb; a.total_frames = frames; a.total_ttiles = ttiles; a.amp_min = p->amp_min;
     a.connectivity = p->connectivity; a.nbhd = p->nbhd; a.d_bitmap = c->bitmap;
     Timer t(c, s, T_PEAKS, 1);
-    if ((rc = peaks_bitmap_launch(a, s))) return rc;
+    if ((rc = peaks_bitmap_launch(a, s, &striped))) return rc;
   }
   {
     Timer t(c, s, T_COMPACT, 1);
-    if ((rc = peaks_rowcount_launch(c->bitmap, frames, c->row_count, s))) return rc;
+    if ((rc = peaks_rowcount_launch(c->bitmap, striped, frames, c->row_count, s))) return rc;
   }
   {
     Timer t(c, s, T_SCAN, 3);
@@ -240,7 +241,7 @@ int run_peaks(sia_ctx *c, const void *d_spec, int in_type, const MetaView &m, in
   }
   {
     Timer t(c, s, T_COMPACT, 1);
-    if ((rc = peaks_extract_launch(c->bitmap, c->row_off, m.frame_starts, nb, frames, 0, d_peak_t, d_peak_f, cap_peaks,
+    if ((rc = peaks_extract_launch(c->bitmap, striped, c->row_off, m.frame_starts, nb, frames, 0, d_peak_t, d_peak_f, cap_peaks,
                                    d_track_peak_starts, d_status, s)))
       return rc;
   }
@@ -348,7 +349,7 @@ int sia_ctx_create(int device, int64_t max_chunk_frames, sia_ctx **out) {
     }                                                                          \
   } while (0)
   ALLOC(c->spec, (size_t)c->max_frames * SIA_F_STRIDE * sizeof(float));
-  ALLOC(c->bitmap, (size_t)c->max_frames * SIA_ROW_WORDS * sizeof(uint32_t));
+  ALLOC(c->bitmap, (size_t)c->max_frames * kBitmapRowWords * sizeof(uint32_t));
   ALLOC(c->row_count, (size_t)c->max_frames * sizeof(uint32_t));
   ALLOC(c->row_off, (size_t)(c->max_frames + 1) * sizeof(int64_t));
   ALLOC(c->peak_t, (size_t)c->cap_peaks * sizeof(int32_t));

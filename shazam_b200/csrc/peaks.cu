@@ -22,6 +22,7 @@
 #include "sia_common.cuh"
 #include "stft.cuh"
 
+#include <math.h>
 #include <math_constants.h>
 
 namespace sia {
@@ -55,6 +56,18 @@ __device__ __forceinline__ void sliding(T (&v)[LEN]) {
       v[i] = IS_MAX ? max(v[i], x) : min(v[i], x);
     }
   }
+}
+
+// 21-wide window with 3-input max (FMNMX3): 3 -> 9 -> 21, 78 ops per 16 outputs
+template <int LEN, int OUTN>
+__device__ __forceinline__ void sliding21_max3(float (&v)[LEN]) {
+  static_assert(LEN >= OUTN + 20, "window does not fit");
+#pragma unroll
+  for (int i = 0; i + 2 < LEN; ++i) v[i] = fmaxf(fmaxf(v[i], v[i + 1]), v[i + 2]);          // [i, i+3)
+#pragma unroll
+  for (int i = 0; i + 8 < LEN; ++i) v[i] = fmaxf(fmaxf(v[i], v[i + 3]), v[i + 6]);          // [i, i+9)
+#pragma unroll
+  for (int i = 0; i < OUTN; ++i) v[i] = fmaxf(fmaxf(v[i], v[i + 9]), v[i + 12]);             // [i, i+21)
 }
 
 struct TileCoord {
@@ -165,9 +178,125 @@ peaks_square_kernel(const T *__restrict__ spec, const int64_t *__restrict__ fram
     const int gw = tc.f0 / 32 + w;
     if (g < tc.row_hi && gw < SIA_ROW_WORDS) {
       const uint32_t word = (uint32_t)sbits[r * (TF / 16) + 2 * w] | ((uint32_t)sbits[r * (TF / 16) + 2 * w + 1] << 16);
-      bitmap[g * SIA_ROW_WORDS + gw] = word;
+      bitmap[g * kBitmapRowWords + gw] = word;
     }
   }
+}
+
+// ---- production path: float32, square 21x21, amp_min >= 0 ------------------------------------------------
+// One CTA = 64 frames x 96 bins (3 bitmap words per frame); 4 warps, warp q owns frames 16q..16q+15.
+// The 84 x 120 halo tile is staged in shared memory as float4 (conflict-free 128-bit accesses).  Each lane
+// owns one float4 column: it slides the 21-frame max down its 4 bins entirely in registers (log-doubling,
+// 36 float4 in flight), then takes the 21-bin max across lanes with 10 shuffles of per-lane prefix /
+// suffix / block maxima — no second shared-memory pass, no transposes.  Lanes 0..23 produce the 96
+// outputs, lanes 24..29 carry the +-12-bin halo columns, lanes 30..31 idle.
+constexpr int kW2Rows = kPeakTileT;                                 // 64
+constexpr int kW2Bins = 96;
+constexpr int kW2Cols4 = 30;                                        // (96 + 2*12) / 4
+constexpr int kW2Strips = (SIA_NBINS + kW2Bins - 1) / kW2Bins;      // 22
+constexpr int kW2Threads = 128;
+constexpr int kW2TileRows = kW2Rows + 20;                           // 84
+
+__global__ void __launch_bounds__(kW2Threads, 3)
+peaks_square_warp_kernel(const float *__restrict__ spec, const int64_t *__restrict__ frame_starts,
+                         const int64_t *__restrict__ ttile_starts, int n_tracks, float amp_lo,
+                         uint32_t *__restrict__ bitmap) {
+  __shared__ float4 A[kW2TileRows * kW2Cols4];                      // 40 320 B
+  const int64_t tt = blockIdx.x / kW2Strips;
+  const int strip = (int)(blockIdx.x - tt * kW2Strips);
+  const int f0 = strip * kW2Bins;
+  const int trk = find_segment(ttile_starts, n_tracks, tt);
+  const int64_t row_lo = frame_starts[trk], row_hi = frame_starts[trk + 1];
+  const int64_t r0 = row_lo + (tt - ttile_starts[trk]) * kW2Rows;
+
+  // Stage the halo tile with cp.async (16-byte LDGSTS, no register round trip, ~20 requests in flight per
+  // thread).  Out-of-track frames and out-of-range bins are ZERO-filled (src-size 0): with amp_min >= 0 a
+  // zero can neither exceed nor equal a candidate (> amp_min), so it is as good as -inf here.
+  const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(A);
+  if (threadIdx.x < 4 * kW2Cols4) {                     // 120 loader threads: fixed column, rows rs, rs+4, ...
+    const int j = threadIdx.x % kW2Cols4, rs = threadIdx.x / kW2Cols4;
+    const int f = f0 - 12 + 4 * j;
+    const bool col_in = f >= 0 && f < SIA_NBINS;
+    const bool edge = f == SIA_NBINS - 1;               // bin 2048 shares its float4 with row padding: patch it
+    int64_t g = r0 - 10 + rs;
+    const float *gp = spec + g * SIA_F_STRIDE + f;
+    uint32_t sa = a_base + (uint32_t)(rs * kW2Cols4 + j) * 16u;
+#pragma unroll 3
+    for (int r = rs; r < kW2TileRows; r += 4, g += 4, gp += 4 * SIA_F_STRIDE, sa += 4 * kW2Cols4 * 16) {
+      const bool in = col_in && g >= row_lo && g < row_hi;
+      if (edge) {
+        A[r * kW2Cols4 + j] = make_float4(in ? __ldg(gp) : 0.f, 0.f, 0.f, 0.f);
+      } else {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(in ? gp : spec), "r"(in ? 16 : 0));
+      }
+    }
+  }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const int col = lane < kW2Cols4 ? (lane + 3) % kW2Cols4 : 0;      // lanes 0..23 -> columns 3..26 (outputs)
+  auto src = [&](int k) { return lane < kW2Cols4 ? (lane + k + kW2Cols4) % kW2Cols4 : lane; };
+  const int s_m1 = src(-1), s_m2 = src(-2), s_m3 = src(-3), s_p1 = src(1), s_p2 = src(2), s_p3 = src(3);
+
+  float vx[36], vy[36], vz[36], vw[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) {
+    const float4 t = A[(16 * q + i) * kW2Cols4 + col];
+    vx[i] = t.x; vy[i] = t.y; vz[i] = t.z; vw[i] = t.w;
+  }
+  sliding21_max3<36, 16>(vx);
+  sliding21_max3<36, 16>(vy);
+  sliding21_max3<36, 16>(vz);
+  sliding21_max3<36, 16>(vw);
+
+  const unsigned FULL = 0xffffffffu;
+  const int64_t g0 = r0 + 16 * q;                                   // first output frame of this warp
+  const int nvalid = (int)min((int64_t)16, row_hi - g0);            // frames of the chunk inside the track
+  const int fl = f0 + 4 * lane;
+  const bool v0 = lane < 24 && fl < SIA_NBINS, v1 = lane < 24 && fl + 1 < SIA_NBINS;
+  const bool v2 = lane < 24 && fl + 2 < SIA_NBINS, v3 = lane < 24 && fl + 3 < SIA_NBINS;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float a0 = vx[i], a1 = vy[i], a2 = vz[i], a3 = vw[i];
+    const float S2 = fmaxf(a2, a3), S1 = fmaxf(a1, S2), M = fmaxf(a0, S1);
+    const float P1 = fmaxf(a0, a1), P2 = fmaxf(P1, a2);
+    const float Mm1 = __shfl_sync(FULL, M, s_m1), Mp1 = __shfl_sync(FULL, M, s_p1);
+    const float Mm2 = __shfl_sync(FULL, M, s_m2), Mp2 = __shfl_sync(FULL, M, s_p2);
+    const float S1m2 = __shfl_sync(FULL, S1, s_m2);
+    const float S2m3 = __shfl_sync(FULL, S2, s_m3), S3m3 = __shfl_sync(FULL, a3, s_m3);
+    const float P2p2 = __shfl_sync(FULL, P2, s_p2);
+    const float P0p3 = __shfl_sync(FULL, a0, s_p3), P1p3 = __shfl_sync(FULL, P1, s_p3);
+    const float common = fmaxf(fmaxf(Mm1, M), Mp1);
+    const float cl = fmaxf(common, Mm2);
+    const float h0 = fmaxf(cl, fmaxf(S2m3, P2p2));          // bins -10..+10 around element 0
+    const float h1 = fmaxf(cl, fmaxf(S3m3, Mp2));
+    const float h2 = fmaxf(cl, fmaxf(Mp2, P0p3));
+    const float h3 = fmaxf(fmaxf(common, S1m2), fmaxf(Mp2, P1p3));
+    // re-read the centre row from shared memory (volatile: keeps 16 float4 out of the register file)
+    float4 c;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w)
+                 : "r"(a_base + (uint32_t)((16 * q + i + 10) * kW2Cols4 + col) * 16u));
+    // one ballot per element index: word e, bit l  <->  bin f0 + 4*l + e   (striped bitmap layout)
+    const uint32_t b0 = __ballot_sync(FULL, c.x == h0 && c.x > amp_lo && v0);
+    const uint32_t b1 = __ballot_sync(FULL, c.y == h1 && c.y > amp_lo && v1);
+    const uint32_t b2 = __ballot_sync(FULL, c.z == h2 && c.z > amp_lo && v2);
+    const uint32_t b3 = __ballot_sync(FULL, c.w == h3 && c.w > amp_lo && v3);
+    if (lane == 0 && i < nvalid)
+      *reinterpret_cast<uint4 *>(bitmap + (g0 + i) * kBitmapRowWords + 4 * strip) = make_uint4(b0, b1, b2, b3);
+  }
+}
+
+int launch_square_warp(const PeaksLaunch &a, cudaStream_t s) {
+  // float c > (double) amp_min  <=>  c > amp_lo with amp_lo = amp_min rounded DOWN to float
+  float amp_lo = (float)a.amp_min;
+  if ((double)amp_lo > a.amp_min) amp_lo = nextafterf(amp_lo, -INFINITY);
+  const int64_t blocks = a.total_ttiles * kW2Strips;
+  peaks_square_warp_kernel<<<(unsigned)blocks, kW2Threads, 0, s>>>((const float *)a.d_spec, a.d_frame_starts,
+                                                                   a.d_ttile_starts, a.n_tracks, amp_lo, a.d_bitmap);
+  SIA_CHECK_LAUNCH();
+  return SIA_OK;
 }
 
 // ---- generic path: any half-width <= SIA_MAX_NBHD, square or diamond, brute force -----------------
@@ -207,7 +336,7 @@ peaks_generic_kernel(const T *__restrict__ spec, const int64_t *__restrict__ fra
     }
     const uint32_t word = __ballot_sync(0xffffffffu, pk);
     const int gw = f >> 5;
-    if ((threadIdx.x & 31) == 0 && g < tc.row_hi && gw < SIA_ROW_WORDS) bitmap[g * SIA_ROW_WORDS + gw] = word;
+    if ((threadIdx.x & 31) == 0 && g < tc.row_hi && gw < SIA_ROW_WORDS) bitmap[g * kBitmapRowWords + gw] = word;
   }
 }
 
@@ -239,19 +368,32 @@ int launch_generic(const PeaksLaunch &a, cudaStream_t s) {
 }
 
 // ---- stage 2 ------------------------------------------------------------------------------------------
+// Two bitmap layouts, both with a row stride of kBitmapRowWords words:
+//   plain   : word w, bit b            <-> bin 32*w + b              (65 words; tile / generic kernels)
+//   striped : word 4*s + e, bit l      <-> bin 96*s + 4*l + e        (22 strips x 4 words; warp kernel)
+template <bool STRIPED>
 __global__ void __launch_bounds__(256)
 rowcount_kernel(const uint32_t *__restrict__ bitmap, int64_t total_frames, uint32_t *__restrict__ row_count) {
   const int lane = threadIdx.x & 31;
   const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= total_frames) return;
-  const uint32_t *row = bitmap + g * SIA_ROW_WORDS;
-  int c = __popc(row[lane]) + __popc(row[lane + 32]);
-  if (lane == 0) c += __popc(row[64]);
+  const uint32_t *row = bitmap + g * kBitmapRowWords;
+  int c = 0;
+  if (STRIPED) {
+    if (lane < kW2Strips) {
+      const uint4 w = *reinterpret_cast<const uint4 *>(row + 4 * lane);
+      c = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+    }
+  } else {
+    c = __popc(row[lane]) + __popc(row[lane + 32]);
+    if (lane == 0) c += __popc(row[64]);
+  }
 #pragma unroll
   for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
   if (lane == 0) row_count[g] = (uint32_t)c;
 }
 
+template <bool STRIPED>
 __global__ void __launch_bounds__(256)
 extract_kernel(const uint32_t *__restrict__ bitmap, const int64_t *__restrict__ row_off,
                const int64_t *__restrict__ frame_starts, int n_tracks, int64_t total_frames, int64_t peak_base,
@@ -267,34 +409,60 @@ extract_kernel(const uint32_t *__restrict__ bitmap, const int64_t *__restrict__ 
     if (k == 0) track_peak_starts[trk] = base;
     if (g == total_frames - 1) track_peak_starts[n_tracks] = row_off[total_frames] + peak_base;
   }
-  const uint32_t *row = bitmap + g * SIA_ROW_WORDS;
+  const uint32_t *row = bitmap + g * kBitmapRowWords;
   bool overflow = false;
-#pragma unroll
-  for (int round = 0; round < 3; ++round) {
-    const int w = round * 32 + lane;
-    uint32_t word = w < SIA_ROW_WORDS ? row[w] : 0u;
-    const int cnt = __popc(word);
+  auto excl_scan = [&](int cnt, int &total) {
     int incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       int o = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += o;
     }
-    int64_t idx = base + incl - cnt;
-    while (word) {
-      const int bit = __ffs(word) - 1;
-      word &= word - 1;
-      if (idx < cap) { peak_t[idx] = k; peak_f[idx] = w * 32 + bit; } else overflow = true;
-      ++idx;
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - cnt;
+  };
+  if (STRIPED) {
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (lane < kW2Strips) w = *reinterpret_cast<const uint4 *>(row + 4 * lane);
+    const int cnt = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+    int total;
+    int64_t idx = base + excl_scan(cnt, total);
+    uint32_t any = w.x | w.y | w.z | w.w;
+    while (any) {                                   // ascending bin order: lane-bit l major, element e minor
+      const int l = __ffs(any) - 1;
+      any &= any - 1;
+      const uint32_t nib = ((w.x >> l) & 1u) | (((w.y >> l) & 1u) << 1) | (((w.z >> l) & 1u) << 2) | (((w.w >> l) & 1u) << 3);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if ((nib >> e) & 1u) {
+          if (idx < cap) { peak_t[idx] = k; peak_f[idx] = kW2Bins * lane + 4 * l + e; } else overflow = true;
+          ++idx;
+        }
     }
-    base += __shfl_sync(0xffffffffu, incl, 31);
+  } else {
+#pragma unroll
+    for (int round = 0; round < 3; ++round) {
+      const int w = round * 32 + lane;
+      uint32_t word = w < SIA_ROW_WORDS ? row[w] : 0u;
+      const int cnt = __popc(word);
+      int total;
+      int64_t idx = base + excl_scan(cnt, total);
+      while (word) {
+        const int bit = __ffs(word) - 1;
+        word &= word - 1;
+        if (idx < cap) { peak_t[idx] = k; peak_f[idx] = w * 32 + bit; } else overflow = true;
+        ++idx;
+      }
+      base += total;
+    }
   }
   if (overflow) atomicOr(status, 1);
 }
 
 }  // namespace
 
-int peaks_bitmap_launch(const PeaksLaunch &a, cudaStream_t s) {
+int peaks_bitmap_launch(const PeaksLaunch &a, cudaStream_t s, bool *striped) {
+  *striped = false;
   if (a.total_ttiles == 0) return SIA_OK;
   SIA_REQUIRE(a.nbhd >= 1 && a.nbhd <= SIA_MAX_NBHD, SIA_E_UNSUPPORTED, "peaks: nbhd must be in 1..16");
   SIA_REQUIRE(a.connectivity == 1 || a.connectivity == 2, SIA_E_UNSUPPORTED, "peaks: connectivity must be 1 or 2");
@@ -302,26 +470,34 @@ int peaks_bitmap_launch(const PeaksLaunch &a, cudaStream_t s) {
   if (a.connectivity == 2 && a.nbhd == 10) {
     // (double + erosion would need 255 KB of shared memory: it takes the generic kernel)
     if (a.in_type == SIA_F64 && !erosion) return launch_square<double, 10, false>(a, s);
-    if (a.in_type == SIA_F32) return erosion ? launch_square<float, 10, true>(a, s) : launch_square<float, 10, false>(a, s);
+    if (a.in_type == SIA_F32 && !erosion) { *striped = true; return launch_square_warp(a, s); }
+    if (a.in_type == SIA_F32) return launch_square<float, 10, true>(a, s);
   }
   return a.in_type == SIA_F64 ? launch_generic<double>(a, s) : launch_generic<float>(a, s);
 }
 
-int peaks_rowcount_launch(const uint32_t *d_bitmap, int64_t total_frames, uint32_t *d_row_count, cudaStream_t s) {
+int peaks_rowcount_launch(const uint32_t *d_bitmap, bool striped, int64_t total_frames, uint32_t *d_row_count,
+                          cudaStream_t s) {
   if (total_frames == 0) return SIA_OK;
-  rowcount_kernel<<<(unsigned)ceil_div(total_frames * 32, 256), 256, 0, s>>>(d_bitmap, total_frames, d_row_count);
+  const unsigned blocks = (unsigned)ceil_div(total_frames * 32, 256);
+  if (striped) rowcount_kernel<true><<<blocks, 256, 0, s>>>(d_bitmap, total_frames, d_row_count);
+  else rowcount_kernel<false><<<blocks, 256, 0, s>>>(d_bitmap, total_frames, d_row_count);
   SIA_CHECK_LAUNCH();
   return SIA_OK;
 }
 
-int peaks_extract_launch(const uint32_t *d_bitmap, const int64_t *d_row_off, const int64_t *d_frame_starts,
-                         int n_tracks, int64_t total_frames, int64_t peak_base, int32_t *d_peak_t,
+int peaks_extract_launch(const uint32_t *d_bitmap, bool striped, const int64_t *d_row_off,
+                         const int64_t *d_frame_starts, int n_tracks, int64_t total_frames, int64_t peak_base, int32_t *d_peak_t,
                          int32_t *d_peak_f, int64_t cap_peaks, int64_t *d_track_peak_starts, int32_t *d_status,
                          cudaStream_t s) {
   if (total_frames == 0) return SIA_OK;
-  extract_kernel<<<(unsigned)ceil_div(total_frames * 32, 256), 256, 0, s>>>(
-      d_bitmap, d_row_off, d_frame_starts, n_tracks, total_frames, peak_base, d_peak_t, d_peak_f, cap_peaks,
-      d_track_peak_starts, d_status);
+  const unsigned blocks = (unsigned)ceil_div(total_frames * 32, 256);
+  if (striped)
+    extract_kernel<true><<<blocks, 256, 0, s>>>(d_bitmap, d_row_off, d_frame_starts, n_tracks, total_frames, peak_base,
+                                                d_peak_t, d_peak_f, cap_peaks, d_track_peak_starts, d_status);
+  else
+    extract_kernel<false><<<blocks, 256, 0, s>>>(d_bitmap, d_row_off, d_frame_starts, n_tracks, total_frames, peak_base,
+                                                 d_peak_t, d_peak_f, cap_peaks, d_track_peak_starts, d_status);
   SIA_CHECK_LAUNCH();
   return SIA_OK;
 }

@@ -44,16 +44,19 @@ struct PeaksLaunch {
   double amp_min;
   int connectivity;               // 1 diamond, 2 square
   int nbhd;
-  uint32_t *d_bitmap;             // [total_frames][SIA_ROW_WORDS]
+  uint32_t *d_bitmap;             // [total_frames][kBitmapRowWords]
 };
+constexpr int kBitmapRowWords = 88;   // row stride of the peak bitmap: 22 strips x 4 words (striped) >= 65 (plain)
 constexpr int kPeakTileT = 64;    // output rows per tile
 constexpr int kPeakTileF = 128;   // output bins per tile
-int peaks_bitmap_launch(const PeaksLaunch &a, cudaStream_t s);
+// *striped tells which bitmap layout was written (see peaks.cu)
+int peaks_bitmap_launch(const PeaksLaunch &a, cudaStream_t s, bool *striped);
 
 // bitmap -> ordered (t, f) lists.  d_row_count/d_row_off: [total_frames(+1)] workspaces.
-int peaks_rowcount_launch(const uint32_t *d_bitmap, int64_t total_frames, uint32_t *d_row_count, cudaStream_t s);
-int peaks_extract_launch(const uint32_t *d_bitmap, const int64_t *d_row_off, const int64_t *d_frame_starts,
-                         int n_tracks, int64_t total_frames, int64_t peak_base, int32_t *d_peak_t,
+int peaks_rowcount_launch(const uint32_t *d_bitmap, bool striped, int64_t total_frames, uint32_t *d_row_count,
+                          cudaStream_t s);
+int peaks_extract_launch(const uint32_t *d_bitmap, bool striped, const int64_t *d_row_off,
+                         const int64_t *d_frame_starts, int n_tracks, int64_t total_frames, int64_t peak_base, int32_t *d_peak_t,
                          int32_t *d_peak_f, int64_t cap_peaks, int64_t *d_track_peak_starts, int32_t *d_status,
                          cudaStream_t s);
 

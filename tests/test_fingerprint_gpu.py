@@ -145,6 +145,37 @@ def test_k2_other_neighbourhoods_and_float32(fpr):
             assert got == want, (amp, k)
 
 
+def test_k2_float32_production_kernel(fpr):
+    """The float32 square-footprint kernel (the one the pipeline runs): ties, thresholds that are not
+    float32-representable, ragged multi-track layouts whose tiles end mid-way."""
+    import torch
+    rng = np.random.default_rng(12)
+    frames = [130, 1, 64, 65, 7, 200]
+    arrs = []
+    for k, T in enumerate(frames):
+        a = rng.normal(6, 9, (2049, T))
+        if k % 2 == 0:
+            a = np.round(a * 2) / 2                      # plateaus / exact ties
+        if k == 2:
+            a[:, 10:30] = 0.0                            # a zero slab (digital silence)
+        arrs.append(a.astype(np.float32))
+    host = np.zeros((sum(frames), 2080), np.float32)
+    host[:, 2049:] = 1e30                                # row padding must be ignored
+    r = 0
+    for a in arrs:
+        host[r:r + a.shape[1], :2049] = a.T
+        r += a.shape[1]
+    spec = torch.from_numpy(host).to(fpr.tdev)
+    for amp in (10, 0, 10.1, 9.5, 40):
+        p = fpr.params(amp_min=amp)
+        pt, pf, tps = fpr.peaks(spec, np.array(frames, np.int64), p)
+        tps = tps.cpu().numpy(); pt = pt.cpu().numpy(); pf = pf.cpu().numpy()
+        for k, a in enumerate(arrs):
+            want = sorted((int(t), int(f)) for f, t in O.get_2D_peaks(a.astype(np.float64), amp))
+            got = list(zip(pt[tps[k]:tps[k + 1]].tolist(), pf[tps[k]:tps[k + 1]].tolist()))
+            assert got == want, (amp, k, len(got), len(want))
+
+
 def test_k3_hashes_from_reference_peaks(fpr, wav_fixture):
     import torch
     from shazam_b200.fingerprinter import digests_to_hex
