@@ -104,33 +104,76 @@ __device__ __forceinline__ void fft8(T (&r)[8], T (&i)[8]) {
 }
 __host__ __device__ constexpr int pos8(int k) { return 2 * (k & 3) + (k >> 2); }
 
-// 10*log10(p) + c for p > 0.  The mantissa's log2 is taken in float (MUFU.LG2 on [1,2):
-// absolute error ~2^-22) and recombined with the exponent in double: |error| < 1e-6 dB,
-// below the float32 rounding of the stored value.
-__device__ __forceinline__ double db_from_power(double p, double c) {
-  const int hi = __double2hiint(p), lo = __double2loint(p);
-  const int e = (hi >> 20) - 1023;
-  if (e == -1023 || e == 1024) return 10.0 * log10(p) + c;   // subnormal / inf / nan: exact path
-  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-  const float l2 = __log2f((float)m);
-  return ((double)e + (double)l2) * 3.01029995663981195 + c;
+// ---- constants in the constant bank (operands of DFMA/FFMA, no load instruction) ----------------------
+__constant__ double2 c_winA_d[16];   // (cos, sin)(2*pi*256*a/4095)
+__constant__ float2 c_winA_f[16];
+__constant__ double2 c_w32_d[8];     // W32^it = (cos, -sin)(2*pi*it/32)
+__constant__ float2 c_w32_f[8];
+template <typename T> __device__ __forceinline__ typename Vec2<T>::type winA(int a);
+template <> __device__ __forceinline__ double2 winA<double>(int a) { return c_winA_d[a]; }
+template <> __device__ __forceinline__ float2 winA<float>(int a) { return c_winA_f[a]; }
+template <typename T> __device__ __forceinline__ typename Vec2<T>::type w32(int k);
+template <> __device__ __forceinline__ double2 w32<double>(int k) { return c_w32_d[k]; }
+template <> __device__ __forceinline__ float2 w32<float>(int k) { return c_w32_f[k]; }
+
+// int16 sample -> real, exactly, without the (slow) I2F.F64 conversion: splice the integer into the mantissa
+// of 2^52+2^31 (resp. 1.5*2^23) and subtract the magic constant on the FP pipe.
+template <typename T> __device__ __forceinline__ T sample_to_real(int s);
+template <> __device__ __forceinline__ double sample_to_real<double>(int s) {
+  return __hiloint2double(0x43300000, (int)(0x80000000u ^ (uint32_t)s)) - 4503601774854144.0;
 }
-__device__ __forceinline__ float db_from_power(float p, float c) {
-  return __log2f(p) * 3.0102999566f + c;
+template <> __device__ __forceinline__ float sample_to_real<float>(int s) {
+  return __int_as_float(0x4b400000 + s) - 12582912.0f;
+}
+
+// dB epilogue.  dB = 10*log10(p*scale) = C*(e + Ki + log2(m) + Kf),  C = 10*log10(2), p = m*2^e, log2(scale) = Ki+Kf.
+// log2 of the mantissa: MUFU.LG2 on a float built from the top 23 mantissa bits (rounded) — absolute error
+// ~2^-22; the integer part is recombined with a split constant (E*C_hi is exact), so the result carries
+// 0.5 ulp(float) + ~1.4e-6 dB.  p == 0 -> 0 dB (__init__.py:241).  Subnormal / non-finite p: exact slow path.
+struct DbScale { int ki; float kf; double c; };
+constexpr float kC = 3.01029995663981195f;
+constexpr float kC_hi = 6165.0f / 2048.0f;                                   // 13 significant bits
+constexpr float kC_lo = (float)(3.01029995663981195 - 6165.0 / 2048.0);
+
+// rare path (subnormal / non-finite power): kept out of line so that it does not bloat the unrolled epilogue
+__device__ __noinline__ float db_slow(double p, double c) { return (float)(10.0 * log10(p) + c); }
+
+__device__ __forceinline__ float db_combine(int E, float L) {
+  const float Ef = __int_as_float(0x4b400000 + E) - 12582912.0f;             // exact int -> float, |E| < 2^22
+  return fmaf(Ef, kC_hi, fmaf(Ef, kC_lo, L * kC));
+}
+template <typename OutT>
+__device__ __forceinline__ OutT db_out(double p, const DbScale &sc) {
+  const int hi = __double2hiint(p), lo = __double2loint(p);
+  if ((hi | lo) == 0) return (OutT)0;
+  if (sizeof(OutT) == 8) return (OutT)(10.0 * log10(p) + sc.c);             // float64 output (tests): exact path
+  const int e = (hi >> 20) - 1023;
+  if (e == -1023 || e == 1024) return (OutT)db_slow(p, sc.c);
+  const uint32_t bits = 0x3f800000u + (((uint32_t)hi & 0xfffffu) << 3) + ((uint32_t)lo >> 29) + (((uint32_t)lo >> 28) & 1u);
+  return (OutT)db_combine(e + sc.ki, __log2f(__uint_as_float(bits)) + sc.kf);
+}
+template <typename OutT>
+__device__ __forceinline__ OutT db_out(float p, const DbScale &sc) {
+  if (p == 0.f) return (OutT)0;
+  const int b = __float_as_int(p);
+  const int e = (b >> 23) - 127;
+  if (e == -127 || e == 128) return (OutT)db_slow((double)p, sc.c);
+  return (OutT)db_combine(e + sc.ki, __log2f(__int_as_float((b & 0x7fffff) | 0x3f800000)) + sc.kf);
 }
 
 template <typename T, typename OutT>
-__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 8)
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6)
 stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ track_starts,
                const int64_t *__restrict__ track_len, const int64_t *__restrict__ frame_starts, int n_tracks,
-               int64_t total_frames, int frames_per_cta, OutT *__restrict__ out, T c_mid, T c_edge,
-               const typename Vec2<T>::type *__restrict__ win2, const typename Vec2<T>::type *__restrict__ twA,
+               int64_t total_frames, int frames_per_cta, OutT *__restrict__ out, DbScale sc_mid, DbScale sc_edge,
+               const typename Vec2<T>::type *__restrict__ winB, const typename Vec2<T>::type *__restrict__ twA,
                const typename Vec2<T>::type *__restrict__ twB, const typename Vec2<T>::type *__restrict__ twP) {
   using V2 = typename Vec2<T>::type;
   __shared__ T sre[kBufElems];
   __shared__ T sim[kBufElems];
 
   const int t = threadIdx.x;
+
   int64_t g = (int64_t)blockIdx.x * frames_per_cta;
   if (g >= total_frames) return;
   int64_t g_end = g + frames_per_cta;
@@ -161,23 +204,40 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
           w[a] = v;
         }
       }
+      const V2 wb0 = __ldg(winB + 2 * t), wb1 = __ldg(winB + 2 * t + 1);   // window phase of samples 2t, 2t+1
 #pragma unroll
       for (int a = 0; a < 16; ++a) {
-        const V2 wn = __ldg(win2 + 128 * a + t);
-        xr[a] = (T)(int)(short)(w[a] & 0xffffu) * wn.x;
-        xi[a] = (T)(int)(short)(w[a] >> 16) * wn.y;
+        // np.hanning: w[m] = 0.5 - 0.5*cos(2*pi*m/4095), m = 256a + 2t (+1): cos(A_a + B_t) by angle addition
+        const V2 ca = winA<T>(a);
+        const T w0 = fma(ca.x * wb0.x - ca.y * wb0.y, (T)-0.5, (T)0.5);
+        const T w1 = fma(ca.x * wb1.x - ca.y * wb1.y, (T)-0.5, (T)0.5);
+        xr[a] = sample_to_real<T>((int)(short)(w[a] & 0xffffu)) * w0;
+        xi[a] = sample_to_real<T>((int)w[a] >> 16) * w1;
       }
       fft16(xr, xi);
-#pragma unroll
-      for (int ka = 0; ka < 16; ++ka) {
+      // twiddles W2048^(t*ka): four loaded (ka = 1, 2, 4, 8), the rest by products (<= 3 deep)
+      const V2 b1 = __ldg(twA + 1 * 128 + t), b2 = __ldg(twA + 2 * 128 + t);
+      const V2 b4 = __ldg(twA + 4 * 128 + t), b8 = __ldg(twA + 8 * 128 + t);
+      auto put = [&](int ka, T wr, T wi) {
         T r = xr[pos16(ka)], i = xi[pos16(ka)];
-        if (ka) {
-          const V2 tw = __ldg(twA + ka * 128 + t);
-          cmul(r, i, tw.x, tw.y);
-        }
+        cmul(r, i, wr, wi);
         sre[ka * kL1Stride + t] = r;
         sim[ka * kL1Stride + t] = i;
-      }
+      };
+      auto mul = [](V2 a, V2 b) { V2 o; o.x = a.x * b.x - a.y * b.y; o.y = a.x * b.y + a.y * b.x; return o; };
+      sre[t] = xr[0]; sim[t] = xi[0];
+      put(1, b1.x, b1.y); put(2, b2.x, b2.y);
+      { const V2 w3 = mul(b2, b1); put(3, w3.x, w3.y); }
+      put(4, b4.x, b4.y);
+      { const V2 w5 = mul(b4, b1); put(5, w5.x, w5.y); }
+      { const V2 w6 = mul(b4, b2); put(6, w6.x, w6.y); const V2 w7 = mul(w6, b1); put(7, w7.x, w7.y); }
+      put(8, b8.x, b8.y);
+      { const V2 w9 = mul(b8, b1); put(9, w9.x, w9.y); }
+      { const V2 w10 = mul(b8, b2); put(10, w10.x, w10.y); const V2 w11 = mul(w10, b1); put(11, w11.x, w11.y); }
+      { const V2 w12 = mul(b8, b4); put(12, w12.x, w12.y);
+        const V2 w13 = mul(w12, b1); put(13, w13.x, w13.y);
+        const V2 w14 = mul(w12, b2); put(14, w14.x, w14.y);
+        const V2 w15 = mul(w14, b1); put(15, w15.x, w15.y); }
     }
     __syncthreads();
     // ---- pass B: FFT16 over b -----------------------------------------------------------
@@ -227,12 +287,17 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
     // ---- post-pass: bins k and 2048-k from Z[k], Z[2048-k] ------------------------------------
     {
       OutT *__restrict__ row = out + g * (int64_t)SIA_F_STRIDE;
+      const V2 twp = __ldg(twP + t);                                         // W4096^t
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int kk = t + 128 * it;            // 0..1023
         const int kn = (2048 - kk) & 2047;
         const T ar = sre[kk], ai = sim[kk], br = sre[kn], bi = sim[kn];
-        const V2 tw = __ldg(twP + kk);
+        // W4096^(t + 128 it) = W4096^t * W32^it
+        const V2 c32 = w32<T>(it);
+        V2 tw;
+        tw.x = twp.x * c32.x - twp.y * c32.y;
+        tw.y = twp.x * c32.y + twp.y * c32.x;
         // 2E = A + conj(B), 2O = -i (A - conj(B))
         const T er = ar + br, ei = ai - bi;
         const T orr = ai + bi, oi = br - ar;
@@ -241,14 +306,14 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
         const T qr = er - tr, qi = ei - ti;     // 2 conj(X[2048-k])
         const T p1 = pr * pr + pi * pi;
         const T p2 = qr * qr + qi * qi;
-        const T c1 = kk == 0 ? c_edge : c_mid;
-        row[kk] = (OutT)(p1 == (T)0 ? (T)0 : (T)db_from_power(p1, c1));
-        row[2048 - kk] = (OutT)(p2 == (T)0 ? (T)0 : (T)db_from_power(p2, c1));
+        const DbScale &sc = kk == 0 ? sc_edge : sc_mid;
+        row[kk] = db_out<OutT>(p1, sc);
+        row[2048 - kk] = db_out<OutT>(p2, sc);
       }
       if (t == 0) {                              // k = 1024 pairs with itself: X = conj(Z[1024])
         const T ar = sre[1024], ai = sim[1024];
         const T p1 = (T)4 * (ar * ar + ai * ai);
-        row[1024] = (OutT)(p1 == (T)0 ? (T)0 : (T)db_from_power(p1, c_mid));
+        row[1024] = db_out<OutT>(p1, sc_mid);
       }
     }
     __syncthreads();   // L3 is overwritten by the next frame's pass A
@@ -264,12 +329,28 @@ template <typename T>
 static int upload_tables(StftTables<T> &tb) {
   using V2 = typename Vec2<T>::type;
   const long double PI = 3.141592653589793238462643383279502884L;
-  std::vector<V2> win(2048), twA(16 * 128), twB(16 * 8), twP(1025);
-  for (int n = 0; n < 2048; ++n) {
-    // np.hanning(4096): 0.5 - 0.5*cos(2*pi*n/(M-1)), symmetric
-    long double w0 = 0.5L - 0.5L * cosl(2 * PI * (2 * n) / 4095.0L);
-    long double w1 = 0.5L - 0.5L * cosl(2 * PI * (2 * n + 1) / 4095.0L);
-    win[n].x = (T)w0; win[n].y = (T)w1;
+  std::vector<V2> win(256), twA(16 * 128), twB(16 * 8), twP(1025);
+  for (int m = 0; m < 256; ++m) {
+    // np.hanning(4096)[m'] = 0.5 - 0.5*cos(2*pi*m'/4095) (symmetric); the kernel forms the cosine of
+    // m' = 256a + m by angle addition from (cos, sin)(2*pi*m/4095) here and the per-a constants below
+    win[m].x = (T)cosl(2 * PI * m / 4095.0L);
+    win[m].y = (T)sinl(2 * PI * m / 4095.0L);
+  }
+  V2 wa[16], w32c[8];
+  for (int a = 0; a < 16; ++a) {
+    wa[a].x = (T)cosl(2 * PI * 256.0L * a / 4095.0L);
+    wa[a].y = (T)sinl(2 * PI * 256.0L * a / 4095.0L);
+  }
+  for (int k = 0; k < 8; ++k) {
+    w32c[k].x = (T)cosl(-2 * PI * k / 32.0L);
+    w32c[k].y = (T)sinl(-2 * PI * k / 32.0L);
+  }
+  if (sizeof(T) == 8) {
+    SIA_CUDA(cudaMemcpyToSymbol(c_winA_d, wa, sizeof wa));
+    SIA_CUDA(cudaMemcpyToSymbol(c_w32_d, w32c, sizeof w32c));
+  } else {
+    SIA_CUDA(cudaMemcpyToSymbol(c_winA_f, wa, sizeof wa));
+    SIA_CUDA(cudaMemcpyToSymbol(c_w32_f, w32c, sizeof w32c));
   }
   for (int ka = 0; ka < 16; ++ka)
     for (int t = 0; t < 128; ++t) {
@@ -330,14 +411,21 @@ template <typename T, typename OutT>
 static int launch(const StftLaunch &a, const StftTables<T> &tb, cudaStream_t s) {
   using V2 = typename Vec2<T>::type;
   const double scale = 1.0 / (4.0 * a.Fs * hann_power_sum());  // the 1/4: the post-pass keeps 2E, 2O
-  const double c_edge = 10.0 * log10(scale);
-  const double c_mid = 10.0 * log10(2.0 * scale);
+  auto mk = [](double sc) {
+    DbScale d;
+    const double K = log2(sc);
+    d.ki = (int)floor(K);
+    d.kf = (float)(K - floor(K));
+    d.c = 10.0 * log10(sc);
+    return d;
+  };
+  const DbScale sc_edge = mk(scale), sc_mid = mk(2.0 * scale);   // bins 0 and 2048 are not doubled
   const int G = a.frames_per_cta;
   const int64_t blocks = ceil_div(a.total_frames, G);
   if (blocks == 0) return SIA_OK;
   stft_db_kernel<T, OutT><<<(unsigned)blocks, 128, 0, s>>>(
       a.d_pcm, a.d_track_starts, a.d_track_len, a.d_frame_starts, a.n_tracks, a.total_frames, G, (OutT *)a.d_spec,
-      (T)c_mid, (T)c_edge, (const V2 *)tb.win2, (const V2 *)tb.twA, (const V2 *)tb.twB, (const V2 *)tb.twP);
+      sc_mid, sc_edge, (const V2 *)tb.win2, (const V2 *)tb.twA, (const V2 *)tb.twB, (const V2 *)tb.twP);
   SIA_CHECK_LAUNCH();
   return SIA_OK;
 }
