@@ -10,8 +10,8 @@
 //   n = 128a + 8b + c      k = ka + 16kb + 256kc
 //   pass A  thread t=8b+c   : FFT16 over a, x W2048^(t*ka)      -> L1[ka*136 + t]
 //   pass B  thread (ka,c)   : FFT16 over b, x W128^(c*kb)       -> L2[c*258 + kb*16 + ka]
-//   pass C  thread u=kb*16+ka (2 per thread): FFT8 over c       -> L3[u + 256kc] = Z[k]
-//   post    pairs (k, 2048-k): E +/- W4096^k O, |.|^2, dB       -> global, coalesced
+//   pass C  thread t: FFT8 over c of columns u = t and 256-t (u = kb*16+ka)  -> Z[u + 256kc] in registers
+//   post    the same thread holds Z[k] and Z[2048-k]: E +/- W4096^k O, |.|^2, dB -> global, coalesced
 //
 // The strides 136 and 258 make every shared-memory access of every pass conflict-free
 // for 8-byte (and 4-byte) elements.  PCM is read straight from global memory as packed
@@ -172,6 +172,12 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
   __shared__ T sre[kBufElems];
   __shared__ T sim[kBufElems];
 
+  // PCM ring: three 2048-sample half-blocks.  Frame k of a track reads half-blocks k and k+1; the half-block
+  // the NEXT frame adds is fetched with cp.async while this frame is being transformed, so the DRAM latency
+  // of the PCM never sits in front of pass A.  Bytes past the end of a track are zero-filled (src-size),
+  // which is exactly mlab.specgram's zero padding of a short input.
+  __shared__ __align__(16) uint32_t spcm[3][1024];
+
   const int t = threadIdx.x;
 
   int64_t g = (int64_t)blockIdx.x * frames_per_cta;
@@ -180,39 +186,50 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
   if (g_end > total_frames) g_end = total_frames;
   int trk = find_segment(frame_starts, n_tracks, g);
 
+  const uint32_t spcm_base = (uint32_t)__cvta_generic_to_shared(&spcm[0][0]);
+  // copy half-block h of track `tr` into ring slot `slot` (2 x 16-byte chunks per thread)
+  auto fetch_half = [&](int tr, int64_t h, int slot) {
+    const int64_t valid = (track_len[tr] - h * SIA_HOP) * 2;          // bytes of this half-block inside the track
+    const char *src = reinterpret_cast<const char *>(pcm + track_starts[tr] + h * SIA_HOP);
+#pragma unroll
+    for (int c = t; c < 256; c += 128) {
+      const int64_t rest = valid - 16 * c;
+      const int nbytes = rest >= 16 ? 16 : (rest > 0 ? (int)rest : 0);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(spcm_base + (uint32_t)(slot * 4096 + 16 * c)),
+                   "l"(nbytes ? src + 16 * c : reinterpret_cast<const char *>(pcm)), "r"(nbytes));
+    }
+  };
+  int slot = 0;
+  bool primed = false;
+
   for (; g < g_end; ++g) {
     while (g >= frame_starts[trk + 1]) ++trk;
     const int64_t k = g - frame_starts[trk];
-    const int64_t off = track_starts[trk] + k * SIA_HOP;
-    const int64_t rem = track_len[trk] - k * SIA_HOP;   // >= 4096 except for a short (zero padded) track
-    const uint32_t *__restrict__ p32 = reinterpret_cast<const uint32_t *>(pcm + off);
+    if (!primed) {                       // first frame of the run or of a track: both half-blocks, synchronously
+      fetch_half(trk, k, slot);
+      fetch_half(trk, k + 1, (slot + 1) % 3);
+      asm volatile("cp.async.wait_all;\n" ::: "memory");
+      __syncthreads();
+    }
+    primed = g + 1 < frame_starts[trk + 1];           // the next frame continues this track
+    if (primed && g + 1 < g_end) fetch_half(trk, k + 2, (slot + 2) % 3);
+    const uint32_t *__restrict__ h0 = spcm[slot], *__restrict__ h1 = spcm[(slot + 1) % 3];
 
     T xr[16], xi[16];
     // ---- pass A: window, pack even/odd samples as complex, FFT16 over a -----------------
     {
       uint32_t w[16];
-      if (rem >= SIA_NFFT) {
 #pragma unroll
-        for (int a = 0; a < 16; ++a) w[a] = __ldg(p32 + 128 * a + t);
-      } else {
-#pragma unroll
-        for (int a = 0; a < 16; ++a) {
-          const int s = 2 * (128 * a + t);
-          uint32_t v = 0;
-          if (s + 1 < rem) v = p32[128 * a + t];
-          else if (s < rem) v = (uint32_t)(uint16_t)pcm[off + s];
-          w[a] = v;
-        }
-      }
+      for (int a = 0; a < 8; ++a) { w[a] = h0[128 * a + t]; w[a + 8] = h1[128 * a + t]; }
       const V2 wb0 = __ldg(winB + 2 * t), wb1 = __ldg(winB + 2 * t + 1);   // window phase of samples 2t, 2t+1
 #pragma unroll
       for (int a = 0; a < 16; ++a) {
         // np.hanning: w[m] = 0.5 - 0.5*cos(2*pi*m/4095), m = 256a + 2t (+1): cos(A_a + B_t) by angle addition
         const V2 ca = winA<T>(a);
-        const T w0 = fma(ca.x * wb0.x - ca.y * wb0.y, (T)-0.5, (T)0.5);
-        const T w1 = fma(ca.x * wb1.x - ca.y * wb1.y, (T)-0.5, (T)0.5);
-        xr[a] = sample_to_real<T>((int)(short)(w[a] & 0xffffu)) * w0;
-        xi[a] = sample_to_real<T>((int)w[a] >> 16) * w1;
+        // x*(1 - cos) = 2*x*w: one FMA; the factor 2 is folded into the dB constant
+        const T s0 = sample_to_real<T>((int)(short)(w[a] & 0xffffu)), s1 = sample_to_real<T>((int)w[a] >> 16);
+        xr[a] = fma(-s0, ca.x * wb0.x - ca.y * wb0.y, s0);
+        xi[a] = fma(-s1, ca.x * wb1.x - ca.y * wb1.y, s1);
       }
       fft16(xr, xi);
       // twiddles W2048^(t*ka): four loaded (ka = 1, 2, 4, 8), the rest by products (<= 3 deep)
@@ -262,61 +279,71 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
       }
     }
     __syncthreads();
-    // ---- pass C: two FFT8 over c per thread ------------------------------------------------
+    // ---- pass C + split post-pass, fused in registers ---------------------------------------------
+    // Z[k] and its mirror Z[2048-k] are produced by columns u and 256-u of pass C (k = u + 256kc,
+    // 2048-k = (256-u) + 256(7-kc)), so thread t takes columns t and 256-t and never writes Z back to
+    // shared memory.  Thread 0 takes the two self-mirrored columns 0 and 128 (17 bins instead of 16).
     {
       T yr[2][8], yi[2][8];
+      const int u1 = t == 0 ? 128 : 256 - t;
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          yr[h][c] = sre[c * kL2Stride + t + 128 * h];
-          yi[h][c] = sim[c * kL2Stride + t + 128 * h];
-        }
-      __syncthreads();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        fft8(yr[h], yi[h]);
-#pragma unroll
-        for (int kc = 0; kc < 8; ++kc) {
-          sre[t + 128 * h + 256 * kc] = yr[h][pos8(kc)];
-          sim[t + 128 * h + 256 * kc] = yi[h][pos8(kc)];
-        }
+      for (int c = 0; c < 8; ++c) {
+        yr[0][c] = sre[c * kL2Stride + t];  yi[0][c] = sim[c * kL2Stride + t];
+        yr[1][c] = sre[c * kL2Stride + u1]; yi[1][c] = sim[c * kL2Stride + u1];
       }
-    }
-    __syncthreads();
-    // ---- post-pass: bins k and 2048-k from Z[k], Z[2048-k] ------------------------------------
-    {
+      fft8(yr[0], yi[0]);
+      fft8(yr[1], yi[1]);
       OutT *__restrict__ row = out + g * (int64_t)SIA_F_STRIDE;
-      const V2 twp = __ldg(twP + t);                                         // W4096^t
+      const V2 twp = __ldg(twP + t);                       // W4096^t
+      const T C1 = (T)0.92387953251128675613, S1 = (T)0.38268343236508977173, H = (T)0.70710678118654752440;
+      // bins k and 2048-k from A = Z[k], B = Z[2048-k], tw = W4096^k
+      auto emit = [&](T ar, T ai, T br, T bi, T twr, T twi, int k) {
+        const T er = ar + br, ei = ai - bi;                // 2E = A + conj(B)
+        const T orr = ai + bi, oi = br - ar;               // 2O = -i (A - conj(B))
+        const T tr = orr * twr - oi * twi, ti = orr * twi + oi * twr;
+        const T pr = er + tr, pi = ei + ti;                // 2 X[k]
+        const T qr = er - tr, qi = ei - ti;                // 2 conj(X[2048-k])
+        const DbScale &sc = k == 0 ? sc_edge : sc_mid;
+        row[k] = db_out<OutT>(pr * pr + pi * pi, sc);
+        row[2048 - k] = db_out<OutT>(qr * qr + qi * qi, sc);
+      };
+      const bool t0 = t == 0;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int kk = t + 128 * it;            // 0..1023
-        const int kn = (2048 - kk) & 2047;
-        const T ar = sre[kk], ai = sim[kk], br = sre[kn], bi = sim[kn];
-        // W4096^(t + 128 it) = W4096^t * W32^it
-        const V2 c32 = w32<T>(it);
-        V2 tw;
-        tw.x = twp.x * c32.x - twp.y * c32.y;
-        tw.y = twp.x * c32.y + twp.y * c32.x;
-        // 2E = A + conj(B), 2O = -i (A - conj(B))
-        const T er = ar + br, ei = ai - bi;
-        const T orr = ai + bi, oi = br - ar;
-        const T tr = orr * tw.x - oi * tw.y, ti = orr * tw.y + oi * tw.x;
-        const T pr = er + tr, pi = ei + ti;     // 2 X[k]
-        const T qr = er - tr, qi = ei - ti;     // 2 conj(X[2048-k])
-        const T p1 = pr * pr + pi * pi;
-        const T p2 = qr * qr + qi * qi;
-        const DbScale &sc = kk == 0 ? sc_edge : sc_mid;
-        row[kk] = db_out<OutT>(p1, sc);
-        row[2048 - kk] = db_out<OutT>(p2, sc);
+      for (int j = 0; j < 8; ++j) {
+        // W16^j = W4096^(256 j)
+        const T wr16 = j == 0 ? (T)1 : j == 1 ? C1 : j == 2 ? H : j == 3 ? S1 : j == 4 ? (T)0 : j == 5 ? -S1 : j == 6 ? -H : -C1;
+        const T wi16 = j == 0 ? (T)0 : j == 1 ? -S1 : j == 2 ? -H : j == 3 ? -C1 : j == 4 ? (T)-1 : j == 5 ? -C1 : j == 6 ? -H : -S1;
+        T twr = twp.x * wr16 - twp.y * wi16, twi = twp.x * wi16 + twp.y * wr16;
+        T ar = yr[0][pos8(j)], ai = yi[0][pos8(j)];
+        T br = yr[1][pos8(7 - j)], bi = yi[1][pos8(7 - j)];
+        int k = t + 256 * j;
+        if (j <= 4) {
+          // thread 0, column 0: the mirror of k = 256 j is 256 (8-j) in the SAME column
+          const T zr = yr[0][pos8((8 - j) & 7)], zi = yi[0][pos8((8 - j) & 7)];
+          br = t0 ? zr : br; bi = t0 ? zi : bi;
+        } else {
+          // thread 0, column 128: k = 128 + 256 (j-5), mirror 128 + 256 (12-j) in the same column
+          const int kc = j - 5;
+          const T zr = yr[1][pos8(kc)], zi = yi[1][pos8(kc)], mr = yr[1][pos8(7 - kc)], mi = yi[1][pos8(7 - kc)];
+          // W4096^(128 + 256 kc) = W32^1 * W16^kc
+          const V2 w1 = w32<T>(1);
+          const T cr16 = kc == 0 ? (T)1 : kc == 1 ? C1 : H, ci16 = kc == 0 ? (T)0 : kc == 1 ? -S1 : -H;
+          const T c0r = w1.x * cr16 - w1.y * ci16, c0i = w1.x * ci16 + w1.y * cr16;
+          ar = t0 ? zr : ar; ai = t0 ? zi : ai; br = t0 ? mr : br; bi = t0 ? mi : bi;
+          twr = t0 ? c0r : twr; twi = t0 ? c0i : twi;
+          k = t0 ? 128 + 256 * kc : k;
+        }
+        emit(ar, ai, br, bi, twr, twi, k);
       }
-      if (t == 0) {                              // k = 1024 pairs with itself: X = conj(Z[1024])
-        const T ar = sre[1024], ai = sim[1024];
-        const T p1 = (T)4 * (ar * ar + ai * ai);
-        row[1024] = db_out<OutT>(p1, sc_mid);
+      if (t0) {   // the 9th pair of thread 0: k = 896 (column 128, kc = 3), mirror 1152 (kc = 4)
+        const V2 w1 = w32<T>(1);
+        emit(yr[1][pos8(3)], yi[1][pos8(3)], yr[1][pos8(4)], yi[1][pos8(4)], w1.x * S1 + w1.y * C1, w1.y * S1 - w1.x * C1,
+             896);
       }
     }
-    __syncthreads();   // L3 is overwritten by the next frame's pass A
+    asm volatile("cp.async.wait_all;\n" ::: "memory");   // next frame's half-block has landed
+    __syncthreads();   // ... and the L2 layout may be overwritten by the next frame's pass A
+    slot = (slot + 1) % 3;
   }
 }
 
@@ -410,7 +437,8 @@ double hann_power_sum() {
 template <typename T, typename OutT>
 static int launch(const StftLaunch &a, const StftTables<T> &tb, cudaStream_t s) {
   using V2 = typename Vec2<T>::type;
-  const double scale = 1.0 / (4.0 * a.Fs * hann_power_sum());  // the 1/4: the post-pass keeps 2E, 2O
+  // 1/16: the post-pass keeps 2E, 2O (x4 in power) and the window is applied as 2w (x4 in power)
+  const double scale = 1.0 / (16.0 * a.Fs * hann_power_sum());
   auto mk = [](double sc) {
     DbScale d;
     const double K = log2(sc);
