@@ -205,6 +205,20 @@ int sia_vote_bins(int device, const uint64_t *d_bin_key, const int32_t *d_bin_co
                   int32_t n_queries, int32_t topn, int32_t *d_out_song, int32_t *d_out_diff,
                   int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres, void *stream);
 
+/* The same split one step earlier (the cheaper exchange: vote keys travel unsorted, the query's owner sorts
+ * once).  sia_index_expand: for routed query hashes, the (query, song, diff) vote keys and the
+ * (query, song) row keys of the postings this shard owns, grouped by ascending query id (ids < n_queries),
+ * with per-query prefix offsets d_tuple_starts / d_row_starts [n_queries+1].  Passing NULL key buffers
+ * only sizes (*h_ntuples, *h_nrows).  sia_vote_tuples: sort + count + vote of concatenated keys (the
+ * key buffers are used as scratch). */
+int sia_index_expand(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff, const int32_t *d_qid, int64_t n,
+                     int32_t n_queries, uint64_t *d_tuple_key, int64_t cap_tuples, int64_t *h_ntuples,
+                     uint64_t *d_row_key, int64_t cap_rows, int64_t *h_nrows, int64_t *d_tuple_starts,
+                     int64_t *d_row_starts, void *stream);
+int sia_vote_tuples(int device, uint64_t *d_tuple_key, int64_t n_tuples, uint64_t *d_row_key, int64_t n_rows,
+                    int32_t n_queries, int32_t topn, int32_t *d_out_song, int32_t *d_out_diff,
+                    int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres, void *stream);
+
 /* bin key layout (64 bits): query id (15 bits) | song id (24 bits) | offset difference + 2^24
  * (25 bits); row keys use the same layout with a zero difference field.  At most 32768 queries
  * per sia_index_query_partial / sia_vote_bins call (sia_index_query_batch splits internally). */

@@ -66,6 +66,9 @@ SIGNATURES = {
     "sia_index_query_batch": (C.c_int, [_p, _p, _p, _i64p, C.c_int32, C.c_int32, _p, _p, _p, _p, _p, _i64p, _p]),
     "sia_index_query_partial": (C.c_int, [_p, _p, _p, _p, C.c_int64, _p, _p, C.c_int64, _i64p, _p, _p, C.c_int64,
                                           _i64p, _p]),
+    "sia_index_expand": (C.c_int, [_p, _p, _p, _p, C.c_int64, C.c_int32, _p, C.c_int64, _i64p, _p, C.c_int64, _i64p, _p,
+                                   _p, _p]),
+    "sia_vote_tuples": (C.c_int, [C.c_int, _p, C.c_int64, _p, C.c_int64, C.c_int32, C.c_int32, _p, _p, _p, _p, _p, _p]),
     "sia_vote_bins": (C.c_int, [C.c_int, _p, _p, C.c_int64, _p, _p, C.c_int64, C.c_int32, C.c_int32, _p, _p, _p,
                                 _p, _p, _p]),
 }

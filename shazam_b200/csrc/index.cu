@@ -54,6 +54,19 @@ struct Arena {
 
 }  // namespace
 
+namespace {
+// Sorted, de-duplicated query entries for queries [q0, q1) (entries [i0, i1) of the caller's arrays).
+struct Lookup {
+  ulonglong2 *ent = nullptr;
+  uint32_t *first = nullptr;
+  int64_t *off_all = nullptr, *off_head = nullptr;
+  int64_t n = 0, tuples = 0, head_rows = 0, distinct = 0;
+};
+}  // namespace
+
+// scratch of the handle-less vote entry points, kept per device (cudaMalloc of tens of GB per call is slow)
+static Arena g_vote_arena[64];
+
 struct sia_index {
   int device = 0;
   int64_t capacity = 0;
@@ -64,6 +77,11 @@ struct sia_index {
   int32_t *status = nullptr;    // device flag: 1 = song/offset out of range on insert, 2 = query offset out of range
   Arena arena;                  // build / lookup scratch
   Arena arena2;                 // per-group vote scratch
+  // lookup of the last sizing call of sia_index_expand, reused by the call that fills the buffers
+  bool cache_valid = false;
+  const void *cache_hash = nullptr, *cache_qoff = nullptr, *cache_qid = nullptr;
+  int64_t cache_n = 0;
+  Lookup cache_lookup;
 };
 
 namespace {
@@ -379,6 +397,18 @@ __global__ void gather_offsets_kernel(const int64_t *__restrict__ off_all, const
   }
 }
 
+// first sorted entry of every query id (entries are sorted by query id first) -> tuple / row offsets per query
+__global__ void query_starts_kernel(const ulonglong2 *__restrict__ ent, int64_t n, const int64_t *__restrict__ off_all,
+                                    const int64_t *__restrict__ off_head, int nq, int64_t *__restrict__ tuple_starts,
+                                    int64_t *__restrict__ row_starts) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q <= nq; q += gridDim.x * blockDim.x) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if ((int64_t)(ent[mid].y >> 40) < q) lo = mid + 1; else hi = mid; }
+    tuple_starts[q] = off_all[lo];
+    row_starts[q] = off_head[lo];
+  }
+}
+
 inline unsigned grid_for(int64_t n, int threads = 256) {
   int64_t b = ceil_div(n > 0 ? n : 1, threads);
   return (unsigned)std::min<int64_t>(b, kNumSMs * 32);
@@ -451,13 +481,6 @@ int vote_sorted(Arena &ar, const uint64_t *bin_key, const int32_t *bin_count, in
 
 size_t vote_bytes(int64_t nbins) { return (size_t)nbins * (4 + 8 + 8 + 8) + scan_tmp_bytes(nbins) + 4096; }
 
-// Sorted, de-duplicated query entries for queries [q0, q1) (entries [i0, i1) of the caller's arrays).
-struct Lookup {
-  ulonglong2 *ent = nullptr;
-  uint32_t *first = nullptr;
-  int64_t *off_all = nullptr, *off_head = nullptr;
-  int64_t n = 0, tuples = 0, head_rows = 0, distinct = 0;
-};
 
 int lookup_pass(sia_index *ix, Arena &ar, const uint8_t *d_hash, const int32_t *d_qoff, const int32_t *d_qid,
                 const int64_t *d_query_starts, int n_queries, int qid_base, int64_t i0, int64_t n, Lookup &L,
@@ -616,6 +639,7 @@ int sia_index_insert_rows(sia_index *ix, const int32_t *d_song, const uint8_t *d
 }
 
 int sia_index_insert_host(sia_index *ix, int32_t song_id, const uint8_t *h_hash, const int32_t *h_off, int64_t n) {
+  if (ix) ix->cache_valid = false;
   SIA_REQUIRE(ix != nullptr, SIA_E_INVALID, "index is NULL");
   if (n == 0) return SIA_OK;
   SIA_REQUIRE(h_hash && h_off && n > 0, SIA_E_INVALID, "bad argument");
@@ -633,6 +657,7 @@ int sia_index_insert_host(sia_index *ix, int32_t song_id, const uint8_t *h_hash,
 }
 
 int sia_index_finalize(sia_index *ix, int64_t *h_rows) {
+  if (ix) ix->cache_valid = false;
   SIA_REQUIRE(ix != nullptr, SIA_E_INVALID, "index is NULL");
   int rc = set_device(ix);
   if (rc) return rc;
@@ -692,6 +717,7 @@ int sia_index_finalize(sia_index *ix, int64_t *h_rows) {
 }
 
 int sia_index_delete_songs(sia_index *ix, const int32_t *h_song_ids, int32_t n, int64_t *h_rows) {
+  if (ix) ix->cache_valid = false;
   SIA_REQUIRE(ix != nullptr, SIA_E_INVALID, "index is NULL");
   SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
   if (h_rows) *h_rows = ix->n_rows;
@@ -737,6 +763,7 @@ int sia_index_delete_songs(sia_index *ix, const int32_t *h_song_ids, int32_t n, 
 
 int sia_index_select_host(sia_index *ix, const uint8_t *h_hash, int64_t n, int32_t *h_row_hashidx, int32_t *h_row_song,
                           int32_t *h_row_off, int64_t cap, int64_t *h_nrows) {
+  if (ix) ix->cache_valid = false;
   SIA_REQUIRE(ix && h_nrows, SIA_E_INVALID, "NULL argument");
   SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
   *h_nrows = 0;
@@ -776,6 +803,7 @@ int sia_index_select_host(sia_index *ix, const uint8_t *h_hash, int64_t n, int32
 int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff, const int64_t *h_query_starts,
                           int32_t n_queries, int32_t topn, int32_t *d_out_song, int32_t *d_out_diff,
                           int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres, int64_t *h_stats, void *stream) {
+  if (ix) ix->cache_valid = false;
   SIA_REQUIRE(ix && h_query_starts, SIA_E_INVALID, "NULL argument");
   SIA_REQUIRE(n_queries >= 0 && topn >= 1, SIA_E_INVALID, "n_queries >= 0 and topn >= 1 required");
   SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
@@ -849,6 +877,7 @@ int sia_index_query_partial(sia_index *ix, const uint8_t *d_hash, const int32_t 
                             uint64_t *d_bin_key, int32_t *d_bin_count, int64_t cap_bins, int64_t *h_nbins,
                             uint64_t *d_row_key, int32_t *d_row_count, int64_t cap_rowbins, int64_t *h_nrowbins,
                             void *stream) {
+  if (ix) ix->cache_valid = false;
   SIA_REQUIRE(ix && h_nbins && h_nrowbins, SIA_E_INVALID, "NULL argument");
   SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
   *h_nbins = *h_nrowbins = 0;
@@ -902,8 +931,9 @@ int sia_vote_bins(int device, const uint64_t *d_bin_key, const int32_t *d_bin_co
   if (n_queries == 0) return SIA_OK;
   SIA_REQUIRE(d_out_song && d_out_diff && d_out_count && d_out_rows && d_out_nres, SIA_E_INVALID, "NULL output");
   SIA_CUDA(cudaSetDevice(device));
+  SIA_REQUIRE(device >= 0 && device < 64, SIA_E_INVALID, "device index");
   cudaStream_t s = (cudaStream_t)stream;
-  Arena ar;
+  Arena &ar = g_vote_arena[device];
   int rc = ar.reserve((size_t)(nbins + nrowbins) * (16 * 2 + 12) + radix_sort_tmp_bytes(nbins) +
                       radix_sort_tmp_bytes(nrowbins) + reduce_runs_bytes(nbins) + reduce_runs_bytes(nrowbins) +
                       vote_bytes(nbins) + (1 << 20));
@@ -934,7 +964,92 @@ int sia_vote_bins(int device, const uint64_t *d_bin_key, const int32_t *d_bin_co
                      d_out_count, d_out_rows, d_out_nres, s);
   }
   cudaStreamSynchronize(s);
-  ar.release();
+  return rc;
+}
+
+int sia_index_expand(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff, const int32_t *d_qid, int64_t n,
+                     int32_t n_queries, uint64_t *d_tuple_key, int64_t cap_tuples, int64_t *h_ntuples,
+                     uint64_t *d_row_key, int64_t cap_rows, int64_t *h_nrows, int64_t *d_tuple_starts,
+                     int64_t *d_row_starts, void *stream) {
+  SIA_REQUIRE(ix && h_ntuples && h_nrows, SIA_E_INVALID, "NULL argument");
+  SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
+  SIA_REQUIRE(n >= 0 && n_queries >= 0 && n_queries <= kMaxQueriesPerPass, SIA_E_INVALID, "expand: bad sizes");
+  *h_ntuples = *h_nrows = 0;
+  int rc = set_device(ix);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) {
+    if (d_tuple_starts) SIA_CUDA(cudaMemsetAsync(d_tuple_starts, 0, sizeof(int64_t) * (n_queries + 1), s));
+    if (d_row_starts) SIA_CUDA(cudaMemsetAsync(d_row_starts, 0, sizeof(int64_t) * (n_queries + 1), s));
+    return SIA_OK;
+  }
+  SIA_REQUIRE(d_hash && d_qoff && d_qid, SIA_E_INVALID, "NULL input");
+  Lookup &L = ix->cache_lookup;      // lookup of the sizing call, reused when the same inputs come back
+  const bool reuse = ix->cache_valid && ix->cache_hash == d_hash && ix->cache_qoff == d_qoff &&
+                     ix->cache_qid == d_qid && ix->cache_n == n && d_tuple_key && d_row_key;
+  ix->cache_valid = false;
+  if (!reuse) {
+    if ((rc = ix->arena.reserve(lookup_bytes(n) + (1 << 20)))) return rc;
+    if ((rc = lookup_pass(ix, ix->arena, d_hash, d_qoff, d_qid, nullptr, 0, 0, 0, n, L, s))) return rc;
+    if ((rc = check_status(ix, s, 2, "query: offset outside 0..2^24-1 or query id outside 0..32767"))) return rc;
+  }
+  *h_ntuples = L.tuples;
+  *h_nrows = L.head_rows;
+  if (!d_tuple_key || !d_row_key) {                                 // sizing call: keep the lookup for the next call
+    ix->cache_valid = true; ix->cache_hash = d_hash; ix->cache_qoff = d_qoff;
+    ix->cache_qid = d_qid; ix->cache_n = n;
+    return SIA_OK;
+  }
+  if (L.tuples > cap_tuples || L.head_rows > cap_rows) {
+    set_error("expand: output capacity exceeded; *h_ntuples / *h_nrows hold the required sizes");
+    return SIA_E_CAPACITY;
+  }
+  SIA_REQUIRE(d_tuple_starts && d_row_starts, SIA_E_INVALID, "NULL output");
+  const unsigned blocks = (unsigned)ceil_div(n, 256);
+  if (L.tuples) expand_kernel<false><<<blocks, 256, 0, s>>>(L.ent, 0, n, L.first, L.off_all, ix->rows, d_tuple_key, 0);
+  if (L.head_rows) expand_kernel<true><<<blocks, 256, 0, s>>>(L.ent, 0, n, L.first, L.off_head, ix->rows, d_row_key, 0);
+  query_starts_kernel<<<grid_for(n_queries + 1), 256, 0, s>>>(L.ent, n, L.off_all, L.off_head, n_queries, d_tuple_starts,
+                                                            d_row_starts);
+  SIA_CHECK_LAUNCH();
+  SIA_CUDA(cudaStreamSynchronize(s));      // the lookup scratch is reused by the next call
+  return SIA_OK;
+}
+
+int sia_vote_tuples(int device, uint64_t *d_tuple_key, int64_t n_tuples, uint64_t *d_row_key, int64_t n_rows,
+                    int32_t n_queries, int32_t topn, int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
+                    int32_t *d_out_rows, int32_t *d_out_nres, void *stream) {
+  SIA_REQUIRE(n_queries >= 0 && n_queries <= kMaxQueriesPerPass && topn >= 1, SIA_E_INVALID,
+              "vote_tuples: 0..32768 queries, topn >= 1");
+  SIA_REQUIRE(n_tuples >= 0 && n_rows >= 0, SIA_E_INVALID, "negative size");
+  if (n_queries == 0) return SIA_OK;
+  SIA_REQUIRE(d_out_song && d_out_diff && d_out_count && d_out_rows && d_out_nres, SIA_E_INVALID, "NULL output");
+  SIA_CUDA(cudaSetDevice(device));
+  SIA_REQUIRE(device >= 0 && device < 64, SIA_E_INVALID, "device index");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena &ar = g_vote_arena[device];
+  int rc = ar.reserve((size_t)(n_tuples + n_rows) * 8 + radix_sort_tmp_bytes(n_tuples) + radix_sort_tmp_bytes(n_rows) +
+                      reduce_runs_bytes(n_tuples) + reduce_runs_bytes(n_rows) + vote_bytes(n_tuples) + (1 << 20));
+  if (rc) return rc;
+  uint64_t *bk[2] = {nullptr, nullptr};
+  int32_t *bc[2] = {nullptr, nullptr};
+  int64_t nb[2] = {0, 0};
+  for (int pass = 0; pass < 2 && !rc; ++pass) {
+    const int64_t m = pass == 0 ? n_tuples : n_rows;
+    uint64_t *keys = pass == 0 ? d_tuple_key : d_row_key;      // sorted in place (the caller's buffer is scratch)
+    if (m == 0) continue;
+    uint64_t *alt = ar.take<uint64_t>(m);
+    void *stmp = ar.take<char>(radix_sort_tmp_bytes(m));
+    if (!alt || !stmp) { set_error("vote_tuples: scratch"); rc = SIA_E_NOMEM; break; }
+    bool in_b = false;
+    if ((rc = radix_sort(keys, alt, m, 8, 0, 8, stmp, s, &in_b))) break;
+    rc = reduce_runs(ar, in_b ? alt : keys, nullptr, m, &bk[pass], &bc[pass], &nb[pass], s);
+  }
+  if (!rc) {
+    cudaMemsetAsync(d_out_nres, 0, sizeof(int32_t) * n_queries, s);
+    rc = vote_sorted(ar, bk[0], bc[0], nb[0], bk[1], bc[1], nb[1], 0, n_queries, 0, topn, d_out_song, d_out_diff,
+                     d_out_count, d_out_rows, d_out_nres, s);
+  }
+  cudaStreamSynchronize(s);
   return rc;
 }
 

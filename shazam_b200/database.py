@@ -173,6 +173,25 @@ class FingerprintIndex:
             return (*outs, nres, list(stats))
         return (*outs, nres)
 
+    def expand(self, digests: torch.Tensor, qoffsets: torch.Tensor, qids: torch.Tensor, n_queries: int):
+        """Vote keys of the postings this shard owns for routed query hashes (multi-GPU path, before the
+        sort): (tuple_key i64[T], row_key i64[R], tuple_starts i64[n_queries+1], row_starts i64[n_queries+1]),
+        keys grouped by ascending query id."""
+        self.finalize()
+        n = qoffsets.numel()
+        d = digests.contiguous(); o = qoffsets.to(torch.int32).contiguous(); q = qids.to(torch.int32).contiguous()
+        ts = torch.zeros(n_queries + 1, dtype=torch.int64, device=self.tdev)
+        rs = torch.zeros(n_queries + 1, dtype=torch.int64, device=self.tdev)
+        nt = C.c_int64(); nr = C.c_int64()
+        args = (self._h, C.c_void_p(d.data_ptr()), C.c_void_p(o.data_ptr()), C.c_void_p(q.data_ptr()), n, int(n_queries))
+        N.check(self.lib.sia_index_expand(*args, None, 0, C.byref(nt), None, 0, C.byref(nr), None, None, self._stream()))
+        tk = torch.empty(nt.value, dtype=torch.int64, device=self.tdev)
+        rk = torch.empty(nr.value, dtype=torch.int64, device=self.tdev)
+        N.check(self.lib.sia_index_expand(*args, C.c_void_p(tk.data_ptr()), tk.numel(), C.byref(nt),
+                                          C.c_void_p(rk.data_ptr()), rk.numel(), C.byref(nr),
+                                          C.c_void_p(ts.data_ptr()), C.c_void_p(rs.data_ptr()), self._stream()))
+        return tk, rk, ts, rs
+
     def query_partial(self, digests: torch.Tensor, qoffsets: torch.Tensor, qids: torch.Tensor):
         """Partial vote histograms of this shard for routed query hashes (multi-GPU path).
         Returns (bin_key u64, bin_count i32, row_key u64, row_count i32) CUDA tensors."""
@@ -193,6 +212,21 @@ class FingerprintIndex:
                 continue
             N.check(rc)
             return bk[:nb.value], bc[:nb.value], rk[:nr.value], rc_[:nr.value]
+
+
+def vote_tuples(device: int, tuple_key: torch.Tensor, row_key: torch.Tensor, n_queries: int, topn: int):
+    """Sort, count and vote concatenated (query, song, diff) keys (+ (query, song) row keys).  The key
+    tensors are used as scratch.  CUDA tensors in and out."""
+    lib = N.lib()
+    tdev = torch.device("cuda", device)
+    outs = [torch.zeros((n_queries, topn), dtype=torch.int32, device=tdev) for _ in range(4)]
+    nres = torch.zeros(n_queries, dtype=torch.int32, device=tdev)
+    tk = tuple_key.contiguous(); rk = row_key.contiguous()
+    N.check(lib.sia_vote_tuples(device, C.c_void_p(tk.data_ptr()), tk.numel(), C.c_void_p(rk.data_ptr()), rk.numel(),
+                                n_queries, int(topn), C.c_void_p(outs[0].data_ptr()), C.c_void_p(outs[1].data_ptr()),
+                                C.c_void_p(outs[2].data_ptr()), C.c_void_p(outs[3].data_ptr()),
+                                C.c_void_p(nres.data_ptr()), C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)))
+    return (*outs, nres)
 
 
 def vote_bins(device: int, bin_key: torch.Tensor, bin_count: torch.Tensor, row_key: torch.Tensor,

@@ -62,6 +62,26 @@ def exchange(buffers: Sequence[torch.Tensor], dest: torch.Tensor, world: int, gr
     return out
 
 
+def exchange_grouped(buffers: Sequence[torch.Tensor], send_counts: Sequence[int], world: int, group=None):
+    """Like ``exchange`` for rows that are ALREADY grouped by destination rank (``send_counts[r]`` rows for
+    rank r, in order): no reordering, just the all-to-all."""
+    if world == 1:
+        return [b for b in buffers]
+    dev = buffers[0].device
+    counts = torch.tensor(list(send_counts), dtype=torch.int64, device=dev)
+    recv_counts = torch.empty_like(counts)
+    dist.all_to_all_single(recv_counts, counts, group=group)
+    out_split = recv_counts.tolist()
+    total = int(sum(out_split))
+    out = []
+    for b in buffers:
+        recv = b.new_empty((total,) + tuple(b.shape[1:]))
+        dist.all_to_all_single(recv, b.contiguous(), output_split_sizes=out_split, input_split_sizes=list(send_counts),
+                               group=group)
+        out.append(recv)
+    return out
+
+
 class ShardBackend:
     """What the orchestration needs from one shard."""
 
@@ -77,6 +97,15 @@ class ShardBackend:
         raise NotImplementedError
 
     def vote(self, bin_key, bin_count, row_key, row_count, n_queries: int, topn: int):
+        raise NotImplementedError
+
+    def expand(self, digests, qoffsets, qids, n_queries: int):
+        raise NotImplementedError
+
+    def vote_tuples(self, tuple_key, row_key, n_queries: int, topn: int):
+        raise NotImplementedError
+
+    def query_batch(self, digests, qoffsets, query_starts, topn: int):
         raise NotImplementedError
 
 
@@ -102,6 +131,16 @@ class CudaShard(ShardBackend):
         from .database import vote_bins
         return vote_bins(self._dev_index, bin_key, bin_count, row_key, row_count, n_queries, topn)
 
+    def expand(self, digests, qoffsets, qids, n_queries):
+        return self.index.expand(digests, qoffsets, qids, n_queries)
+
+    def vote_tuples(self, tuple_key, row_key, n_queries, topn):
+        from .database import vote_tuples
+        return vote_tuples(self._dev_index, tuple_key, row_key, n_queries, topn)
+
+    def query_batch(self, digests, qoffsets, query_starts, topn):
+        return self.index.query_batch(digests, qoffsets, query_starts, topn)
+
     def close(self):
         self.index.close()
 
@@ -109,7 +148,13 @@ class CudaShard(ShardBackend):
 class ShardedIndex:
     """The hash-prefix-sharded fingerprints table over ``world`` ranks."""
 
-    def __init__(self, backend: ShardBackend, rank: Optional[int] = None, world: Optional[int] = None, group=None):
+    def __init__(self, backend: ShardBackend, rank: Optional[int] = None, world: Optional[int] = None, group=None,
+                 exchange: str = "tuples"):
+        """``exchange``: what travels to the query's owner in the second all-to-all — ``"tuples"`` (unsorted
+        vote keys; the owner sorts once: the default) or ``"bins"`` (each shard sorts and run-length counts
+        first; the owner re-sorts and sums).  Both are exact."""
+        assert exchange in ("tuples", "bins")
+        self.exchange_mode = exchange
         self.backend = backend
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
@@ -131,7 +176,8 @@ class ShardedIndex:
         return int(n.item())
 
     # ---- query ---------------------------------------------------------------------------
-    def query(self, digests: torch.Tensor, qoffsets: torch.Tensor, query_starts: np.ndarray, topn: int):
+    def query(self, digests: torch.Tensor, qoffsets: torch.Tensor, query_starts: np.ndarray, topn: int,
+              queries_per_pass: int = 2048):
         """Collective.  Each rank submits ITS queries (``query_starts`` local, int64[Q_r+1]) and gets
         their results back: int32 tensors (song[Q_r,topn], diff, count, rows, nres[Q_r])."""
         dev = self.backend.device
@@ -148,7 +194,8 @@ class ShardedIndex:
         outs = [torch.zeros((q_local, topn), dtype=torch.int32, device=dev) for _ in range(4)]
         nres = torch.zeros(q_local, dtype=torch.int32, device=dev)
         # passes of at most 32768 queries in total: every rank contributes the same local range per pass
-        step = max(1, MAX_QUERIES_PER_PASS // self.world)
+        # (and at most queries_per_pass per rank, which bounds the vote scratch of a pass)
+        step = max(1, min(MAX_QUERIES_PER_PASS // self.world, int(queries_per_pass)))
         for lo in range(0, max_q, step):
             a, b = min(lo, q_local), min(lo + step, q_local)
             sizes = [max(0, min(lo + step, c) - min(lo, c)) for c in per_rank]
@@ -167,10 +214,22 @@ class ShardedIndex:
         # exchange #1: query hashes to their owning shard
         dest = hash_owner(digests, self.world)
         d, o, q = exchange([digests, qoffsets.to(torch.int32), qid.to(torch.int32)], dest, self.world, self.group)
+        shift = SONG_BITS + DIFF_BITS
+        if self.exchange_mode == "tuples":
+            total_q = int(sum(sizes))
+            tk, rk, ts, rs = self.backend.expand(d, o, q, total_q)
+            # keys are grouped by ascending query id = by ascending owner rank: split points from the offsets
+            cuts = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64, device=ts.device)
+            tcut = ts[cuts].cpu().numpy()
+            rcut = rs[cuts].cpu().numpy()
+            (tk2,) = exchange_grouped([tk], np.diff(tcut).tolist(), self.world, self.group)
+            (rk2,) = exchange_grouped([rk], np.diff(rcut).tolist(), self.world, self.group)
+            tk2 = tk2 - (base << shift)
+            rk2 = rk2 - (base << shift)
+            return self.backend.vote_tuples(tk2, rk2, nq, topn)
         bk, bc, rk, rc = self.backend.query_partial(d, o, q)
         # exchange #2: partial bins to the rank that owns the query (sum-by-key happens there)
         bounds = torch.as_tensor(np.cumsum(sizes), dtype=torch.int64, device=dev)
-        shift = SONG_BITS + DIFF_BITS
         qmask = (1 << QID_BITS) - 1          # keys are uint64 carried in int64 tensors
         bk2, bc2 = exchange([bk, bc], torch.bucketize((bk >> shift) & qmask, bounds, right=True), self.world, self.group)
         rk2, rc2 = exchange([rk, rc], torch.bucketize((rk >> shift) & qmask, bounds, right=True), self.world, self.group)
@@ -178,6 +237,72 @@ class ShardedIndex:
         bk2 = bk2 - (base << shift)
         rk2 = rk2 - (base << shift)
         return self.backend.vote(bk2, bc2, rk2, rc2, nq, topn)
+
+
+class TrackShardedIndex:
+    """The alternative SURVEY.md §8e documents: every rank keeps ALL rows of ITS songs (the tracks it
+    fingerprinted), so building needs no exchange and a song's vote bins are complete on one rank.  A query
+    is broadcast (all-gather of its hashes), voted exactly and locally on every rank, and the G x topn
+    candidates are merged by (count desc, song asc).  Exact, and the only traffic is the query hashes and
+    G x topn results per query; the price is that every rank probes its directory for every query hash."""
+
+    def __init__(self, backend: ShardBackend, rank: Optional[int] = None, world: Optional[int] = None, group=None):
+        self.backend = backend
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+
+    def insert(self, songs, digests, offsets) -> None:
+        self.backend.insert_rows(songs.to(torch.int32), digests, offsets.to(torch.int32))
+
+    def finalize(self) -> int:
+        n = torch.tensor([self.backend.finalize()], dtype=torch.int64, device=self.backend.device)
+        if self.world > 1:
+            dist.all_reduce(n, group=self.group)
+        return int(n.item())
+
+    def _all_gather_ragged(self, t: torch.Tensor, sizes):
+        mx = max(sizes)
+        pad = t.new_zeros((mx,) + tuple(t.shape[1:]))
+        pad[: t.shape[0]] = t
+        bufs = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(bufs, pad, group=self.group)
+        return [b[:n] for b, n in zip(bufs, sizes)]
+
+    def query(self, digests, qoffsets, query_starts, topn: int):
+        dev = self.backend.device
+        qs = np.asarray(query_starts, np.int64)
+        if self.world == 1:
+            return self.backend.query_batch(digests, qoffsets, qs, topn)
+        meta = torch.tensor([len(qs) - 1, int(qs[-1])], dtype=torch.int64, device=dev)
+        metas = [torch.zeros_like(meta) for _ in range(self.world)]
+        dist.all_gather(metas, meta, group=self.group)
+        nq = [int(m[0]) for m in metas]
+        nh = [int(m[1]) for m in metas]
+        all_d = self._all_gather_ragged(digests, nh)
+        all_o = self._all_gather_ragged(qoffsets.to(torch.int32), nh)
+        lens = self._all_gather_ragged(torch.as_tensor(np.diff(qs), dtype=torch.int64, device=dev), nq)
+        starts = np.concatenate([[0], np.cumsum(torch.cat(lens).cpu().numpy())])
+        song, diff, cnt, rows, nres = self.backend.query_batch(torch.cat(all_d), torch.cat(all_o), starts, topn)
+        # candidates of MY queries from every rank: [G, Q_me, topn]
+        qbase = int(sum(nq[: self.rank]))
+        mine = slice(qbase, qbase + nq[self.rank])
+        valid = torch.arange(topn, device=dev)[None, :] < nres[:, None]
+        cnt = torch.where(valid, cnt, torch.full_like(cnt, -1))
+        packed = torch.stack([song, diff, cnt, rows], 0).contiguous()            # [4, Q_all, topn]
+        gathered = [torch.empty_like(packed) for _ in range(self.world)]
+        dist.all_gather(gathered, packed, group=self.group)
+        cand = torch.stack([g[:, mine, :] for g in gathered], 0)                 # [G, 4, Q_me, topn]
+        cand = cand.permute(1, 2, 0, 3).reshape(4, nq[self.rank], self.world * topn)
+        c_song, c_diff, c_cnt, c_rows = cand[0].long(), cand[1], cand[2].long(), cand[3]
+        # rank by count descending, then ascending song id (stable sort of recognizer.py:307-310)
+        key = torch.where(c_cnt >= 0, (c_cnt << 24) | ((1 << 24) - 1 - c_song), torch.full_like(c_cnt, -1))
+        top = torch.topk(key, min(topn, key.shape[1]), dim=1).indices
+        pick = lambda x: torch.gather(x, 1, top)
+        o_cnt = pick(c_cnt)
+        ok = o_cnt >= 0
+        z = lambda x: torch.where(ok, pick(x).to(torch.int32), torch.zeros_like(o_cnt, dtype=torch.int32))
+        return z(c_song), z(c_diff), z(c_cnt), z(c_rows), ok.sum(1).to(torch.int32)
 
 
 def gather_results(results, group=None, dst: int = 0):

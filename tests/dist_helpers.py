@@ -42,6 +42,33 @@ class CpuShard(ShardBackend):
         rk, rc = pack(rowbins)
         return bk, bc, rk, rc
 
+    def expand(self, digests, qoffsets, qids, n_queries):
+        entries = sorted(set(zip(qids.tolist(), [bytes(d) for d in digests.numpy()], qoffsets.tolist())))
+        tk, rk = [], []
+        ts, rs = [0] * (n_queries + 1), [0] * (n_queries + 1)
+        seen = set()
+        for q, h, qo in entries:
+            for song, off in sorted(self.rows.get(h, ())):
+                tk.append((q << (SONG_BITS + DIFF_BITS)) | (song << DIFF_BITS) | (off - qo + BIAS))
+                ts[q + 1] += 1
+                if (q, h) not in seen:
+                    rk.append((q << (SONG_BITS + DIFF_BITS)) | (song << DIFF_BITS))
+                    rs[q + 1] += 1
+            seen.add((q, h))
+        ts = np.cumsum(ts); rs = np.cumsum(rs)
+        return (torch.tensor(tk, dtype=torch.int64).reshape(-1), torch.tensor(rk, dtype=torch.int64).reshape(-1),
+                torch.tensor(ts, dtype=torch.int64), torch.tensor(rs, dtype=torch.int64))
+
+    def vote_tuples(self, tuple_key, row_key, n_queries, topn):
+        one = lambda k: torch.ones(k.numel(), dtype=torch.int32)
+        return self.vote(tuple_key, one(tuple_key), row_key, one(row_key), n_queries, topn)
+
+    def query_batch(self, digests, qoffsets, query_starts, topn):
+        qs = np.asarray(query_starts)
+        qid = torch.repeat_interleave(torch.arange(len(qs) - 1), torch.as_tensor(np.diff(qs)))
+        tk, rk, _, _ = self.expand(digests, qoffsets, qid, len(qs) - 1)
+        return self.vote_tuples(tk, rk, len(qs) - 1, topn)
+
     def vote(self, bin_key, bin_count, row_key, row_count, n_queries, topn):
         bins, rows = {}, {}
         for k, c in zip(bin_key.tolist(), bin_count.tolist()):

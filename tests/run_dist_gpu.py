@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import sia_oracle as O                      # noqa: E402  (checker / data generator only)
 from shazam_b200.database import FingerprintIndex       # noqa: E402
-from shazam_b200.distributed import CudaShard, ShardedIndex, shard_tracks   # noqa: E402
+from shazam_b200.distributed import CudaShard, ShardedIndex, TrackShardedIndex, shard_tracks   # noqa: E402
 from shazam_b200.fingerprinter import Fingerprinter     # noqa: E402
 
 
@@ -31,6 +31,9 @@ def main():
     sharded = ShardedIndex(CudaShard(local, 1 << 22))
     sharded.insert(songs.to(dev), torch.from_numpy(b.hash).to(dev), torch.from_numpy(b.t1).to(dev))
     total = sharded.finalize()
+    by_track = TrackShardedIndex(CudaShard(local, 1 << 22))
+    by_track.insert(songs.to(dev), torch.from_numpy(b.hash).to(dev), torch.from_numpy(b.t1).to(dev))
+    assert by_track.finalize() == total
     # reference: one index with every track's rows (fingerprinted locally, deterministic)
     allb = fp.fingerprint_tracks(tracks, fan_value=15)
     single = FingerprintIndex(local, 1 << 22)
@@ -44,10 +47,15 @@ def main():
     myq = list(range(rank, len(clips), world))
     qb = fp.fingerprint_tracks([clips[i] for i in myq], fan_value=15)
     D, Oq = torch.from_numpy(qb.hash).to(dev), torch.from_numpy(qb.t1).to(dev)
-    got = sharded.query(D, Oq, qb.starts, 3)
     want = single.query_batch(D, Oq, qb.starts, 3)
-    for a, w in zip(got, want):
-        assert torch.equal(a, w), (rank, a, w)
+    for name in ("tuples", "bins", "track"):
+        if name == "track":
+            got = by_track.query(D, Oq, qb.starts, 3)
+        else:
+            sharded.exchange_mode = name
+            got = sharded.query(D, Oq, qb.starts, 3)
+        for a, w in zip(got, want):
+            assert torch.equal(a, w), (name, rank, a, w)
     top = got[0][:, 0].cpu().tolist()
     assert top == [(i % ntracks) + 1 for i in myq], (top, myq)
     dist.barrier()

@@ -44,15 +44,15 @@ def _oracle_results(songs, queries, topn):
     return out, table.num_rows()
 
 
-def _worker(rank, world, port, topn):
+def _worker(rank, world, port, topn, mode="tuples"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from shazam_b200.distributed import ShardedIndex, shard_tracks, hash_owner, gather_results
+        from shazam_b200.distributed import ShardedIndex, TrackShardedIndex, shard_tracks, hash_owner, gather_results
         from tests.dist_helpers import CpuShard
         songs, queries = _world()
         want, nrows = _oracle_results(songs, queries, topn)
-        ix = ShardedIndex(CpuShard())
+        ix = TrackShardedIndex(CpuShard()) if mode == "track" else ShardedIndex(CpuShard(), exchange=mode)
         mine = shard_tracks(len(songs), rank, world)            # tracks fingerprinted by this rank
         assert sorted(np.concatenate([shard_tracks(len(songs), r, world) for r in range(world)]).tolist()) == list(range(len(songs)))
         sid = torch.tensor([songs[i][0] for i in mine for _ in songs[i][1]], dtype=torch.int32)
@@ -60,9 +60,11 @@ def _worker(rank, world, port, topn):
         off = torch.tensor([o for i in mine for _, o in songs[i][1]], dtype=torch.int32)
         ix.insert(sid, dig, off)
         assert ix.finalize() == nrows                           # set semantics survive the exchange
-        # every row landed on the shard that owns its hash prefix
-        for h in ix.backend.rows:
-            assert int(hash_owner(torch.tensor(np.frombuffer(h, np.uint8)).reshape(1, 10), world)) == rank
+        if mode != "track":       # every row landed on the shard that owns its hash prefix
+            for h in ix.backend.rows:
+                assert int(hash_owner(torch.tensor(np.frombuffer(h, np.uint8)).reshape(1, 10), world)) == rank
+        else:                     # every rank kept exactly the songs it fingerprinted
+            assert {s for v in ix.backend.rows.values() for s, _ in v} == {songs[i][0] for i in mine}
         # queries are submitted round-robin by rank
         myq = list(range(rank, len(queries), world))
         D = np.array([np.frombuffer(h, np.uint8) for qi in myq for h, _ in queries[qi]], np.uint8).reshape(-1, 10)
@@ -88,9 +90,9 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("topn", [1, 3])
-def test_sharded_index_world2_gloo(topn):
-    mp.spawn(_worker, args=(2, _free_port(), topn), nprocs=2, join=True)
+@pytest.mark.parametrize("topn,mode", [(1, "tuples"), (3, "tuples"), (3, "bins"), (2, "track")])
+def test_sharded_index_world2_gloo(topn, mode):
+    mp.spawn(_worker, args=(2, _free_port(), topn, mode), nprocs=2, join=True)
 
 
 def test_single_rank_path_matches_oracle():

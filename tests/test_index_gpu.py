@@ -226,6 +226,21 @@ def test_partial_bins_merge_equals_single_index(gpudb):
         got = vote_bins(0, *merged, len(queries), 3)
         for a, b in zip(ref, got):
             assert torch.equal(a, b)
+        # the same split one step earlier: unsorted vote keys from each shard, one sort at the owner
+        from shazam_b200.database import vote_tuples
+        tks, rks = [], []
+        for g in range(2):
+            m = (D[:, 0] >> 7) == g
+            tk, rk, ts, rs = shards[g].expand(torch.from_numpy(D[m]).to(dev), torch.from_numpy(Oq[m]).to(dev),
+                                              torch.from_numpy(qid[m]).to(dev), len(queries))
+            assert int(ts[-1]) == tk.numel() and int(rs[-1]) == rk.numel()
+            q_of = (tk >> 49) & 0x7fff
+            assert torch.all(q_of[1:] >= q_of[:-1])                     # grouped by ascending query id
+            assert torch.equal(torch.bincount(q_of, minlength=len(queries)), ts[1:] - ts[:-1])
+            tks.append(tk); rks.append(rk)
+        got2 = vote_tuples(0, torch.cat(tks), torch.cat(rks), len(queries), 3)
+        for a, b in zip(ref, got2):
+            assert torch.equal(a, b)
         # and both equal the oracle
         song, dif, cnt, rws, nres = [t.cpu().numpy() for t in got]
         for i, q in enumerate(queries):
