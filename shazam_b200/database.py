@@ -173,13 +173,29 @@ class FingerprintIndex:
             return (*outs, nres, list(stats))
         return (*outs, nres)
 
+    def expand_size(self, digests: torch.Tensor, qoffsets: torch.Tensor, qids: torch.Tensor, n_queries: int) -> int:
+        """Vote keys ``expand`` would produce for these inputs (the lookup is cached for the following call)."""
+        self.finalize()
+        self._exp_args = (digests.contiguous(), qoffsets.to(torch.int32).contiguous(), qids.to(torch.int32).contiguous())
+        d, o, q = self._exp_args
+        nt = C.c_int64(); nr = C.c_int64()
+        N.check(self.lib.sia_index_expand(self._h, C.c_void_p(d.data_ptr()), C.c_void_p(o.data_ptr()),
+                                          C.c_void_p(q.data_ptr()), o.numel(), int(n_queries), None, 0, C.byref(nt),
+                                          None, 0, C.byref(nr), None, None, self._stream()))
+        return int(nt.value)
+
     def expand(self, digests: torch.Tensor, qoffsets: torch.Tensor, qids: torch.Tensor, n_queries: int):
         """Vote keys of the postings this shard owns for routed query hashes (multi-GPU path, before the
         sort): (tuple_key i64[T], row_key i64[R], tuple_starts i64[n_queries+1], row_starts i64[n_queries+1]),
         keys grouped by ascending query id."""
         self.finalize()
         n = qoffsets.numel()
-        d = digests.contiguous(); o = qoffsets.to(torch.int32).contiguous(); q = qids.to(torch.int32).contiguous()
+        prev = getattr(self, "_exp_args", None)          # same tensors as the sizing call -> same device pointers
+        if prev is not None and prev[1].numel() == n and digests.data_ptr() == prev[0].data_ptr():
+            d, o, q = prev
+        else:
+            d = digests.contiguous(); o = qoffsets.to(torch.int32).contiguous(); q = qids.to(torch.int32).contiguous()
+        self._exp_args = None
         ts = torch.zeros(n_queries + 1, dtype=torch.int64, device=self.tdev)
         rs = torch.zeros(n_queries + 1, dtype=torch.int64, device=self.tdev)
         nt = C.c_int64(); nr = C.c_int64()

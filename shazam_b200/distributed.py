@@ -102,6 +102,10 @@ class ShardBackend:
     def expand(self, digests, qoffsets, qids, n_queries: int):
         raise NotImplementedError
 
+    def expand_size(self, digests, qoffsets, qids, n_queries: int) -> int:
+        """Number of vote keys ``expand`` would produce (sizing only)."""
+        raise NotImplementedError
+
     def vote_tuples(self, tuple_key, row_key, n_queries: int, topn: int):
         raise NotImplementedError
 
@@ -133,6 +137,9 @@ class CudaShard(ShardBackend):
 
     def expand(self, digests, qoffsets, qids, n_queries):
         return self.index.expand(digests, qoffsets, qids, n_queries)
+
+    def expand_size(self, digests, qoffsets, qids, n_queries):
+        return self.index.expand_size(digests, qoffsets, qids, n_queries)
 
     def vote_tuples(self, tuple_key, row_key, n_queries, topn):
         from .database import vote_tuples
@@ -177,7 +184,7 @@ class ShardedIndex:
 
     # ---- query ---------------------------------------------------------------------------
     def query(self, digests: torch.Tensor, qoffsets: torch.Tensor, query_starts: np.ndarray, topn: int,
-              queries_per_pass: int = 2048):
+              queries_per_pass: int = 2048, tuple_budget: int = 400_000_000):
         """Collective.  Each rank submits ITS queries (``query_starts`` local, int64[Q_r+1]) and gets
         their results back: int32 tensors (song[Q_r,topn], diff, count, rows, nres[Q_r])."""
         dev = self.backend.device
@@ -194,19 +201,26 @@ class ShardedIndex:
         outs = [torch.zeros((q_local, topn), dtype=torch.int32, device=dev) for _ in range(4)]
         nres = torch.zeros(q_local, dtype=torch.int32, device=dev)
         # passes of at most 32768 queries in total: every rank contributes the same local range per pass
-        # (and at most queries_per_pass per rank, which bounds the vote scratch of a pass)
+        # (and at most queries_per_pass per rank).  A pass whose vote keys would exceed `tuple_budget` on some
+        # shard is retried with half the queries — decided collectively, so all ranks stay in step.
         step = max(1, min(MAX_QUERIES_PER_PASS // self.world, int(queries_per_pass)))
-        for lo in range(0, max_q, step):
+        lo = 0
+        while lo < max_q:
             a, b = min(lo, q_local), min(lo + step, q_local)
             sizes = [max(0, min(lo + step, c) - min(lo, c)) for c in per_rank]
             base = int(sum(sizes[: self.rank]))
-            res = self._query_pass(digests[qs[a]:qs[b]], qoffsets[qs[a]:qs[b]], qs[a:b + 1] - qs[a], sizes, base, topn)
+            res = self._query_pass(digests[qs[a]:qs[b]], qoffsets[qs[a]:qs[b]], qs[a:b + 1] - qs[a], sizes, base, topn,
+                                   tuple_budget if step > 1 else None)
+            if res is None:
+                step = max(1, step // 2)
+                continue
             for o, r in zip(outs, res[:4]):
                 o[a:b] = r
             nres[a:b] = res[4]
+            lo += step
         return (*outs, nres)
 
-    def _query_pass(self, digests, qoffsets, qs, sizes, base, topn):
+    def _query_pass(self, digests, qoffsets, qs, sizes, base, topn, tuple_budget=None):
         dev = self.backend.device
         nq = len(qs) - 1
         lens = torch.as_tensor(np.diff(qs), dtype=torch.int64, device=dev)
@@ -217,6 +231,11 @@ class ShardedIndex:
         shift = SONG_BITS + DIFF_BITS
         if self.exchange_mode == "tuples":
             total_q = int(sum(sizes))
+            if tuple_budget is not None and self.world > 1:
+                need = torch.tensor([self.backend.expand_size(d, o, q, total_q)], dtype=torch.int64, device=dev)
+                dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+                if int(need.item()) > tuple_budget:
+                    return None
             tk, rk, ts, rs = self.backend.expand(d, o, q, total_q)
             # keys are grouped by ascending query id = by ascending owner rank: split points from the offsets
             cuts = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64, device=ts.device)

@@ -59,6 +59,9 @@ class CpuShard(ShardBackend):
         return (torch.tensor(tk, dtype=torch.int64).reshape(-1), torch.tensor(rk, dtype=torch.int64).reshape(-1),
                 torch.tensor(ts, dtype=torch.int64), torch.tensor(rs, dtype=torch.int64))
 
+    def expand_size(self, digests, qoffsets, qids, n_queries):
+        return int(self.expand(digests, qoffsets, qids, n_queries)[0].numel())
+
     def vote_tuples(self, tuple_key, row_key, n_queries, topn):
         one = lambda k: torch.ones(k.numel(), dtype=torch.int32)
         return self.vote(tuple_key, one(tuple_key), row_key, one(row_key), n_queries, topn)

@@ -70,7 +70,8 @@ def _worker(rank, world, port, topn, mode="tuples"):
         D = np.array([np.frombuffer(h, np.uint8) for qi in myq for h, _ in queries[qi]], np.uint8).reshape(-1, 10)
         Oq = np.array([o for qi in myq for _, o in queries[qi]], np.int32)
         starts = np.cumsum([0] + [len(queries[qi]) for qi in myq])
-        res = ix.query(torch.from_numpy(D), torch.from_numpy(Oq), starts, topn)
+        kw = dict(queries_per_pass=3, tuple_budget=40) if mode == "tuples" else {}      # forces split passes + retries
+        res = ix.query(torch.from_numpy(D), torch.from_numpy(Oq), starts, topn, **kw)
         song, diff, cnt, rows, nres = [t.numpy() for t in res]
         for k, qi in enumerate(myq):
             got = [(int(song[k, r]), int(diff[k, r]), int(cnt[k, r]), int(rows[k, r])) for r in range(nres[k])]
