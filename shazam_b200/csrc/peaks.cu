@@ -251,6 +251,7 @@ peaks_square_warp_kernel(const float *__restrict__ spec, const int64_t *__restri
   sliding21_max3<36, 16>(vw);
 
   const unsigned FULL = 0xffffffffu;
+  const float amp_up = nextafterf(amp_lo, CUDART_INF_F);
   const int64_t g0 = r0 + 16 * q;                                   // first output frame of this warp
   const int nvalid = (int)min((int64_t)16, row_hi - g0);            // frames of the chunk inside the track
   const int fl = f0 + 4 * lane;
@@ -259,7 +260,9 @@ peaks_square_warp_kernel(const float *__restrict__ spec, const int64_t *__restri
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const float a0 = vx[i], a1 = vy[i], a2 = vz[i], a3 = vw[i];
-    const float S2 = fmaxf(a2, a3), S1 = fmaxf(a1, S2), M = fmaxf(a0, S1);
+    // amp_up (the smallest float above the threshold) rides in the block maximum M, which every window
+    // includes, so "centre == window max and centre > amp_min" becomes the single test centre >= h
+    const float S2 = fmaxf(a2, a3), S1 = fmaxf(a1, S2), M = fmaxf(fmaxf(a0, S1), amp_up);
     const float P1 = fmaxf(a0, a1), P2 = fmaxf(P1, a2);
     const float Mm1 = __shfl_sync(FULL, M, s_m1), Mp1 = __shfl_sync(FULL, M, s_p1);
     const float Mm2 = __shfl_sync(FULL, M, s_m2), Mp2 = __shfl_sync(FULL, M, s_p2);
@@ -279,10 +282,10 @@ peaks_square_warp_kernel(const float *__restrict__ spec, const int64_t *__restri
                  : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w)
                  : "r"(a_base + (uint32_t)((16 * q + i + 10) * kW2Cols4 + col) * 16u));
     // one ballot per element index: word e, bit l  <->  bin f0 + 4*l + e   (striped bitmap layout)
-    const uint32_t b0 = __ballot_sync(FULL, c.x == h0 && c.x > amp_lo && v0);
-    const uint32_t b1 = __ballot_sync(FULL, c.y == h1 && c.y > amp_lo && v1);
-    const uint32_t b2 = __ballot_sync(FULL, c.z == h2 && c.z > amp_lo && v2);
-    const uint32_t b3 = __ballot_sync(FULL, c.w == h3 && c.w > amp_lo && v3);
+    const uint32_t b0 = __ballot_sync(FULL, c.x >= h0 && v0);
+    const uint32_t b1 = __ballot_sync(FULL, c.y >= h1 && v1);
+    const uint32_t b2 = __ballot_sync(FULL, c.z >= h2 && v2);
+    const uint32_t b3 = __ballot_sync(FULL, c.w >= h3 && v3);
     if (lane == 0 && i < nvalid)
       *reinterpret_cast<uint4 *>(bitmap + (g0 + i) * kBitmapRowWords + 4 * strip) = make_uint4(b0, b1, b2, b3);
   }
