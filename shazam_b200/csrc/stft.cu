@@ -109,6 +109,11 @@ __constant__ double2 c_winA_d[16];   // (cos, sin)(2*pi*256*a/4095)
 __constant__ float2 c_winA_f[16];
 __constant__ double2 c_w32_d[8];     // W32^it = (cos, -sin)(2*pi*it/32)
 __constant__ float2 c_w32_f[8];
+__constant__ double2 c_spc_d[9];     // W4096^k of the self-mirrored columns: k = 256 i (i<5), 128 + 256 (i-5)
+__constant__ float2 c_spc_f[9];
+template <typename T> __device__ __forceinline__ typename Vec2<T>::type spc_tw(int i);
+template <> __device__ __forceinline__ double2 spc_tw<double>(int i) { return c_spc_d[i]; }
+template <> __device__ __forceinline__ float2 spc_tw<float>(int i) { return c_spc_f[i]; }
 template <typename T> __device__ __forceinline__ typename Vec2<T>::type winA(int a);
 template <> __device__ __forceinline__ double2 winA<double>(int a) { return c_winA_d[a]; }
 template <> __device__ __forceinline__ float2 winA<float>(int a) { return c_winA_f[a]; }
@@ -129,14 +134,12 @@ template <> __device__ __forceinline__ float sample_to_real<float>(int s) {
 // dB epilogue.  dB = 10*log10(p*scale) = C*(e + Ki + log2(m) + Kf),  C = 10*log10(2), p = m*2^e, log2(scale) = Ki+Kf.
 // log2 of the mantissa: MUFU.LG2 on a float built from the top 23 mantissa bits (rounded) — absolute error
 // ~2^-22; the integer part is recombined with a split constant (E*C_hi is exact), so the result carries
-// 0.5 ulp(float) + ~1.4e-6 dB.  p == 0 -> 0 dB (__init__.py:241).  Subnormal / non-finite p: exact slow path.
-struct DbScale { int ki; float kf; double c; };
+// 0.5 ulp(float) + ~1.4e-6 dB.  p == 0 -> 0 dB (__init__.py:241).  Branch-free: powers below 2^-1019
+// (unreachable from int16 PCM: the smallest non-zero |X|^2 is ~1e-26) are clamped to 2^-1019.
+struct DbScale { int ke; float kf; double c; };     // ke = Ki - 1023
 constexpr float kC = 3.01029995663981195f;
 constexpr float kC_hi = 6165.0f / 2048.0f;                                   // 13 significant bits
 constexpr float kC_lo = (float)(3.01029995663981195 - 6165.0 / 2048.0);
-
-// rare path (subnormal / non-finite power): kept out of line so that it does not bloat the unrolled epilogue
-__device__ __noinline__ float db_slow(double p, double c) { return (float)(10.0 * log10(p) + c); }
 
 __device__ __forceinline__ float db_combine(int E, float L) {
   const float Ef = __int_as_float(0x4b400000 + E) - 12582912.0f;             // exact int -> float, |E| < 2^22
@@ -144,21 +147,48 @@ __device__ __forceinline__ float db_combine(int E, float L) {
 }
 template <typename OutT>
 __device__ __forceinline__ OutT db_out(double p, const DbScale &sc) {
-  const int hi = __double2hiint(p), lo = __double2loint(p);
-  if ((hi | lo) == 0) return (OutT)0;
-  if (sizeof(OutT) == 8) return (OutT)(10.0 * log10(p) + sc.c);             // float64 output (tests): exact path
-  const int e = (hi >> 20) - 1023;
-  if (e == -1023 || e == 1024) return (OutT)db_slow(p, sc.c);
-  const uint32_t bits = 0x3f800000u + (((uint32_t)hi & 0xfffffu) << 3) + ((uint32_t)lo >> 29) + (((uint32_t)lo >> 28) & 1u);
-  return (OutT)db_combine(e + sc.ki, __log2f(__uint_as_float(bits)) + sc.kf);
+  int hi = __double2hiint(p);
+  const int lo = __double2loint(p);
+  if (sizeof(OutT) == 8)                                                     // float64 output (tests): exact path
+    return (OutT)((hi | lo) == 0 ? 0.0 : 10.0 * log10(p) + sc.c);
+  const bool zero = (hi | lo) == 0;
+  hi = max(hi, 0x00400000);                                                  // clamp subnormals (see above)
+  // 2*mantissa23 + round bit = bits 51..28 of the significand
+  const uint32_t m2 = __funnelshift_l((uint32_t)lo, (uint32_t)hi, 4) & 0x00ffffffu;
+  const float mf = __uint_as_float(0x3f800000u + ((m2 + 1u) >> 1));          // a carry rolls into the exponent: 2.0
+  const float r = db_combine((hi >> 20) + sc.ke, __log2f(mf) + sc.kf);
+  return (OutT)(zero ? 0.f : r);
 }
 template <typename OutT>
 __device__ __forceinline__ OutT db_out(float p, const DbScale &sc) {
-  if (p == 0.f) return (OutT)0;
-  const int b = __float_as_int(p);
-  const int e = (b >> 23) - 127;
-  if (e == -127 || e == 128) return (OutT)db_slow((double)p, sc.c);
-  return (OutT)db_combine(e + sc.ki, __log2f(__int_as_float((b & 0x7fffff) | 0x3f800000)) + sc.kf);
+  const int b = max(__float_as_int(p), 0x00800000);                          // clamp float subnormals
+  const float r = db_combine((b >> 23) - 127 + sc.ke + 1023,
+                             __log2f(__int_as_float((b & 0x7fffff) | 0x3f800000)) + sc.kf);
+  return (OutT)(p == 0.f ? 0.f : r);
+}
+
+// bins k and 2048-k from A = Z[k], B = Z[2048-k], tw = W4096^k (split post-pass of the packed real FFT)
+template <typename T, typename OutT>
+__device__ __forceinline__ void emit_pair(OutT *__restrict__ row, T ar, T ai, T br, T bi, T twr, T twi, int k,
+                                          const DbScale &sc) {
+  const T er = ar + br, ei = ai - bi;                // 2E = A + conj(B)
+  const T orr = ai + bi, oi = br - ar;               // 2O = -i (A - conj(B))
+  const T tr = orr * twr - oi * twi, ti = orr * twi + oi * twr;
+  const T pr = er + tr, pi = ei + ti;                // 2 X[k]
+  const T qr = er - tr, qi = ei - ti;                // 2 conj(X[2048-k])
+  row[k] = db_out<OutT>(pr * pr + pi * pi, sc);
+  row[2048 - k] = db_out<OutT>(qr * qr + qi * qi, sc);
+}
+
+// the 17 bins of the self-mirrored columns 0 and 128 (parked by thread 0), one pair per lane i = 0..8
+template <typename T, typename OutT>
+__device__ __forceinline__ void emit_special(OutT *__restrict__ row, const T *__restrict__ pr, const T *__restrict__ pi,
+                                             int i, const DbScale &sc_mid, const DbScale &sc_edge) {
+  const int a = i < 5 ? i : 8 + (i - 5);              // A index: column 0 kc = i, or column 128 kc = i-5
+  const int b = i < 5 ? ((8 - i) & 7) : 8 + (12 - i); // its mirror in the same column
+  const int k = i < 5 ? 256 * i : 128 + 256 * (i - 5);
+  const typename Vec2<T>::type tw = spc_tw<T>(i);
+  emit_pair<T, OutT>(row, pr[a], pi[a], pr[b], pi[b], tw.x, tw.y, k, k == 0 ? sc_edge : sc_mid);
 }
 
 template <typename T, typename OutT>
@@ -177,6 +207,7 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
   // of the PCM never sits in front of pass A.  Bytes past the end of a track are zero-filled (src-size),
   // which is exactly mlab.specgram's zero padding of a short input.
   __shared__ __align__(16) uint32_t spcm[3][1024];
+  __shared__ T sspc[2][2][16];     // parked columns 0 / 128 of the last two frames (re, im)
 
   const int t = threadIdx.x;
 
@@ -202,7 +233,12 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
   int slot = 0;
   bool primed = false;
 
+  const int64_t g_first = g;
   for (; g < g_end; ++g) {
+    // lanes 1..9: finish the previous frame (its parked columns became visible at the barrier)
+    if (g > g_first && t >= 1 && t <= 9)
+      emit_special<T, OutT>(out + (g - 1) * (int64_t)SIA_F_STRIDE, sspc[(g - 1) & 1][0], sspc[(g - 1) & 1][1], t - 1,
+                            sc_mid, sc_edge);
     while (g >= frame_starts[trk + 1]) ++trk;
     const int64_t k = g - frame_starts[trk];
     if (!primed) {                       // first frame of the run or of a track: both half-blocks, synchronously
@@ -293,58 +329,35 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
       }
       fft8(yr[0], yi[0]);
       fft8(yr[1], yi[1]);
-      OutT *__restrict__ row = out + g * (int64_t)SIA_F_STRIDE;
-      const V2 twp = __ldg(twP + t);                       // W4096^t
-      const T C1 = (T)0.92387953251128675613, S1 = (T)0.38268343236508977173, H = (T)0.70710678118654752440;
-      // bins k and 2048-k from A = Z[k], B = Z[2048-k], tw = W4096^k
-      auto emit = [&](T ar, T ai, T br, T bi, T twr, T twi, int k) {
-        const T er = ar + br, ei = ai - bi;                // 2E = A + conj(B)
-        const T orr = ai + bi, oi = br - ar;               // 2O = -i (A - conj(B))
-        const T tr = orr * twr - oi * twi, ti = orr * twi + oi * twr;
-        const T pr = er + tr, pi = ei + ti;                // 2 X[k]
-        const T qr = er - tr, qi = ei - ti;                // 2 conj(X[2048-k])
-        const DbScale &sc = k == 0 ? sc_edge : sc_mid;
-        row[k] = db_out<OutT>(pr * pr + pi * pi, sc);
-        row[2048 - k] = db_out<OutT>(qr * qr + qi * qi, sc);
-      };
-      const bool t0 = t == 0;
+      if (t == 0) {
+        // columns 0 and 128 mirror onto themselves: park them; nine lanes emit their 17 bins after the barrier
+        T *pr = sspc[g & 1][0], *pi = sspc[g & 1][1];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        // W16^j = W4096^(256 j)
-        const T wr16 = j == 0 ? (T)1 : j == 1 ? C1 : j == 2 ? H : j == 3 ? S1 : j == 4 ? (T)0 : j == 5 ? -S1 : j == 6 ? -H : -C1;
-        const T wi16 = j == 0 ? (T)0 : j == 1 ? -S1 : j == 2 ? -H : j == 3 ? -C1 : j == 4 ? (T)-1 : j == 5 ? -C1 : j == 6 ? -H : -S1;
-        T twr = twp.x * wr16 - twp.y * wi16, twi = twp.x * wi16 + twp.y * wr16;
-        T ar = yr[0][pos8(j)], ai = yi[0][pos8(j)];
-        T br = yr[1][pos8(7 - j)], bi = yi[1][pos8(7 - j)];
-        int k = t + 256 * j;
-        if (j <= 4) {
-          // thread 0, column 0: the mirror of k = 256 j is 256 (8-j) in the SAME column
-          const T zr = yr[0][pos8((8 - j) & 7)], zi = yi[0][pos8((8 - j) & 7)];
-          br = t0 ? zr : br; bi = t0 ? zi : bi;
-        } else {
-          // thread 0, column 128: k = 128 + 256 (j-5), mirror 128 + 256 (12-j) in the same column
-          const int kc = j - 5;
-          const T zr = yr[1][pos8(kc)], zi = yi[1][pos8(kc)], mr = yr[1][pos8(7 - kc)], mi = yi[1][pos8(7 - kc)];
-          // W4096^(128 + 256 kc) = W32^1 * W16^kc
-          const V2 w1 = w32<T>(1);
-          const T cr16 = kc == 0 ? (T)1 : kc == 1 ? C1 : H, ci16 = kc == 0 ? (T)0 : kc == 1 ? -S1 : -H;
-          const T c0r = w1.x * cr16 - w1.y * ci16, c0i = w1.x * ci16 + w1.y * cr16;
-          ar = t0 ? zr : ar; ai = t0 ? zi : ai; br = t0 ? mr : br; bi = t0 ? mi : bi;
-          twr = t0 ? c0r : twr; twi = t0 ? c0i : twi;
-          k = t0 ? 128 + 256 * kc : k;
+        for (int kc = 0; kc < 8; ++kc) {
+          pr[kc] = yr[0][pos8(kc)]; pi[kc] = yi[0][pos8(kc)];
+          pr[8 + kc] = yr[1][pos8(kc)]; pi[8 + kc] = yi[1][pos8(kc)];
         }
-        emit(ar, ai, br, bi, twr, twi, k);
-      }
-      if (t0) {   // the 9th pair of thread 0: k = 896 (column 128, kc = 3), mirror 1152 (kc = 4)
-        const V2 w1 = w32<T>(1);
-        emit(yr[1][pos8(3)], yi[1][pos8(3)], yr[1][pos8(4)], yi[1][pos8(4)], w1.x * S1 + w1.y * C1, w1.y * S1 - w1.x * C1,
-             896);
+      } else {
+        OutT *__restrict__ row = out + g * (int64_t)SIA_F_STRIDE;
+        const V2 twp = __ldg(twP + t);                       // W4096^t
+        const T C1 = (T)0.92387953251128675613, S1 = (T)0.38268343236508977173, H = (T)0.70710678118654752440;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // W4096^(t + 256 j) = W4096^t * W16^j
+          const T wr16 = j == 0 ? (T)1 : j == 1 ? C1 : j == 2 ? H : j == 3 ? S1 : j == 4 ? (T)0 : j == 5 ? -S1 : j == 6 ? -H : -C1;
+          const T wi16 = j == 0 ? (T)0 : j == 1 ? -S1 : j == 2 ? -H : j == 3 ? -C1 : j == 4 ? (T)-1 : j == 5 ? -C1 : j == 6 ? -H : -S1;
+          emit_pair<T, OutT>(row, yr[0][pos8(j)], yi[0][pos8(j)], yr[1][pos8(7 - j)], yi[1][pos8(7 - j)],
+                             twp.x * wr16 - twp.y * wi16, twp.x * wi16 + twp.y * wr16, t + 256 * j, sc_mid);
+        }
       }
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");   // next frame's half-block has landed
     __syncthreads();   // ... and the L2 layout may be overwritten by the next frame's pass A
     slot = (slot + 1) % 3;
   }
+  if (t >= 1 && t <= 9)
+    emit_special<T, OutT>(out + (g_end - 1) * (int64_t)SIA_F_STRIDE, sspc[(g_end - 1) & 1][0], sspc[(g_end - 1) & 1][1],
+                          t - 1, sc_mid, sc_edge);
 }
 
 }  // namespace
@@ -372,10 +385,18 @@ static int upload_tables(StftTables<T> &tb) {
     w32c[k].x = (T)cosl(-2 * PI * k / 32.0L);
     w32c[k].y = (T)sinl(-2 * PI * k / 32.0L);
   }
+  V2 spc[9];
+  for (int i = 0; i < 9; ++i) {
+    const int k = i < 5 ? 256 * i : 128 + 256 * (i - 5);
+    spc[i].x = (T)cosl(-2 * PI * k / 4096.0L);
+    spc[i].y = (T)sinl(-2 * PI * k / 4096.0L);
+  }
   if (sizeof(T) == 8) {
+    SIA_CUDA(cudaMemcpyToSymbol(c_spc_d, spc, sizeof spc));
     SIA_CUDA(cudaMemcpyToSymbol(c_winA_d, wa, sizeof wa));
     SIA_CUDA(cudaMemcpyToSymbol(c_w32_d, w32c, sizeof w32c));
   } else {
+    SIA_CUDA(cudaMemcpyToSymbol(c_spc_f, spc, sizeof spc));
     SIA_CUDA(cudaMemcpyToSymbol(c_winA_f, wa, sizeof wa));
     SIA_CUDA(cudaMemcpyToSymbol(c_w32_f, w32c, sizeof w32c));
   }
@@ -442,7 +463,7 @@ static int launch(const StftLaunch &a, const StftTables<T> &tb, cudaStream_t s) 
   auto mk = [](double sc) {
     DbScale d;
     const double K = log2(sc);
-    d.ki = (int)floor(K);
+    d.ke = (int)floor(K) - 1023;
     d.kf = (float)(K - floor(K));
     d.c = 10.0 * log10(sc);
     return d;
