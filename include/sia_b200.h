@@ -168,6 +168,12 @@ int64_t sia_index_rows(const sia_index *ix);
  * 132-139): remove every stored row of the listed songs.  *h_rows = rows left.  Synchronous. */
 int sia_index_delete_songs(sia_index *ix, const int32_t *h_song_ids, int32_t n, int64_t *h_rows);
 
+/* Rows [first_row, first_row+n) of the sorted table back in the schema's vocabulary (hash BINARY(10),
+ * song_id, offset) — for dumping the index to / seeding it from the MySQL `fingerprints` table
+ * (mysql_database.py:46-59).  Stream-ordered; rows come in (hash, song_id, offset) order. */
+int sia_index_export(sia_index *ix, int64_t first_row, int64_t n, uint8_t *d_hash, int32_t *d_song, int32_t *d_off,
+                     void *stream);
+
 /* SELECT HEX(hash), song_id, offset WHERE hash IN (...) (recognizer.py:60-64, 252-259):
  * every stored row whose hash is in the list of n DISTINCT hashes.  Row order: by
  * position in h_hash, then (song_id, offset).  Fills up to cap rows; *h_nrows = total. */

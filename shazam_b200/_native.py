@@ -62,6 +62,7 @@ SIGNATURES = {
     "sia_index_finalize": (C.c_int, [_p, _i64p]),
     "sia_index_rows": (C.c_int64, [_p]),
     "sia_index_delete_songs": (C.c_int, [_p, _i32p, C.c_int32, _i64p]),
+    "sia_index_export": (C.c_int, [_p, C.c_int64, C.c_int64, _p, _p, _p, _p]),
     "sia_index_select_host": (C.c_int, [_p, _p, C.c_int64, _p, _p, _p, C.c_int64, _i64p]),
     "sia_index_query_batch": (C.c_int, [_p, _p, _p, _i64p, C.c_int32, C.c_int32, _p, _p, _p, _p, _p, _i64p, _p]),
     "sia_index_query_partial": (C.c_int, [_p, _p, _p, _p, C.c_int64, _p, _p, C.c_int64, _i64p, _p, _p, C.c_int64,

@@ -108,6 +108,21 @@ pack_rows_kernel(const uint8_t *__restrict__ hash, const int32_t *__restrict__ o
   }
 }
 
+__global__ void __launch_bounds__(256)
+unpack_rows_kernel(const ulonglong2 *__restrict__ rows, int64_t n, uint8_t *__restrict__ hash, int32_t *__restrict__ song,
+                   int32_t *__restrict__ off) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const ulonglong2 r = rows[i];
+    uint16_t *h = reinterpret_cast<uint16_t *>(hash + i * SIA_HASH_BYTES);
+    const uint32_t w[5] = {(uint32_t)(r.y >> 48) & 0xffffu, (uint32_t)(r.y >> 32) & 0xffffu, (uint32_t)(r.y >> 16) & 0xffffu,
+                           (uint32_t)r.y & 0xffffu, (uint32_t)(r.x >> 48) & 0xffffu};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) h[k] = (uint16_t)(((w[k] & 0xff) << 8) | (w[k] >> 8));   // big-endian digest bytes
+    song[i] = (int32_t)((r.x >> 24) & 0xffffffu);
+    off[i] = (int32_t)(r.x & 0xffffffu);
+  }
+}
+
 __device__ __forceinline__ bool rec_eq(const ulonglong2 &a, const ulonglong2 &b) { return a.x == b.x && a.y == b.y; }
 
 __global__ void __launch_bounds__(256)
@@ -758,6 +773,20 @@ int sia_index_delete_songs(sia_index *ix, const int32_t *h_song_ids, int32_t n, 
     SIA_CUDA(cudaDeviceSynchronize());
   }
   if (h_rows) *h_rows = ix->n_rows;
+  return SIA_OK;
+}
+
+int sia_index_export(sia_index *ix, int64_t first_row, int64_t n, uint8_t *d_hash, int32_t *d_song, int32_t *d_off,
+                     void *stream) {
+  SIA_REQUIRE(ix != nullptr, SIA_E_INVALID, "index is NULL");
+  SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
+  SIA_REQUIRE(first_row >= 0 && n >= 0 && first_row + n <= ix->n_rows, SIA_E_INVALID, "export: row range outside the index");
+  if (n == 0) return SIA_OK;
+  SIA_REQUIRE(d_hash && d_song && d_off, SIA_E_INVALID, "NULL output");
+  int rc = set_device(ix);
+  if (rc) return rc;
+  unpack_rows_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(ix->rows + first_row, n, d_hash, d_song, d_off);
+  SIA_CHECK_LAUNCH();
   return SIA_OK;
 }
 

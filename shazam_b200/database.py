@@ -132,6 +132,19 @@ class FingerprintIndex:
         N.check(self.lib.sia_index_delete_songs(self._h, ids.ctypes.data_as(C.POINTER(C.c_int32)), len(ids), C.byref(r)))
         return int(r.value)
 
+    def export(self, first_row: int = 0, n: Optional[int] = None):
+        """Rows ``[first_row, first_row + n)`` of the sorted table as CUDA tensors
+        (digest uint8[n,10], song_id int32[n], offset int32[n]), in (hash, song_id, offset) order."""
+        total = self.finalize()
+        n = total - first_row if n is None else int(n)
+        d = torch.empty((n, N.HASH_BYTES), dtype=torch.uint8, device=self.tdev)
+        s = torch.empty(n, dtype=torch.int32, device=self.tdev)
+        o = torch.empty(n, dtype=torch.int32, device=self.tdev)
+        N.check(self.lib.sia_index_export(self._h, int(first_row), n, C.c_void_p(d.data_ptr()), C.c_void_p(s.data_ptr()),
+                                          C.c_void_p(o.data_ptr()), self._stream()))
+        torch.cuda.current_stream(self.tdev).synchronize()
+        return d, s, o
+
     # ---- lookup ------------------------------------------------------------------------
     def select(self, digests: np.ndarray):
         """SELECT_MULTIPLE: every stored row whose hash is in ``digests`` (distinct).
@@ -409,6 +422,64 @@ class GPUDatabase:
         idx, sid, off = self.index.select(hex_to_digests(hx))
         for i, s, o in zip(idx.tolist(), sid.tolist(), off.tolist()):
             yield {"_source": {FIELD_HASH: hx[i], FIELD_SONG_ID: int(s), FIELD_OFFSET: int(o)}}
+
+    # ---- persistence in the reference's on-disk vocabulary -----------------------------------------
+    ROW_DTYPE = np.dtype([("hash", "V10"), ("song_id", "<u4"), ("offset", "<u4")])    # BINARY(10), MEDIUMINT, INT
+
+    def iter_sql_rows(self, chunk_rows: int = 1 << 20):
+        """``(song_id, HEXUPPER, offset)`` tuples — the parameter rows of ``INSERT_FINGERPRINT``
+        (``mysql_database.py:62-68``), so ``cur.executemany(MySQLDatabase.INSERT_FINGERPRINT, rows)`` seeds a
+        MySQL `fingerprints` table from this index."""
+        total = self.index.finalize()
+        for first in range(0, total, chunk_rows):
+            d, s, o = self.index.export(first, min(chunk_rows, total - first))
+            hx = digests_to_hex(d)
+            for h, sid, off in zip(hx, s.cpu().tolist(), o.cpu().tolist()):
+                yield sid, h.upper(), off
+
+    def dump(self, path: str, chunk_rows: int = 1 << 24) -> int:
+        """Write ``<path>/songs.json`` (the `songs` table) and ``<path>/fingerprints.bin`` (the `fingerprints`
+        table as packed ``ROW_DTYPE`` records).  Returns the number of fingerprint rows."""
+        import json
+        import os
+        os.makedirs(path, exist_ok=True)
+        total = self.index.finalize()
+        with open(os.path.join(path, "fingerprints.bin"), "wb") as f:
+            for first in range(0, total, chunk_rows):
+                n = min(chunk_rows, total - first)
+                d, s, o = self.index.export(first, n)
+                rec = np.empty(n, self.ROW_DTYPE)
+                rec["hash"] = np.frombuffer(d.cpu().numpy().tobytes(), dtype="V10")
+                rec["song_id"] = s.cpu().numpy()
+                rec["offset"] = o.cpu().numpy()
+                rec.tofile(f)
+        songs = {str(sid): {k: (v.isoformat() if hasattr(v, "isoformat") else v) for k, v in row.items()}
+                 for sid, row in self.songs.items()}
+        with open(os.path.join(path, "songs.json"), "w") as f:
+            json.dump({"next_id": self._next_id, "songs": songs, "rows": total}, f)
+        return total
+
+    @classmethod
+    def load(cls, path: str, device: Optional[int] = None, capacity_rows: Optional[int] = None,
+             chunk_rows: int = 1 << 24, **options) -> "GPUDatabase":
+        """Rebuild a database from ``dump``'s files (or from rows exported out of MySQL in ``ROW_DTYPE``)."""
+        import json
+        import os
+        meta = json.load(open(os.path.join(path, "songs.json")))
+        rec = np.memmap(os.path.join(path, "fingerprints.bin"), dtype=cls.ROW_DTYPE, mode="r")
+        db = cls(device=device, capacity_rows=capacity_rows or max(len(rec) + (len(rec) >> 3), 1 << 16), **options)
+        for sid, row in meta["songs"].items():
+            row = dict(row)
+            row["date_created"] = datetime.datetime.fromisoformat(row["date_created"])
+            db.songs[int(sid)] = row
+        db._next_id = int(meta["next_id"])
+        for first in range(0, len(rec), chunk_rows):
+            part = np.ascontiguousarray(rec[first:first + chunk_rows])
+            d = torch.from_numpy(np.frombuffer(part["hash"].tobytes(), np.uint8).reshape(-1, N.HASH_BYTES).copy())
+            db.index.insert_rows(torch.from_numpy(part["song_id"].astype(np.int32)).to(db.index.tdev), d.to(db.index.tdev),
+                                 torch.from_numpy(part["offset"].astype(np.int32)).to(db.index.tdev))
+        db.index.finalize()
+        return db
 
     def __getstate__(self):
         return (self._options,)

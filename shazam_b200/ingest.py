@@ -86,6 +86,24 @@ def union_channels(batch: FingerprintBatch, first: int, count: int):
     return h[keep], t[keep]
 
 
+def union_channels_device(digests, offsets, scratch_index=None):
+    """The same set union on the GPU: rows of all channels go through the index's own
+    sort + adjacent-duplicate drop (UNIQUE(song_id, offset, hash) with one song id).  CUDA tensors in,
+    (uint8[n,10], int32[n]) CUDA tensors out, in (hash, offset) order."""
+    import torch
+    from .database import FingerprintIndex
+    n = int(offsets.numel())
+    ix = scratch_index or FingerprintIndex(digests.device.index or 0, max(n, 1024))
+    try:
+        ix.insert(0, digests, offsets)
+        ix.finalize()
+        d, _, o = ix.export()
+        return d, o
+    finally:
+        if scratch_index is None:
+            ix.close()
+
+
 def get_file_fingerprints(file_name: str, limit: Optional[int] = None, print_output: bool = False):
     """``__init__.py:248-268``: ``(set[(hex20, offset)], file_sha1)``."""
     channels, fs, file_hash = read(file_name, limit)

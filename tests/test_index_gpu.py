@@ -348,3 +348,49 @@ def test_ingest_directory_flow(tmp_path, fpr):
     finally:
         compat.set_fingerprinter(None)
         db.index.close()
+
+
+def test_dump_load_and_sql_rows(tmp_path, gpudb):
+    """Index persistence in the schema's vocabulary: dump -> load gives the same table and answers."""
+    import torch
+    from shazam_b200 import recognize
+    from shazam_b200.database import GPUDatabase
+    rng = np.random.default_rng(31)
+    table, rows = _random_table(rng, 12, 200, 500)
+    db = gpudb()
+    _load(db, rows, table)
+    n = db.dump(str(tmp_path / "dump"))
+    assert n == table.num_rows()
+    sql = sorted(db.iter_sql_rows(chunk_rows=700))                       # (song_id, HEXUPPER, offset) for INSERT_FINGERPRINT
+    assert sql == sorted((sid, h.upper(), o) for h, v in ((k, v) for k, v in table.rows.items()) for sid, o in v)
+    d, s, o = db.index.export()
+    key = [bytes(x) for x in d.cpu().numpy()]
+    assert key == sorted(key) and len(key) == n                          # (hash, song, offset) order
+    db2 = GPUDatabase.load(str(tmp_path / "dump"), device=0)
+    try:
+        assert db2.get_num_fingerprints() == n and db2.get_songs() == db.get_songs()
+        assert db2.insert_song("new", "CD" * 20, 0) == len(rows) + 1     # AUTO_INCREMENT state survives
+        q = [(h, max(0, off - 5)) for h, off in rows[3][1][:80]]
+        recognize.set_database(db)
+        want = recognize.recognize_batch([recognize.hashes_to_arrays(q)], 3)
+        recognize.set_database(db2)
+        got = recognize.recognize_batch([recognize.hashes_to_arrays(q)], 3)
+        assert _strip(got[0]) == _strip(want[0]) and got[0][0]["song_id"] == rows[3][0]
+    finally:
+        db2.index.close()
+
+
+def test_union_channels_device(fpr):
+    """Stereo set-union on the device equals the host union / Python set."""
+    import torch
+    from shazam_b200 import ingest
+    a = O.synth_track(70, 4 * 44100)
+    b = a.copy(); b[44100:] = O.synth_track(71, 3 * 44100)               # second channel shares its first second
+    batch = fpr.fingerprint_tracks([a, b], fan_value=15)
+    hd, td = ingest.union_channels_device(torch.from_numpy(batch.hash).to(fpr.tdev), torch.from_numpy(batch.t1).to(fpr.tdev))
+    hh, th = ingest.union_channels(batch, 0, 2)
+    dev_set = set(zip(map(bytes, hd.cpu().numpy()), td.cpu().tolist()))
+    host_set = set(zip(map(bytes, hh), th.tolist()))
+    want = set(O.fingerprint(a, fan_value=15)) | set(O.fingerprint(b, fan_value=15))
+    assert dev_set == host_set == {(bytes.fromhex(h), int(t)) for h, t in want}
+    assert len(dev_set) == hd.shape[0] < len(batch.t1)                   # duplicates existed and were dropped
