@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--gen-batch", type=int, default=500, help="tracks generated per batch")
     ap.add_argument("--mode", default="hash", choices=["hash", "bins", "track"],
                     help="N>1: hash-prefix sharding exchanging vote keys (default) or sorted bins; or track sharding")
+    ap.add_argument("--vote-sweep", default="", help="world 1: comma list of vote settings timed after the main run, "
+                    "e.g. 'sort,hash:262144,hash:4194304' (SIA_VOTE / SIA_VOTE_GROUP_TUPLES)")
     ap.add_argument("--cpu-baseline-tracks", type=int, default=0, help=">0: time the oracle port on a small index")
     return ap.parse_args()
 
@@ -190,6 +192,23 @@ def main():
         out = shard.index.query_batch(qh, qt1, q_starts, args.topn, want_stats=True)
         qstats = out[5]
 
+    sweep = {}
+    if world == 1 and args.vote_sweep:
+        for setting in args.vote_sweep.split(","):
+            mode, _, budget = setting.partition(":")
+            os.environ["SIA_VOTE"] = mode
+            if budget:
+                os.environ["SIA_VOTE_GROUP_TUPLES"] = budget
+            else:
+                os.environ.pop("SIA_VOTE_GROUP_TUPLES", None)
+            step(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step()
+            torch.cuda.synchronize()
+            sweep[setting] = round((time.perf_counter() - t0) / args.steps * 1e3, 2)
+        os.environ.pop("SIA_VOTE", None); os.environ.pop("SIA_VOTE_GROUP_TUPLES", None)
+
     if rank == 0:
         line = {
             "metric": "match_queries_per_second", "value": args.queries / (ms_step * 1e-3), "unit": "queries/s",
@@ -207,6 +226,8 @@ def main():
             "index_build_seconds": round(t_build, 2),
             "index_build_rows_per_second": rows / t_build,
         }
+        if sweep:
+            line["vote_sweep_ms_per_step"] = sweep
         if qstats:
             line["per_step"] = {"query_pairs": qstats[0], "db_rows_matched": qstats[1], "vote_tuples": qstats[2],
                                 "distinct_bins": qstats[3],

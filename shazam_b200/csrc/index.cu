@@ -21,6 +21,8 @@
 #include "sort.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 using namespace sia;
@@ -58,7 +60,7 @@ namespace {
 // Sorted, de-duplicated query entries for queries [q0, q1) (entries [i0, i1) of the caller's arrays).
 struct Lookup {
   ulonglong2 *ent = nullptr;
-  uint32_t *first = nullptr;
+  uint32_t *first = nullptr, *cnt_head = nullptr;
   int64_t *off_all = nullptr, *off_head = nullptr;
   int64_t n = 0, tuples = 0, head_rows = 0, distinct = 0;
 };
@@ -424,6 +426,183 @@ __global__ void query_starts_kernel(const ulonglong2 *__restrict__ ent, int64_t 
   }
 }
 
+
+// ---- hash-table vote -------------------------------------------------------------------------
+// The sort-free vote behind sia_index_query_batch.  Queries are taken in groups whose tables fit in L2.
+// Every query owns two open-addressing sub-tables (linear probing inside the query's slot range):
+//   bins : key = song (24) | biased diff (25)  -> count            (the run-length bins of recognizer.py:303-305)
+//   songs: key = song                          -> rows (dedup_hashes[song], recognizer.py:259-264)
+//                                                 best = max(count << 25 | inverted diff)  (recognizer.py:308)
+// Posting runs are expanded straight into the tables (no vote keys are written or sorted).
+struct QMeta {
+  int64_t bin_base, song_base;    // first slot of the query's sub-tables, relative to the group's tables
+  uint32_t bin_cap, song_cap;
+};
+constexpr uint64_t kEmptyBin = ~0ull;
+constexpr uint32_t kEmptySong = ~0u;
+constexpr int kTopK = 4;          // results extracted per scan of a query's song table
+
+__device__ __forceinline__ uint32_t mix64(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)(k >> 16);
+}
+__device__ __forceinline__ uint32_t mix32(uint32_t k) {
+  k ^= k >> 16; k *= 0x85ebca6bu; k ^= k >> 13; k *= 0xc2b2ae35u; k ^= k >> 16;
+  return k;
+}
+__device__ __forceinline__ uint32_t slot_of(uint32_t h, uint32_t cap) { return (uint32_t)(((uint64_t)h * cap) >> 32); }
+
+__device__ __forceinline__ int64_t song_slot_find(const uint32_t *__restrict__ song_key, const QMeta &m, uint32_t song) {
+  uint32_t s = slot_of(mix32(song), m.song_cap);
+  for (uint32_t probes = 0; probes < m.song_cap; ++probes) {
+    const uint32_t k = song_key[m.song_base + s];
+    if (k == song) return m.song_base + s;
+    if (k == kEmptySong) return -1;
+    if (++s == m.song_cap) s = 0;
+  }
+  return -1;
+}
+
+// One block handles 256 consecutive entries and spreads their postings evenly over its threads.
+__global__ void __launch_bounds__(256)
+expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, const uint32_t *__restrict__ first,
+                   const int64_t *__restrict__ off, const uint32_t *__restrict__ cnt_head,
+                   const ulonglong2 *__restrict__ rows, const QMeta *__restrict__ meta,
+                   unsigned long long *__restrict__ bin_key, uint32_t *__restrict__ bin_cnt,
+                   uint32_t *__restrict__ song_key, uint32_t *__restrict__ song_rows) {
+  __shared__ int64_t s_off[257];
+  const int64_t b0 = e0 + (int64_t)blockIdx.x * 256;
+  const int nloc = (int)min((int64_t)256, e0 + n - b0);
+  if (threadIdx.x < nloc) s_off[threadIdx.x] = off[b0 + threadIdx.x];
+  if (threadIdx.x == 0) s_off[nloc] = off[b0 + nloc];
+  __syncthreads();
+  const int64_t base = s_off[0], total = s_off[nloc] - base;
+  for (int64_t j = threadIdx.x; j < total; j += 256) {
+    int lo = 0, hi = nloc;               // largest e with s_off[e] - base <= j
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] - base <= j) lo = mid; else hi = mid; }
+    const int64_t ei = b0 + lo;
+    const uint32_t k = (uint32_t)(j - (s_off[lo] - base));
+    const ulonglong2 e = ent[ei];
+    const ulonglong2 r = rows[first[ei] + k];
+    const QMeta m = meta[e.y >> 40];
+    const uint32_t song = (uint32_t)(r.x >> 24) & 0xffffffu;
+    const int32_t diff = (int32_t)(r.x & kM24) - (int32_t)(e.x & kM24);   // db offset - query offset
+    const uint64_t key = ((uint64_t)song << kDiffBits) | (uint64_t)(uint32_t)(diff + SIA_DIFF_BIAS);
+    uint32_t s = slot_of(mix64(key), m.bin_cap);
+    for (;;) {
+      const unsigned long long old = atomicCAS(&bin_key[m.bin_base + s], kEmptyBin, key);
+      if (old == kEmptyBin || old == key) { atomicAdd(&bin_cnt[m.bin_base + s], 1u); break; }
+      if (++s == m.bin_cap) s = 0;
+    }
+    if (cnt_head[ei]) {                   // first entry of its (query, hash): the row counts once
+      uint32_t t = slot_of(mix32(song), m.song_cap);
+      for (;;) {
+        const uint32_t old = atomicCAS(&song_key[m.song_base + t], kEmptySong, song);
+        if (old == kEmptySong || old == song) { atomicAdd(&song_rows[m.song_base + t], 1u); break; }
+        if (++t == m.song_cap) t = 0;
+      }
+    }
+  }
+}
+
+// every occupied bin slot -> its song's best (count, smallest diff)
+__global__ void __launch_bounds__(256)
+bins_to_songs_kernel(const unsigned long long *__restrict__ bin_key, const uint32_t *__restrict__ bin_cnt, int64_t nslots,
+                     const QMeta *__restrict__ meta, int qa, int qb, const uint32_t *__restrict__ song_key,
+                     unsigned long long *__restrict__ song_best, unsigned long long *__restrict__ n_bins) {
+  uint32_t mine = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = bin_key[i];
+    if (k == kEmptyBin) continue;
+    ++mine;
+    int lo = qa, hi = qb;                // largest q with meta[q].bin_base <= i
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (meta[mid].bin_base <= i) lo = mid; else hi = mid; }
+    const QMeta m = meta[lo];
+    const int64_t ss = song_slot_find(song_key, m, (uint32_t)(k >> kDiffBits));
+    if (ss < 0) continue;                // cannot happen: every voted song has at least one head row
+    const uint64_t inv = ((1ull << kDiffBits) - 1) - (k & ((1ull << kDiffBits) - 1));
+    atomicMax(&song_best[ss], ((unsigned long long)bin_cnt[i] << kDiffBits) | inv);
+  }
+  if (n_bins) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_bins, (unsigned long long)mine);
+  }
+}
+
+// one block per query: top-n songs by (count desc, song asc), kTopK results per scan of the query's song table
+__global__ void __launch_bounds__(256)
+topn_hash_kernel(const uint32_t *__restrict__ song_key, const uint32_t *__restrict__ song_rows,
+                 const unsigned long long *__restrict__ song_best, const QMeta *__restrict__ meta, int q_lo, int qid_base,
+                 int topn, int32_t *__restrict__ out_song, int32_t *__restrict__ out_diff, int32_t *__restrict__ out_count,
+                 int32_t *__restrict__ out_rows, int32_t *__restrict__ out_nres) {
+  __shared__ unsigned long long s_key[8];
+  __shared__ uint32_t s_slot[8];
+  __shared__ unsigned long long s_win;
+  const int q = (int)blockIdx.x + q_lo;
+  const QMeta m = meta[q];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long prev = ~0ull;
+  int nres = 0;
+  while (nres < topn) {
+    // rank key: count (high) then inverted song id, so equal counts order by ascending song id
+    unsigned long long tk[kTopK];
+    uint32_t ts[kTopK];
+#pragma unroll
+    for (int i = 0; i < kTopK; ++i) { tk[i] = 0; ts[i] = 0; }
+    for (uint32_t s = threadIdx.x; s < m.song_cap; s += 256) {
+      const uint32_t song = song_key[m.song_base + s];
+      if (song == kEmptySong) continue;
+      const unsigned long long c = song_best[m.song_base + s] >> kDiffBits;
+      unsigned long long k = (c << kSongBits) | (kM24 - song);
+      if (k >= prev || k <= tk[kTopK - 1]) continue;
+      uint32_t sl = s;
+#pragma unroll
+      for (int i = 0; i < kTopK; ++i)
+        if (k > tk[i]) { const unsigned long long a = tk[i]; const uint32_t b = ts[i]; tk[i] = k; ts[i] = sl; k = a; sl = b; }
+    }
+    int got = 0;
+    for (int r = 0; r < kTopK && nres < topn; ++r) {
+      unsigned long long bk = tk[0];
+      uint32_t bs = ts[0];
+#pragma unroll
+      for (int d = 16; d; d >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, d);
+        const uint32_t os = __shfl_xor_sync(0xffffffffu, bs, d);
+        if (ok > bk) { bk = ok; bs = os; }
+      }
+      if (lane == 0) { s_key[warp] = bk; s_slot[warp] = bs; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long w = 0; uint32_t ws = 0;
+        for (int i = 0; i < 8; ++i) if (s_key[i] > w) { w = s_key[i]; ws = s_slot[i]; }
+        s_win = w;
+        if (w) {
+          const unsigned long long v = song_best[m.song_base + ws];
+          const int64_t o = ((int64_t)q + qid_base) * topn + nres;
+          out_song[o] = (int32_t)(kM24 - (w & kM24));
+          out_count[o] = (int32_t)(v >> kDiffBits);
+          out_diff[o] = (int32_t)(((1ull << kDiffBits) - 1) - (v & ((1ull << kDiffBits) - 1))) - SIA_DIFF_BIAS;
+          out_rows[o] = (int32_t)song_rows[m.song_base + ws];
+        }
+      }
+      __syncthreads();
+      const unsigned long long w = s_win;
+      if (w == 0) break;
+      if (tk[0] == w) {                   // the winner leaves its owner's list
+#pragma unroll
+        for (int i = 0; i + 1 < kTopK; ++i) { tk[i] = tk[i + 1]; ts[i] = ts[i + 1]; }
+        tk[kTopK - 1] = 0;
+      }
+      prev = w;
+      ++nres; ++got;
+      __syncthreads();
+    }
+    if (got < kTopK) break;               // the table is exhausted
+  }
+  if (threadIdx.x == 0) out_nres[q + qid_base] = nres;
+}
+
 inline unsigned grid_for(int64_t n, int threads = 256) {
   int64_t b = ceil_div(n > 0 ? n : 1, threads);
   return (unsigned)std::min<int64_t>(b, kNumSMs * 32);
@@ -524,7 +703,7 @@ int lookup_pass(sia_index *ix, Arena &ar, const uint8_t *d_hash, const int32_t *
   SIA_CUDA(cudaMemcpyAsync(&tot[0], off_all + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   SIA_CUDA(cudaMemcpyAsync(&tot[1], off_head + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   SIA_CUDA(cudaStreamSynchronize(s));
-  L.first = first; L.off_all = off_all; L.off_head = off_head; L.tuples = tot[0]; L.head_rows = tot[1];
+  L.first = first; L.cnt_head = c_head; L.off_all = off_all; L.off_head = off_head; L.tuples = tot[0]; L.head_rows = tot[1];
   return SIA_OK;
 }
 
@@ -847,7 +1026,13 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
   SIA_REQUIRE(h_query_starts[n_queries] == h_query_starts[0] || (d_hash && d_qoff), SIA_E_INVALID, "NULL input");
   SIA_CUDA(cudaMemsetAsync(d_out_nres, 0, sizeof(int32_t) * n_queries, s));
 
-  const int64_t tuple_budget = 96ll << 20;   // vote keys expanded at once (x ~70 B of scratch each)
+  // SIA_VOTE=sort keeps the sort-based vote (the first implementation; A/B checks); default: hash tables
+  // (read per call, so a test can run both paths in one process)
+  const bool use_hash = !(getenv("SIA_VOTE") && std::string(getenv("SIA_VOTE")) == "sort");
+  const int64_t hash_budget = getenv("SIA_VOTE_GROUP_TUPLES") ? std::max(1ll, atoll(getenv("SIA_VOTE_GROUP_TUPLES")))
+                                                               : (1ll << 20);
+  // tuples voted at once: sort path x ~70 B of scratch each; hash path x ~56 B of tables, sized to stay in L2
+  const int64_t tuple_budget = use_hash ? hash_budget : (96ll << 20);
   for (int64_t q0 = 0; q0 < n_queries; q0 += kMaxQueriesPerPass) {
     const int nq = (int)std::min<int64_t>(kMaxQueriesPerPass, n_queries - q0);
     const int64_t i0 = h_query_starts[q0], n = h_query_starts[q0 + nq] - i0;
@@ -880,24 +1065,85 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
       need = std::max(need, bins_bytes(t, h) + vote_bytes(t) + (1 << 20));
       qa = qb;
     }
-    if ((rc = ix->arena2.reserve(need))) return rc;
+    if (!use_hash) {
+      if ((rc = ix->arena2.reserve(need))) return rc;
+      for (const Group &g : groups) {
+        const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
+        const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa], heads = h_off_head[g.qb] - h_off_head[g.qa];
+        ix->arena2.used = 0;
+        uint64_t *bk = nullptr, *rk = nullptr;
+        int32_t *bc = nullptr, *rcnt = nullptr;
+        int64_t nbins = 0, nrowbins = 0;
+        if (ne > 0 && (rc = bins_from_entries(ix, ix->arena2, L, e0, ne, tuples, h_off_all[g.qa], heads, h_off_head[g.qa],
+                                              &bk, &bc, &nbins, &rk, &rcnt, &nrowbins, s)))
+          return rc;
+        if (h_stats) h_stats[3] += nbins;
+        // keys carry the pass-local query id; outputs are indexed by q0 + q
+        if ((rc = vote_sorted(ix->arena2, bk, bc, nbins, rk, rcnt, nrowbins, g.qa, g.qb, (int)q0, topn, d_out_song,
+                              d_out_diff, d_out_count, d_out_rows, d_out_nres, s)))
+          return rc;
+        SIA_CUDA(cudaStreamSynchronize(s));
+      }
+      continue;
+    }
+    // hash-table vote: per-query sub-tables, one group's tables live at a time (stream-ordered reuse)
+    std::vector<QMeta> h_meta(nq);
+    int64_t max_bin = 0, max_song = 0;
+    for (const Group &g : groups) {
+      int64_t bb = 0, sb = 0;
+      for (int q = g.qa; q < g.qb; ++q) {
+        const int64_t t = h_off_all[q + 1] - h_off_all[q], h = h_off_head[q + 1] - h_off_head[q];
+        SIA_REQUIRE(t < (1ll << 30), SIA_E_UNSUPPORTED, "query_batch: more than 2^30 vote tuples in one query");
+        h_meta[q].bin_base = bb; h_meta[q].song_base = sb;
+        h_meta[q].bin_cap = (uint32_t)(2 * t + 32); h_meta[q].song_cap = (uint32_t)(2 * h + 32);
+        bb += h_meta[q].bin_cap; sb += h_meta[q].song_cap;
+      }
+      max_bin = std::max(max_bin, bb); max_song = std::max(max_song, sb);
+    }
+    const size_t ff_bytes = (size_t)max_bin * 8 + (size_t)max_song * 4;                 // keys: memset 0xff
+    const size_t zero_bytes = (size_t)max_bin * 4 + (size_t)max_song * 12;              // counts, rows, best: memset 0
+    if ((rc = ix->arena2.reserve(ff_bytes + zero_bytes + (size_t)nq * sizeof(QMeta) + 4096))) return rc;
+    unsigned long long *bin_key = ix->arena2.take<unsigned long long>(max_bin);
+    uint32_t *song_key = ix->arena2.take<uint32_t>(max_song);
+    unsigned long long *song_best = ix->arena2.take<unsigned long long>(max_song);
+    uint32_t *bin_cnt = ix->arena2.take<uint32_t>(max_bin);
+    uint32_t *song_rows = ix->arena2.take<uint32_t>(max_song);
+    QMeta *d_meta = ix->arena2.take<QMeta>(nq);
+    unsigned long long *d_nbins = ix->arena2.take<unsigned long long>(1);
+    SIA_REQUIRE(bin_key && song_key && song_best && bin_cnt && song_rows && d_meta && d_nbins, SIA_E_NOMEM,
+                "index scratch arena too small (vote tables)");
+    SIA_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(QMeta) * nq, cudaMemcpyHostToDevice, s));
+    SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long), s));
     for (const Group &g : groups) {
       const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
-      const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa], heads = h_off_head[g.qb] - h_off_head[g.qa];
-      ix->arena2.used = 0;
-      uint64_t *bk = nullptr, *rk = nullptr;
-      int32_t *bc = nullptr, *rcnt = nullptr;
-      int64_t nbins = 0, nrowbins = 0;
-      if (ne > 0 && (rc = bins_from_entries(ix, ix->arena2, L, e0, ne, tuples, h_off_all[g.qa], heads, h_off_head[g.qa],
-                                            &bk, &bc, &nbins, &rk, &rcnt, &nrowbins, s)))
-        return rc;
-      if (h_stats) h_stats[3] += nbins;
-      // keys carry the pass-local query id; outputs are indexed by q0 + q
-      if ((rc = vote_sorted(ix->arena2, bk, bc, nbins, rk, rcnt, nrowbins, g.qa, g.qb, (int)q0, topn, d_out_song,
-                            d_out_diff, d_out_count, d_out_rows, d_out_nres, s)))
-        return rc;
-      SIA_CUDA(cudaStreamSynchronize(s));
+      const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa];
+      const QMeta &last = h_meta[g.qb - 1];
+      const int64_t nb = last.bin_base + last.bin_cap, ns = last.song_base + last.song_cap;
+      if (tuples > 0) {
+        SIA_CUDA(cudaMemsetAsync(bin_key, 0xff, (size_t)nb * 8, s));
+        SIA_CUDA(cudaMemsetAsync(song_key, 0xff, (size_t)ns * 4, s));
+        SIA_CUDA(cudaMemsetAsync(song_best, 0, (size_t)ns * 8, s));
+        SIA_CUDA(cudaMemsetAsync(bin_cnt, 0, (size_t)nb * 4, s));
+        SIA_CUDA(cudaMemsetAsync(song_rows, 0, (size_t)ns * 4, s));
+        expand_vote_kernel<<<(unsigned)ceil_div(ne, 256), 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head,
+                                                                      ix->rows, d_meta, bin_key, bin_cnt, song_key,
+                                                                      song_rows);
+        SIA_CHECK_LAUNCH();
+        bins_to_songs_kernel<<<grid_for(nb), 256, 0, s>>>(bin_key, bin_cnt, nb, d_meta, g.qa, g.qb, song_key, song_best,
+                                                         h_stats ? d_nbins : nullptr);
+        SIA_CHECK_LAUNCH();
+        topn_hash_kernel<<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, d_meta, g.qa, (int)q0, topn,
+                                                     d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
+        SIA_CHECK_LAUNCH();
+      }
     }
+    if (h_stats) {
+      unsigned long long nbv = 0;
+      SIA_CUDA(cudaMemcpyAsync(&nbv, d_nbins, sizeof nbv, cudaMemcpyDeviceToHost, s));
+      SIA_CUDA(cudaStreamSynchronize(s));
+      h_stats[3] += (int64_t)nbv;
+    }
+    SIA_CUDA(cudaStreamSynchronize(s));      // the lookup scratch and the tables are reused by the next pass / call
   }
   return SIA_OK;
 }

@@ -394,3 +394,50 @@ def test_union_channels_device(fpr):
     want = set(O.fingerprint(a, fan_value=15)) | set(O.fingerprint(b, fan_value=15))
     assert dev_set == host_set == {(bytes.fromhex(h), int(t)) for h, t in want}
     assert len(dev_set) == hd.shape[0] < len(batch.t1)                   # duplicates existed and were dropped
+
+
+def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch):
+    """The hash-table vote (default) and the sort-based vote give identical results — counts, smallest-diff and
+    ascending-song tie-breaks, dedup rows, stats — for any grouping of the queries (recognizer.py:303-310)."""
+    import torch
+    rng = np.random.default_rng(77)
+    nsongs, per_song, universe = 300, 4000, 6000       # ~200 postings per key; offsets in a small range -> many ties
+    n = nsongs * per_song
+    keys = rng.integers(0, universe, n)
+    pool = np.frombuffer(b"".join(hashlib.sha1(str(i).encode()).digest()[:10] for i in range(universe)),
+                         np.uint8).reshape(universe, 10)
+    dig = pool[keys]
+    song = np.repeat(np.arange(1, nsongs + 1, dtype=np.int32), per_song)
+    off = rng.integers(0, 64, n).astype(np.int32)
+    db = gpudb(capacity_rows=n + 16)
+    ix = db.index
+    dev = ix.tdev
+    ix.insert_rows(torch.from_numpy(song).to(dev), torch.from_numpy(dig).to(dev), torch.from_numpy(off).to(dev))
+    ix.finalize()
+    sizes = rng.integers(0, 400, 120)
+    sizes[3] = 0; sizes[50] = 3000                      # an empty query and a big one
+    qs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    qk = rng.integers(0, universe + 500, qs[-1])        # some absent keys
+    pool2 = np.concatenate([pool, rng.integers(0, 256, (500, 10), dtype=np.uint8)])
+    qd = torch.from_numpy(pool2[qk]).to(dev)
+    qo = torch.from_numpy(rng.integers(0, 16, qs[-1]).astype(np.int32)).to(dev)
+
+    def run(topn):
+        out = ix.query_batch(qd, qo, qs, topn, want_stats=True)
+        return [t.cpu().numpy() for t in out[:5]], out[5]
+
+    for topn in (1, 3, 9):
+        monkeypatch.setenv("SIA_VOTE", "sort")
+        want, want_stats = run(topn)
+        assert want[4].max() == topn and want_stats[2] > 1_000_000
+        monkeypatch.delenv("SIA_VOTE")
+        for budget in (None, "1000", "200000", str(1 << 40)):
+            if budget is None:
+                monkeypatch.delenv("SIA_VOTE_GROUP_TUPLES", raising=False)
+            else:
+                monkeypatch.setenv("SIA_VOTE_GROUP_TUPLES", budget)
+            got, got_stats = run(topn)
+            assert got_stats == want_stats, (topn, budget)
+            for a, b, name in zip(got, want, ("song", "diff", "count", "rows", "nres")):
+                assert np.array_equal(a, b), (name, topn, budget)
+        monkeypatch.delenv("SIA_VOTE_GROUP_TUPLES", raising=False)
