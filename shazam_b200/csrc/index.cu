@@ -76,9 +76,12 @@ struct sia_index {
   int64_t n_rows = 0, n_pending = 0;
   uint32_t *dir = nullptr;      // [2^dir_bits + 1]
   int dir_bits = 0;
-  int32_t *status = nullptr;    // device flag: 1 = song/offset out of range on insert, 2 = query offset out of range
+  int32_t *status = nullptr;    // [0] device flag: 1 = song/offset out of range on insert, 2 = query offset out of range
+                                // [1] largest song id ever inserted
+  int32_t max_song = 0;         // host copy of status[1], refreshed by finalize
   Arena arena;                  // build / lookup scratch
-  Arena arena2;                 // per-group vote scratch
+  Arena arena2;                 // per-group vote scratch (sort-based vote)
+  Arena arena3;                 // vote tables (hash-table vote)
   // lookup of the last sizing call of sia_index_expand, reused by the call that fills the buffers
   bool cache_valid = false;
   const void *cache_hash = nullptr, *cache_qoff = nullptr, *cache_qid = nullptr;
@@ -100,14 +103,19 @@ __device__ __forceinline__ void load_digest(const uint8_t *__restrict__ h, uint6
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const uint8_t *__restrict__ hash, const int32_t *__restrict__ off, const int32_t *__restrict__ song_arr,
                  int32_t song_const, int64_t n, ulonglong2 *__restrict__ out, int32_t *__restrict__ status) {
+  int32_t smax = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     uint64_t hi; uint32_t lo16;
     load_digest(hash + i * SIA_HASH_BYTES, hi, lo16);
     const int32_t song = song_arr ? song_arr[i] : song_const;
     const int32_t o = off[i];
     if (song < 0 || song > (int32_t)kM24 || o < 0 || o > (int32_t)kM24) atomicOr(status, 1);
+    else smax = max(smax, song);
     out[i] = make_ulonglong2(((uint64_t)lo16 << 48) | (((uint64_t)song & kM24) << 24) | ((uint64_t)o & kM24), hi);
   }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, d));
+  if ((threadIdx.x & 31) == 0 && smax > 0) atomicMax(status + 1, smax);
 }
 
 __global__ void __launch_bounds__(256)
@@ -428,55 +436,49 @@ __global__ void query_starts_kernel(const ulonglong2 *__restrict__ ent, int64_t 
 
 
 // ---- hash-table vote -------------------------------------------------------------------------
-// The sort-free vote behind sia_index_query_batch.  Queries are taken in groups whose tables fit in L2.
-// Every query owns two open-addressing sub-tables (linear probing inside the query's slot range):
-//   bins : key = song (24) | biased diff (25)  -> count            (the run-length bins of recognizer.py:303-305)
-//   songs: key = song                          -> rows (dedup_hashes[song], recognizer.py:259-264)
-//                                                 best = max(count << 25 | inverted diff)  (recognizer.py:308)
-// Posting runs are expanded straight into the tables (no vote keys are written or sorted).
+// The sort-free vote behind sia_index_query_batch.  Queries are taken in groups whose tables stay in L2.
+// Every query owns two sub-tables inside the group's (zero-initialised) tables:
+//   bins : open addressing, linear probing inside the query's slot range; one 64-bit word per slot =
+//          key (song 24 | biased diff 25) << 15 | count — the run-length bins of recognizer.py:303-305.
+//          A bin holds at most one tuple per query entry, so 15 bits suffice for queries of <= 32767
+//          (hash, offset) pairs; larger queries go through the sort-based vote.  key != 0 always
+//          (the biased diff is >= 1), so 0 is the empty slot.
+//   songs: dense (slot = song id) when the id range is small next to the query's matches, else open
+//          addressing on song id; per slot rows (dedup_hashes[song], recognizer.py:259-264) and
+//          best = max over the song's bins of (count << 25 | inverted diff) (recognizer.py:308), which is
+//          kept current while the bins fill: the thread that brings a bin to count c posts (c, diff).
+// Posting runs are expanded straight into the tables — no vote keys are written or sorted.
 struct QMeta {
   int64_t bin_base, song_base;    // first slot of the query's sub-tables, relative to the group's tables
   uint32_t bin_cap, song_cap;
 };
-constexpr uint64_t kEmptyBin = ~0ull;
-constexpr uint32_t kEmptySong = ~0u;
+constexpr int kBinCountBits = 15;
+constexpr int64_t kMaxHashVoteEntries = (1 << kBinCountBits) - 1;
 constexpr int kTopK = 4;          // results extracted per scan of a query's song table
+constexpr int kVoteChunk = 64;    // entries per block of expand_vote_kernel
 
-__device__ __forceinline__ uint32_t mix64(uint64_t k) {
-  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-  return (uint32_t)(k >> 16);
-}
 __device__ __forceinline__ uint32_t mix32(uint32_t k) {
   k ^= k >> 16; k *= 0x85ebca6bu; k ^= k >> 13; k *= 0xc2b2ae35u; k ^= k >> 16;
   return k;
 }
 __device__ __forceinline__ uint32_t slot_of(uint32_t h, uint32_t cap) { return (uint32_t)(((uint64_t)h * cap) >> 32); }
 
-__device__ __forceinline__ int64_t song_slot_find(const uint32_t *__restrict__ song_key, const QMeta &m, uint32_t song) {
-  uint32_t s = slot_of(mix32(song), m.song_cap);
-  for (uint32_t probes = 0; probes < m.song_cap; ++probes) {
-    const uint32_t k = song_key[m.song_base + s];
-    if (k == song) return m.song_base + s;
-    if (k == kEmptySong) return -1;
-    if (++s == m.song_cap) s = 0;
-  }
-  return -1;
-}
-
-// One block handles 256 consecutive entries and spreads their postings evenly over its threads.
+// One block handles kVoteChunk consecutive entries and spreads their postings evenly over its threads.
+template <bool DENSE>
 __global__ void __launch_bounds__(256)
 expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, const uint32_t *__restrict__ first,
                    const int64_t *__restrict__ off, const uint32_t *__restrict__ cnt_head,
                    const ulonglong2 *__restrict__ rows, const QMeta *__restrict__ meta,
-                   unsigned long long *__restrict__ bin_key, uint32_t *__restrict__ bin_cnt,
-                   uint32_t *__restrict__ song_key, uint32_t *__restrict__ song_rows) {
-  __shared__ int64_t s_off[257];
-  const int64_t b0 = e0 + (int64_t)blockIdx.x * 256;
-  const int nloc = (int)min((int64_t)256, e0 + n - b0);
-  if (threadIdx.x < nloc) s_off[threadIdx.x] = off[b0 + threadIdx.x];
-  if (threadIdx.x == 0) s_off[nloc] = off[b0 + nloc];
+                   unsigned long long *__restrict__ bins, uint32_t *__restrict__ song_key,
+                   uint32_t *__restrict__ song_rows, unsigned long long *__restrict__ song_best,
+                   unsigned long long *__restrict__ n_bins) {
+  __shared__ int64_t s_off[kVoteChunk + 1];
+  const int64_t b0 = e0 + (int64_t)blockIdx.x * kVoteChunk;
+  const int nloc = (int)min((int64_t)kVoteChunk, e0 + n - b0);
+  if (threadIdx.x <= nloc) s_off[threadIdx.x] = off[b0 + threadIdx.x];
   __syncthreads();
   const int64_t base = s_off[0], total = s_off[nloc] - base;
+  uint32_t fresh = 0;
   for (int64_t j = threadIdx.x; j < total; j += 256) {
     int lo = 0, hi = nloc;               // largest e with s_off[e] - base <= j
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] - base <= j) lo = mid; else hi = mid; }
@@ -486,51 +488,42 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
     const ulonglong2 r = rows[first[ei] + k];
     const QMeta m = meta[e.y >> 40];
     const uint32_t song = (uint32_t)(r.x >> 24) & 0xffffffu;
-    const int32_t diff = (int32_t)(r.x & kM24) - (int32_t)(e.x & kM24);   // db offset - query offset
-    const uint64_t key = ((uint64_t)song << kDiffBits) | (uint64_t)(uint32_t)(diff + SIA_DIFF_BIAS);
-    uint32_t s = slot_of(mix64(key), m.bin_cap);
+    const uint32_t dbits = (uint32_t)((int32_t)(r.x & kM24) - (int32_t)(e.x & kM24) + SIA_DIFF_BIAS);   // db - query offset
+    const unsigned long long key = ((unsigned long long)song << kDiffBits) | dbits;
+    uint32_t s = slot_of(mix32(song * 0x9e3779b1u + dbits), m.bin_cap);
+    unsigned long long count;
     for (;;) {
-      const unsigned long long old = atomicCAS(&bin_key[m.bin_base + s], kEmptyBin, key);
-      if (old == kEmptyBin || old == key) { atomicAdd(&bin_cnt[m.bin_base + s], 1u); break; }
+      unsigned long long *p = bins + m.bin_base + s;
+      const unsigned long long old = atomicCAS(p, 0ull, (key << kBinCountBits) | 1ull);
+      if (old == 0ull) { count = 1; ++fresh; break; }
+      if ((old >> kBinCountBits) == key) { count = (atomicAdd(p, 1ull) & ((1ull << kBinCountBits) - 1)) + 1; break; }
       if (++s == m.bin_cap) s = 0;
     }
-    if (cnt_head[ei]) {                   // first entry of its (query, hash): the row counts once
+    int64_t ss;
+    if (DENSE) {
+      ss = m.song_base + song;
+    } else {
       uint32_t t = slot_of(mix32(song), m.song_cap);
       for (;;) {
-        const uint32_t old = atomicCAS(&song_key[m.song_base + t], kEmptySong, song);
-        if (old == kEmptySong || old == song) { atomicAdd(&song_rows[m.song_base + t], 1u); break; }
+        const uint32_t old = atomicCAS(&song_key[m.song_base + t], 0u, song + 1u);
+        if (old == 0u || old == song + 1u) break;
         if (++t == m.song_cap) t = 0;
       }
+      ss = m.song_base + t;
     }
-  }
-}
-
-// every occupied bin slot -> its song's best (count, smallest diff)
-__global__ void __launch_bounds__(256)
-bins_to_songs_kernel(const unsigned long long *__restrict__ bin_key, const uint32_t *__restrict__ bin_cnt, int64_t nslots,
-                     const QMeta *__restrict__ meta, int qa, int qb, const uint32_t *__restrict__ song_key,
-                     unsigned long long *__restrict__ song_best, unsigned long long *__restrict__ n_bins) {
-  uint32_t mine = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned long long k = bin_key[i];
-    if (k == kEmptyBin) continue;
-    ++mine;
-    int lo = qa, hi = qb;                // largest q with meta[q].bin_base <= i
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (meta[mid].bin_base <= i) lo = mid; else hi = mid; }
-    const QMeta m = meta[lo];
-    const int64_t ss = song_slot_find(song_key, m, (uint32_t)(k >> kDiffBits));
-    if (ss < 0) continue;                // cannot happen: every voted song has at least one head row
-    const uint64_t inv = ((1ull << kDiffBits) - 1) - (k & ((1ull << kDiffBits) - 1));
-    atomicMax(&song_best[ss], ((unsigned long long)bin_cnt[i] << kDiffBits) | inv);
+    const unsigned long long inv = ((1ull << kDiffBits) - 1) - dbits;
+    atomicMax(&song_best[ss], (count << kDiffBits) | inv);
+    if (cnt_head[ei]) atomicAdd(&song_rows[ss], 1u);    // first entry of its (query, hash): the row counts once
   }
   if (n_bins) {
 #pragma unroll
-    for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_bins, (unsigned long long)mine);
+    for (int d = 16; d; d >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
+    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(n_bins, (unsigned long long)fresh);
   }
 }
 
 // one block per query: top-n songs by (count desc, song asc), kTopK results per scan of the query's song table
+template <bool DENSE>
 __global__ void __launch_bounds__(256)
 topn_hash_kernel(const uint32_t *__restrict__ song_key, const uint32_t *__restrict__ song_rows,
                  const unsigned long long *__restrict__ song_best, const QMeta *__restrict__ meta, int q_lo, int qid_base,
@@ -551,10 +544,10 @@ topn_hash_kernel(const uint32_t *__restrict__ song_key, const uint32_t *__restri
 #pragma unroll
     for (int i = 0; i < kTopK; ++i) { tk[i] = 0; ts[i] = 0; }
     for (uint32_t s = threadIdx.x; s < m.song_cap; s += 256) {
-      const uint32_t song = song_key[m.song_base + s];
-      if (song == kEmptySong) continue;
-      const unsigned long long c = song_best[m.song_base + s] >> kDiffBits;
-      unsigned long long k = (c << kSongBits) | (kM24 - song);
+      const unsigned long long best = song_best[m.song_base + s];
+      if (best == 0ull) continue;          // empty slot / song without a match
+      const uint32_t song = DENSE ? s : song_key[m.song_base + s] - 1u;
+      unsigned long long k = ((best >> kDiffBits) << kSongBits) | (kM24 - song);
       if (k >= prev || k <= tk[kTopK - 1]) continue;
       uint32_t sl = s;
 #pragma unroll
@@ -773,8 +766,8 @@ int sia_index_create(int device, int64_t capacity_rows, sia_index **out) {
   ix->device = device;
   ix->capacity = capacity_rows;
   cudaError_t e = cudaMalloc(&ix->rows, (size_t)capacity_rows * sizeof(ulonglong2));
-  if (e == cudaSuccess) e = cudaMalloc(&ix->status, sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMemset(ix->status, 0, sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&ix->status, 2 * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemset(ix->status, 0, 2 * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMalloc(&ix->dir, 2 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemset(ix->dir, 0, 2 * sizeof(uint32_t));
   if (e != cudaSuccess) {
@@ -796,6 +789,7 @@ int sia_index_destroy(sia_index *ix) {
   if (ix->status) cudaFree(ix->status);
   ix->arena.release();
   ix->arena2.release();
+  ix->arena3.release();
   delete ix;
   return SIA_OK;
 }
@@ -860,6 +854,7 @@ int sia_index_finalize(sia_index *ix, int64_t *h_rows) {
     ix->n_pending = 0;   // drop the offending batch
     return rc;
   }
+  SIA_CUDA(cudaMemcpy(&ix->max_song, ix->status + 1, sizeof(int32_t), cudaMemcpyDeviceToHost));
   const int64_t n = ix->n_rows + ix->n_pending;
   if (ix->n_pending > 0 && n > 0) {
     ulonglong2 *alt = nullptr;
@@ -1030,8 +1025,8 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
   // (read per call, so a test can run both paths in one process)
   const bool use_hash = !(getenv("SIA_VOTE") && std::string(getenv("SIA_VOTE")) == "sort");
   const int64_t hash_budget = getenv("SIA_VOTE_GROUP_TUPLES") ? std::max(1ll, atoll(getenv("SIA_VOTE_GROUP_TUPLES")))
-                                                               : (1ll << 20);
-  // tuples voted at once: sort path x ~70 B of scratch each; hash path x ~56 B of tables, sized to stay in L2
+                                                               : (4ll << 20);
+  // tuples voted at once: sort path x ~70 B of scratch each; hash path x ~16 B of tables, sized to stay in L2
   const int64_t tuple_budget = use_hash ? hash_budget : (96ll << 20);
   for (int64_t q0 = 0; q0 < n_queries; q0 += kMaxQueriesPerPass) {
     const int nq = (int)std::min<int64_t>(kMaxQueriesPerPass, n_queries - q0);
@@ -1054,22 +1049,65 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     SIA_CUDA(cudaMemcpyAsync(h_goff.data(), d_goff, h_goff.size() * 8, cudaMemcpyDeviceToHost, s));
     SIA_CUDA(cudaStreamSynchronize(s));
     const int64_t *h_off_all = h_goff.data(), *h_off_head = h_goff.data() + nq + 1;
-    struct Group { int qa, qb; };
+    // Groups of consecutive queries voted together.  Hash-table vote: the group's tables should stay in L2.
+    // A query with more entries than a packed bin count can hold is voted alone, by sorting.
+    struct Group { int qa, qb; bool sorted; };
     std::vector<Group> groups;
     size_t need = 0;
+    auto too_big = [&](int q) { return h_query_starts[q0 + q + 1] - h_query_starts[q0 + q] > kMaxHashVoteEntries; };
     for (int qa = 0; qa < nq;) {
       int qb = qa + 1;
-      while (qb < nq && h_off_all[qb + 1] - h_off_all[qa] <= tuple_budget) ++qb;
-      groups.push_back({qa, qb});
-      const int64_t t = h_off_all[qb] - h_off_all[qa], h = h_off_head[qb] - h_off_head[qa];
-      need = std::max(need, bins_bytes(t, h) + vote_bytes(t) + (1 << 20));
+      const bool sorted = !use_hash || too_big(qa);
+      while (qb < nq && h_off_all[qb + 1] - h_off_all[qa] <= tuple_budget && !(use_hash && (sorted || too_big(qb)))) ++qb;
+      groups.push_back({qa, qb, sorted});
+      if (sorted) {
+        const int64_t t = h_off_all[qb] - h_off_all[qa], h = h_off_head[qb] - h_off_head[qa];
+        need = std::max(need, bins_bytes(t, h) + vote_bytes(t) + (1 << 20));
+      }
       qa = qb;
     }
-    if (!use_hash) {
-      if ((rc = ix->arena2.reserve(need))) return rc;
-      for (const Group &g : groups) {
-        const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
-        const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa], heads = h_off_head[g.qb] - h_off_head[g.qa];
+    if (need && (rc = ix->arena2.reserve(need))) return rc;
+    // hash-table vote: table layout per group; song tables dense when that is the smaller layout
+    std::vector<QMeta> h_meta(nq);
+    std::vector<char> dense(groups.size(), 0);
+    int64_t max_bin = 0, max_song = 0;
+    const int64_t span = (int64_t)ix->max_song + 1;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      const Group &g = groups[gi];
+      if (g.sorted) continue;
+      int64_t hashed_slots = 0;
+      for (int q = g.qa; q < g.qb; ++q) hashed_slots += 2 * (h_off_head[q + 1] - h_off_head[q]) + 32;
+      dense[gi] = span * (g.qb - g.qa) * 12 <= hashed_slots * 16 * 2;
+      int64_t bb = 0, sb = 0;
+      for (int q = g.qa; q < g.qb; ++q) {
+        const int64_t t = h_off_all[q + 1] - h_off_all[q], h = h_off_head[q + 1] - h_off_head[q];
+        SIA_REQUIRE(t < (1ll << 30), SIA_E_UNSUPPORTED, "query_batch: more than 2^30 vote tuples in one query");
+        h_meta[q].bin_base = bb; h_meta[q].song_base = sb;
+        h_meta[q].bin_cap = (uint32_t)(2 * t + 32);
+        h_meta[q].song_cap = dense[gi] ? (uint32_t)span : (uint32_t)(2 * h + 32);
+        bb += h_meta[q].bin_cap; sb += h_meta[q].song_cap;
+      }
+      max_bin = std::max(max_bin, bb); max_song = std::max(max_song, sb);
+    }
+    unsigned long long *bins = nullptr, *song_best = nullptr, *d_nbins = nullptr;
+    uint32_t *song_key = nullptr, *song_rows = nullptr;
+    QMeta *d_meta = nullptr;
+    if (max_bin > 0) {
+      // one zero-fill per group covers [bins | song_best | song_rows | song_key] up to the group's sizes,
+      // so the arrays are laid out per group: offsets are recomputed below from the group's own totals
+      if ((rc = ix->arena3.reserve((size_t)max_bin * 8 + (size_t)max_song * 16 + (size_t)nq * sizeof(QMeta) + 8192))) return rc;
+      d_meta = ix->arena3.take<QMeta>(nq);
+      d_nbins = ix->arena3.take<unsigned long long>(1);
+      bins = ix->arena3.take<unsigned long long>((size_t)max_bin + 2 * (size_t)max_song);
+      SIA_REQUIRE(d_meta && d_nbins && bins, SIA_E_NOMEM, "index scratch arena too small (vote tables)");
+      SIA_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(QMeta) * nq, cudaMemcpyHostToDevice, s));
+      SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long), s));
+    }
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      const Group &g = groups[gi];
+      const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
+      const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa], heads = h_off_head[g.qb] - h_off_head[g.qa];
+      if (g.sorted) {
         ix->arena2.used = 0;
         uint64_t *bk = nullptr, *rk = nullptr;
         int32_t *bc = nullptr, *rcnt = nullptr;
@@ -1083,61 +1121,31 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
                               d_out_diff, d_out_count, d_out_rows, d_out_nres, s)))
           return rc;
         SIA_CUDA(cudaStreamSynchronize(s));
+        continue;
       }
-      continue;
-    }
-    // hash-table vote: per-query sub-tables, one group's tables live at a time (stream-ordered reuse)
-    std::vector<QMeta> h_meta(nq);
-    int64_t max_bin = 0, max_song = 0;
-    for (const Group &g : groups) {
-      int64_t bb = 0, sb = 0;
-      for (int q = g.qa; q < g.qb; ++q) {
-        const int64_t t = h_off_all[q + 1] - h_off_all[q], h = h_off_head[q + 1] - h_off_head[q];
-        SIA_REQUIRE(t < (1ll << 30), SIA_E_UNSUPPORTED, "query_batch: more than 2^30 vote tuples in one query");
-        h_meta[q].bin_base = bb; h_meta[q].song_base = sb;
-        h_meta[q].bin_cap = (uint32_t)(2 * t + 32); h_meta[q].song_cap = (uint32_t)(2 * h + 32);
-        bb += h_meta[q].bin_cap; sb += h_meta[q].song_cap;
-      }
-      max_bin = std::max(max_bin, bb); max_song = std::max(max_song, sb);
-    }
-    const size_t ff_bytes = (size_t)max_bin * 8 + (size_t)max_song * 4;                 // keys: memset 0xff
-    const size_t zero_bytes = (size_t)max_bin * 4 + (size_t)max_song * 12;              // counts, rows, best: memset 0
-    if ((rc = ix->arena2.reserve(ff_bytes + zero_bytes + (size_t)nq * sizeof(QMeta) + 4096))) return rc;
-    unsigned long long *bin_key = ix->arena2.take<unsigned long long>(max_bin);
-    uint32_t *song_key = ix->arena2.take<uint32_t>(max_song);
-    unsigned long long *song_best = ix->arena2.take<unsigned long long>(max_song);
-    uint32_t *bin_cnt = ix->arena2.take<uint32_t>(max_bin);
-    uint32_t *song_rows = ix->arena2.take<uint32_t>(max_song);
-    QMeta *d_meta = ix->arena2.take<QMeta>(nq);
-    unsigned long long *d_nbins = ix->arena2.take<unsigned long long>(1);
-    SIA_REQUIRE(bin_key && song_key && song_best && bin_cnt && song_rows && d_meta && d_nbins, SIA_E_NOMEM,
-                "index scratch arena too small (vote tables)");
-    SIA_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(QMeta) * nq, cudaMemcpyHostToDevice, s));
-    SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long), s));
-    for (const Group &g : groups) {
-      const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
-      const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa];
+      if (tuples == 0) continue;           // out_nres is already 0 for these queries
       const QMeta &last = h_meta[g.qb - 1];
       const int64_t nb = last.bin_base + last.bin_cap, ns = last.song_base + last.song_cap;
-      if (tuples > 0) {
-        SIA_CUDA(cudaMemsetAsync(bin_key, 0xff, (size_t)nb * 8, s));
-        SIA_CUDA(cudaMemsetAsync(song_key, 0xff, (size_t)ns * 4, s));
-        SIA_CUDA(cudaMemsetAsync(song_best, 0, (size_t)ns * 8, s));
-        SIA_CUDA(cudaMemsetAsync(bin_cnt, 0, (size_t)nb * 4, s));
-        SIA_CUDA(cudaMemsetAsync(song_rows, 0, (size_t)ns * 4, s));
-        expand_vote_kernel<<<(unsigned)ceil_div(ne, 256), 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head,
-                                                                      ix->rows, d_meta, bin_key, bin_cnt, song_key,
-                                                                      song_rows);
-        SIA_CHECK_LAUNCH();
-        bins_to_songs_kernel<<<grid_for(nb), 256, 0, s>>>(bin_key, bin_cnt, nb, d_meta, g.qa, g.qb, song_key, song_best,
-                                                         h_stats ? d_nbins : nullptr);
-        SIA_CHECK_LAUNCH();
-        topn_hash_kernel<<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, d_meta, g.qa, (int)q0, topn,
-                                                     d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
-        SIA_CHECK_LAUNCH();
+      song_best = bins + nb;
+      song_rows = reinterpret_cast<uint32_t *>(song_best + ns);
+      song_key = song_rows + ns;
+      SIA_CUDA(cudaMemsetAsync(bins, 0, (size_t)nb * 8 + (size_t)ns * (dense[gi] ? 12 : 16), s));
+      const unsigned blocks = (unsigned)ceil_div(ne, kVoteChunk);
+      unsigned long long *nbp = h_stats ? d_nbins : nullptr;
+      if (dense[gi]) {
+        expand_vote_kernel<true><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->rows, d_meta,
+                                                        bins, song_key, song_rows, song_best, nbp);
+        topn_hash_kernel<true><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, d_meta, g.qa, (int)q0, topn,
+                                                           d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
+      } else {
+        expand_vote_kernel<false><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->rows, d_meta,
+                                                         bins, song_key, song_rows, song_best, nbp);
+        topn_hash_kernel<false><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, d_meta, g.qa, (int)q0, topn,
+                                                            d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
       }
+      SIA_CHECK_LAUNCH();
     }
-    if (h_stats) {
+    if (h_stats && max_bin > 0) {
       unsigned long long nbv = 0;
       SIA_CUDA(cudaMemcpyAsync(&nbv, d_nbins, sizeof nbv, cudaMemcpyDeviceToHost, s));
       SIA_CUDA(cudaStreamSynchronize(s));

@@ -396,9 +396,12 @@ def test_union_channels_device(fpr):
     assert len(dev_set) == hd.shape[0] < len(batch.t1)                   # duplicates existed and were dropped
 
 
-def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch):
+@pytest.mark.parametrize("id_stride", [1, 50000])
+def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch, id_stride):
     """The hash-table vote (default) and the sort-based vote give identical results — counts, smallest-diff and
-    ascending-song tie-breaks, dedup rows, stats — for any grouping of the queries (recognizer.py:303-310)."""
+    ascending-song tie-breaks, dedup rows, stats — for any grouping of the queries (recognizer.py:303-310).
+    id_stride 1: dense song tables; 50000: song ids up to 1.5e7 -> open-addressing song tables.  One query has
+    more entries than a packed bin count can hold and takes the sort-based vote inside the hash-table pass."""
     import torch
     rng = np.random.default_rng(77)
     nsongs, per_song, universe = 300, 4000, 6000       # ~200 postings per key; offsets in a small range -> many ties
@@ -407,7 +410,7 @@ def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch):
     pool = np.frombuffer(b"".join(hashlib.sha1(str(i).encode()).digest()[:10] for i in range(universe)),
                          np.uint8).reshape(universe, 10)
     dig = pool[keys]
-    song = np.repeat(np.arange(1, nsongs + 1, dtype=np.int32), per_song)
+    song = np.repeat(np.arange(1, nsongs + 1, dtype=np.int32) * id_stride, per_song)
     off = rng.integers(0, 64, n).astype(np.int32)
     db = gpudb(capacity_rows=n + 16)
     ix = db.index
@@ -415,7 +418,7 @@ def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch):
     ix.insert_rows(torch.from_numpy(song).to(dev), torch.from_numpy(dig).to(dev), torch.from_numpy(off).to(dev))
     ix.finalize()
     sizes = rng.integers(0, 400, 120)
-    sizes[3] = 0; sizes[50] = 3000                      # an empty query and a big one
+    sizes[3] = 0; sizes[50] = 3000; sizes[70] = 40000   # an empty query, a big one, one beyond 32767 entries
     qs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     qk = rng.integers(0, universe + 500, qs[-1])        # some absent keys
     pool2 = np.concatenate([pool, rng.integers(0, 256, (500, 10), dtype=np.uint8)])
