@@ -195,19 +195,21 @@ def main():
     sweep = {}
     if world == 1 and args.vote_sweep:
         for setting in args.vote_sweep.split(","):
-            mode, _, budget = setting.partition(":")
-            os.environ["SIA_VOTE"] = mode
-            if budget:
-                os.environ["SIA_VOTE_GROUP_TUPLES"] = budget
-            else:
-                os.environ.pop("SIA_VOTE_GROUP_TUPLES", None)
+            parts = setting.split(":")          # mode[:group tuples[:tuples per block[:bin slots per tuple]]]
+            os.environ["SIA_VOTE"] = parts[0]
+            for name, val in zip(("SIA_VOTE_GROUP_TUPLES", "SIA_VOTE_CHUNK", "SIA_VOTE_LOAD"), parts[1:] + [""] * 3):
+                if val:
+                    os.environ[name] = val
+                else:
+                    os.environ.pop(name, None)
             step(); torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 step()
             torch.cuda.synchronize()
             sweep[setting] = round((time.perf_counter() - t0) / args.steps * 1e3, 2)
-        os.environ.pop("SIA_VOTE", None); os.environ.pop("SIA_VOTE_GROUP_TUPLES", None)
+        for name in ("SIA_VOTE", "SIA_VOTE_GROUP_TUPLES", "SIA_VOTE_CHUNK", "SIA_VOTE_LOAD"):
+            os.environ.pop(name, None)
 
     if rank == 0:
         line = {

@@ -455,7 +455,7 @@ struct QMeta {
 constexpr int kBinCountBits = 15;
 constexpr int64_t kMaxHashVoteEntries = (1 << kBinCountBits) - 1;
 constexpr int kTopK = 4;          // results extracted per scan of a query's song table
-constexpr int kVoteChunk = 64;    // entries per block of expand_vote_kernel
+constexpr int kVoteTuplesDefault = 2048; // vote tuples per block of expand_vote_kernel
 
 __device__ __forceinline__ uint32_t mix32(uint32_t k) {
   k ^= k >> 16; k *= 0x85ebca6bu; k ^= k >> 13; k *= 0xc2b2ae35u; k ^= k >> 16;
@@ -463,7 +463,47 @@ __device__ __forceinline__ uint32_t mix32(uint32_t k) {
 }
 __device__ __forceinline__ uint32_t slot_of(uint32_t h, uint32_t cap) { return (uint32_t)(((uint64_t)h * cap) >> 32); }
 
-// One block handles kVoteChunk consecutive entries and spreads their postings evenly over its threads.
+// song slot of `song` in query m's song table (dense: the id itself; else find-or-insert by open addressing)
+template <bool DENSE>
+__device__ __forceinline__ int64_t song_slot(const QMeta &m, uint32_t song, uint32_t *__restrict__ song_key) {
+  if (DENSE) return m.song_base + song;
+  uint32_t t = slot_of(mix32(song), m.song_cap);
+  for (;;) {
+    const uint32_t old = atomicCAS(&song_key[m.song_base + t], 0u, song + 1u);
+    if (old == 0u || old == song + 1u) break;
+    if (++t == m.song_cap) t = 0;
+  }
+  return m.song_base + t;
+}
+
+// one vote tuple (song, biased diff) of query m: count its bin, keep the song's best current; returns the song slot
+template <bool DENSE>
+__device__ __forceinline__ int64_t vote_insert(const QMeta &m, uint32_t song, uint32_t dbits,
+                                               unsigned long long *__restrict__ bins, uint32_t *__restrict__ song_key,
+                                               unsigned long long *__restrict__ song_best, uint32_t &fresh,
+                                               int32_t *__restrict__ overflow) {
+  const unsigned long long key = ((unsigned long long)song << kDiffBits) | dbits;
+  uint32_t s = slot_of(mix32(song * 0x9e3779b1u + dbits), m.bin_cap);
+  unsigned long long count;
+  for (;;) {
+    unsigned long long *p = bins + m.bin_base + s;
+    const unsigned long long old = atomicCAS(p, 0ull, (key << kBinCountBits) | 1ull);
+    if (old == 0ull) { count = 1; ++fresh; break; }
+    if ((old >> kBinCountBits) == key) {
+      count = (atomicAdd(p, 1ull) & ((1ull << kBinCountBits) - 1)) + 1;
+      if (overflow && count == (1ull << kBinCountBits)) atomicOr(overflow, 1);   // the count field wrapped: redo by sorting
+      break;
+    }
+    if (++s == m.bin_cap) s = 0;
+  }
+  const int64_t ss = song_slot<DENSE>(m, song, song_key);
+  const unsigned long long inv = ((1ull << kDiffBits) - 1) - dbits;
+  atomicMax(&song_best[ss], (count << kDiffBits) | inv);
+  return ss;
+}
+
+// One block handles tuples_per_block consecutive vote tuples (postings of the entries [e0, e0+n), numbered by the
+// exclusive scan off[]), whatever entries they belong to: a heavy key's run is shared by many blocks.
 template <bool DENSE>
 __global__ void __launch_bounds__(256)
 expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, const uint32_t *__restrict__ first,
@@ -471,54 +511,134 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
                    const ulonglong2 *__restrict__ rows, const QMeta *__restrict__ meta,
                    unsigned long long *__restrict__ bins, uint32_t *__restrict__ song_key,
                    uint32_t *__restrict__ song_rows, unsigned long long *__restrict__ song_best,
-                   unsigned long long *__restrict__ n_bins) {
-  __shared__ int64_t s_off[kVoteChunk + 1];
-  const int64_t b0 = e0 + (int64_t)blockIdx.x * kVoteChunk;
-  const int nloc = (int)min((int64_t)kVoteChunk, e0 + n - b0);
-  if (threadIdx.x <= nloc) s_off[threadIdx.x] = off[b0 + threadIdx.x];
+                   unsigned long long *__restrict__ n_bins, int tuples_per_block) {
+  __shared__ int64_t s_off[257];
+  __shared__ int64_t s_first;
+  const int64_t j_lo = off[e0] + (int64_t)blockIdx.x * tuples_per_block;
+  const int64_t j_hi = min(off[e0 + n], j_lo + tuples_per_block);
+  if (threadIdx.x == 0) {                // largest entry e in [e0, e0+n) with off[e] <= j_lo
+    int64_t lo = e0, hi = e0 + n;
+    while (hi - lo > 1) { const int64_t mid = lo + ((hi - lo) >> 1); if (off[mid] <= j_lo) lo = mid; else hi = mid; }
+    s_first = lo;
+  }
   __syncthreads();
-  const int64_t base = s_off[0], total = s_off[nloc] - base;
   uint32_t fresh = 0;
-  for (int64_t j = threadIdx.x; j < total; j += 256) {
-    int lo = 0, hi = nloc;               // largest e with s_off[e] - base <= j
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] - base <= j) lo = mid; else hi = mid; }
+  for (int64_t b0 = s_first; b0 < e0 + n; b0 += 256) {      // pieces of 256 entries until the block's tuples are covered
+    const int nloc = (int)min((int64_t)256, e0 + n - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nloc; i += 256) s_off[i] = off[b0 + i];
+    __syncthreads();
+    const int64_t p_lo = max(j_lo, s_off[0]), p_hi = min(j_hi, s_off[nloc]);
+    // warp-uniform trip count; the warp reconverges at the top of every iteration (the probe loops below diverge)
+    for (int64_t jw = p_lo + (threadIdx.x & ~31); jw < p_hi; jw += 256) {
+    __syncwarp();
+    const int64_t j = jw + (threadIdx.x & 31);
+    int lo = 0, hi = nloc;               // largest e with s_off[e] <= jw (same for the whole warp)
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= jw) lo = mid; else hi = mid; }
+    if (j >= p_hi) continue;
+    while (s_off[lo + 1] <= j) ++lo;     // a warp's 32 consecutive tuples rarely span more than two entries
     const int64_t ei = b0 + lo;
-    const uint32_t k = (uint32_t)(j - (s_off[lo] - base));
+    const uint32_t k = (uint32_t)(j - s_off[lo]);
     const ulonglong2 e = ent[ei];
     const ulonglong2 r = rows[first[ei] + k];
     const QMeta m = meta[e.y >> 40];
     const uint32_t song = (uint32_t)(r.x >> 24) & 0xffffffu;
     const uint32_t dbits = (uint32_t)((int32_t)(r.x & kM24) - (int32_t)(e.x & kM24) + SIA_DIFF_BIAS);   // db - query offset
-    const unsigned long long key = ((unsigned long long)song << kDiffBits) | dbits;
-    uint32_t s = slot_of(mix32(song * 0x9e3779b1u + dbits), m.bin_cap);
-    unsigned long long count;
-    for (;;) {
-      unsigned long long *p = bins + m.bin_base + s;
-      const unsigned long long old = atomicCAS(p, 0ull, (key << kBinCountBits) | 1ull);
-      if (old == 0ull) { count = 1; ++fresh; break; }
-      if ((old >> kBinCountBits) == key) { count = (atomicAdd(p, 1ull) & ((1ull << kBinCountBits) - 1)) + 1; break; }
-      if (++s == m.bin_cap) s = 0;
-    }
-    int64_t ss;
-    if (DENSE) {
-      ss = m.song_base + song;
-    } else {
-      uint32_t t = slot_of(mix32(song), m.song_cap);
-      for (;;) {
-        const uint32_t old = atomicCAS(&song_key[m.song_base + t], 0u, song + 1u);
-        if (old == 0u || old == song + 1u) break;
-        if (++t == m.song_cap) t = 0;
-      }
-      ss = m.song_base + t;
-    }
-    const unsigned long long inv = ((1ull << kDiffBits) - 1) - dbits;
-    atomicMax(&song_best[ss], (count << kDiffBits) | inv);
+    const int64_t ss = vote_insert<DENSE>(m, song, dbits, bins, song_key, song_best, fresh, nullptr);
     if (cnt_head[ei]) atomicAdd(&song_rows[ss], 1u);    // first entry of its (query, hash): the row counts once
+    }
+    if (s_off[nloc] >= j_hi) break;      // uniform: every thread reads the same shared value
   }
   if (n_bins) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
     if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(n_bins, (unsigned long long)fresh);
+  }
+}
+
+// ---- hash-table vote of exchanged vote keys (sia_vote_tuples) --------------------------------
+// keys: query (15) | song (24) | biased diff (25); row keys carry no diff.  Per-query sizes are counted on the
+// device, the table layout (QMeta) is built there too; only the largest song id travels to the host.
+__global__ void __launch_bounds__(256)
+count_keys_kernel(const uint64_t *__restrict__ key, int64_t n, int nq, uint32_t *__restrict__ cnt, int32_t *__restrict__ info) {
+  int32_t smax = 0;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    const bool valid = i < n;
+    const uint64_t k = valid ? key[i] : 0;
+    const uint32_t q = (uint32_t)(k >> (kSongBits + kDiffBits));
+    if (valid && q >= (uint32_t)nq) atomicOr(info + 1, 2);
+    smax = max(smax, (int32_t)((k >> kDiffBits) & kM24));
+    const uint32_t active = __ballot_sync(0xffffffffu, valid && q < (uint32_t)nq);
+    if (valid && q < (uint32_t)nq) {       // keys arrive grouped by query: one atomic per run inside the warp
+      const uint32_t peers = __match_any_sync(active, q);
+      if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&cnt[q], (uint32_t)__popc(peers));
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, d));
+  if ((threadIdx.x & 31) == 0 && smax > 0) atomicMax(info, smax);
+}
+
+// single block: exclusive scans of the per-query table sizes -> QMeta
+__global__ void __launch_bounds__(1024)
+build_meta_kernel(const uint32_t *__restrict__ cnt_t, const uint32_t *__restrict__ cnt_r, int nq, int mult, int64_t dense_span,
+                  QMeta *__restrict__ meta, int32_t *__restrict__ info) {
+  __shared__ int64_t s_b[1024], s_s[1024];
+  const int per = (nq + 1023) / 1024;
+  const int a = min(nq, (int)threadIdx.x * per), b = min(nq, a + per);
+  int64_t sb = 0, ss = 0;
+  for (int q = a; q < b; ++q) {
+    if ((uint64_t)mult * cnt_t[q] + 32 > 0xffffffffull) atomicOr(info + 1, 4);
+    sb += (int64_t)mult * cnt_t[q] + 32;
+    ss += dense_span > 0 ? dense_span : 2 * (int64_t)cnt_r[q] + 32;
+  }
+  s_b[threadIdx.x] = sb; s_s[threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t rb = 0, rs = 0;
+    for (int i = 0; i < 1024; ++i) { const int64_t x = s_b[i], y = s_s[i]; s_b[i] = rb; s_s[i] = rs; rb += x; rs += y; }
+  }
+  __syncthreads();
+  sb = s_b[threadIdx.x]; ss = s_s[threadIdx.x];
+  for (int q = a; q < b; ++q) {
+    QMeta m;
+    m.bin_base = sb; m.song_base = ss;
+    m.bin_cap = (uint32_t)((int64_t)mult * cnt_t[q] + 32);
+    m.song_cap = dense_span > 0 ? (uint32_t)dense_span : 2 * cnt_r[q] + 32;
+    meta[q] = m;
+    sb += m.bin_cap; ss += m.song_cap;
+  }
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(256)
+vote_keys_kernel(const uint64_t *__restrict__ key, int64_t n, const QMeta *__restrict__ meta,
+                 unsigned long long *__restrict__ bins, uint32_t *__restrict__ song_key,
+                 unsigned long long *__restrict__ song_best, int32_t *__restrict__ info) {
+  uint32_t fresh = 0;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+    __syncwarp();
+    const int64_t i = i0 + threadIdx.x;
+    if (i >= n) continue;
+    const uint64_t k = key[i];
+    const QMeta m = meta[k >> (kSongBits + kDiffBits)];
+    vote_insert<DENSE>(m, (uint32_t)(k >> kDiffBits) & 0xffffffu, (uint32_t)k & ((1u << kDiffBits) - 1u), bins, song_key,
+                       song_best, fresh, info + 1);
+  }
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(256)
+row_keys_kernel(const uint64_t *__restrict__ key, int64_t n, const QMeta *__restrict__ meta,
+                uint32_t *__restrict__ song_key, uint32_t *__restrict__ song_rows) {
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+    __syncwarp();
+    const int64_t i = i0 + threadIdx.x;
+    if (i >= n) continue;
+    const uint64_t k = key[i];
+    const QMeta m = meta[k >> (kSongBits + kDiffBits)];
+    atomicAdd(&song_rows[song_slot<DENSE>(m, (uint32_t)(k >> kDiffBits) & 0xffffffu, song_key)], 1u);
   }
 }
 
@@ -749,6 +869,61 @@ int check_status(sia_index *ix, cudaStream_t s, int mask, const char *msg) {
 }
 
 }  // namespace
+
+// hash-table vote of concatenated vote keys; SIA_E_UNSUPPORTED = fall back to the sort-based vote
+static Arena g_vote_tables[64];
+static int vote_tuples_hash(int device, const uint64_t *d_tuple_key, int64_t n_tuples, const uint64_t *d_row_key,
+                            int64_t n_rows, int32_t n_queries, int32_t topn, int32_t *d_out_song, int32_t *d_out_diff,
+                            int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres, cudaStream_t s) {
+  const int mult = 2;
+  if ((int64_t)mult * n_tuples + 32 > 0xffffffffll) return SIA_E_UNSUPPORTED;      // per-query slot ranges are 32 bit
+  Arena &ar = g_vote_tables[device];
+  // sizes that need no device round trip: bins; the hashed song layout is the fallback if dense is larger
+  const int64_t nb = (int64_t)mult * n_tuples + 32ll * n_queries;
+  const int64_t ns_hashed = 2 * n_rows + 32ll * n_queries;
+  const size_t small = (size_t)n_queries * (8 + sizeof(QMeta)) + 4096;
+  int rc = ar.reserve(small + (size_t)nb * 8 + (size_t)ns_hashed * 16 + 4096);
+  if (rc) return rc;
+  uint32_t *cnt = ar.take<uint32_t>(2 * (size_t)n_queries);
+  int32_t *info = ar.take<int32_t>(2);                      // [0] largest song id, [1] flags
+  QMeta *meta = ar.take<QMeta>(n_queries);
+  unsigned long long *bins = ar.take<unsigned long long>((size_t)nb + 2 * (size_t)ns_hashed);
+  SIA_REQUIRE(cnt && info && meta && bins, SIA_E_NOMEM, "vote_tuples: scratch");
+  SIA_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * 2 * n_queries, s));
+  SIA_CUDA(cudaMemsetAsync(info, 0, 2 * sizeof(int32_t), s));
+  SIA_CUDA(cudaMemsetAsync(d_out_nres, 0, sizeof(int32_t) * n_queries, s));
+  if (n_tuples) count_keys_kernel<<<grid_for(n_tuples), 256, 0, s>>>(d_tuple_key, n_tuples, n_queries, cnt, info);
+  if (n_rows) count_keys_kernel<<<grid_for(n_rows), 256, 0, s>>>(d_row_key, n_rows, n_queries, cnt + n_queries, info);
+  SIA_CHECK_LAUNCH();
+  int32_t h_info[2] = {0, 0};
+  SIA_CUDA(cudaMemcpyAsync(h_info, info, sizeof h_info, cudaMemcpyDeviceToHost, s));
+  SIA_CUDA(cudaStreamSynchronize(s));
+  SIA_REQUIRE(!(h_info[1] & 2), SIA_E_INVALID, "vote_tuples: query id outside 0..n_queries-1");
+  const int64_t span = (int64_t)h_info[0] + 1;
+  const bool dense = span * n_queries * 12 <= ns_hashed * 16;    // dense must fit where the hashed layout would
+  const int64_t ns = dense ? span * n_queries : ns_hashed;
+  unsigned long long *song_best = bins + nb;
+  uint32_t *song_rows = reinterpret_cast<uint32_t *>(song_best + ns);
+  uint32_t *song_key = song_rows + ns;
+  build_meta_kernel<<<1, 1024, 0, s>>>(cnt, cnt + n_queries, n_queries, mult, dense ? span : 0, meta, info);
+  SIA_CUDA(cudaMemsetAsync(bins, 0, (size_t)nb * 8 + (size_t)ns * (dense ? 12 : 16), s));
+  if (dense) {
+    if (n_tuples) vote_keys_kernel<true><<<grid_for(n_tuples), 256, 0, s>>>(d_tuple_key, n_tuples, meta, bins, song_key, song_best, info);
+    if (n_rows) row_keys_kernel<true><<<grid_for(n_rows), 256, 0, s>>>(d_row_key, n_rows, meta, song_key, song_rows);
+    topn_hash_kernel<true><<<n_queries, 256, 0, s>>>(song_key, song_rows, song_best, meta, 0, 0, topn, d_out_song, d_out_diff,
+                                                     d_out_count, d_out_rows, d_out_nres);
+  } else {
+    if (n_tuples) vote_keys_kernel<false><<<grid_for(n_tuples), 256, 0, s>>>(d_tuple_key, n_tuples, meta, bins, song_key, song_best, info);
+    if (n_rows) row_keys_kernel<false><<<grid_for(n_rows), 256, 0, s>>>(d_row_key, n_rows, meta, song_key, song_rows);
+    topn_hash_kernel<false><<<n_queries, 256, 0, s>>>(song_key, song_rows, song_best, meta, 0, 0, topn, d_out_song, d_out_diff,
+                                                      d_out_count, d_out_rows, d_out_nres);
+  }
+  SIA_CHECK_LAUNCH();
+  SIA_CUDA(cudaMemcpyAsync(h_info, info, sizeof h_info, cudaMemcpyDeviceToHost, s));
+  SIA_CUDA(cudaStreamSynchronize(s));
+  if (h_info[1] & (1 | 4)) return SIA_E_UNSUPPORTED;
+  return SIA_OK;
+}
 
 extern "C" {
 
@@ -1025,8 +1200,10 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
   // (read per call, so a test can run both paths in one process)
   const bool use_hash = !(getenv("SIA_VOTE") && std::string(getenv("SIA_VOTE")) == "sort");
   const int64_t hash_budget = getenv("SIA_VOTE_GROUP_TUPLES") ? std::max(1ll, atoll(getenv("SIA_VOTE_GROUP_TUPLES")))
-                                                               : (4ll << 20);
-  // tuples voted at once: sort path x ~70 B of scratch each; hash path x ~16 B of tables, sized to stay in L2
+                                                               : (512ll << 20);
+  const int vote_chunk = getenv("SIA_VOTE_CHUNK") ? std::max(256, atoi(getenv("SIA_VOTE_CHUNK"))) : kVoteTuplesDefault;
+  const int vote_mult = getenv("SIA_VOTE_LOAD") ? std::min(16, std::max(2, atoi(getenv("SIA_VOTE_LOAD")))) : 2;   // bin slots per tuple
+  // tuples voted at once: sort path x ~70 B of scratch each; hash path x ~16 B of tables, one launch per group
   const int64_t tuple_budget = use_hash ? hash_budget : (96ll << 20);
   for (int64_t q0 = 0; q0 < n_queries; q0 += kMaxQueriesPerPass) {
     const int nq = (int)std::min<int64_t>(kMaxQueriesPerPass, n_queries - q0);
@@ -1038,8 +1215,12 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     int64_t *d_goff = ix->arena.take<int64_t>(2 * (size_t)(nq + 1));
     SIA_CUDA(cudaMemcpyAsync(d_qs, h_query_starts + q0, sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, s));
     Lookup L;
+    const bool timing = getenv("SIA_QUERY_TIMING") != nullptr;     // stage times of this pass on stderr
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (timing) { for (auto &e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
     if ((rc = lookup_pass(ix, ix->arena, d_hash, d_qoff, nullptr, d_qs, nq, 0, i0, n, L, s))) return rc;
     if ((rc = check_status(ix, s, 2, "query: offset outside 0..2^24-1"))) return rc;
+    if (timing) cudaEventRecord(ev[1], s);
     if (h_stats) { h_stats[1] += L.head_rows; h_stats[2] += L.tuples; }
     // After the sort query q still owns entries [starts[q]-i0, starts[q+1]-i0) (duplicates stay, with no
     // postings), so the scanned offsets at those positions split the pass into groups that fit the budget.
@@ -1083,7 +1264,7 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
         const int64_t t = h_off_all[q + 1] - h_off_all[q], h = h_off_head[q + 1] - h_off_head[q];
         SIA_REQUIRE(t < (1ll << 30), SIA_E_UNSUPPORTED, "query_batch: more than 2^30 vote tuples in one query");
         h_meta[q].bin_base = bb; h_meta[q].song_base = sb;
-        h_meta[q].bin_cap = (uint32_t)(2 * t + 32);
+        h_meta[q].bin_cap = (uint32_t)(std::min<int64_t>(vote_mult, 0xffffff00ll / std::max<int64_t>(t, 1)) * t + 32);
         h_meta[q].song_cap = dense[gi] ? (uint32_t)span : (uint32_t)(2 * h + 32);
         bb += h_meta[q].bin_cap; sb += h_meta[q].song_cap;
       }
@@ -1130,16 +1311,16 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
       song_rows = reinterpret_cast<uint32_t *>(song_best + ns);
       song_key = song_rows + ns;
       SIA_CUDA(cudaMemsetAsync(bins, 0, (size_t)nb * 8 + (size_t)ns * (dense[gi] ? 12 : 16), s));
-      const unsigned blocks = (unsigned)ceil_div(ne, kVoteChunk);
+      const unsigned blocks = (unsigned)ceil_div(tuples, vote_chunk);
       unsigned long long *nbp = h_stats ? d_nbins : nullptr;
       if (dense[gi]) {
         expand_vote_kernel<true><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->rows, d_meta,
-                                                        bins, song_key, song_rows, song_best, nbp);
+                                                        bins, song_key, song_rows, song_best, nbp, vote_chunk);
         topn_hash_kernel<true><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, d_meta, g.qa, (int)q0, topn,
                                                            d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
       } else {
         expand_vote_kernel<false><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->rows, d_meta,
-                                                         bins, song_key, song_rows, song_best, nbp);
+                                                         bins, song_key, song_rows, song_best, nbp, vote_chunk);
         topn_hash_kernel<false><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, d_meta, g.qa, (int)q0, topn,
                                                             d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
       }
@@ -1151,7 +1332,15 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
       SIA_CUDA(cudaStreamSynchronize(s));
       h_stats[3] += (int64_t)nbv;
     }
+    if (timing) cudaEventRecord(ev[2], s);
     SIA_CUDA(cudaStreamSynchronize(s));      // the lookup scratch and the tables are reused by the next pass / call
+    if (timing) {
+      float t_lookup = 0, t_vote = 0;
+      cudaEventElapsedTime(&t_lookup, ev[0], ev[1]); cudaEventElapsedTime(&t_vote, ev[1], ev[2]);
+      fprintf(stderr, "[sia] query pass: %d queries, %lld entries, %lld tuples, %zu groups: lookup %.2f ms, vote %.2f ms\n",
+              nq, (long long)n, (long long)L.tuples, groups.size(), t_lookup, t_vote);
+      for (auto &e : ev) cudaEventDestroy(e);
+    }
   }
   return SIA_OK;
 }
@@ -1309,6 +1498,13 @@ int sia_vote_tuples(int device, uint64_t *d_tuple_key, int64_t n_tuples, uint64_
   SIA_CUDA(cudaSetDevice(device));
   SIA_REQUIRE(device >= 0 && device < 64, SIA_E_INVALID, "device index");
   cudaStream_t s = (cudaStream_t)stream;
+  if (!(getenv("SIA_VOTE") && std::string(getenv("SIA_VOTE")) == "sort")) {
+    const int rc_hash = vote_tuples_hash(device, d_tuple_key, n_tuples, d_row_key, n_rows, n_queries, topn, d_out_song,
+                                         d_out_diff, d_out_count, d_out_rows, d_out_nres, s);
+    if (rc_hash != SIA_E_UNSUPPORTED) return rc_hash;      // else: a bin count beyond 15 bits -> the sort-based vote
+    for (int32_t *o : {d_out_song, d_out_diff, d_out_count, d_out_rows})
+      SIA_CUDA(cudaMemsetAsync(o, 0, sizeof(int32_t) * (size_t)n_queries * topn, s));
+  }
   Arena &ar = g_vote_arena[device];
   int rc = ar.reserve((size_t)(n_tuples + n_rows) * 8 + radix_sort_tmp_bytes(n_tuples) + radix_sort_tmp_bytes(n_rows) +
                       reduce_runs_bytes(n_tuples) + reduce_runs_bytes(n_rows) + vote_bytes(n_tuples) + (1 << 20));

@@ -412,6 +412,12 @@ def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch, id_stride):
     dig = pool[keys]
     song = np.repeat(np.arange(1, nsongs + 1, dtype=np.int32) * id_stride, per_song)
     off = rng.integers(0, 64, n).astype(np.int32)
+    # one more song whose 33000 rows all align with query 70 at the same difference: a bin count beyond 15 bits
+    n_big = 33000
+    big = np.frombuffer(b"".join(hashlib.sha1(b"big%d" % i).digest()[:10] for i in range(n_big)), np.uint8).reshape(n_big, 10)
+    dig = np.concatenate([dig, big]); song = np.concatenate([song, np.full(n_big, (nsongs + 1) * id_stride, np.int32)])
+    off = np.concatenate([off, (np.arange(n_big) % 3000 + 16).astype(np.int32)])
+    n += n_big
     db = gpudb(capacity_rows=n + 16)
     ix = db.index
     dev = ix.tdev
@@ -422,8 +428,14 @@ def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch, id_stride):
     qs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     qk = rng.integers(0, universe + 500, qs[-1])        # some absent keys
     pool2 = np.concatenate([pool, rng.integers(0, 256, (500, 10), dtype=np.uint8)])
-    qd = torch.from_numpy(pool2[qk]).to(dev)
-    qo = torch.from_numpy(rng.integers(0, 16, qs[-1]).astype(np.int32)).to(dev)
+    qd_h = pool2[qk]
+    qo_h = rng.integers(0, 16, qs[-1]).astype(np.int32)
+    qd_h[qs[70]:qs[70] + n_big] = big
+    qo_h[qs[70]:qs[70] + n_big] = np.arange(n_big) % 3000
+    qd = torch.from_numpy(qd_h).to(dev)
+    qo = torch.from_numpy(qo_h).to(dev)
+    qid = torch.from_numpy(np.repeat(np.arange(len(sizes), dtype=np.int32), sizes)).to(dev)
+    from shazam_b200.database import vote_tuples
 
     def run(topn):
         out = ix.query_batch(qd, qo, qs, topn, want_stats=True)
@@ -433,7 +445,18 @@ def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch, id_stride):
         monkeypatch.setenv("SIA_VOTE", "sort")
         want, want_stats = run(topn)
         assert want[4].max() == topn and want_stats[2] > 1_000_000
+        assert want[2][70, 0] == n_big and want[0][70, 0] == (nsongs + 1) * id_stride and want[1][70, 0] == 16
         monkeypatch.delenv("SIA_VOTE")
+        # the exchanged-keys vote (hash-prefix sharding): overflowing bin count -> falls back to sorting, same answer;
+        # without query 70 it stays on the hash tables
+        for drop70 in (False, True):
+            keep = (qid != 70) if drop70 else torch.ones_like(qid, dtype=torch.bool)
+            tk, rk, _, _ = ix.expand(qd[keep], qo[keep], qid[keep], len(sizes))
+            got = [t.cpu().numpy() for t in vote_tuples(0, tk, rk, len(sizes), topn)]
+            for a, b, name in zip(got, want, ("song", "diff", "count", "rows", "nres")):
+                if drop70:
+                    a = np.delete(a, 70, axis=0); b = np.delete(b, 70, axis=0)
+                assert np.array_equal(a, b), ("vote_tuples", drop70, name, topn)
         for budget in (None, "1000", "200000", str(1 << 40)):
             if budget is None:
                 monkeypatch.delenv("SIA_VOTE_GROUP_TUPLES", raising=False)
