@@ -1204,7 +1204,12 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
   const int vote_chunk = getenv("SIA_VOTE_CHUNK") ? std::max(256, atoi(getenv("SIA_VOTE_CHUNK"))) : kVoteTuplesDefault;
   const int vote_mult = getenv("SIA_VOTE_LOAD") ? std::min(16, std::max(2, atoi(getenv("SIA_VOTE_LOAD")))) : 2;   // bin slots per tuple
   // tuples voted at once: sort path x ~70 B of scratch each; hash path x ~16 B of tables, one launch per group
-  const int64_t tuple_budget = use_hash ? hash_budget : (96ll << 20);
+  int64_t tuple_budget = use_hash ? hash_budget : (96ll << 20);
+  if (use_hash) {                            // never ask for more than ~60 % of what the device has left (+ what arena3 holds)
+    size_t free_b = 0, total_b = 0;
+    SIA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    tuple_budget = std::max<int64_t>(1 << 20, std::min<int64_t>(tuple_budget, (int64_t)((free_b + ix->arena3.cap) * 0.6 / 20)));
+  }
   for (int64_t q0 = 0; q0 < n_queries; q0 += kMaxQueriesPerPass) {
     const int nq = (int)std::min<int64_t>(kMaxQueriesPerPass, n_queries - q0);
     const int64_t i0 = h_query_starts[q0], n = h_query_starts[q0 + nq] - i0;
