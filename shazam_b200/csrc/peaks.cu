@@ -24,6 +24,8 @@
 
 #include <math.h>
 #include <math_constants.h>
+#include <cstdlib>
+#include <string>
 
 namespace sia {
 
@@ -302,6 +304,132 @@ int launch_square_warp(const PeaksLaunch &a, cudaStream_t s) {
   return SIA_OK;
 }
 
+// ---- production path v2: candidate pruning (float32, square 21x21, amp_min >= 0) ---------------------------
+// A peak is the maximum of its 21x21 window, so it is also the maximum of any block of elements that lies inside
+// that window — in particular of the aligned 8-frame x 4-bin block that contains it.  One CTA stages a
+// 64-frame x 128-bin tile plus halo (88 x 152 floats, cp.async, zero fill outside the track / the 2049 bins:
+// with amp_min >= 0 a zero can neither exceed nor equal a candidate) and then
+//   P1  takes the maximum of every 8x4 block (one thread per block: 8 conflict-free 128-bit loads, 31 max);
+//   P2  visits only blocks whose maximum exceeds amp_min: the elements equal to the block maximum are the
+//       candidates.  A candidate is checked against the maxima of the ~24 blocks its window touches: a block
+//       entirely inside the window with a larger maximum rejects it at once, a partially covered one has the
+//       covered elements compared one by one, everything else is skipped.  Ties keep every tied element
+//       (maximum_filter(A) == A, __init__.py:143).
+// Cost is ~1 instruction per element plus work proportional to the number of block maxima above the
+// threshold, instead of a full separable max filter over every element.  Plain bitmap layout.
+constexpr int kP_Rows = kPeakTileT;                  // 64 output frames
+constexpr int kP_Cols = 128;                         // output bins (the last strip also owns bin 2048)
+constexpr int kP_Strips = (SIA_NBINS - 1) / kP_Cols; // 16
+constexpr int kP_TileRows = 88;                      // 10 + 64 + 10, rounded up to a multiple of 8
+constexpr int kP_C4 = 38;                            // float4 columns: 12 + 129 + 10 -> 152 floats
+constexpr int kP_TileCols = 4 * kP_C4;
+constexpr int kP_BlockRows = kP_TileRows / 8;        // 11
+constexpr int kP_Blocks = kP_BlockRows * kP_C4;      // 418 blocks of 8 x 4
+constexpr int kP_Threads = 256;
+static_assert(SIA_NBINS == kP_Strips * kP_Cols + 1, "strip layout assumes 2049 bins");
+
+__global__ void __launch_bounds__(kP_Threads, 3)
+peaks_square_prune_kernel(const float *__restrict__ spec, const int64_t *__restrict__ frame_starts,
+                          const int64_t *__restrict__ ttile_starts, int n_tracks, float amp_lo,
+                          uint32_t *__restrict__ bitmap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];       // 53 504 B tile + block maxima + tile bitmap
+  float4 *A4 = reinterpret_cast<float4 *>(smem_raw);
+  float *Bm = reinterpret_cast<float *>(A4 + kP_TileRows * kP_C4);
+  uint32_t *sbits = reinterpret_cast<uint32_t *>(Bm + kP_Blocks + 2);
+  const float *A = reinterpret_cast<const float *>(A4);
+  const int64_t tt = blockIdx.x / kP_Strips;
+  const int strip = (int)(blockIdx.x - tt * kP_Strips);
+  const int f0 = strip * kP_Cols;
+  const int ncols = strip == kP_Strips - 1 ? kP_Cols + 1 : kP_Cols;
+  const int trk = find_segment(ttile_starts, n_tracks, tt);
+  const int64_t row_lo = frame_starts[trk], row_hi = frame_starts[trk + 1];
+  const int64_t r0 = row_lo + (tt - ttile_starts[trk]) * kP_Rows;
+  const int nvalid = (int)min((int64_t)kP_Rows, row_hi - r0);       // output frames of this tile inside the track
+
+  const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(A4);
+  if (threadIdx.x < 6 * kP_C4) {                        // 228 loader threads: fixed column, rows rs, rs+6, ...
+    const int j = threadIdx.x % kP_C4, rs = threadIdx.x / kP_C4;
+    const int f = f0 - 12 + 4 * j;
+    // bin 2048 shares its float4 with the (unwritten) row padding: copy 4 bytes, zero-fill the rest
+    const int col_bytes = f < 0 || f >= SIA_NBINS ? 0 : (f == SIA_NBINS - 1 ? 4 : 16);
+    int64_t g = r0 - 10 + rs;
+    const float *gp = spec + g * SIA_F_STRIDE + f;
+    uint32_t sa = a_base + (uint32_t)(rs * kP_C4 + j) * 16u;
+#pragma unroll 5
+    for (int r = rs; r < kP_TileRows; r += 6, g += 6, gp += 6 * SIA_F_STRIDE, sa += 6 * kP_C4 * 16) {
+      const int nbytes = g >= row_lo && g < row_hi ? col_bytes : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(nbytes ? gp : spec), "r"(nbytes));
+    }
+  }
+  for (int i = threadIdx.x; i < kP_Rows * 5; i += kP_Threads) sbits[i] = 0;
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
+
+  // P1: block maxima
+  for (int b = threadIdx.x; b < kP_Blocks; b += kP_Threads) {
+    const int br = b / kP_C4, c4 = b - br * kP_C4;
+    float m = 0.f;                                        // every candidate is > amp_min >= 0
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 v = A4[(8 * br + k) * kP_C4 + c4];
+      m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    Bm[b] = m;
+  }
+  __syncthreads();
+
+  // P2: candidates of the blocks above the threshold
+  for (int b = threadIdx.x; b < kP_Blocks; b += kP_Threads) {
+    const float m = Bm[b];
+    if (!(m > amp_lo)) continue;
+    const int br = b / kP_C4, c4 = b - br * kP_C4;
+    // block rows / columns inside the output region of this tile
+    const int ra = max(8 * br, 10), rb = min(8 * br + 7, 10 + nvalid - 1);
+    const int ca = max(4 * c4, 12), cb = min(4 * c4 + 3, 12 + ncols - 1);
+    if (ra > rb || ca > cb) continue;
+    for (int rt = ra; rt <= rb; ++rt) {
+      for (int ct = ca; ct <= cb; ++ct) {
+        if (A[rt * kP_TileCols + ct] != m) continue;
+        // candidate (rt, ct) with value m: compare with the blocks its window [rt-10, rt+10] x [ct-10, ct+10] touches
+        const int wr0 = rt - 10, wr1 = rt + 10, wc0 = ct - 10, wc1 = ct + 10;
+        bool peak = true;
+        for (int bR = wr0 >> 3; bR <= (wr1 >> 3) && peak; ++bR) {
+          const int rr0 = max(wr0, 8 * bR), rr1 = min(wr1, 8 * bR + 7);
+          for (int bC = wc0 >> 2; bC <= (wc1 >> 2) && peak; ++bC) {
+            if (!(Bm[bR * kP_C4 + bC] > m)) continue;
+            const int cc0 = max(wc0, 4 * bC), cc1 = min(wc1, 4 * bC + 3);
+            if (rr1 - rr0 == 7 && cc1 - cc0 == 3) { peak = false; break; }     // the larger element is inside the window
+            for (int r = rr0; r <= rr1 && peak; ++r)
+              for (int c = cc0; c <= cc1; ++c)
+                if (A[r * kP_TileCols + c] > m) { peak = false; break; }
+          }
+        }
+        if (peak) atomicOr(&sbits[(rt - 10) * 5 + ((ct - 12) >> 5)], 1u << ((ct - 12) & 31));
+      }
+    }
+  }
+  __syncthreads();
+
+  // plain layout: word w of a row, bit b <-> bin 32 w + b; this strip owns words 4*strip .. 4*strip+3 (+ word 64)
+  for (int i = threadIdx.x; i < kP_Rows * 5; i += kP_Threads) {
+    const int row = i / 5, w = i - row * 5;
+    if (row < nvalid && (w < 4 || strip == kP_Strips - 1)) bitmap[(r0 + row) * kBitmapRowWords + 4 * strip + w] = sbits[i];
+  }
+}
+
+int launch_square_prune(const PeaksLaunch &a, cudaStream_t s) {
+  // float c > (double) amp_min  <=>  c > amp_lo with amp_lo = amp_min rounded DOWN to float
+  float amp_lo = (float)a.amp_min;
+  if ((double)amp_lo > a.amp_min) amp_lo = nextafterf(amp_lo, -INFINITY);
+  const int64_t blocks = a.total_ttiles * kP_Strips;
+  const size_t smem = sizeof(float4) * kP_TileRows * kP_C4 + sizeof(float) * (kP_Blocks + 2) + sizeof(uint32_t) * kP_Rows * 5;
+  SIA_CUDA(cudaFuncSetAttribute(peaks_square_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  peaks_square_prune_kernel<<<(unsigned)blocks, kP_Threads, smem, s>>>((const float *)a.d_spec, a.d_frame_starts,
+                                                                    a.d_ttile_starts, a.n_tracks, amp_lo, a.d_bitmap);
+  SIA_CHECK_LAUNCH();
+  return SIA_OK;
+}
+
 // ---- generic path: any half-width <= SIA_MAX_NBHD, square or diamond, brute force -----------------
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -473,7 +601,12 @@ int peaks_bitmap_launch(const PeaksLaunch &a, cudaStream_t s, bool *striped) {
   if (a.connectivity == 2 && a.nbhd == 10) {
     // (double + erosion would need 255 KB of shared memory: it takes the generic kernel)
     if (a.in_type == SIA_F64 && !erosion) return launch_square<double, 10, false>(a, s);
-    if (a.in_type == SIA_F32 && !erosion) { *striped = true; return launch_square_warp(a, s); }
+    if (a.in_type == SIA_F32 && !erosion) {
+      // SIA_PEAKS_KERNEL=warp keeps the full separable max filter (the previous production kernel; A/B checks)
+      const char *k = getenv("SIA_PEAKS_KERNEL");
+      if (k && std::string(k) == "warp") { *striped = true; return launch_square_warp(a, s); }
+      return launch_square_prune(a, s);
+    }
     if (a.in_type == SIA_F32) return launch_square<float, 10, true>(a, s);
   }
   return a.in_type == SIA_F64 ? launch_generic<double>(a, s) : launch_generic<float>(a, s);

@@ -145,12 +145,15 @@ def test_k2_other_neighbourhoods_and_float32(fpr):
             assert got == want, (amp, k)
 
 
-def test_k2_float32_production_kernel(fpr):
-    """The float32 square-footprint kernel (the one the pipeline runs): ties, thresholds that are not
-    float32-representable, ragged multi-track layouts whose tiles end mid-way."""
+@pytest.mark.parametrize("kernel", ["prune", "warp"])
+def test_k2_float32_production_kernel(fpr, monkeypatch, kernel):
+    """The float32 square-footprint kernels (candidate pruning: the one the pipeline runs; and the full
+    separable max filter it replaced): ties, thresholds that are not float32-representable, ragged multi-track
+    layouts whose tiles end mid-way, loud tracks where every block is above the threshold, coarse plateaus."""
     import torch
+    monkeypatch.setenv("SIA_PEAKS_KERNEL", kernel)
     rng = np.random.default_rng(12)
-    frames = [130, 1, 64, 65, 7, 200]
+    frames = [130, 1, 64, 65, 7, 200, 90, 75]
     arrs = []
     for k, T in enumerate(frames):
         a = rng.normal(6, 9, (2049, T))
@@ -158,6 +161,11 @@ def test_k2_float32_production_kernel(fpr):
             a = np.round(a * 2) / 2                      # plateaus / exact ties
         if k == 2:
             a[:, 10:30] = 0.0                            # a zero slab (digital silence)
+        if k == 6:
+            a = np.round(rng.normal(45, 3, (2049, T)))   # loud and coarse: wide plateaus of tied maxima
+        if k == 7:
+            a = rng.normal(50, 12, (2049, T))            # loud: every block maximum is a candidate
+            a[100:140, 20:50] = 77.0                     # a constant plateau larger than the window
         arrs.append(a.astype(np.float32))
     host = np.zeros((sum(frames), 2080), np.float32)
     host[:, 2049:] = 1e30                                # row padding must be ignored
