@@ -304,7 +304,7 @@ int launch_square_warp(const PeaksLaunch &a, cudaStream_t s) {
   return SIA_OK;
 }
 
-// ---- production path v2: candidate pruning (float32, square 21x21, amp_min >= 0) ---------------------------
+// ---- alternative path: candidate pruning (float32, square 21x21, amp_min >= 0; SIA_PEAKS_KERNEL=prune) -----
 // A peak is the maximum of its 21x21 window, so it is also the maximum of any block of elements that lies inside
 // that window — in particular of the aligned 8-frame x 4-bin block that contains it.  One CTA stages a
 // 64-frame x 128-bin tile plus halo (88 x 152 floats, cp.async, zero fill outside the track / the 2049 bins:
@@ -328,6 +328,26 @@ constexpr int kP_Blocks = kP_BlockRows * kP_C4;      // 418 blocks of 8 x 4
 constexpr int kP_Threads = 256;
 static_assert(SIA_NBINS == kP_Strips * kP_Cols + 1, "strip layout assumes 2049 bins");
 
+constexpr int kP_MaxCand = 1024;
+
+// candidate (rt, ct) of value m (tile coordinates): is it the maximum of its window?  Serial version.
+__device__ __forceinline__ bool peak_window_serial(const float *__restrict__ A, const float *__restrict__ Bm, int rt, int ct,
+                                                   float m) {
+  const int wr0 = rt - 10, wr1 = rt + 10, wc0 = ct - 10, wc1 = ct + 10;
+  for (int bR = wr0 >> 3; bR <= (wr1 >> 3); ++bR) {
+    const int rr0 = max(wr0, 8 * bR), rr1 = min(wr1, 8 * bR + 7);
+    for (int bC = wc0 >> 2; bC <= (wc1 >> 2); ++bC) {
+      if (!(Bm[bR * kP_C4 + bC] > m)) continue;
+      const int cc0 = max(wc0, 4 * bC), cc1 = min(wc1, 4 * bC + 3);
+      if (rr1 - rr0 == 7 && cc1 - cc0 == 3) return false;      // the larger element is inside the window
+      for (int r = rr0; r <= rr1; ++r)
+        for (int c = cc0; c <= cc1; ++c)
+          if (A[r * kP_TileCols + c] > m) return false;
+    }
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(kP_Threads, 3)
 peaks_square_prune_kernel(const float *__restrict__ spec, const int64_t *__restrict__ frame_starts,
                           const int64_t *__restrict__ ttile_starts, int n_tracks, float amp_lo,
@@ -336,6 +356,8 @@ peaks_square_prune_kernel(const float *__restrict__ spec, const int64_t *__restr
   float4 *A4 = reinterpret_cast<float4 *>(smem_raw);
   float *Bm = reinterpret_cast<float *>(A4 + kP_TileRows * kP_C4);
   uint32_t *sbits = reinterpret_cast<uint32_t *>(Bm + kP_Blocks + 2);
+  uint16_t *cand = reinterpret_cast<uint16_t *>(sbits + kP_Rows * 5);
+  int *ncand = reinterpret_cast<int *>(cand + kP_MaxCand);
   const float *A = reinterpret_cast<const float *>(A4);
   const int64_t tt = blockIdx.x / kP_Strips;
   const int strip = (int)(blockIdx.x - tt * kP_Strips);
@@ -362,6 +384,7 @@ peaks_square_prune_kernel(const float *__restrict__ spec, const int64_t *__restr
     }
   }
   for (int i = threadIdx.x; i < kP_Rows * 5; i += kP_Threads) sbits[i] = 0;
+  if (threadIdx.x == 0) *ncand = 0;
   asm volatile("cp.async.wait_all;\n" ::: "memory");
   __syncthreads();
 
@@ -378,34 +401,60 @@ peaks_square_prune_kernel(const float *__restrict__ spec, const int64_t *__restr
   }
   __syncthreads();
 
-  // P2: candidates of the blocks above the threshold
+  // P2a: blocks above the threshold list their candidates (the elements equal to the block maximum).  The two
+  // column neighbours of a block lie inside the window of every element of the block: a larger maximum there
+  // rules the whole block out.
   for (int b = threadIdx.x; b < kP_Blocks; b += kP_Threads) {
     const float m = Bm[b];
     if (!(m > amp_lo)) continue;
     const int br = b / kP_C4, c4 = b - br * kP_C4;
-    // block rows / columns inside the output region of this tile
-    const int ra = max(8 * br, 10), rb = min(8 * br + 7, 10 + nvalid - 1);
+    const int ra = max(8 * br, 10), rb = min(8 * br + 7, 10 + nvalid - 1);   // inside the output region of this tile
     const int ca = max(4 * c4, 12), cb = min(4 * c4 + 3, 12 + ncols - 1);
     if (ra > rb || ca > cb) continue;
+    if (Bm[b - 1] > m || Bm[b + 1] > m) continue;        // c4 is in 3..35 here: both neighbours exist
     for (int rt = ra; rt <= rb; ++rt) {
-      for (int ct = ca; ct <= cb; ++ct) {
-        if (A[rt * kP_TileCols + ct] != m) continue;
-        // candidate (rt, ct) with value m: compare with the blocks its window [rt-10, rt+10] x [ct-10, ct+10] touches
-        const int wr0 = rt - 10, wr1 = rt + 10, wc0 = ct - 10, wc1 = ct + 10;
-        bool peak = true;
-        for (int bR = wr0 >> 3; bR <= (wr1 >> 3) && peak; ++bR) {
-          const int rr0 = max(wr0, 8 * bR), rr1 = min(wr1, 8 * bR + 7);
-          for (int bC = wc0 >> 2; bC <= (wc1 >> 2) && peak; ++bC) {
-            if (!(Bm[bR * kP_C4 + bC] > m)) continue;
-            const int cc0 = max(wc0, 4 * bC), cc1 = min(wc1, 4 * bC + 3);
-            if (rr1 - rr0 == 7 && cc1 - cc0 == 3) { peak = false; break; }     // the larger element is inside the window
-            for (int r = rr0; r <= rr1 && peak; ++r)
-              for (int c = cc0; c <= cc1; ++c)
-                if (A[r * kP_TileCols + c] > m) { peak = false; break; }
-          }
-        }
-        if (peak) atomicOr(&sbits[(rt - 10) * 5 + ((ct - 12) >> 5)], 1u << ((ct - 12) & 31));
+      const float4 v = A4[rt * kP_C4 + c4];
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ct = 4 * c4 + k;
+        if (e[k] != m || ct < ca || ct > cb) continue;
+        const int slot = atomicAdd(ncand, 1);
+        if (slot < kP_MaxCand) cand[slot] = (uint16_t)(rt << 8 | ct);
+        else if (peak_window_serial(A, Bm, rt, ct, m))       // list full (wide plateaus): check it here
+          atomicOr(&sbits[(rt - 10) * 5 + ((ct - 12) >> 5)], 1u << ((ct - 12) & 31));
       }
+    }
+  }
+  __syncthreads();
+
+  // P2b: one warp per candidate; lane l takes one of the <= 4 x 7 blocks the window touches
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = min(*ncand, kP_MaxCand);
+    for (int i = warp; i < n; i += kP_Threads / 32) {
+      const int rt = cand[i] >> 8, ct = cand[i] & 0xff;
+      const float m = A[rt * kP_TileCols + ct];
+      const int wr0 = rt - 10, wr1 = rt + 10, wc0 = ct - 10, wc1 = ct + 10;
+      const int bR0 = wr0 >> 3, nR = (wr1 >> 3) - bR0 + 1, bC0 = wc0 >> 2, nC = (wc1 >> 2) - bC0 + 1;   // nR <= 4, nC <= 7
+      const int lr = lane / nC, bR = bR0 + lr, bC = bC0 + (lane - lr * nC);
+      bool bigger = false, inside = false;
+      int rr0 = 0, rr1 = -1, cc0 = 0, cc1 = -1;
+      if (lr < nR && Bm[bR * kP_C4 + bC] > m) {
+        bigger = true;
+        rr0 = max(wr0, 8 * bR); rr1 = min(wr1, 8 * bR + 7);
+        cc0 = max(wc0, 4 * bC); cc1 = min(wc1, 4 * bC + 3);
+        inside = rr1 - rr0 == 7 && cc1 - cc0 == 3;       // the larger element certainly lies in the window
+      }
+      if (__any_sync(0xffffffffu, inside)) continue;
+      bool found = false;
+      if (bigger) {
+        for (int r = rr0; r <= rr1 && !found; ++r)
+          for (int c = cc0; c <= cc1; ++c)
+            if (A[r * kP_TileCols + c] > m) { found = true; break; }
+      }
+      if (!__any_sync(0xffffffffu, found) && lane == 0)
+        atomicOr(&sbits[(rt - 10) * 5 + ((ct - 12) >> 5)], 1u << ((ct - 12) & 31));
     }
   }
   __syncthreads();
@@ -422,7 +471,8 @@ int launch_square_prune(const PeaksLaunch &a, cudaStream_t s) {
   float amp_lo = (float)a.amp_min;
   if ((double)amp_lo > a.amp_min) amp_lo = nextafterf(amp_lo, -INFINITY);
   const int64_t blocks = a.total_ttiles * kP_Strips;
-  const size_t smem = sizeof(float4) * kP_TileRows * kP_C4 + sizeof(float) * (kP_Blocks + 2) + sizeof(uint32_t) * kP_Rows * 5;
+  const size_t smem = sizeof(float4) * kP_TileRows * kP_C4 + sizeof(float) * (kP_Blocks + 2) + sizeof(uint32_t) * kP_Rows * 5 +
+                      sizeof(uint16_t) * kP_MaxCand + 16;
   SIA_CUDA(cudaFuncSetAttribute(peaks_square_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   peaks_square_prune_kernel<<<(unsigned)blocks, kP_Threads, smem, s>>>((const float *)a.d_spec, a.d_frame_starts,
                                                                     a.d_ttile_starts, a.n_tracks, amp_lo, a.d_bitmap);
@@ -602,10 +652,12 @@ int peaks_bitmap_launch(const PeaksLaunch &a, cudaStream_t s, bool *striped) {
     // (double + erosion would need 255 KB of shared memory: it takes the generic kernel)
     if (a.in_type == SIA_F64 && !erosion) return launch_square<double, 10, false>(a, s);
     if (a.in_type == SIA_F32 && !erosion) {
-      // SIA_PEAKS_KERNEL=warp keeps the full separable max filter (the previous production kernel; A/B checks)
+      // SIA_PEAKS_KERNEL=prune selects the candidate-pruning kernel: faster on sparse spectrograms (few block
+      // maxima above amp_min), slower on dense ones (22.9 vs 16.0 ms per 1000 benchmark tracks) — not the default
       const char *k = getenv("SIA_PEAKS_KERNEL");
-      if (k && std::string(k) == "warp") { *striped = true; return launch_square_warp(a, s); }
-      return launch_square_prune(a, s);
+      if (k && std::string(k) == "prune") return launch_square_prune(a, s);
+      *striped = true;
+      return launch_square_warp(a, s);
     }
     if (a.in_type == SIA_F32) return launch_square<float, 10, true>(a, s);
   }

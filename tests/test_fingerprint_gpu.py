@@ -145,10 +145,10 @@ def test_k2_other_neighbourhoods_and_float32(fpr):
             assert got == want, (amp, k)
 
 
-@pytest.mark.parametrize("kernel", ["prune", "warp"])
+@pytest.mark.parametrize("kernel", ["warp", "prune"])
 def test_k2_float32_production_kernel(fpr, monkeypatch, kernel):
-    """The float32 square-footprint kernels (candidate pruning: the one the pipeline runs; and the full
-    separable max filter it replaced): ties, thresholds that are not float32-representable, ragged multi-track
+    """The float32 square-footprint kernels (the full separable max filter the pipeline runs, and the
+    candidate-pruning alternative): ties, thresholds that are not float32-representable, ragged multi-track
     layouts whose tiles end mid-way, loud tracks where every block is above the threshold, coarse plateaus."""
     import torch
     monkeypatch.setenv("SIA_PEAKS_KERNEL", kernel)
