@@ -35,6 +35,10 @@ template <typename T> struct Vec2;
 template <> struct Vec2<float> { using type = float2; };
 template <> struct Vec2<double> { using type = double2; };
 
+#ifndef SIA_STFT_CTAS_F64
+#define SIA_STFT_CTAS_F64 4
+#endif
+constexpr int kStftCtasF64 = SIA_STFT_CTAS_F64;   // resident CTAs per SM of the float64 kernel (5 fit in shared memory and 96 registers, measured no faster: the FP64 pipe is the limit)
 constexpr int kL1Stride = 136;
 constexpr int kL2Stride = 258;
 constexpr int kBufElems = 16 * kL1Stride;  // 2176 >= 8*258=2064 >= 2048
@@ -192,7 +196,7 @@ __device__ __forceinline__ void emit_special(OutT *__restrict__ row, const T *__
 }
 
 template <typename T, typename OutT>
-__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 6)
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? kStftCtasF64 : 6)
 stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ track_starts,
                const int64_t *__restrict__ track_len, const int64_t *__restrict__ frame_starts, int n_tracks,
                int64_t total_frames, int frames_per_cta, OutT *__restrict__ out, DbScale sc_mid, DbScale sc_edge,
@@ -202,11 +206,12 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
   __shared__ T sre[kBufElems];
   __shared__ T sim[kBufElems];
 
-  // PCM ring: three 2048-sample half-blocks.  Frame k of a track reads half-blocks k and k+1; the half-block
-  // the NEXT frame adds is fetched with cp.async while this frame is being transformed, so the DRAM latency
-  // of the PCM never sits in front of pass A.  Bytes past the end of a track are zero-filled (src-size),
-  // which is exactly mlab.specgram's zero padding of a short input.
-  __shared__ __align__(16) uint32_t spcm[3][1024];
+  // PCM ring: two 2048-sample half-blocks.  Frame k of a track reads half-blocks k and k+1 (slots k&1, ~k&1) in
+  // pass A; once pass A is over (first barrier) the half-block the NEXT frame adds, k+2, is fetched with
+  // cp.async into the slot of half-block k while passes B and C run, so the DRAM latency of the PCM never sits
+  // in front of pass A.  Bytes past the end of a track are zero-filled (src-size), which is exactly
+  // mlab.specgram's zero padding of a short input.
+  __shared__ __align__(16) uint32_t spcm[2][1024];
   __shared__ T sspc[2][2][16];     // parked columns 0 / 128 of the last two frames (re, im)
 
   const int t = threadIdx.x;
@@ -243,13 +248,12 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
     const int64_t k = g - frame_starts[trk];
     if (!primed) {                       // first frame of the run or of a track: both half-blocks, synchronously
       fetch_half(trk, k, slot);
-      fetch_half(trk, k + 1, (slot + 1) % 3);
+      fetch_half(trk, k + 1, slot ^ 1);
       asm volatile("cp.async.wait_all;\n" ::: "memory");
       __syncthreads();
     }
     primed = g + 1 < frame_starts[trk + 1];           // the next frame continues this track
-    if (primed && g + 1 < g_end) fetch_half(trk, k + 2, (slot + 2) % 3);
-    const uint32_t *__restrict__ h0 = spcm[slot], *__restrict__ h1 = spcm[(slot + 1) % 3];
+    const uint32_t *__restrict__ h0 = spcm[slot], *__restrict__ h1 = spcm[slot ^ 1];
 
     T xr[16], xi[16];
     // ---- pass A: window, pack even/odd samples as complex, FFT16 over a -----------------
@@ -293,6 +297,7 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
         const V2 w15 = mul(w14, b1); put(15, w15.x, w15.y); }
     }
     __syncthreads();
+    if (primed && g + 1 < g_end) fetch_half(trk, k + 2, slot);     // pass A has consumed this slot
     // ---- pass B: FFT16 over b -----------------------------------------------------------
     {
       const int ka = t >> 3, c = t & 7;
@@ -353,7 +358,7 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");   // next frame's half-block has landed
     __syncthreads();   // ... and the L2 layout may be overwritten by the next frame's pass A
-    slot = (slot + 1) % 3;
+    slot ^= 1;
   }
   if (t >= 1 && t <= 9)
     emit_special<T, OutT>(out + (g_end - 1) * (int64_t)SIA_F_STRIDE, sspc[(g_end - 1) & 1][0], sspc[(g_end - 1) & 1][1],
@@ -472,6 +477,9 @@ static int launch(const StftLaunch &a, const StftTables<T> &tb, cudaStream_t s) 
   const int G = a.frames_per_cta;
   const int64_t blocks = ceil_div(a.total_frames, G);
   if (blocks == 0) return SIA_OK;
+  // 4-5 resident CTAs x 44.5 KB of the SM's 228 KB: ask for the largest shared-memory carveout
+  SIA_CUDA(cudaFuncSetAttribute(stft_db_kernel<T, OutT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                (int)cudaSharedmemCarveoutMaxShared));
   stft_db_kernel<T, OutT><<<(unsigned)blocks, 128, 0, s>>>(
       a.d_pcm, a.d_track_starts, a.d_track_len, a.d_frame_starts, a.n_tracks, a.total_frames, G, (OutT *)a.d_spec,
       sc_mid, sc_edge, (const V2 *)tb.win2, (const V2 *)tb.twA, (const V2 *)tb.twB, (const V2 *)tb.twP);
