@@ -184,7 +184,7 @@ class ShardedIndex:
 
     # ---- query ---------------------------------------------------------------------------
     def query(self, digests: torch.Tensor, qoffsets: torch.Tensor, query_starts: np.ndarray, topn: int,
-              queries_per_pass: int = 2048, tuple_budget: int = 400_000_000):
+              queries_per_pass: int = 4096, tuple_budget: int = 1_000_000_000):
         """Collective.  Each rank submits ITS queries (``query_starts`` local, int64[Q_r+1]) and gets
         their results back: int32 tensors (song[Q_r,topn], diff, count, rows, nres[Q_r])."""
         dev = self.backend.device
