@@ -157,6 +157,26 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(gpu_index: int):
+    """Multi-GPU runs: pin this rank to the CPUs NVML lists as local to its GPU, so the pinned host buffers of
+    the e2e leg are first-touched on the GPU's own NUMA node (8 ranks sharing one socket's memory and PCIe
+    root halve each other's copy bandwidth).  Returns the number of CPUs bound, or None if NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -206,6 +226,7 @@ def main():
     from shazam_b200.fingerprinter import Fingerprinter
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    host_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -291,6 +312,8 @@ def main():
                "api": "Fingerprinter.fingerprint_host -> sia_fingerprint_batch_host (pinned host PCM in, "
                       "digests + offsets out to pinned host memory)",
                "host_pool_tracks": pool}
+        if host_cpus:
+            e2e["host_cpus_bound_per_rank"] = host_cpus
         del h_pcm, h_hash, h_t1
 
     if rank != 0:
@@ -312,6 +335,17 @@ def main():
                 "algorithmic_bytes_per_launch": algo_bytes_per_launch, "launches_timed": k1_launches,
                 "avg_launch_ms": k1_ms / k1_launches, "kernel_ms_per_step": kernel_ms,
                 "share_of_step": round(k1_ms / max(sum(kms), 1e-9), 4)}
+    if args.compute == "f64" and k1_ms > 0:
+        # what actually bounds K1: the FP64 pipe.  880 DP instructions per thread and frame (static SASS count =
+        # ncu's 3 520 DP warp instructions per frame); a B200 SM sub-partition issues one DP warp instruction
+        # every 2 cycles -> 148 x 4 / 2 per clock at the sampled SM clock
+        dp_warp_inst = 3520.0 * B * frames_per_track * args.steps
+        clk = (clocks or {}).get("sm_mhz") or 1965.0
+        dp_peak = 148 * 4 / 2 * clk * 1e6
+        roofline["fp64_pipe"] = {"achieved_warp_inst_per_s": dp_warp_inst / (k1_ms * 1e-3), "peak_warp_inst_per_s": dp_peak,
+                                 "frac": dp_warp_inst / (k1_ms * 1e-3) / dp_peak,
+                                 "note": "K1 computes in float64 (1e-3 dB bound on every bin); 3520 DP warp instructions "
+                                         "per frame (ncu, profiles/), DP issue rate 1 per 2 cycles per sub-partition"}
     prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(prof):
         try:

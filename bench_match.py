@@ -216,7 +216,7 @@ def main():
             "metric": "match_queries_per_second", "value": args.queries / (ms_step * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong (fixed index and query set)",
-            "sharding": {"hash": "hash prefix, vote keys exchanged, owner sorts (exact)",
+            "sharding": {"hash": "hash prefix, vote keys exchanged, owner votes with hash tables (exact)",
                          "bins": "hash prefix, sorted partial bins exchanged, owner re-sorts and sums (exact)",
                          "track": "by track, queries all-gathered, G x topn candidates merged (exact)"}[args.mode],
             "dtype": "u64 keys / 16-byte rows", "data": "synthetic",

@@ -498,7 +498,10 @@ __device__ __forceinline__ int64_t vote_insert(const QMeta &m, uint32_t song, ui
   }
   const int64_t ss = song_slot<DENSE>(m, song, song_key);
   const unsigned long long inv = ((1ull << kDiffBits) - 1) - dbits;
-  atomicMax(&song_best[ss], (count << kDiffBits) | inv);
+  const unsigned long long val = (count << kDiffBits) | inv;
+  // best only grows: a (possibly stale) read that already covers val makes the atomic unnecessary — most of a
+  // song's count-1 bins lose against the first one that was posted
+  if (__ldcg(&song_best[ss]) < val) atomicMax(&song_best[ss], val);
   return ss;
 }
 

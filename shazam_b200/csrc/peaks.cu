@@ -22,9 +22,12 @@
 #include "sia_common.cuh"
 #include "stft.cuh"
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <math.h>
 #include <math_constants.h>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 
 namespace sia {
@@ -199,11 +202,13 @@ constexpr int kW2Strips = (SIA_NBINS + kW2Bins - 1) / kW2Bins;      // 22
 constexpr int kW2Threads = 128;
 constexpr int kW2TileRows = kW2Rows + 20;                           // 84
 
+template <bool TMA>
 __global__ void __launch_bounds__(kW2Threads, 3)
 peaks_square_warp_kernel(const float *__restrict__ spec, const int64_t *__restrict__ frame_starts,
                          const int64_t *__restrict__ ttile_starts, int n_tracks, float amp_lo,
-                         uint32_t *__restrict__ bitmap) {
-  __shared__ float4 A[kW2TileRows * kW2Cols4];                      // 40 320 B
+                         uint32_t *__restrict__ bitmap, const __grid_constant__ CUtensorMap tmap) {
+  __shared__ __align__(128) float4 A[kW2TileRows * kW2Cols4];       // 40 320 B
+  __shared__ __align__(8) unsigned long long tma_bar;
   const int64_t tt = blockIdx.x / kW2Strips;
   const int strip = (int)(blockIdx.x - tt * kW2Strips);
   const int f0 = strip * kW2Bins;
@@ -211,10 +216,38 @@ peaks_square_warp_kernel(const float *__restrict__ spec, const int64_t *__restri
   const int64_t row_lo = frame_starts[trk], row_hi = frame_starts[trk + 1];
   const int64_t r0 = row_lo + (tt - ttile_starts[trk]) * kW2Rows;
 
-  // Stage the halo tile with cp.async (16-byte LDGSTS, no register round trip, ~20 requests in flight per
-  // thread).  Out-of-track frames and out-of-range bins are ZERO-filled (src-size 0): with amp_min >= 0 a
-  // zero can neither exceed nor equal a candidate (> amp_min), so it is as good as -inf here.
   const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(A);
+  if (TMA) {
+    // Stage the 84 x 120 halo tile with ONE bulk tensor copy (TMA): the tensor is [frames][2049 bins] with a row
+    // pitch of 2080 floats, so bins < 0 or > 2048 (including the unwritten row padding) and frames outside the
+    // chunk arrive as zeros.  Frames of the neighbouring tracks are zeroed below.  With amp_min >= 0 a zero can
+    // neither exceed nor equal a candidate (> amp_min), so it is as good as -inf here.
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
+                   "r"((uint32_t)(sizeof(float4) * kW2TileRows * kW2Cols4)) : "memory");
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                   ::"r"(a_base), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(f0 - 12), "r"((int)(r0 - 10)), "r"(bar)
+                   : "memory");
+    }
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n"
+                 ::"r"(bar) : "memory");
+    const int64_t g_first = r0 - 10;
+    if (g_first < row_lo || g_first + kW2TileRows > row_hi) {      // first / last tiles of a track
+      for (int i = threadIdx.x; i < kW2TileRows * kW2Cols4; i += kW2Threads) {
+        const int64_t g = g_first + i / kW2Cols4;
+        if (g < row_lo || g >= row_hi) A[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();
+    }
+  } else {
+  // Stage the halo tile with cp.async (16-byte LDGSTS, no register round trip, ~20 requests in flight per
+  // thread).  Out-of-track frames and out-of-range bins are ZERO-filled (src-size 0).
   if (threadIdx.x < 4 * kW2Cols4) {                     // 120 loader threads: fixed column, rows rs, rs+4, ...
     const int j = threadIdx.x % kW2Cols4, rs = threadIdx.x / kW2Cols4;
     const int f = f0 - 12 + 4 * j;
@@ -235,6 +268,7 @@ peaks_square_warp_kernel(const float *__restrict__ spec, const int64_t *__restri
   }
   asm volatile("cp.async.wait_all;\n" ::: "memory");
   __syncthreads();
+  }
 
   const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
   const int col = lane < kW2Cols4 ? (lane + 3) % kW2Cols4 : 0;      // lanes 0..23 -> columns 3..26 (outputs)
@@ -293,13 +327,46 @@ peaks_square_warp_kernel(const float *__restrict__ spec, const int64_t *__restri
   }
 }
 
+// tensor map of the chunk's spectrogram for the TMA tile loads: [total_frames][2049] float32, row pitch 2080 floats,
+// box = one halo tile (84 frames x 120 bins), zero fill outside
+int make_spec_tensor_map(const float *spec, int64_t total_frames, CUtensorMap *tm) {
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult qres;
+    void *fn = nullptr;
+    SIA_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    SIA_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, SIA_E_CUDA, "cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)SIA_NBINS, (cuuint64_t)total_frames};
+  const cuuint64_t gstride[1] = {(cuuint64_t)SIA_F_STRIDE * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)(4 * kW2Cols4), (cuuint32_t)kW2TileRows};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(spec), gdim, gstride, box, estride,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SIA_REQUIRE(r == CUDA_SUCCESS, SIA_E_CUDA, "cuTensorMapEncodeTiled failed for the spectrogram");
+  return SIA_OK;
+}
+
 int launch_square_warp(const PeaksLaunch &a, cudaStream_t s) {
   // float c > (double) amp_min  <=>  c > amp_lo with amp_lo = amp_min rounded DOWN to float
   float amp_lo = (float)a.amp_min;
   if ((double)amp_lo > a.amp_min) amp_lo = nextafterf(amp_lo, -INFINITY);
   const int64_t blocks = a.total_ttiles * kW2Strips;
-  peaks_square_warp_kernel<<<(unsigned)blocks, kW2Threads, 0, s>>>((const float *)a.d_spec, a.d_frame_starts,
-                                                                   a.d_ttile_starts, a.n_tracks, amp_lo, a.d_bitmap);
+  // SIA_PEAKS_STAGING=cpasync keeps the LDGSTS tile staging (A/B checks); default: one TMA tensor copy per tile
+  const char *st = getenv("SIA_PEAKS_STAGING");
+  alignas(64) CUtensorMap tm;
+  memset(&tm, 0, sizeof tm);
+  if (st && std::string(st) == "cpasync") {
+    peaks_square_warp_kernel<false><<<(unsigned)blocks, kW2Threads, 0, s>>>((const float *)a.d_spec, a.d_frame_starts,
+                                                                            a.d_ttile_starts, a.n_tracks, amp_lo, a.d_bitmap, tm);
+  } else {
+    int rc = make_spec_tensor_map((const float *)a.d_spec, a.total_frames, &tm);
+    if (rc) return rc;
+    peaks_square_warp_kernel<true><<<(unsigned)blocks, kW2Threads, 0, s>>>((const float *)a.d_spec, a.d_frame_starts,
+                                                                           a.d_ttile_starts, a.n_tracks, amp_lo, a.d_bitmap, tm);
+  }
   SIA_CHECK_LAUNCH();
   return SIA_OK;
 }
