@@ -26,6 +26,7 @@
 #include <cudaTypedefs.h>
 #include <math.h>
 #include <math_constants.h>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -202,6 +203,66 @@ constexpr int kW2Strips = (SIA_NBINS + kW2Bins - 1) / kW2Bins;      // 22
 constexpr int kW2Threads = 128;
 constexpr int kW2TileRows = kW2Rows + 20;                           // 84
 
+// The filter proper, on a staged tile A (84 x 30 float4): see the kernel comment above.
+__device__ __forceinline__ void warp_tile_peaks(const float4 *__restrict__ A, uint32_t a_base, int64_t r0, int64_t row_hi,
+                                                int strip, int f0, float amp_lo, uint32_t *__restrict__ bitmap) {
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const int col = lane < kW2Cols4 ? (lane + 3) % kW2Cols4 : 0;      // lanes 0..23 -> columns 3..26 (outputs)
+  auto src = [&](int k) { return lane < kW2Cols4 ? (lane + k + kW2Cols4) % kW2Cols4 : lane; };
+  const int s_m1 = src(-1), s_m2 = src(-2), s_m3 = src(-3), s_p1 = src(1), s_p2 = src(2), s_p3 = src(3);
+
+  float vx[36], vy[36], vz[36], vw[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) {
+    const float4 t = A[(16 * q + i) * kW2Cols4 + col];
+    vx[i] = t.x; vy[i] = t.y; vz[i] = t.z; vw[i] = t.w;
+  }
+  sliding21_max3<36, 16>(vx);
+  sliding21_max3<36, 16>(vy);
+  sliding21_max3<36, 16>(vz);
+  sliding21_max3<36, 16>(vw);
+
+  const unsigned FULL = 0xffffffffu;
+  const float amp_up = nextafterf(amp_lo, CUDART_INF_F);
+  const int64_t g0 = r0 + 16 * q;                                   // first output frame of this warp
+  const int nvalid = (int)min((int64_t)16, row_hi - g0);            // frames of the chunk inside the track
+  const int fl = f0 + 4 * lane;
+  const bool v0 = lane < 24 && fl < SIA_NBINS, v1 = lane < 24 && fl + 1 < SIA_NBINS;
+  const bool v2 = lane < 24 && fl + 2 < SIA_NBINS, v3 = lane < 24 && fl + 3 < SIA_NBINS;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float a0 = vx[i], a1 = vy[i], a2 = vz[i], a3 = vw[i];
+    // amp_up (the smallest float above the threshold) rides in the block maximum M, which every window
+    // includes, so "centre == window max and centre > amp_min" becomes the single test centre >= h
+    const float S2 = fmaxf(a2, a3), S1 = fmaxf(a1, S2), M = fmaxf(fmaxf(a0, S1), amp_up);
+    const float P1 = fmaxf(a0, a1), P2 = fmaxf(P1, a2);
+    const float Mm1 = __shfl_sync(FULL, M, s_m1), Mp1 = __shfl_sync(FULL, M, s_p1);
+    const float Mm2 = __shfl_sync(FULL, M, s_m2), Mp2 = __shfl_sync(FULL, M, s_p2);
+    const float S1m2 = __shfl_sync(FULL, S1, s_m2);
+    const float S2m3 = __shfl_sync(FULL, S2, s_m3), S3m3 = __shfl_sync(FULL, a3, s_m3);
+    const float P2p2 = __shfl_sync(FULL, P2, s_p2);
+    const float P0p3 = __shfl_sync(FULL, a0, s_p3), P1p3 = __shfl_sync(FULL, P1, s_p3);
+    const float common = fmaxf(fmaxf(Mm1, M), Mp1);
+    const float cl = fmaxf(common, Mm2);
+    const float h0 = fmaxf(cl, fmaxf(S2m3, P2p2));          // bins -10..+10 around element 0
+    const float h1 = fmaxf(cl, fmaxf(S3m3, Mp2));
+    const float h2 = fmaxf(cl, fmaxf(Mp2, P0p3));
+    const float h3 = fmaxf(fmaxf(common, S1m2), fmaxf(Mp2, P1p3));
+    // re-read the centre row from shared memory (volatile: keeps 16 float4 out of the register file)
+    float4 c;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w)
+                 : "r"(a_base + (uint32_t)((16 * q + i + 10) * kW2Cols4 + col) * 16u));
+    // one ballot per element index: word e, bit l  <->  bin f0 + 4*l + e   (striped bitmap layout)
+    const uint32_t b0 = __ballot_sync(FULL, c.x >= h0 && v0);
+    const uint32_t b1 = __ballot_sync(FULL, c.y >= h1 && v1);
+    const uint32_t b2 = __ballot_sync(FULL, c.z >= h2 && v2);
+    const uint32_t b3 = __ballot_sync(FULL, c.w >= h3 && v3);
+    if (lane == 0 && i < nvalid)
+      *reinterpret_cast<uint4 *>(bitmap + (g0 + i) * kBitmapRowWords + 4 * strip) = make_uint4(b0, b1, b2, b3);
+  }
+}
+
 template <bool TMA>
 __global__ void __launch_bounds__(kW2Threads, 3)
 peaks_square_warp_kernel(const float *__restrict__ spec, const int64_t *__restrict__ frame_starts,
@@ -270,60 +331,67 @@ peaks_square_warp_kernel(const float *__restrict__ spec, const int64_t *__restri
   __syncthreads();
   }
 
-  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
-  const int col = lane < kW2Cols4 ? (lane + 3) % kW2Cols4 : 0;      // lanes 0..23 -> columns 3..26 (outputs)
-  auto src = [&](int k) { return lane < kW2Cols4 ? (lane + k + kW2Cols4) % kW2Cols4 : lane; };
-  const int s_m1 = src(-1), s_m2 = src(-2), s_m3 = src(-3), s_p1 = src(1), s_p2 = src(2), s_p3 = src(3);
+  warp_tile_peaks(A, a_base, r0, row_hi, strip, f0, amp_lo, bitmap);
+}
 
-  float vx[36], vy[36], vz[36], vw[36];
-#pragma unroll
-  for (int i = 0; i < 36; ++i) {
-    const float4 t = A[(16 * q + i) * kW2Cols4 + col];
-    vx[i] = t.x; vy[i] = t.y; vz[i] = t.z; vw[i] = t.w;
+// Persistent form of the kernel above: 2 CTAs per SM walk the tiles with a stride of the grid, two tile buffers
+// each; the TMA copy of the next tile is in flight while the current one is filtered, so no warp ever waits for
+// the tile it is about to read (the copy engine does the staging, the 128 threads only compute).
+constexpr size_t kW2TileBytes = sizeof(float4) * kW2TileRows * kW2Cols4;
+constexpr size_t kW2PersistSmem = 2 * kW2TileBytes + 128;
+
+__global__ void __launch_bounds__(kW2Threads, 2)
+peaks_square_warp_tma_kernel(const int64_t *__restrict__ frame_starts, const int64_t *__restrict__ ttile_starts, int n_tracks,
+                             int64_t n_tiles, float amp_lo, uint32_t *__restrict__ bitmap,
+                             const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char w2_smem[];
+  float4 *bufs[2] = {reinterpret_cast<float4 *>(w2_smem), reinterpret_cast<float4 *>(w2_smem + kW2TileBytes)};
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(w2_smem + 2 * kW2TileBytes);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+  const uint32_t base0 = (uint32_t)__cvta_generic_to_shared(w2_smem);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  sliding21_max3<36, 16>(vx);
-  sliding21_max3<36, 16>(vy);
-  sliding21_max3<36, 16>(vz);
-  sliding21_max3<36, 16>(vw);
-
-  const unsigned FULL = 0xffffffffu;
-  const float amp_up = nextafterf(amp_lo, CUDART_INF_F);
-  const int64_t g0 = r0 + 16 * q;                                   // first output frame of this warp
-  const int nvalid = (int)min((int64_t)16, row_hi - g0);            // frames of the chunk inside the track
-  const int fl = f0 + 4 * lane;
-  const bool v0 = lane < 24 && fl < SIA_NBINS, v1 = lane < 24 && fl + 1 < SIA_NBINS;
-  const bool v2 = lane < 24 && fl + 2 < SIA_NBINS, v3 = lane < 24 && fl + 3 < SIA_NBINS;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float a0 = vx[i], a1 = vy[i], a2 = vz[i], a3 = vw[i];
-    // amp_up (the smallest float above the threshold) rides in the block maximum M, which every window
-    // includes, so "centre == window max and centre > amp_min" becomes the single test centre >= h
-    const float S2 = fmaxf(a2, a3), S1 = fmaxf(a1, S2), M = fmaxf(fmaxf(a0, S1), amp_up);
-    const float P1 = fmaxf(a0, a1), P2 = fmaxf(P1, a2);
-    const float Mm1 = __shfl_sync(FULL, M, s_m1), Mp1 = __shfl_sync(FULL, M, s_p1);
-    const float Mm2 = __shfl_sync(FULL, M, s_m2), Mp2 = __shfl_sync(FULL, M, s_p2);
-    const float S1m2 = __shfl_sync(FULL, S1, s_m2);
-    const float S2m3 = __shfl_sync(FULL, S2, s_m3), S3m3 = __shfl_sync(FULL, a3, s_m3);
-    const float P2p2 = __shfl_sync(FULL, P2, s_p2);
-    const float P0p3 = __shfl_sync(FULL, a0, s_p3), P1p3 = __shfl_sync(FULL, P1, s_p3);
-    const float common = fmaxf(fmaxf(Mm1, M), Mp1);
-    const float cl = fmaxf(common, Mm2);
-    const float h0 = fmaxf(cl, fmaxf(S2m3, P2p2));          // bins -10..+10 around element 0
-    const float h1 = fmaxf(cl, fmaxf(S3m3, Mp2));
-    const float h2 = fmaxf(cl, fmaxf(Mp2, P0p3));
-    const float h3 = fmaxf(fmaxf(common, S1m2), fmaxf(Mp2, P1p3));
-    // re-read the centre row from shared memory (volatile: keeps 16 float4 out of the register file)
-    float4 c;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
-                 : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w)
-                 : "r"(a_base + (uint32_t)((16 * q + i + 10) * kW2Cols4 + col) * 16u));
-    // one ballot per element index: word e, bit l  <->  bin f0 + 4*l + e   (striped bitmap layout)
-    const uint32_t b0 = __ballot_sync(FULL, c.x >= h0 && v0);
-    const uint32_t b1 = __ballot_sync(FULL, c.y >= h1 && v1);
-    const uint32_t b2 = __ballot_sync(FULL, c.z >= h2 && v2);
-    const uint32_t b3 = __ballot_sync(FULL, c.w >= h3 && v3);
-    if (lane == 0 && i < nvalid)
-      *reinterpret_cast<uint4 *>(bitmap + (g0 + i) * kBitmapRowWords + 4 * strip) = make_uint4(b0, b1, b2, b3);
+  __syncthreads();
+  // thread 0: start the tensor copy of tile `tile` into buffer b
+  auto issue = [&](int64_t tile, int b) {
+    const int64_t tt = tile / kW2Strips;
+    const int strip = (int)(tile - tt * kW2Strips);
+    const int trk = find_segment(ttile_starts, n_tracks, tt);
+    const int64_t r0 = frame_starts[trk] + (tt - ttile_starts[trk]) * kW2Rows;
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // earlier generic writes (zeroed frames) vs the copy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar0 + 8 * b), "r"((uint32_t)kW2TileBytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 ::"r"(base0 + (uint32_t)(b * kW2TileBytes)), "l"(reinterpret_cast<uint64_t>(&tmap)),
+                 "r"(strip * kW2Bins - 12), "r"((int)(r0 - 10)), "r"(bar0 + 8 * b) : "memory");
+  };
+  int64_t tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < n_tiles) issue(tile, 0);
+  for (int k = 0; tile < n_tiles; tile += gridDim.x, ++k) {
+    const int b = k & 1;
+    // the other buffer was released by the barrier that ended the previous iteration
+    if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, b ^ 1);
+    const int64_t tt = tile / kW2Strips;
+    const int strip = (int)(tile - tt * kW2Strips);
+    const int trk = find_segment(ttile_starts, n_tracks, tt);
+    const int64_t row_lo = frame_starts[trk], row_hi = frame_starts[trk + 1];
+    const int64_t r0 = row_lo + (tt - ttile_starts[trk]) * kW2Rows;
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n"
+                 ::"r"(bar0 + 8 * b), "r"((k >> 1) & 1) : "memory");
+    float4 *A = bufs[b];
+    const int64_t g_first = r0 - 10;
+    if (g_first < row_lo || g_first + kW2TileRows > row_hi) {      // first / last tiles of a track: zero the other tracks' frames
+      for (int i = threadIdx.x; i < kW2TileRows * kW2Cols4; i += kW2Threads) {
+        const int64_t g = g_first + i / kW2Cols4;
+        if (g < row_lo || g >= row_hi) A[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();
+    }
+    warp_tile_peaks(A, base0 + (uint32_t)(b * kW2TileBytes), r0, row_hi, strip, strip * kW2Bins, amp_lo, bitmap);
+    __syncthreads();                                               // buffer b may be refilled two tiles from now
   }
 }
 
@@ -364,8 +432,16 @@ int launch_square_warp(const PeaksLaunch &a, cudaStream_t s) {
   } else {
     int rc = make_spec_tensor_map((const float *)a.d_spec, a.total_frames, &tm);
     if (rc) return rc;
-    peaks_square_warp_kernel<true><<<(unsigned)blocks, kW2Threads, 0, s>>>((const float *)a.d_spec, a.d_frame_starts,
-                                                                           a.d_ttile_starts, a.n_tracks, amp_lo, a.d_bitmap, tm);
+    if (st && std::string(st) == "tma1") {            // one tile per CTA
+      peaks_square_warp_kernel<true><<<(unsigned)blocks, kW2Threads, 0, s>>>((const float *)a.d_spec, a.d_frame_starts,
+                                                                             a.d_ttile_starts, a.n_tracks, amp_lo, a.d_bitmap, tm);
+    } else {
+      SIA_CUDA(cudaFuncSetAttribute(peaks_square_warp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kW2PersistSmem));
+      const unsigned grid = (unsigned)std::min<int64_t>(blocks, 2 * kNumSMs);
+      peaks_square_warp_tma_kernel<<<grid, kW2Threads, kW2PersistSmem, s>>>(a.d_frame_starts, a.d_ttile_starts, a.n_tracks, blocks,
+                                                                            amp_lo, a.d_bitmap, tm);
+    }
   }
   SIA_CHECK_LAUNCH();
   return SIA_OK;
