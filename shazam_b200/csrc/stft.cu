@@ -40,7 +40,8 @@ template <> struct Vec2<double> { using type = double2; };
 #endif
 constexpr int kStftCtasF64 = SIA_STFT_CTAS_F64;   // resident CTAs per SM of the float64 kernel (5 fit in shared memory and 96 registers, measured no faster: the FP64 pipe is the limit)
 constexpr int kL1Stride = 136;
-constexpr int kL2Stride = 258;
+// pass-C layout stride in (re, im) elements: odd for 16-byte elements (a quarter-warp of 8 lanes stores c = 0..7 at one
+// ka), 2 mod 16 for 8-byte elements (a half-warp stores c = 0..7 at two consecutive ka)
 constexpr int kBufElems = 16 * kL1Stride;  // 2176 >= 8*258=2064 >= 2048
 
 template <typename T>
@@ -136,10 +137,9 @@ template <> __device__ __forceinline__ float sample_to_real<float>(int s) {
 }
 
 // dB epilogue.  dB = 10*log10(p*scale) = C*(e + Ki + log2(m) + Kf),  C = 10*log10(2), p = m*2^e, log2(scale) = Ki+Kf.
-// log2 of the mantissa: MUFU.LG2 on a float built from the top 23 mantissa bits (rounded) — absolute error
-// ~2^-22; the integer part is recombined with a split constant (E*C_hi is exact), so the result carries
-// 0.5 ulp(float) + ~1.4e-6 dB.  p == 0 -> 0 dB (__init__.py:241).  Branch-free: powers below 2^-1019
-// (unreachable from int16 PCM: the smallest non-zero |X|^2 is ~1e-26) are clamped to 2^-1019.
+// p is rounded to float once (F2F), log2 of its mantissa is one MUFU.LG2 (absolute error ~2^-22); the integer part
+// is recombined with a split constant (E*C_hi is exact), so the result carries 0.5 ulp(float) + ~1.4e-6 dB.
+// p == 0 -> 0 dB (__init__.py:241).  Branch-free.
 struct DbScale { int ke; float kf; double c; };     // ke = Ki - 1023
 constexpr float kC = 3.01029995663981195f;
 constexpr float kC_hi = 6165.0f / 2048.0f;                                   // 13 significant bits
@@ -151,17 +151,14 @@ __device__ __forceinline__ float db_combine(int E, float L) {
 }
 template <typename OutT>
 __device__ __forceinline__ OutT db_out(double p, const DbScale &sc) {
-  int hi = __double2hiint(p);
-  const int lo = __double2loint(p);
   if (sizeof(OutT) == 8)                                                     // float64 output (tests): exact path
-    return (OutT)((hi | lo) == 0 ? 0.0 : 10.0 * log10(p) + sc.c);
-  const bool zero = (hi | lo) == 0;
-  hi = max(hi, 0x00400000);                                                  // clamp subnormals (see above)
-  // 2*mantissa23 + round bit = bits 51..28 of the significand
-  const uint32_t m2 = __funnelshift_l((uint32_t)lo, (uint32_t)hi, 4) & 0x00ffffffu;
-  const float mf = __uint_as_float(0x3f800000u + ((m2 + 1u) >> 1));          // a carry rolls into the exponent: 2.0
-  const float r = db_combine((hi >> 20) + sc.ke, __log2f(mf) + sc.kf);
-  return (OutT)(zero ? 0.f : r);
+    return (OutT)(p == 0.0 ? 0.0 : 10.0 * log10(p) + sc.c);
+  // one conversion (round to nearest: the 24-bit mantissa the logarithm sees), then the float's exponent and
+  // mantissa fields; |X|^2 of int16 PCM lies in [1e-26, 1e21], inside the float range
+  const float pf = __double2float_rn(p);
+  const int b = __float_as_int(pf);
+  const float r = db_combine((b >> 23) + (sc.ke + 1023 - 127), __log2f(__int_as_float((b & 0x7fffff) | 0x3f800000)) + sc.kf);
+  return (OutT)(pf == 0.f ? 0.f : r);
 }
 template <typename OutT>
 __device__ __forceinline__ OutT db_out(float p, const DbScale &sc) {
@@ -203,8 +200,8 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
                const typename Vec2<T>::type *__restrict__ winB, const typename Vec2<T>::type *__restrict__ twA,
                const typename Vec2<T>::type *__restrict__ twB, const typename Vec2<T>::type *__restrict__ twP) {
   using V2 = typename Vec2<T>::type;
-  __shared__ T sre[kBufElems];
-  __shared__ T sim[kBufElems];
+  __shared__ __align__(16) V2 sbuf[kBufElems];      // (re, im) interleaved: one 128-bit (64-bit) access per element
+  constexpr int kL2Stride = sizeof(T) == 8 ? 257 : 258;
 
   // PCM ring: two 2048-sample half-blocks.  Frame k of a track reads half-blocks k and k+1 (slots k&1, ~k&1) in
   // pass A; once pass A is over (first barrier) the half-block the NEXT frame adds, k+2, is fetched with
@@ -262,14 +259,25 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
 #pragma unroll
       for (int a = 0; a < 8; ++a) { w[a] = h0[128 * a + t]; w[a + 8] = h1[128 * a + t]; }
       const V2 wb0 = __ldg(winB + 2 * t), wb1 = __ldg(winB + 2 * t + 1);   // window phase of samples 2t, 2t+1
+      // np.hanning: w[m] = 0.5 - 0.5*cos(2*pi*m/4095), m = 256a + 2t (+1).  cos(a*D + B_t), D = 2*pi*256/4095, by the
+      // three-term recurrence c[a+1] = 2cos(D) c[a] - c[a-1]: one FMA per sample (16 steps: error growth ~1e-15)
+      const V2 cd = winA<T>(1);
+      const T K2 = cd.x + cd.x;
+      T c0p = wb0.x, c1p = wb1.x;                                   // c[a-1]
+      T c0 = cd.x * wb0.x - cd.y * wb0.y, c1 = cd.x * wb1.x - cd.y * wb1.y;   // c[a], a = 1
 #pragma unroll
       for (int a = 0; a < 16; ++a) {
-        // np.hanning: w[m] = 0.5 - 0.5*cos(2*pi*m/4095), m = 256a + 2t (+1): cos(A_a + B_t) by angle addition
-        const V2 ca = winA<T>(a);
+        T ca0, ca1;
+        if (a == 0) { ca0 = c0p; ca1 = c1p; }
+        else if (a == 1) { ca0 = c0; ca1 = c1; }
+        else {
+          ca0 = fma(K2, c0, -c0p); ca1 = fma(K2, c1, -c1p);
+          c0p = c0; c1p = c1; c0 = ca0; c1 = ca1;
+        }
         // x*(1 - cos) = 2*x*w: one FMA; the factor 2 is folded into the dB constant
         const T s0 = sample_to_real<T>((int)(short)(w[a] & 0xffffu)), s1 = sample_to_real<T>((int)w[a] >> 16);
-        xr[a] = fma(-s0, ca.x * wb0.x - ca.y * wb0.y, s0);
-        xi[a] = fma(-s1, ca.x * wb1.x - ca.y * wb1.y, s1);
+        xr[a] = fma(-s0, ca0, s0);
+        xi[a] = fma(-s1, ca1, s1);
       }
       fft16(xr, xi);
       // twiddles W2048^(t*ka): four loaded (ka = 1, 2, 4, 8), the rest by products (<= 3 deep)
@@ -278,11 +286,11 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
       auto put = [&](int ka, T wr, T wi) {
         T r = xr[pos16(ka)], i = xi[pos16(ka)];
         cmul(r, i, wr, wi);
-        sre[ka * kL1Stride + t] = r;
-        sim[ka * kL1Stride + t] = i;
+        V2 o; o.x = r; o.y = i;
+        sbuf[ka * kL1Stride + t] = o;
       };
       auto mul = [](V2 a, V2 b) { V2 o; o.x = a.x * b.x - a.y * b.y; o.y = a.x * b.y + a.y * b.x; return o; };
-      sre[t] = xr[0]; sim[t] = xi[0];
+      { V2 o; o.x = xr[0]; o.y = xi[0]; sbuf[t] = o; }
       put(1, b1.x, b1.y); put(2, b2.x, b2.y);
       { const V2 w3 = mul(b2, b1); put(3, w3.x, w3.y); }
       put(4, b4.x, b4.y);
@@ -303,8 +311,8 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
       const int ka = t >> 3, c = t & 7;
 #pragma unroll
       for (int b = 0; b < 16; ++b) {
-        xr[b] = sre[ka * kL1Stride + 8 * b + c];
-        xi[b] = sim[ka * kL1Stride + 8 * b + c];
+        const V2 v = sbuf[ka * kL1Stride + 8 * b + c];
+        xr[b] = v.x; xi[b] = v.y;
       }
       __syncthreads();
       fft16(xr, xi);
@@ -315,8 +323,8 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
           const V2 tw = __ldg(twB + kb * 8 + c);
           cmul(r, i, tw.x, tw.y);
         }
-        sre[c * kL2Stride + kb * 16 + ka] = r;
-        sim[c * kL2Stride + kb * 16 + ka] = i;
+        V2 o; o.x = r; o.y = i;
+        sbuf[c * kL2Stride + kb * 16 + ka] = o;
       }
     }
     __syncthreads();
@@ -329,8 +337,9 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
       const int u1 = t == 0 ? 128 : 256 - t;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        yr[0][c] = sre[c * kL2Stride + t];  yi[0][c] = sim[c * kL2Stride + t];
-        yr[1][c] = sre[c * kL2Stride + u1]; yi[1][c] = sim[c * kL2Stride + u1];
+        const V2 v0 = sbuf[c * kL2Stride + t], v1 = sbuf[c * kL2Stride + u1];
+        yr[0][c] = v0.x; yi[0][c] = v0.y;
+        yr[1][c] = v1.x; yi[1][c] = v1.y;
       }
       fft8(yr[0], yi[0]);
       fft8(yr[1], yi[1]);
