@@ -18,6 +18,9 @@ Everything here is host-side orchestration over a ``ShardBackend`` — the CUDA 
 """
 from __future__ import annotations
 
+import os
+import sys
+import time
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -223,11 +226,20 @@ class ShardedIndex:
     def _query_pass(self, digests, qoffsets, qs, sizes, base, topn, tuple_budget=None):
         dev = self.backend.device
         nq = len(qs) - 1
+        timing = os.environ.get("SIA_DIST_TIMING") and self.rank == 0
+        marks = []
+
+        def mark(name):
+            if timing:
+                torch.cuda.synchronize(dev)
+                marks.append((name, time.perf_counter()))
+        mark("start")
         lens = torch.as_tensor(np.diff(qs), dtype=torch.int64, device=dev)
         qid = torch.repeat_interleave(torch.arange(nq, dtype=torch.int64, device=dev), lens) + base   # pass-global ids
         # exchange #1: query hashes to their owning shard
         dest = hash_owner(digests, self.world)
         d, o, q = exchange([digests, qoffsets.to(torch.int32), qid.to(torch.int32)], dest, self.world, self.group)
+        mark("route hashes")
         shift = SONG_BITS + DIFF_BITS
         if self.exchange_mode == "tuples":
             total_q = int(sum(sizes))
@@ -236,16 +248,26 @@ class ShardedIndex:
                 dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
                 if int(need.item()) > tuple_budget:
                     return None
+            mark("lookup (sizing)")
             tk, rk, ts, rs = self.backend.expand(d, o, q, total_q)
+            mark("expand")
             # keys are grouped by ascending query id = by ascending owner rank: split points from the offsets
             cuts = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64, device=ts.device)
             tcut = ts[cuts].cpu().numpy()
             rcut = rs[cuts].cpu().numpy()
             (tk2,) = exchange_grouped([tk], np.diff(tcut).tolist(), self.world, self.group)
             (rk2,) = exchange_grouped([rk], np.diff(rcut).tolist(), self.world, self.group)
+            mark("exchange vote keys")
             tk2 = tk2 - (base << shift)
             rk2 = rk2 - (base << shift)
-            return self.backend.vote_tuples(tk2, rk2, nq, topn)
+            mark("rebase")
+            res = self.backend.vote_tuples(tk2, rk2, nq, topn)
+            mark("vote")
+            if timing:
+                print("[sia dist] pass: %d local queries, %d vote keys out, %d in: " % (nq, tk.numel(), tk2.numel()) +
+                      ", ".join("%s %.1f ms" % (n, (t - marks[i][1]) * 1e3) for i, (n, t) in enumerate(marks[1:])),
+                      file=sys.stderr)
+            return res
         bk, bc, rk, rc = self.backend.query_partial(d, o, q)
         # exchange #2: partial bins to the rank that owns the query (sum-by-key happens there)
         bounds = torch.as_tensor(np.cumsum(sizes), dtype=torch.int64, device=dev)
