@@ -190,6 +190,8 @@ int sia_index_select_host(sia_index *ix, const uint8_t *h_hash, int64_t n, int32
  *   out_rows             — dedup_hashes[song]: DB rows matched, counted once per row,
  *   out_nres[q]          — number of valid results (<= topn).
  * Equal counts order by ascending song id (stable sort, recognizer.py:307-310).
+ * The vote uses per-query hash tables (no vote keys are written or sorted); a query of more than 32 767
+ * (hash, offset) pairs is voted by sorting.  SIA_VOTE=sort forces the sort-based vote for every query.
  * h_stats (optional, 4 x int64): query (hash, offset) pairs, DB rows matched (the total of
  * dedup_hashes), (song, diff) tuples voted (len(results) of return_matches), distinct bins. */
 int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff,
@@ -215,8 +217,8 @@ int sia_vote_bins(int device, const uint64_t *d_bin_key, const int32_t *d_bin_co
  * once).  sia_index_expand: for routed query hashes, the (query, song, diff) vote keys and the
  * (query, song) row keys of the postings this shard owns, grouped by ascending query id (ids < n_queries),
  * with per-query prefix offsets d_tuple_starts / d_row_starts [n_queries+1].  Passing NULL key buffers
- * only sizes (*h_ntuples, *h_nrows).  sia_vote_tuples: sort + count + vote of concatenated keys (the
- * key buffers are used as scratch). */
+ * only sizes (*h_ntuples, *h_nrows).  sia_vote_tuples: count + vote of concatenated keys with per-query hash
+ * tables (a bin count beyond 15 bits falls back to sort + run lengths; the key buffers may be used as scratch). */
 int sia_index_expand(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff, const int32_t *d_qid, int64_t n,
                      int32_t n_queries, uint64_t *d_tuple_key, int64_t cap_tuples, int64_t *h_ntuples,
                      uint64_t *d_row_key, int64_t cap_rows, int64_t *h_nrows, int64_t *d_tuple_starts,
