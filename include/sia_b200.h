@@ -90,6 +90,12 @@ int sia_ctx_destroy(sia_ctx *ctx);
 /* frames mlab.specgram yields for a track of n samples (short input -> 1 padded frame) */
 int64_t sia_num_frames(int64_t n_samples);
 
+/* De-interleave decoded PCM on the device — the `data[chn::n_channels]` of read(), __init__.py:91-95:
+ * d_out[c * channel_stride + i] = d_in[i * n_channels + c] for i < n_frames, c < n_channels.  channel_stride >=
+ * n_frames (a multiple of 8 keeps every channel 16-byte aligned for K1).  Stream-ordered. */
+int sia_deinterleave_i16(const int16_t *d_in, int64_t n_frames, int32_t n_channels, int16_t *d_out,
+                         int64_t channel_stride, void *stream);
+
 /* ---- stage entry points (parity tests drive these one by one) -------------------------- */
 
 /* K1. Replaces mlab.specgram(...)[0] + the dB transform, __init__.py:232-241.

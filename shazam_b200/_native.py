@@ -46,6 +46,7 @@ SIGNATURES = {
     "sia_ctx_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(_p)]),
     "sia_ctx_destroy": (C.c_int, [_p]),
     "sia_num_frames": (C.c_int64, [C.c_int64]),
+    "sia_deinterleave_i16": (C.c_int, [_p, C.c_int64, C.c_int32, _p, C.c_int64, _p]),
     "sia_stft_db": (C.c_int, [_p, _p, _i64p, _i64p, C.c_int32, C.POINTER(FpParams), _p, C.c_int32, _i64p, _p]),
     "sia_peaks": (C.c_int, [_p, _p, C.c_int32, _i64p, C.c_int32, C.POINTER(FpParams), _p, _p, C.c_int64, _p, _p, _p]),
     "sia_pairs_sha1": (C.c_int, [_p, _p, _p, _p, C.c_int32, C.c_int32, _p, _p, C.c_int64, _p, _p, _p]),

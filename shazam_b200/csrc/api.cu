@@ -297,6 +297,34 @@ int run_chunk(sia_ctx *c, const int16_t *d_pcm, const Chunk &ch, const sia_fp_pa
   return SIA_OK;
 }
 
+// ---- PCM de-interleave (read(), __init__.py:91-95) ---------------------------------------------------------
+// stereo: one 16-byte load (4 frames) -> two 8-byte stores; other channel counts: scalar, coalesced on the reads
+__global__ void __launch_bounds__(256)
+deinterleave2_kernel(const int16_t *__restrict__ in, int64_t n_frames, int16_t *__restrict__ out, int64_t stride) {
+  const int64_t nq = n_frames >> 2;                       // groups of 4 frames
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4 *>(in)[q];
+    uint2 l, r;
+    l.x = __byte_perm(v.x, v.y, 0x5410); r.x = __byte_perm(v.x, v.y, 0x7632);
+    l.y = __byte_perm(v.z, v.w, 0x5410); r.y = __byte_perm(v.z, v.w, 0x7632);
+    reinterpret_cast<uint2 *>(out)[q] = l;
+    reinterpret_cast<uint2 *>(out + stride)[q] = r;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n_frames & 3)) {   // tail frames
+    const int64_t i = (nq << 2) + threadIdx.x;
+    out[i] = in[2 * i]; out[stride + i] = in[2 * i + 1];
+  }
+}
+__global__ void __launch_bounds__(256)
+deinterleave_kernel(const int16_t *__restrict__ in, int64_t n_frames, int n_channels, int16_t *__restrict__ out, int64_t stride) {
+  const int64_t n = n_frames * n_channels;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = k / n_channels;
+    const int c = (int)(k - i * n_channels);
+    out[c * stride + i] = in[k];
+  }
+}
+
 int64_t env_i64(const char *name, int64_t dflt) {
   const char *v = getenv(name);
   if (!v || !*v) return dflt;
@@ -314,6 +342,26 @@ void sia_fp_params_default(sia_fp_params *p) {
   if (!p) return;
   p->Fs = 44100.0; p->wsize = 4096; p->wratio = 0.5; p->fan_value = 5; p->amp_min = 10.0;
   p->connectivity = 2; p->nbhd = 10; p->compute = SIA_F64;
+}
+
+int sia_deinterleave_i16(const int16_t *d_in, int64_t n_frames, int32_t n_channels, int16_t *d_out, int64_t channel_stride,
+                         void *stream) {
+  SIA_REQUIRE(n_frames >= 0 && n_channels >= 1 && n_channels <= 64, SIA_E_INVALID, "deinterleave: bad sizes");
+  SIA_REQUIRE(channel_stride >= n_frames, SIA_E_INVALID, "deinterleave: channel_stride < n_frames");
+  if (n_frames == 0) return SIA_OK;
+  SIA_REQUIRE(d_in && d_out, SIA_E_INVALID, "NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = n_channels == 2 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d_out) & 7) == 0 && (channel_stride & 3) == 0;
+  if (vec) {
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(std::max<int64_t>(n_frames >> 2, 1), 256), kNumSMs * 16);
+    deinterleave2_kernel<<<blocks, 256, 0, s>>>(d_in, n_frames, d_out, channel_stride);
+  } else {
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n_frames * n_channels, 256), kNumSMs * 16);
+    deinterleave_kernel<<<blocks, 256, 0, s>>>(d_in, n_frames, n_channels, d_out, channel_stride);
+  }
+  SIA_CHECK_LAUNCH();
+  return SIA_OK;
 }
 
 int64_t sia_num_frames(int64_t n_samples) {

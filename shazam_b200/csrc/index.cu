@@ -76,7 +76,8 @@ struct sia_index {
   int64_t n_rows = 0, n_pending = 0;
   uint32_t *dir = nullptr;      // [2^dir_bits + 1]
   int dir_bits = 0;
-  int32_t *status = nullptr;    // [0] device flag: 1 = song/offset out of range on insert, 2 = query offset out of range
+  int32_t *status = nullptr;    // [0] device flags: 1 = song/offset out of range on insert, 2 = query offset out of range,
+                                //     8 / 16 = vote table full / bin count overflow (cannot happen: sizing, 32 767-entry rule)
                                 // [1] largest song id ever inserted
   int32_t max_song = 0;         // host copy of status[1], refreshed by finalize
   Arena arena;                  // build / lookup scratch
@@ -468,15 +469,16 @@ template <bool DENSE>
 __device__ __forceinline__ int64_t song_slot(const QMeta &m, uint32_t song, uint32_t *__restrict__ song_key) {
   if (DENSE) return m.song_base + song;
   uint32_t t = slot_of(mix32(song), m.song_cap);
-  for (;;) {
+  for (uint32_t probes = 0; probes < m.song_cap; ++probes) {     // bounded: a full table (inconsistent inputs) cannot hang
     const uint32_t old = atomicCAS(&song_key[m.song_base + t], 0u, song + 1u);
-    if (old == 0u || old == song + 1u) break;
+    if (old == 0u || old == song + 1u) return m.song_base + t;
     if (++t == m.song_cap) t = 0;
   }
-  return m.song_base + t;
+  return -1;
 }
 
 // one vote tuple (song, biased diff) of query m: count its bin, keep the song's best current; returns the song slot
+// (-1 and flag 8 in *overflow if a table is full, which the table sizing rules out for consistent inputs)
 template <bool DENSE>
 __device__ __forceinline__ int64_t vote_insert(const QMeta &m, uint32_t song, uint32_t dbits,
                                                unsigned long long *__restrict__ bins, uint32_t *__restrict__ song_key,
@@ -484,19 +486,20 @@ __device__ __forceinline__ int64_t vote_insert(const QMeta &m, uint32_t song, ui
                                                int32_t *__restrict__ overflow) {
   const unsigned long long key = ((unsigned long long)song << kDiffBits) | dbits;
   uint32_t s = slot_of(mix32(song * 0x9e3779b1u + dbits), m.bin_cap);
-  unsigned long long count;
-  for (;;) {
+  unsigned long long count = 0;
+  for (uint32_t probes = 0; probes < m.bin_cap; ++probes) {
     unsigned long long *p = bins + m.bin_base + s;
     const unsigned long long old = atomicCAS(p, 0ull, (key << kBinCountBits) | 1ull);
     if (old == 0ull) { count = 1; ++fresh; break; }
     if ((old >> kBinCountBits) == key) {
       count = (atomicAdd(p, 1ull) & ((1ull << kBinCountBits) - 1)) + 1;
-      if (overflow && count == (1ull << kBinCountBits)) atomicOr(overflow, 1);   // the count field wrapped: redo by sorting
+      if (overflow && count == (1ull << kBinCountBits)) atomicOr(overflow, 16);  // the count field wrapped: redo by sorting
       break;
     }
     if (++s == m.bin_cap) s = 0;
   }
-  const int64_t ss = song_slot<DENSE>(m, song, song_key);
+  const int64_t ss = count ? song_slot<DENSE>(m, song, song_key) : -1;
+  if (ss < 0) { if (overflow) atomicOr(overflow, 8); return -1; }
   const unsigned long long inv = ((1ull << kDiffBits) - 1) - dbits;
   const unsigned long long val = (count << kDiffBits) | inv;
   // best only grows: a (possibly stale) read that already covers val makes the atomic unnecessary — most of a
@@ -514,7 +517,7 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
                    const ulonglong2 *__restrict__ rows, const QMeta *__restrict__ meta,
                    unsigned long long *__restrict__ bins, uint32_t *__restrict__ song_key,
                    uint32_t *__restrict__ song_rows, unsigned long long *__restrict__ song_best,
-                   unsigned long long *__restrict__ n_bins, int tuples_per_block) {
+                   unsigned long long *__restrict__ n_bins, int tuples_per_block, int32_t *__restrict__ overflow) {
   __shared__ int64_t s_off[257];
   __shared__ int64_t s_first;
   const int64_t j_lo = off[e0] + (int64_t)blockIdx.x * tuples_per_block;
@@ -547,8 +550,8 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
     const QMeta m = meta[e.y >> 40];
     const uint32_t song = (uint32_t)(r.x >> 24) & 0xffffffu;
     const uint32_t dbits = (uint32_t)((int32_t)(r.x & kM24) - (int32_t)(e.x & kM24) + SIA_DIFF_BIAS);   // db - query offset
-    const int64_t ss = vote_insert<DENSE>(m, song, dbits, bins, song_key, song_best, fresh, nullptr);
-    if (cnt_head[ei]) atomicAdd(&song_rows[ss], 1u);    // first entry of its (query, hash): the row counts once
+    const int64_t ss = vote_insert<DENSE>(m, song, dbits, bins, song_key, song_best, fresh, overflow);
+    if (ss >= 0 && cnt_head[ei]) atomicAdd(&song_rows[ss], 1u);    // first entry of its (query, hash): the row counts once
     }
     if (s_off[nloc] >= j_hi) break;      // uniform: every thread reads the same shared value
   }
@@ -634,14 +637,16 @@ vote_keys_kernel(const uint64_t *__restrict__ key, int64_t n, const QMeta *__res
 template <bool DENSE>
 __global__ void __launch_bounds__(256)
 row_keys_kernel(const uint64_t *__restrict__ key, int64_t n, const QMeta *__restrict__ meta,
-                uint32_t *__restrict__ song_key, uint32_t *__restrict__ song_rows) {
+                uint32_t *__restrict__ song_key, uint32_t *__restrict__ song_rows, int32_t *__restrict__ info) {
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
     __syncwarp();
     const int64_t i = i0 + threadIdx.x;
     if (i >= n) continue;
     const uint64_t k = key[i];
     const QMeta m = meta[k >> (kSongBits + kDiffBits)];
-    atomicAdd(&song_rows[song_slot<DENSE>(m, (uint32_t)(k >> kDiffBits) & 0xffffffu, song_key)], 1u);
+    const int64_t ss = song_slot<DENSE>(m, (uint32_t)(k >> kDiffBits) & 0xffffffu, song_key);
+    if (ss >= 0) atomicAdd(&song_rows[ss], 1u);
+    else atomicOr(info + 1, 8);
   }
 }
 
@@ -912,19 +917,19 @@ static int vote_tuples_hash(int device, const uint64_t *d_tuple_key, int64_t n_t
   SIA_CUDA(cudaMemsetAsync(bins, 0, (size_t)nb * 8 + (size_t)ns * (dense ? 12 : 16), s));
   if (dense) {
     if (n_tuples) vote_keys_kernel<true><<<grid_for(n_tuples), 256, 0, s>>>(d_tuple_key, n_tuples, meta, bins, song_key, song_best, info);
-    if (n_rows) row_keys_kernel<true><<<grid_for(n_rows), 256, 0, s>>>(d_row_key, n_rows, meta, song_key, song_rows);
+    if (n_rows) row_keys_kernel<true><<<grid_for(n_rows), 256, 0, s>>>(d_row_key, n_rows, meta, song_key, song_rows, info);
     topn_hash_kernel<true><<<n_queries, 256, 0, s>>>(song_key, song_rows, song_best, meta, 0, 0, topn, d_out_song, d_out_diff,
                                                      d_out_count, d_out_rows, d_out_nres);
   } else {
     if (n_tuples) vote_keys_kernel<false><<<grid_for(n_tuples), 256, 0, s>>>(d_tuple_key, n_tuples, meta, bins, song_key, song_best, info);
-    if (n_rows) row_keys_kernel<false><<<grid_for(n_rows), 256, 0, s>>>(d_row_key, n_rows, meta, song_key, song_rows);
+    if (n_rows) row_keys_kernel<false><<<grid_for(n_rows), 256, 0, s>>>(d_row_key, n_rows, meta, song_key, song_rows, info);
     topn_hash_kernel<false><<<n_queries, 256, 0, s>>>(song_key, song_rows, song_best, meta, 0, 0, topn, d_out_song, d_out_diff,
                                                       d_out_count, d_out_rows, d_out_nres);
   }
   SIA_CHECK_LAUNCH();
   SIA_CUDA(cudaMemcpyAsync(h_info, info, sizeof h_info, cudaMemcpyDeviceToHost, s));
   SIA_CUDA(cudaStreamSynchronize(s));
-  if (h_info[1] & (1 | 4)) return SIA_E_UNSUPPORTED;
+  if (h_info[1] & (16 | 4 | 8)) return SIA_E_UNSUPPORTED;      // count overflow / oversized query / full table: sort instead
   return SIA_OK;
 }
 
@@ -1323,12 +1328,12 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
       unsigned long long *nbp = h_stats ? d_nbins : nullptr;
       if (dense[gi]) {
         expand_vote_kernel<true><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->rows, d_meta,
-                                                        bins, song_key, song_rows, song_best, nbp, vote_chunk);
+                                                        bins, song_key, song_rows, song_best, nbp, vote_chunk, ix->status);
         topn_hash_kernel<true><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, d_meta, g.qa, (int)q0, topn,
                                                            d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
       } else {
         expand_vote_kernel<false><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->rows, d_meta,
-                                                         bins, song_key, song_rows, song_best, nbp, vote_chunk);
+                                                         bins, song_key, song_rows, song_best, nbp, vote_chunk, ix->status);
         topn_hash_kernel<false><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, d_meta, g.qa, (int)q0, topn,
                                                             d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
       }
@@ -1341,6 +1346,7 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
       h_stats[3] += (int64_t)nbv;
     }
     if (timing) cudaEventRecord(ev[2], s);
+    if (max_bin > 0 && (rc = check_status(ix, s, 8 | 16, "query: vote table overflow (internal error)"))) return rc;
     SIA_CUDA(cudaStreamSynchronize(s));      // the lookup scratch and the tables are reused by the next pass / call
     if (timing) {
       float t_lookup = 0, t_vote = 0;

@@ -261,6 +261,35 @@ class Fingerprinter:
         frames = sum(N.num_frames(int(n)) for n in lens)
         return int(max(4096, frames * 8 * max(fan_value - 1, 1)))
 
+    def deinterleave(self, d_interleaved: torch.Tensor, n_channels: int):
+        """``data[chn::n_channels]`` of ``read()`` (``__init__.py:91-95``) on the device: interleaved int16 PCM
+        -> (d_pcm, starts, lens) with one 8-sample-aligned track per channel, ready for ``fingerprint_device``."""
+        assert d_interleaved.is_cuda and d_interleaved.dtype == torch.int16 and d_interleaved.is_contiguous()
+        n_frames = d_interleaved.numel() // n_channels
+        stride = (n_frames + 7) // 8 * 8
+        out = torch.zeros(max(stride * n_channels, 8), dtype=torch.int16, device=self.tdev)
+        N.check(self.lib.sia_deinterleave_i16(C.c_void_p(d_interleaved.data_ptr()), n_frames, int(n_channels),
+                                              C.c_void_p(out.data_ptr()), stride, self._stream()))
+        return out, np.arange(n_channels, dtype=np.int64) * stride, np.full(n_channels, n_frames, np.int64)
+
+    def fingerprint_interleaved(self, pcm_interleaved, n_channels: int, Fs=44100, fan_value=5, amp_min=10,
+                                connectivity=2, nbhd=10, compute="f64") -> FingerprintBatch:
+        """All channels of one decoded file as one GPU batch: the interleaved samples are copied
+        once, split on the device and fingerprinted channel by channel; digests stay in HBM (one track per
+        channel), e.g. for ``ingest.union_channels_device``."""
+        x = torch.from_numpy(np.ascontiguousarray(pcm_interleaved, np.int16)).to(self.tdev)
+        d_pcm, starts, lens = self.deinterleave(x, n_channels)
+        p = self.params(Fs, fan_value, amp_min, connectivity, nbhd, compute)
+        cap = self.default_cap(lens, fan_value)
+        for _ in range(6):
+            try:
+                return self.fingerprint_device(d_pcm, starts, lens, p, cap_hashes=cap)
+            except N.CapacityError as e:
+                if "hash output capacity" not in str(e):
+                    raise
+                cap *= 4
+        raise N.CapacityError(N.E_CAPACITY, "hash output keeps overflowing")
+
     def fingerprint_tracks(self, tracks: Sequence[np.ndarray], Fs=44100, fan_value=5, amp_min=10,
                            connectivity=2, nbhd=10, compute="f64") -> FingerprintBatch:
         """Convenience: list of int16 arrays -> host digests (with a capacity retry)."""

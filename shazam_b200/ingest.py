@@ -104,6 +104,25 @@ def union_channels_device(digests, offsets, scratch_index=None):
             ix.close()
 
 
+def get_file_fingerprints_device(file_name: str, limit: Optional[int] = None, fan_value: int = DEFAULT_FAN_VALUE,
+                                 amp_min=DEFAULT_AMP_MIN):
+    """``get_file_fingerprints`` with everything after the decode on the GPU: the interleaved
+    samples of a 16-bit PCM WAV go to the device once, are split per channel there, fingerprinted as one batch
+    and set-unioned there.  Returns ``(digests uint8[n,10], offsets int32[n], file_sha1)`` as CUDA tensors in
+    (hash, offset) order — the array form of the reference's ``set[(hex20, offset)]``."""
+    with wave.open(file_name, "rb") as w:
+        if w.getsampwidth() != 2:
+            raise ValueError(f"{file_name}: only 16-bit PCM WAV is decoded here")
+        nch, rate = w.getnchannels(), w.getframerate()
+        nframes = w.getnframes() if not limit else min(w.getnframes(), int(limit) * rate)
+        data = np.frombuffer(w.readframes(nframes), np.int16)
+    fp = compat.get_fingerprinter()
+    batch = fp.fingerprint_interleaved(data, nch, Fs=rate, fan_value=fan_value, amp_min=amp_min,
+                                       connectivity=compat.CONNECTIVITY_MASK, nbhd=compat.PEAK_NEIGHBORHOOD_SIZE)
+    d, o = union_channels_device(batch.hash, batch.t1)
+    return d, o, unique_hash(file_name)
+
+
 def get_file_fingerprints(file_name: str, limit: Optional[int] = None, print_output: bool = False):
     """``__init__.py:248-268``: ``(set[(hex20, offset)], file_sha1)``."""
     channels, fs, file_hash = read(file_name, limit)

@@ -329,3 +329,21 @@ def test_full_size_track_properties(fpr):
     jacc = len(sa & sb) / len(sa | sb)
     assert jacc >= 0.99, jacc
     assert len(h0) == len(oh) or jacc < 1.0
+
+
+def test_deinterleave_device(fpr):
+    """read()'s data[chn::n_channels] (__init__.py:91-95) on the device: stereo (vector path, odd tails), 1, 3 and
+    5 channels, unaligned input views."""
+    import torch
+    rng = np.random.default_rng(4)
+    for nch, nfr in [(2, 100003), (2, 8), (2, 3), (1, 777), (3, 4099), (5, 1000), (2, 0)]:
+        x = rng.integers(-32768, 32767, nfr * nch + 1, dtype=np.int16)
+        full = torch.from_numpy(x).to(fpr.tdev)
+        for shift in (0, 1):                          # shift 1: the device pointer is only 2-byte aligned
+            d = full[shift:shift + nfr * nch]         # a contiguous view
+            src = x[shift:shift + nfr * nch]
+            out, starts, lens = fpr.deinterleave(d, nch)
+            out = out.cpu().numpy()
+            for c in range(nch):
+                assert lens[c] == nfr and starts[c] % 8 == 0
+                assert np.array_equal(out[starts[c]:starts[c] + nfr], src[c::nch]), (nch, nfr, shift, c)

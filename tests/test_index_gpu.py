@@ -336,6 +336,10 @@ def test_ingest_directory_flow(tmp_path, fpr):
             assert row[2] == ingest.unique_hash(str(tmp_path / name))
             fset, fh = ingest.get_file_fingerprints(str(tmp_path / name))
             assert fset == want and fh == row[2]
+            # the same with the channel split and the set union on the device
+            d, o, fh2 = ingest.get_file_fingerprints_device(str(tmp_path / name))
+            got = set(zip((bytes(r).hex() for r in d.cpu().numpy()), o.cpu().tolist()))
+            assert got == want and fh2 == row[2] and d.shape[0] == len(want)
         assert db.get_num_fingerprints() == sum(r[3] for r in songs.values())
         assert ingest.fingerprint_directory(str(tmp_path), ["wav"], None, ingest.load_fingerprinted_audio_hashes(set())) == 0
         # recognise 3 s of the stereo file's left channel (recognizer.py:379-397 flow)
