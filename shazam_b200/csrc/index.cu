@@ -451,7 +451,8 @@ __global__ void query_starts_kernel(const ulonglong2 *__restrict__ ent, int64_t 
 // Posting runs are expanded straight into the tables — no vote keys are written or sorted.
 struct QMeta {
   int64_t bin_base, song_base;    // first slot of the query's sub-tables, relative to the group's tables
-  uint32_t bin_cap, song_cap;
+  int64_t filt_base;              // first word of the query's duplicate filter (filt_words == 0: no filter)
+  uint32_t bin_cap, song_cap, filt_words, pad_;
 };
 constexpr int kBinCountBits = 15;
 constexpr int64_t kMaxHashVoteEntries = (1 << kBinCountBits) - 1;
@@ -477,47 +478,74 @@ __device__ __forceinline__ int64_t song_slot(const QMeta &m, uint32_t song, uint
   return -1;
 }
 
-// one vote tuple (song, biased diff) of query m: count its bin, keep the song's best current; returns the song slot
-// (-1 and flag 8 in *overflow if a table is full, which the table sizing rules out for consistent inputs)
-template <bool DENSE>
-__device__ __forceinline__ int64_t vote_insert(const QMeta &m, uint32_t song, uint32_t dbits,
-                                               unsigned long long *__restrict__ bins, uint32_t *__restrict__ song_key,
-                                               unsigned long long *__restrict__ song_best, uint32_t &fresh,
-                                               int32_t *__restrict__ overflow) {
+// count one vote tuple (song, biased diff) in query m's bin table; returns the bin's count including this tuple
+// (0 and flag 8 in *overflow if the table is full, which the sizing rules out unless the duplicate filter
+// under-estimated: then the group is redone without the filter)
+__device__ __forceinline__ unsigned long long bin_count(const QMeta &m, uint32_t song, uint32_t dbits,
+                                                        unsigned long long *__restrict__ bins, uint32_t &fresh,
+                                                        int32_t *__restrict__ overflow) {
   const unsigned long long key = ((unsigned long long)song << kDiffBits) | dbits;
   uint32_t s = slot_of(mix32(song * 0x9e3779b1u + dbits), m.bin_cap);
-  unsigned long long count = 0;
   for (uint32_t probes = 0; probes < m.bin_cap; ++probes) {
     unsigned long long *p = bins + m.bin_base + s;
     const unsigned long long old = atomicCAS(p, 0ull, (key << kBinCountBits) | 1ull);
-    if (old == 0ull) { count = 1; ++fresh; break; }
+    if (old == 0ull) { ++fresh; return 1; }
     if ((old >> kBinCountBits) == key) {
-      count = (atomicAdd(p, 1ull) & ((1ull << kBinCountBits) - 1)) + 1;
+      const unsigned long long count = (atomicAdd(p, 1ull) & ((1ull << kBinCountBits) - 1)) + 1;
       if (overflow && count == (1ull << kBinCountBits)) atomicOr(overflow, 16);  // the count field wrapped: redo by sorting
-      break;
+      return count;
     }
     if (++s == m.bin_cap) s = 0;
   }
-  const int64_t ss = count ? song_slot<DENSE>(m, song, song_key) : -1;
+  if (overflow) atomicOr(overflow, 8);
+  return 0;
+}
+
+// the song side of a vote tuple whose bin now holds `count`: keep the song's best (count, smallest diff) current
+template <bool DENSE>
+__device__ __forceinline__ int64_t song_update(const QMeta &m, uint32_t song, uint32_t dbits, unsigned long long count,
+                                               uint32_t *__restrict__ song_key, unsigned long long *__restrict__ song_best,
+                                               int32_t *__restrict__ overflow) {
+  const int64_t ss = song_slot<DENSE>(m, song, song_key);
   if (ss < 0) { if (overflow) atomicOr(overflow, 8); return -1; }
-  const unsigned long long inv = ((1ull << kDiffBits) - 1) - dbits;
-  const unsigned long long val = (count << kDiffBits) | inv;
+  const unsigned long long val = (count << kDiffBits) | (((1ull << kDiffBits) - 1) - dbits);
   // best only grows: a (possibly stale) read that already covers val makes the atomic unnecessary — most of a
   // song's count-1 bins lose against the first one that was posted
   if (__ldcg(&song_best[ss]) < val) atomicMax(&song_best[ss], val);
   return ss;
 }
 
+template <bool DENSE>
+__device__ __forceinline__ int64_t vote_insert(const QMeta &m, uint32_t song, uint32_t dbits,
+                                               unsigned long long *__restrict__ bins, uint32_t *__restrict__ song_key,
+                                               unsigned long long *__restrict__ song_best, uint32_t &fresh,
+                                               int32_t *__restrict__ overflow) {
+  const unsigned long long count = bin_count(m, song, dbits, bins, fresh, overflow);
+  return count ? song_update<DENSE>(m, song, dbits, count, song_key, song_best, overflow) : -1;
+}
+
+// duplicate filter: 2 bits per bucket (seen, seen twice), 16 buckets per 32-bit word, ~16 buckets per tuple
+__device__ __forceinline__ uint32_t *filter_word(const QMeta &m, uint32_t song, uint32_t dbits, uint32_t *__restrict__ filter,
+                                                 uint32_t &seen_bit) {
+  const uint32_t h = mix32(song * 0x85ebca6bu ^ (dbits * 0xc2b2ae35u + 0x27d4eb2fu));
+  seen_bit = 1u << (2 * (h & 15u));
+  return filter + m.filt_base + slot_of(h, m.filt_words);
+}
+
 // One block handles tuples_per_block consecutive vote tuples (postings of the entries [e0, e0+n), numbered by the
 // exclusive scan off[]), whatever entries they belong to: a heavy key's run is shared by many blocks.
-template <bool DENSE>
+// MODE 0: every tuple is counted in the bin table.  MODE 1 / 2, the two-pass form that keeps the tables in L2:
+// pass 1 only marks each tuple's bucket in the query's duplicate filter (seen / seen twice); pass 2 counts a tuple in
+// the (then 4x smaller) bin table only if its bucket was seen twice — a tuple alone in its bucket is a bin of count 1.
+template <bool DENSE, int MODE>
 __global__ void __launch_bounds__(256)
 expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, const uint32_t *__restrict__ first,
                    const int64_t *__restrict__ off, const uint32_t *__restrict__ cnt_head,
                    const ulonglong2 *__restrict__ rows, const QMeta *__restrict__ meta,
                    unsigned long long *__restrict__ bins, uint32_t *__restrict__ song_key,
                    uint32_t *__restrict__ song_rows, unsigned long long *__restrict__ song_best,
-                   unsigned long long *__restrict__ n_bins, int tuples_per_block, int32_t *__restrict__ overflow) {
+                   uint32_t *__restrict__ filter, unsigned long long *__restrict__ n_bins, int tuples_per_block,
+                   int32_t *__restrict__ overflow) {
   __shared__ int64_t s_off[257];
   __shared__ int64_t s_first;
   const int64_t j_lo = off[e0] + (int64_t)blockIdx.x * tuples_per_block;
@@ -550,7 +578,23 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
     const QMeta m = meta[e.y >> 40];
     const uint32_t song = (uint32_t)(r.x >> 24) & 0xffffffu;
     const uint32_t dbits = (uint32_t)((int32_t)(r.x & kM24) - (int32_t)(e.x & kM24) + SIA_DIFF_BIAS);   // db - query offset
-    const int64_t ss = vote_insert<DENSE>(m, song, dbits, bins, song_key, song_best, fresh, overflow);
+    if (MODE == 1) {
+      uint32_t seen;
+      uint32_t *w = filter_word(m, song, dbits, filter, seen);
+      const uint32_t old = atomicOr(w, seen);
+      if ((old & seen) && !(old & (seen << 1))) atomicOr(w, seen << 1);
+      continue;
+    }
+    unsigned long long count = 1;
+    if (MODE == 2) {
+      uint32_t seen;
+      const uint32_t *w = filter_word(m, song, dbits, filter, seen);
+      if (__ldcg(w) & (seen << 1)) count = bin_count(m, song, dbits, bins, fresh, overflow);
+      else ++fresh;                                                 // alone in its bucket: a bin of its own
+    } else {
+      count = bin_count(m, song, dbits, bins, fresh, overflow);
+    }
+    const int64_t ss = count ? song_update<DENSE>(m, song, dbits, count, song_key, song_best, overflow) : -1;
     if (ss >= 0 && cnt_head[ei]) atomicAdd(&song_rows[ss], 1u);    // first entry of its (query, hash): the row counts once
     }
     if (s_off[nloc] >= j_hi) break;      // uniform: every thread reads the same shared value
@@ -609,7 +653,7 @@ build_meta_kernel(const uint32_t *__restrict__ cnt_t, const uint32_t *__restrict
   sb = s_b[threadIdx.x]; ss = s_s[threadIdx.x];
   for (int q = a; q < b; ++q) {
     QMeta m;
-    m.bin_base = sb; m.song_base = ss;
+    m.bin_base = sb; m.song_base = ss; m.filt_base = 0; m.filt_words = 0; m.pad_ = 0;
     m.bin_cap = (uint32_t)((int64_t)mult * cnt_t[q] + 32);
     m.song_cap = dense_span > 0 ? (uint32_t)dense_span : 2 * cnt_r[q] + 32;
     meta[q] = m;
@@ -1210,6 +1254,7 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
   const int64_t hash_budget = getenv("SIA_VOTE_GROUP_TUPLES") ? std::max(1ll, atoll(getenv("SIA_VOTE_GROUP_TUPLES")))
                                                                : (512ll << 20);
   const int vote_chunk = getenv("SIA_VOTE_CHUNK") ? std::max(256, atoi(getenv("SIA_VOTE_CHUNK"))) : kVoteTuplesDefault;
+  const bool use_filter = !(getenv("SIA_VOTE_FILTER") && atoi(getenv("SIA_VOTE_FILTER")) == 0);
   const int vote_mult = getenv("SIA_VOTE_LOAD") ? std::min(16, std::max(2, atoi(getenv("SIA_VOTE_LOAD")))) : 2;   // bin slots per tuple
   // tuples voted at once: sort path x ~70 B of scratch each; hash path x ~16 B of tables, one launch per group
   int64_t tuple_budget = use_hash ? hash_budget : (96ll << 20);
@@ -1261,42 +1306,104 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
       qa = qb;
     }
     if (need && (rc = ix->arena2.reserve(need))) return rc;
-    // hash-table vote: table layout per group; song tables dense when that is the smaller layout
-    std::vector<QMeta> h_meta(nq);
+    // hash-table vote: table layout per group; song tables dense when that is the smaller layout.  With the
+    // duplicate filter (default; SIA_VOTE_FILTER=0 turns it off) the bin table holds only tuples whose filter
+    // bucket was hit twice: t/2 + 64 slots instead of 2t + 32, next to t + 1 filter words.
+    std::vector<QMeta> h_meta(nq), h_meta0(nq);        // filtered layout / plain layout (fallback)
     std::vector<char> dense(groups.size(), 0);
-    int64_t max_bin = 0, max_song = 0;
+    int64_t max_bytes = 0;
     const int64_t span = (int64_t)ix->max_song + 1;
+    auto layout = [&](const Group &g, bool dns, bool filt, std::vector<QMeta> &out, int64_t *nb, int64_t *ns, int64_t *nf) {
+      int64_t bb = 0, sb = 0, fb = 0;
+      for (int q = g.qa; q < g.qb; ++q) {
+        const int64_t t = h_off_all[q + 1] - h_off_all[q], h = h_off_head[q + 1] - h_off_head[q];
+        QMeta &m = out[q];
+        m.bin_base = bb; m.song_base = sb; m.filt_base = fb; m.pad_ = 0;
+        m.bin_cap = filt ? (uint32_t)(t / 2 + 64)
+                         : (uint32_t)(std::min<int64_t>(vote_mult, 0xffffff00ll / std::max<int64_t>(t, 1)) * t + 32);
+        m.song_cap = dns ? (uint32_t)span : (uint32_t)(2 * h + 32);
+        m.filt_words = filt ? (uint32_t)(t + 1) : 0u;
+        bb += m.bin_cap; sb += m.song_cap; fb += m.filt_words;
+      }
+      *nb = bb; *ns = sb; *nf = fb;
+    };
+    auto table_bytes = [](int64_t nb, int64_t ns, int64_t nf, bool dns) {
+      return (size_t)nb * 8 + (size_t)ns * (dns ? 12 : 16) + (size_t)nf * 4;
+    };
+    bool any_hash = false;
     for (size_t gi = 0; gi < groups.size(); ++gi) {
       const Group &g = groups[gi];
       if (g.sorted) continue;
+      any_hash = true;
       int64_t hashed_slots = 0;
-      for (int q = g.qa; q < g.qb; ++q) hashed_slots += 2 * (h_off_head[q + 1] - h_off_head[q]) + 32;
-      dense[gi] = span * (g.qb - g.qa) * 12 <= hashed_slots * 16 * 2;
-      int64_t bb = 0, sb = 0;
       for (int q = g.qa; q < g.qb; ++q) {
-        const int64_t t = h_off_all[q + 1] - h_off_all[q], h = h_off_head[q + 1] - h_off_head[q];
-        SIA_REQUIRE(t < (1ll << 30), SIA_E_UNSUPPORTED, "query_batch: more than 2^30 vote tuples in one query");
-        h_meta[q].bin_base = bb; h_meta[q].song_base = sb;
-        h_meta[q].bin_cap = (uint32_t)(std::min<int64_t>(vote_mult, 0xffffff00ll / std::max<int64_t>(t, 1)) * t + 32);
-        h_meta[q].song_cap = dense[gi] ? (uint32_t)span : (uint32_t)(2 * h + 32);
-        bb += h_meta[q].bin_cap; sb += h_meta[q].song_cap;
+        hashed_slots += 2 * (h_off_head[q + 1] - h_off_head[q]) + 32;
+        SIA_REQUIRE(h_off_all[q + 1] - h_off_all[q] < (1ll << 30), SIA_E_UNSUPPORTED,
+                    "query_batch: more than 2^30 vote tuples in one query");
       }
-      max_bin = std::max(max_bin, bb); max_song = std::max(max_song, sb);
+      dense[gi] = span * (g.qb - g.qa) * 12 <= hashed_slots * 16 * 2;
+      int64_t nb, ns, nf;
+      layout(g, dense[gi], false, h_meta0, &nb, &ns, &nf);           // the arena must hold the fallback layout too
+      max_bytes = std::max<int64_t>(max_bytes, table_bytes(nb, ns, nf, dense[gi]));
+      if (use_filter) {
+        layout(g, dense[gi], true, h_meta, &nb, &ns, &nf);
+        max_bytes = std::max<int64_t>(max_bytes, table_bytes(nb, ns, nf, dense[gi]));
+      }
     }
-    unsigned long long *bins = nullptr, *song_best = nullptr, *d_nbins = nullptr;
-    uint32_t *song_key = nullptr, *song_rows = nullptr;
-    QMeta *d_meta = nullptr;
-    if (max_bin > 0) {
-      // one zero-fill per group covers [bins | song_best | song_rows | song_key] up to the group's sizes,
-      // so the arrays are laid out per group: offsets are recomputed below from the group's own totals
-      if ((rc = ix->arena3.reserve((size_t)max_bin * 8 + (size_t)max_song * 16 + (size_t)nq * sizeof(QMeta) + 8192))) return rc;
+    const int max_bin = any_hash ? 1 : 0;
+    char *tables = nullptr;
+    unsigned long long *d_nbins = nullptr;      // [groups]: distinct bins per group
+    int32_t *d_gflags = nullptr;                // [groups]: 8 = a table filled up (filter under-estimate), 16 = count overflow
+    QMeta *d_meta = nullptr, *d_meta0 = nullptr;
+    const size_t ng = groups.size();
+    if (any_hash) {
+      if ((rc = ix->arena3.reserve((size_t)max_bytes + 2 * (size_t)nq * sizeof(QMeta) + ng * 12 + 16384))) return rc;
       d_meta = ix->arena3.take<QMeta>(nq);
-      d_nbins = ix->arena3.take<unsigned long long>(1);
-      bins = ix->arena3.take<unsigned long long>((size_t)max_bin + 2 * (size_t)max_song);
-      SIA_REQUIRE(d_meta && d_nbins && bins, SIA_E_NOMEM, "index scratch arena too small (vote tables)");
+      d_meta0 = ix->arena3.take<QMeta>(nq);
+      d_nbins = ix->arena3.take<unsigned long long>(ng);
+      d_gflags = ix->arena3.take<int32_t>(ng);
+      tables = ix->arena3.take<char>((size_t)max_bytes);
+      SIA_REQUIRE(d_meta && d_meta0 && d_nbins && d_gflags && tables, SIA_E_NOMEM, "index scratch arena too small (vote tables)");
       SIA_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(QMeta) * nq, cudaMemcpyHostToDevice, s));
-      SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long), s));
+      SIA_CUDA(cudaMemcpyAsync(d_meta0, h_meta0.data(), sizeof(QMeta) * nq, cudaMemcpyHostToDevice, s));
+      SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long) * ng, s));
+      SIA_CUDA(cudaMemsetAsync(d_gflags, 0, sizeof(int32_t) * ng, s));
     }
+    // one group through the tables: filt = two-pass form with the duplicate filter
+    auto vote_group = [&](size_t gi, bool filt) -> int {
+      const Group &g = groups[gi];
+      const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
+      const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa];
+      const std::vector<QMeta> &hm = filt ? h_meta : h_meta0;
+      const QMeta *dm = filt ? d_meta : d_meta0;
+      const QMeta &last = hm[g.qb - 1];
+      const int64_t nb = last.bin_base + last.bin_cap, ns = last.song_base + last.song_cap, nf = last.filt_base + last.filt_words;
+      // [bins | song_best | song_rows | song_key (open addressing only) | filter]: one zero-fill
+      unsigned long long *bins = reinterpret_cast<unsigned long long *>(tables);
+      unsigned long long *song_best = bins + nb;
+      uint32_t *song_rows = reinterpret_cast<uint32_t *>(song_best + ns);
+      uint32_t *song_key = song_rows + ns;
+      uint32_t *filter = dense[gi] ? song_key : song_key + ns;
+      SIA_CUDA(cudaMemsetAsync(tables, 0, table_bytes(nb, ns, nf, dense[gi]), s));
+      const unsigned blocks = (unsigned)ceil_div(tuples, vote_chunk);
+      unsigned long long *nbp = d_nbins + gi;
+      int32_t *fl = d_gflags + gi;
+#define SIA_EXPAND(D, M)                                                                                              \
+      expand_vote_kernel<D, M><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->rows, dm, bins, \
+                                                      song_key, song_rows, song_best, filter, nbp, vote_chunk, fl)
+      if (dense[gi]) {
+        if (filt) { SIA_EXPAND(true, 1); SIA_EXPAND(true, 2); } else { SIA_EXPAND(true, 0); }
+        topn_hash_kernel<true><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, dm, g.qa, (int)q0, topn,
+                                                           d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
+      } else {
+        if (filt) { SIA_EXPAND(false, 1); SIA_EXPAND(false, 2); } else { SIA_EXPAND(false, 0); }
+        topn_hash_kernel<false><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, dm, g.qa, (int)q0, topn,
+                                                            d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
+      }
+#undef SIA_EXPAND
+      SIA_CHECK_LAUNCH();
+      return SIA_OK;
+    };
     for (size_t gi = 0; gi < groups.size(); ++gi) {
       const Group &g = groups[gi];
       const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
@@ -1318,35 +1425,33 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
         continue;
       }
       if (tuples == 0) continue;           // out_nres is already 0 for these queries
-      const QMeta &last = h_meta[g.qb - 1];
-      const int64_t nb = last.bin_base + last.bin_cap, ns = last.song_base + last.song_cap;
-      song_best = bins + nb;
-      song_rows = reinterpret_cast<uint32_t *>(song_best + ns);
-      song_key = song_rows + ns;
-      SIA_CUDA(cudaMemsetAsync(bins, 0, (size_t)nb * 8 + (size_t)ns * (dense[gi] ? 12 : 16), s));
-      const unsigned blocks = (unsigned)ceil_div(tuples, vote_chunk);
-      unsigned long long *nbp = h_stats ? d_nbins : nullptr;
-      if (dense[gi]) {
-        expand_vote_kernel<true><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->rows, d_meta,
-                                                        bins, song_key, song_rows, song_best, nbp, vote_chunk, ix->status);
-        topn_hash_kernel<true><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, d_meta, g.qa, (int)q0, topn,
-                                                           d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
-      } else {
-        expand_vote_kernel<false><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->rows, d_meta,
-                                                         bins, song_key, song_rows, song_best, nbp, vote_chunk, ix->status);
-        topn_hash_kernel<false><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, d_meta, g.qa, (int)q0, topn,
-                                                            d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
-      }
-      SIA_CHECK_LAUNCH();
+      if ((rc = vote_group(gi, use_filter))) return rc;
     }
-    if (h_stats && max_bin > 0) {
-      unsigned long long nbv = 0;
-      SIA_CUDA(cudaMemcpyAsync(&nbv, d_nbins, sizeof nbv, cudaMemcpyDeviceToHost, s));
+    if (any_hash) {
+      // groups whose filtered bin table filled up (mostly-duplicate tuples: more than a quarter of them shared a
+      // bucket) are redone without the filter; their results and bin counts are simply overwritten
+      std::vector<int32_t> h_flags(ng);
+      std::vector<unsigned long long> h_nb(ng);
+      SIA_CUDA(cudaMemcpyAsync(h_flags.data(), d_gflags, sizeof(int32_t) * ng, cudaMemcpyDeviceToHost, s));
       SIA_CUDA(cudaStreamSynchronize(s));
-      h_stats[3] += (int64_t)nbv;
+      bool redo = false;
+      for (size_t gi = 0; gi < ng; ++gi) {
+        if (!(h_flags[gi] & 8)) continue;
+        SIA_REQUIRE(use_filter, SIA_E_CUDA, "query: vote table overflow (internal error)");
+        redo = true;
+        SIA_CUDA(cudaMemsetAsync(d_nbins + gi, 0, sizeof(unsigned long long), s));
+        SIA_CUDA(cudaMemsetAsync(d_gflags + gi, 0, sizeof(int32_t), s));
+        if ((rc = vote_group(gi, false))) return rc;
+      }
+      SIA_CUDA(cudaMemcpyAsync(h_nb.data(), d_nbins, sizeof(unsigned long long) * ng, cudaMemcpyDeviceToHost, s));
+      if (redo) SIA_CUDA(cudaMemcpyAsync(h_flags.data(), d_gflags, sizeof(int32_t) * ng, cudaMemcpyDeviceToHost, s));
+      SIA_CUDA(cudaStreamSynchronize(s));
+      for (size_t gi = 0; gi < ng; ++gi) {
+        SIA_REQUIRE(!(h_flags[gi] & (8 | 16)), SIA_E_CUDA, "query: vote table overflow (internal error)");
+        if (h_stats) h_stats[3] += (int64_t)h_nb[gi];
+      }
     }
     if (timing) cudaEventRecord(ev[2], s);
-    if (max_bin > 0 && (rc = check_status(ix, s, 8 | 16, "query: vote table overflow (internal error)"))) return rc;
     SIA_CUDA(cudaStreamSynchronize(s));      // the lookup scratch and the tables are reused by the next pass / call
     if (timing) {
       float t_lookup = 0, t_vote = 0;

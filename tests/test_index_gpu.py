@@ -461,13 +461,17 @@ def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch, id_stride):
                 if drop70:
                     a = np.delete(a, 70, axis=0); b = np.delete(b, 70, axis=0)
                 assert np.array_equal(a, b), ("vote_tuples", drop70, name, topn)
-        for budget in (None, "1000", "200000", str(1 << 40)):
-            if budget is None:
-                monkeypatch.delenv("SIA_VOTE_GROUP_TUPLES", raising=False)
-            else:
-                monkeypatch.setenv("SIA_VOTE_GROUP_TUPLES", budget)
+        # with the duplicate filter (two passes; these tie-heavy queries overflow the small bin table of most
+        # groups, which are then redone without it) and without; any grouping of the queries
+        for budget, filt in ((None, None), ("1000", None), ("200000", None), (str(1 << 40), None), (None, "0"), ("50000", "0")):
+            for name, val in (("SIA_VOTE_GROUP_TUPLES", budget), ("SIA_VOTE_FILTER", filt)):
+                if val is None:
+                    monkeypatch.delenv(name, raising=False)
+                else:
+                    monkeypatch.setenv(name, val)
             got, got_stats = run(topn)
-            assert got_stats == want_stats, (topn, budget)
+            assert got_stats == want_stats, (topn, budget, filt)
             for a, b, name in zip(got, want, ("song", "diff", "count", "rows", "nres")):
-                assert np.array_equal(a, b), (name, topn, budget)
+                assert np.array_equal(a, b), (name, topn, budget, filt)
         monkeypatch.delenv("SIA_VOTE_GROUP_TUPLES", raising=False)
+        monkeypatch.delenv("SIA_VOTE_FILTER", raising=False)
