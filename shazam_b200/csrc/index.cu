@@ -533,7 +533,10 @@ __device__ __forceinline__ uint32_t *filter_word(const QMeta &m, uint32_t song, 
 }
 
 // One block handles tuples_per_block consecutive vote tuples (postings of the entries [e0, e0+n), numbered by the
-// exclusive scan off[]), whatever entries they belong to: a heavy key's run is shared by many blocks.
+// exclusive scan off[]), whatever entries they belong to: a heavy key's run is shared by many blocks.  Each warp
+// takes an eighth of the block's tuples and walks the entries they belong to: everything that depends on the
+// entry (query tables, query offset, head flag, first posting) is warp-uniform and loaded once per entry, the
+// lanes then take the entry's postings 32 at a time.
 // MODE 0: every tuple is counted in the bin table.  MODE 1 / 2, the two-pass form that keeps the tables in L2:
 // pass 1 only marks each tuple's bucket in the query's duplicate filter (seen / seen twice); pass 2 counts a tuple in
 // the (then 4x smaller) bin table only if its bucket was seen twice — a tuple alone in its bucket is a bin of count 1.
@@ -546,63 +549,57 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
                    uint32_t *__restrict__ song_rows, unsigned long long *__restrict__ song_best,
                    uint32_t *__restrict__ filter, unsigned long long *__restrict__ n_bins, int tuples_per_block,
                    int32_t *__restrict__ overflow) {
-  __shared__ int64_t s_off[257];
-  __shared__ int64_t s_first;
-  const int64_t j_lo = off[e0] + (int64_t)blockIdx.x * tuples_per_block;
-  const int64_t j_hi = min(off[e0 + n], j_lo + tuples_per_block);
-  if (threadIdx.x == 0) {                // largest entry e in [e0, e0+n) with off[e] <= j_lo
-    int64_t lo = e0, hi = e0 + n;
-    while (hi - lo > 1) { const int64_t mid = lo + ((hi - lo) >> 1); if (off[mid] <= j_lo) lo = mid; else hi = mid; }
-    s_first = lo;
-  }
-  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per_warp = tuples_per_block >> 3;
+  const int64_t j_lo = off[e0] + (int64_t)blockIdx.x * tuples_per_block + (int64_t)warp * per_warp;
+  const int64_t j_hi = min(off[e0 + n], j_lo + per_warp);
   uint32_t fresh = 0;
-  for (int64_t b0 = s_first; b0 < e0 + n; b0 += 256) {      // pieces of 256 entries until the block's tuples are covered
-    const int nloc = (int)min((int64_t)256, e0 + n - b0);
-    __syncthreads();
-    for (int i = threadIdx.x; i <= nloc; i += 256) s_off[i] = off[b0 + i];
-    __syncthreads();
-    const int64_t p_lo = max(j_lo, s_off[0]), p_hi = min(j_hi, s_off[nloc]);
-    // warp-uniform trip count; the warp reconverges at the top of every iteration (the probe loops below diverge)
-    for (int64_t jw = p_lo + (threadIdx.x & ~31); jw < p_hi; jw += 256) {
-    __syncwarp();
-    const int64_t j = jw + (threadIdx.x & 31);
-    int lo = 0, hi = nloc;               // largest e with s_off[e] <= jw (same for the whole warp)
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= jw) lo = mid; else hi = mid; }
-    if (j >= p_hi) continue;
-    while (s_off[lo + 1] <= j) ++lo;     // a warp's 32 consecutive tuples rarely span more than two entries
-    const int64_t ei = b0 + lo;
-    const uint32_t k = (uint32_t)(j - s_off[lo]);
-    const ulonglong2 e = ent[ei];
-    const ulonglong2 r = rows[first[ei] + k];
-    const QMeta m = meta[e.y >> 40];
-    const uint32_t song = (uint32_t)(r.x >> 24) & 0xffffffu;
-    const uint32_t dbits = (uint32_t)((int32_t)(r.x & kM24) - (int32_t)(e.x & kM24) + SIA_DIFF_BIAS);   // db - query offset
-    if (MODE == 1) {
-      uint32_t seen;
-      uint32_t *w = filter_word(m, song, dbits, filter, seen);
-      const uint32_t old = atomicOr(w, seen);
-      if ((old & seen) && !(old & (seen << 1))) atomicOr(w, seen << 1);
-      continue;
+  if (j_lo < j_hi) {
+    int64_t ei = e0, hi = e0 + n;          // largest entry in [e0, e0+n) with off[ei] <= j_lo (warp-uniform search)
+    while (hi - ei > 1) { const int64_t mid = ei + ((hi - ei) >> 1); if (off[mid] <= j_lo) ei = mid; else hi = mid; }
+    for (; ei < e0 + n; ++ei) {
+      const int64_t o_this = off[ei], o_next = off[ei + 1];
+      if (o_this >= j_hi) break;
+      if (o_next == o_this) continue;                              // a hash without postings (or a duplicate pair)
+      const ulonglong2 e = ent[ei];
+      const QMeta m = meta[e.y >> 40];
+      const uint32_t qoff = (uint32_t)(e.x & kM24);
+      const bool head = cnt_head[ei] != 0;                         // first entry of its (query, hash): rows count once
+      const ulonglong2 *__restrict__ run = rows + first[ei];
+      const uint32_t k_hi = (uint32_t)(min(j_hi, o_next) - o_this);
+      for (uint32_t kw = (uint32_t)(max(j_lo, o_this) - o_this); kw < k_hi; kw += 32) {
+        __syncwarp();                                              // the probe loops below diverge
+        const uint32_t k = kw + lane;
+        if (k >= k_hi) continue;
+        const ulonglong2 r = run[k];
+        const uint32_t song = (uint32_t)(r.x >> 24) & 0xffffffu;
+        const uint32_t dbits = (uint32_t)(r.x & kM24) - qoff + SIA_DIFF_BIAS;    // db offset - query offset, biased
+        if (MODE == 1) {
+          uint32_t seen;
+          uint32_t *w = filter_word(m, song, dbits, filter, seen);
+          const uint32_t old = atomicOr(w, seen);
+          if ((old & seen) && !(old & (seen << 1))) atomicOr(w, seen << 1);
+          continue;
+        }
+        unsigned long long count = 1;
+        if (MODE == 2) {
+          uint32_t seen;
+          const uint32_t *w = filter_word(m, song, dbits, filter, seen);
+          if (__ldcg(w) & (seen << 1)) count = bin_count(m, song, dbits, bins, fresh, overflow);
+          else ++fresh;                                             // alone in its bucket: a bin of its own
+        } else {
+          count = bin_count(m, song, dbits, bins, fresh, overflow);
+        }
+        const int64_t ss = count ? song_update<DENSE>(m, song, dbits, count, song_key, song_best, overflow) : -1;
+        if (ss >= 0 && head) atomicAdd(&song_rows[ss], 1u);
+      }
+      __syncwarp();
     }
-    unsigned long long count = 1;
-    if (MODE == 2) {
-      uint32_t seen;
-      const uint32_t *w = filter_word(m, song, dbits, filter, seen);
-      if (__ldcg(w) & (seen << 1)) count = bin_count(m, song, dbits, bins, fresh, overflow);
-      else ++fresh;                                                 // alone in its bucket: a bin of its own
-    } else {
-      count = bin_count(m, song, dbits, bins, fresh, overflow);
-    }
-    const int64_t ss = count ? song_update<DENSE>(m, song, dbits, count, song_key, song_best, overflow) : -1;
-    if (ss >= 0 && cnt_head[ei]) atomicAdd(&song_rows[ss], 1u);    // first entry of its (query, hash): the row counts once
-    }
-    if (s_off[nloc] >= j_hi) break;      // uniform: every thread reads the same shared value
   }
-  if (n_bins) {
+  if (n_bins && MODE != 1) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
-    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(n_bins, (unsigned long long)fresh);
+    if (lane == 0 && fresh) atomicAdd(n_bins, (unsigned long long)fresh);
   }
 }
 
