@@ -457,7 +457,7 @@ struct QMeta {
 constexpr int kBinCountBits = 15;
 constexpr int64_t kMaxHashVoteEntries = (1 << kBinCountBits) - 1;
 constexpr int kTopK = 4;          // results extracted per scan of a query's song table
-constexpr int kVoteTuplesDefault = 2048; // vote tuples per block of expand_vote_kernel
+constexpr int kVoteTuplesDefault = 4096; // vote tuples per block of expand_vote_kernel (512 per warp)
 
 __device__ __forceinline__ uint32_t mix32(uint32_t k) {
   k ^= k >> 16; k *= 0x85ebca6bu; k ^= k >> 13; k *= 0xc2b2ae35u; k ^= k >> 16;
