@@ -1250,7 +1250,8 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
   const bool use_hash = !(getenv("SIA_VOTE") && std::string(getenv("SIA_VOTE")) == "sort");
   const int64_t hash_budget = getenv("SIA_VOTE_GROUP_TUPLES") ? std::max(1ll, atoll(getenv("SIA_VOTE_GROUP_TUPLES")))
                                                                : (512ll << 20);
-  const int vote_chunk = getenv("SIA_VOTE_CHUNK") ? std::max(256, atoi(getenv("SIA_VOTE_CHUNK"))) : kVoteTuplesDefault;
+  // tuples per block of expand_vote_kernel: a multiple of 8 (every warp takes an eighth)
+  const int vote_chunk = getenv("SIA_VOTE_CHUNK") ? std::max(256, atoi(getenv("SIA_VOTE_CHUNK")) & ~7) : kVoteTuplesDefault;
   const bool use_filter = !(getenv("SIA_VOTE_FILTER") && atoi(getenv("SIA_VOTE_FILTER")) == 0);
   const int vote_mult = getenv("SIA_VOTE_LOAD") ? std::min(16, std::max(2, atoi(getenv("SIA_VOTE_LOAD")))) : 2;   // bin slots per tuple
   // tuples voted at once: sort path x ~70 B of scratch each; hash path x ~16 B of tables, one launch per group
