@@ -463,15 +463,17 @@ def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch, id_stride):
                 assert np.array_equal(a, b), ("vote_tuples", drop70, name, topn)
         # with the duplicate filter (two passes; these tie-heavy queries overflow the small bin table of most
         # groups, which are then redone without it) and without; any grouping of the queries
-        for budget, filt in ((None, None), ("1000", None), ("200000", None), (str(1 << 40), None), (None, "0"), ("50000", "0")):
-            for name, val in (("SIA_VOTE_GROUP_TUPLES", budget), ("SIA_VOTE_FILTER", filt)):
+        names = ("SIA_VOTE_GROUP_TUPLES", "SIA_VOTE_FILTER", "SIA_VOTE_CHUNK")
+        for setting in ((None, None, None), ("1000", None, None), ("200000", None, "1001"), (str(1 << 40), None, None),
+                        (None, "0", None), ("50000", "0", "300")):
+            for name, val in zip(names, setting):
                 if val is None:
                     monkeypatch.delenv(name, raising=False)
                 else:
                     monkeypatch.setenv(name, val)
             got, got_stats = run(topn)
-            assert got_stats == want_stats, (topn, budget, filt)
+            assert got_stats == want_stats, (topn, setting)
             for a, b, name in zip(got, want, ("song", "diff", "count", "rows", "nres")):
-                assert np.array_equal(a, b), (name, topn, budget, filt)
-        monkeypatch.delenv("SIA_VOTE_GROUP_TUPLES", raising=False)
-        monkeypatch.delenv("SIA_VOTE_FILTER", raising=False)
+                assert np.array_equal(a, b), (name, topn, setting)
+        for name in names:
+            monkeypatch.delenv(name, raising=False)
