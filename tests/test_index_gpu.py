@@ -400,11 +400,13 @@ def test_union_channels_device(fpr):
     assert len(dev_set) == hd.shape[0] < len(batch.t1)                   # duplicates existed and were dropped
 
 
-@pytest.mark.parametrize("id_stride", [1, 50000])
-def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch, id_stride):
+@pytest.mark.parametrize("id_stride,off_range", [(1, 64), (50000, 64), (1, 1 << 16)])
+def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch, id_stride, off_range):
     """The hash-table vote (default) and the sort-based vote give identical results — counts, smallest-diff and
     ascending-song tie-breaks, dedup rows, stats — for any grouping of the queries (recognizer.py:303-310).
-    id_stride 1: dense song tables; 50000: song ids up to 1.5e7 -> open-addressing song tables.  One query has
+    id_stride 1: dense song tables; 50000: song ids up to 1.5e7 -> open-addressing song tables.  off_range 64:
+    tie-heavy bins (the two-pass vote's small bin tables overflow and the groups are redone single-pass); 65536:
+    mostly distinct bins (the duplicate filter keeps most tuples out of the bin table).  One query has
     more entries than a packed bin count can hold and takes the sort-based vote inside the hash-table pass."""
     import torch
     rng = np.random.default_rng(77)
@@ -415,7 +417,7 @@ def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch, id_stride):
                          np.uint8).reshape(universe, 10)
     dig = pool[keys]
     song = np.repeat(np.arange(1, nsongs + 1, dtype=np.int32) * id_stride, per_song)
-    off = rng.integers(0, 64, n).astype(np.int32)
+    off = rng.integers(0, off_range, n).astype(np.int32)
     # one more song whose 33000 rows all align with query 70 at the same difference: a bin count beyond 15 bits
     n_big = 33000
     big = np.frombuffer(b"".join(hashlib.sha1(b"big%d" % i).digest()[:10] for i in range(n_big)), np.uint8).reshape(n_big, 10)
