@@ -336,16 +336,17 @@ def main():
                 "avg_launch_ms": k1_ms / k1_launches, "kernel_ms_per_step": kernel_ms,
                 "share_of_step": round(k1_ms / max(sum(kms), 1e-9), 4)}
     if args.compute == "f64" and k1_ms > 0:
-        # what actually bounds K1: the FP64 pipe.  880 DP instructions per thread and frame (static SASS count =
-        # ncu's 3 520 DP warp instructions per frame); a B200 SM sub-partition issues one DP warp instruction
-        # every 2 cycles -> 148 x 4 / 2 per clock at the sampled SM clock
-        dp_warp_inst = 3520.0 * B * frames_per_track * args.steps
+        # what actually bounds K1: the FP64 pipe (+ the integer pipe).  854 DP arithmetic instructions
+        # per thread and frame (static SASS count: 455 DADD, 249 DFMA, 150 DMUL) x 4 warps = 3 416 DP warp
+        # instructions per frame; a B200 SM sub-partition issues one DP warp instruction every 2 cycles
+        # (tools/ubench/fp64_rate.cu: 2.13) -> 148 x 4 / 2 per clock at the sampled SM clock
+        dp_warp_inst = 3416.0 * B * frames_per_track * args.steps
         clk = (clocks or {}).get("sm_mhz") or 1965.0
         dp_peak = 148 * 4 / 2 * clk * 1e6
         roofline["fp64_pipe"] = {"achieved_warp_inst_per_s": dp_warp_inst / (k1_ms * 1e-3), "peak_warp_inst_per_s": dp_peak,
                                  "frac": dp_warp_inst / (k1_ms * 1e-3) / dp_peak,
-                                 "note": "K1 computes in float64 (1e-3 dB bound on every bin); 3520 DP warp instructions "
-                                         "per frame (ncu, profiles/), DP issue rate 1 per 2 cycles per sub-partition"}
+                                 "note": "K1 computes in float64 (1e-3 dB bound on every bin); 3416 DP warp instructions "
+                                         "per frame (SASS), DP issue rate 1 per 2 cycles per sub-partition (tools/ubench)"}
     prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(prof):
         try:
