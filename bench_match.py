@@ -192,6 +192,28 @@ def main():
         out = shard.index.query_batch(qh, qt1, q_starts, args.topn, want_stats=True)
         qstats = out[5]
 
+    # ---- end to end: query hashes start in pinned host memory, results end in host memory, every step ----------
+    h_qh = qh.cpu().pin_memory(); h_qt1 = qt1.cpu().pin_memory()
+
+    def step_host():
+        d_h = h_qh.to(dev, non_blocking=True); d_t = h_qt1.to(dev, non_blocking=True)
+        r = shard.index.query_batch(d_h, d_t, q_starts, args.topn) if world == 1 else index.query(d_h, d_t, q_starts, args.topn)
+        return [x.cpu() for x in r[:5]]
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_host = step_host()
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    e2e = {"value": args.queries / e2e_s, "unit": "queries/s", "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step_per_rank": int(h_qh.numel() + 4 * h_qt1.numel()),
+           "d2h_bytes_per_step_per_rank": int(sum(x.numel() * 4 for x in res_host)),
+           "api": "pinned host (digest, offset) arrays -> query_batch / ShardedIndex.query -> results in host memory"}
+
     sweep = {}
     if world == 1 and args.vote_sweep:
         for setting in args.vote_sweep.split(","):
@@ -227,6 +249,7 @@ def main():
             "accuracy_top1_song_and_offset": stats[0] / max(1, stats[1]),
             "index_build_seconds": round(t_build, 2),
             "index_build_rows_per_second": rows / t_build,
+            "e2e": e2e,
         }
         if sweep:
             line["vote_sweep_ms_per_step"] = sweep
