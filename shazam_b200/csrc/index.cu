@@ -567,11 +567,15 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
       const bool head = cnt_head[ei] != 0;                         // first entry of its (query, hash): rows count once
       const ulonglong2 *__restrict__ run = rows + first[ei];
       const uint32_t k_hi = (uint32_t)(min(j_hi, o_next) - o_this);
-      for (uint32_t kw = (uint32_t)(max(j_lo, o_this) - o_this); kw < k_hi; kw += 32) {
+      const uint32_t k_lo = (uint32_t)(max(j_lo, o_this) - o_this);
+      ulonglong2 r_next = make_ulonglong2(0, 0);
+      if (k_lo + lane < k_hi) r_next = run[k_lo + lane];
+      for (uint32_t kw = k_lo; kw < k_hi; kw += 32) {
         __syncwarp();                                              // the probe loops below diverge
         const uint32_t k = kw + lane;
+        const ulonglong2 r = r_next;
+        if (k + 32 < k_hi) r_next = run[k + 32];                   // the next step's posting is in flight during this one
         if (k >= k_hi) continue;
-        const ulonglong2 r = run[k];
         const uint32_t song = (uint32_t)(r.x >> 24) & 0xffffffu;
         const uint32_t dbits = (uint32_t)(r.x & kM24) - qoff + SIA_DIFF_BIAS;    // db offset - query offset, biased
         if (MODE == 1) {
@@ -582,15 +586,27 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
           continue;
         }
         unsigned long long count = 1;
+        unsigned long long seen_best = 0;                          // a read of the song's best issued before the bin work
         if (MODE == 2) {
           uint32_t seen;
           const uint32_t *w = filter_word(m, song, dbits, filter, seen);
-          if (__ldcg(w) & (seen << 1)) count = bin_count(m, song, dbits, bins, fresh, overflow);
+          const uint32_t fw = __ldcg(w);
+          if (DENSE) seen_best = __ldcg(&song_best[m.song_base + song]);   // both reads depend on the posting only
+          if (fw & (seen << 1)) count = bin_count(m, song, dbits, bins, fresh, overflow);
           else ++fresh;                                             // alone in its bucket: a bin of its own
         } else {
           count = bin_count(m, song, dbits, bins, fresh, overflow);
         }
-        const int64_t ss = count ? song_update<DENSE>(m, song, dbits, count, song_key, song_best, overflow) : -1;
+        int64_t ss = -1;
+        if (count) {
+          if (MODE == 2 && DENSE) {
+            ss = m.song_base + song;
+            const unsigned long long val = (count << kDiffBits) | (((1ull << kDiffBits) - 1) - dbits);
+            if (seen_best < val) atomicMax(&song_best[ss], val);    // best only grows: a stale read that covers val is enough
+          } else {
+            ss = song_update<DENSE>(m, song, dbits, count, song_key, song_best, overflow);
+          }
+        }
         if (ss >= 0 && head) atomicAdd(&song_rows[ss], 1u);
       }
       __syncwarp();
