@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--queries", type=int, default=10000, help="queries per step over all ranks")
     ap.add_argument("--topn", type=int, default=3)
     ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--gen-batch", type=int, default=500, help="tracks generated per batch")
     ap.add_argument("--mode", default="hash", choices=["hash", "bins", "track"],
                     help="N>1: hash-prefix sharding exchanging vote keys (default) or sorted bins; or track sharding")
