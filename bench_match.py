@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--rows-per-track", type=int, default=80000)
     ap.add_argument("--queries", type=int, default=10000, help="queries per step over all ranks")
     ap.add_argument("--topn", type=int, default=3)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--gen-batch", type=int, default=500, help="tracks generated per batch")
     ap.add_argument("--mode", default="hash", choices=["hash", "bins", "track"],

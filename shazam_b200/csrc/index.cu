@@ -21,6 +21,7 @@
 #include "sort.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -1288,6 +1289,7 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     SIA_CUDA(cudaMemcpyAsync(d_qs, h_query_starts + q0, sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, s));
     Lookup L;
     const bool timing = getenv("SIA_QUERY_TIMING") != nullptr;     // stage times of this pass on stderr
+    const auto h0 = std::chrono::steady_clock::now();
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     if (timing) { for (auto &e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
     if ((rc = lookup_pass(ix, ix->arena, d_hash, d_qoff, nullptr, d_qs, nq, 0, i0, n, L, s))) return rc;
@@ -1470,8 +1472,9 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     if (timing) {
       float t_lookup = 0, t_vote = 0;
       cudaEventElapsedTime(&t_lookup, ev[0], ev[1]); cudaEventElapsedTime(&t_vote, ev[1], ev[2]);
-      fprintf(stderr, "[sia] query pass: %d queries, %lld entries, %lld tuples, %zu groups: lookup %.2f ms, vote %.2f ms\n",
-              nq, (long long)n, (long long)L.tuples, groups.size(), t_lookup, t_vote);
+      const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+      fprintf(stderr, "[sia] query pass: %d queries, %lld entries, %lld tuples, %zu groups: lookup %.2f ms, vote %.2f ms, host wall %.2f ms\n",
+              nq, (long long)n, (long long)L.tuples, groups.size(), t_lookup, t_vote, host_ms);
       for (auto &e : ev) cudaEventDestroy(e);
     }
   }
