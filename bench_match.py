@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--queries", type=int, default=10000, help="queries per step over all ranks")
     ap.add_argument("--topn", type=int, default=3)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--gen-batch", type=int, default=500, help="tracks generated per batch")
     ap.add_argument("--mode", default="hash", choices=["hash", "bins", "track"],
                     help="N>1: hash-prefix sharding exchanging vote keys (default) or sorted bins; or track sharding")
@@ -167,16 +167,17 @@ def main():
     for _ in range(max(args.warmup, 1)):
         res = step()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for i in range(args.steps):
         res = step()
-    e1.record()
+        evs[i + 1].record()
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    ms = torch.tensor([evs[0].elapsed_time(evs[-1]) / args.steps, float(np.median(per_step))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = float(ms.item())
+    ms_step, ms_median = float(ms[0].item()), float(ms[1].item())
 
     # accuracy (the answer is known by construction)
     song = res[0][:, 0].cpu().numpy() if n_q_local else np.zeros(0, np.int32)
@@ -237,6 +238,7 @@ def main():
         line = {
             "metric": "match_queries_per_second", "value": args.queries / (ms_step * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_step,
+            "ms_per_step_median": ms_median, "ms_per_step_each_rank0": [round(x, 2) for x in per_step],
             "higher_is_better": True, "scaling": "strong (fixed index and query set)",
             "sharding": {"hash": "hash prefix, vote keys exchanged, owner votes with hash tables (exact)",
                          "bins": "hash prefix, sorted partial bins exchanged, owner re-sorts and sums (exact)",
