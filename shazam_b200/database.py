@@ -18,6 +18,7 @@ from typing import Iterable, Optional, Sequence
 
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -171,8 +172,7 @@ class FingerprintIndex:
                     want_stats: bool = False):
         """return_matches + the align_matches vote for Q queries.  Returns CUDA int32 tensors
         (song[Q,topn], diff[Q,topn], count[Q,topn], rows[Q,topn], nres[Q]) (+ stats)."""
-        import time as _t
-        _t0 = _t.perf_counter()
+        t0 = time.perf_counter()
         self.finalize()
         qs = np.ascontiguousarray(query_starts, np.int64)
         Q = len(qs) - 1
@@ -188,7 +188,7 @@ class FingerprintIndex:
                                                C.c_void_p(outs[2].data_ptr()), C.c_void_p(outs[3].data_ptr()),
                                                C.c_void_p(nres.data_ptr()), stats, self._stream()))
         if os.environ.get("SIA_QUERY_TIMING"):
-            print("[sia] query_batch python wall %.2f ms" % ((_t.perf_counter() - _t0) * 1e3), file=sys.stderr)
+            print("[sia] query_batch python wall %.2f ms" % ((time.perf_counter() - t0) * 1e3), file=sys.stderr)
         if want_stats:
             return (*outs, nres, list(stats))
         return (*outs, nres)
