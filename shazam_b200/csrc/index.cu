@@ -867,17 +867,30 @@ int lookup_pass(sia_index *ix, Arena &ar, const uint8_t *d_hash, const int32_t *
   int64_t *off_all = ar.take<int64_t>(n + 1), *off_head = ar.take<int64_t>(n + 1);
   SIA_REQUIRE(a && b && stmp && first && c_all && c_head && off_all && off_head, SIA_E_NOMEM,
               "index scratch arena too small (lookup)");
+  const bool timing = getenv("SIA_QUERY_TIMING") != nullptr;     // stage times on stderr
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (timing) { for (auto &e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
   pack_queries_kernel<<<grid_for(n), 256, 0, s>>>(d_hash, d_qoff, d_qid, d_query_starts, n_queries, qid_base, i0, n, a,
                                                  ix->status);
   SIA_CHECK_LAUNCH();
   bool in_b = false;
   int rc = radix_sort(a, b, n, 16, 0, 16, stmp, s, &in_b);
   if (rc) return rc;
+  if (timing) cudaEventRecord(ev[1], s);
   L.ent = in_b ? b : a;
   lookup_kernel<<<grid_for(n), 256, 0, s>>>(L.ent, n, ix->rows, ix->dir, ix->dir_bits, ix->n_rows, first, c_all, c_head);
   SIA_CHECK_LAUNCH();
+  if (timing) cudaEventRecord(ev[2], s);
   if ((rc = exclusive_scan_u32(c_all, off_all, n, stmp, s))) return rc;
   if ((rc = exclusive_scan_u32(c_head, off_head, n, stmp, s))) return rc;
+  if (timing) {
+    cudaEventRecord(ev[3], s);
+    cudaEventSynchronize(ev[3]);
+    float t1 = 0, t2 = 0, t3 = 0;
+    cudaEventElapsedTime(&t1, ev[0], ev[1]); cudaEventElapsedTime(&t2, ev[1], ev[2]); cudaEventElapsedTime(&t3, ev[2], ev[3]);
+    fprintf(stderr, "[sia] lookup pass: %lld entries: pack + sort %.2f ms, lookup %.2f ms, scans %.2f ms\n", (long long)n, t1, t2, t3);
+    for (auto &e : ev) cudaEventDestroy(e);
+  }
   int64_t tot[2];
   SIA_CUDA(cudaMemcpyAsync(&tot[0], off_all + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   SIA_CUDA(cudaMemcpyAsync(&tot[1], off_head + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
