@@ -24,6 +24,7 @@
 #include "sia_common.cuh"
 #include "stft.cuh"
 
+#include <cstdlib>
 #include <math.h>
 #include <vector>
 
@@ -489,7 +490,11 @@ static int launch(const StftLaunch &a, const StftTables<T> &tb, cudaStream_t s) 
   // 4-5 resident CTAs x 44.5 KB of the SM's 228 KB: ask for the largest shared-memory carveout
   SIA_CUDA(cudaFuncSetAttribute(stft_db_kernel<T, OutT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 (int)cudaSharedmemCarveoutMaxShared));
-  stft_db_kernel<T, OutT><<<(unsigned)blocks, 128, 0, s>>>(
+  // SIA_STFT_PAD_KB: unused dynamic shared memory per CTA — an occupancy experiment knob
+  const char *pad_env = getenv("SIA_STFT_PAD_KB");
+  const size_t pad = pad_env ? (size_t)atoi(pad_env) * 1024 : 0;
+  if (pad) SIA_CUDA(cudaFuncSetAttribute(stft_db_kernel<T, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+  stft_db_kernel<T, OutT><<<(unsigned)blocks, 128, pad, s>>>(
       a.d_pcm, a.d_track_starts, a.d_track_len, a.d_frame_starts, a.n_tracks, a.total_frames, G, (OutT *)a.d_spec,
       sc_mid, sc_edge, (const V2 *)tb.win2, (const V2 *)tb.twA, (const V2 *)tb.twB, (const V2 *)tb.twP);
   SIA_CHECK_LAUNCH();
