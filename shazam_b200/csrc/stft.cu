@@ -127,11 +127,17 @@ template <typename T> __device__ __forceinline__ typename Vec2<T>::type w32(int 
 template <> __device__ __forceinline__ double2 w32<double>(int k) { return c_w32_d[k]; }
 template <> __device__ __forceinline__ float2 w32<float>(int k) { return c_w32_f[k]; }
 
-// int16 sample -> real, exactly, without the (slow) I2F.F64 conversion: splice the integer into the mantissa
-// of 2^52+2^31 (resp. 1.5*2^23) and subtract the magic constant on the FP pipe.
+// int16 sample -> real, exactly.  float64: one I2F.F64.S32 per sample (conversion pipe); the alternative
+// (-DSIA_STFT_SPLICE, and the float32 kernel) splices the integer into the mantissa of 2^52+2^31 (resp. 1.5*2^23) and
+// subtracts the magic constant on the FP pipe.
 template <typename T> __device__ __forceinline__ T sample_to_real(int s);
 template <> __device__ __forceinline__ double sample_to_real<double>(int s) {
+#ifndef SIA_STFT_SPLICE
+  return (double)s;                     // I2F.F64.S32: runs on the conversion pipe, beside the FP64 / integer pipes K1 is
+                                        // bound by (38.2 -> 37.5 ms per 1000 tracks against the mantissa splice below)
+#else
   return __hiloint2double(0x43300000, (int)(0x80000000u ^ (uint32_t)s)) - 4503601774854144.0;
+#endif
 }
 template <> __device__ __forceinline__ float sample_to_real<float>(int s) {
   return __int_as_float(0x4b400000 + s) - 12582912.0f;
