@@ -142,15 +142,34 @@ template <> __device__ __forceinline__ double sample_to_real<double>(int s) {
 template <> __device__ __forceinline__ float sample_to_real<float>(int s) {
   return __int_as_float(0x4b400000 + s) - 12582912.0f;
 }
+// the two int16 samples of a packed PCM word.  float64: converting from `short` lets the compiler read the halves of
+// the register directly (I2F.F64.S16 R, R / R.H1): no extraction instruction on the integer pipe
+template <typename T> __device__ __forceinline__ void sample_pair(uint32_t w, T &s0, T &s1) {
+  s0 = sample_to_real<T>((int)(short)(w & 0xffffu));
+  s1 = sample_to_real<T>((int)w >> 16);
+}
+#ifndef SIA_STFT_SPLICE
+template <> __device__ __forceinline__ void sample_pair<double>(uint32_t w, double &s0, double &s1) {
+  s0 = (double)(short)(w & 0xffffu);
+  s1 = (double)(short)(w >> 16);
+}
+#endif
 
 // dB epilogue.  dB = 10*log10(p*scale) = C*(e + Ki + log2(m) + Kf),  C = 10*log10(2), p = m*2^e, log2(scale) = Ki+Kf.
 // p is rounded to float once (F2F), log2 of its mantissa is one MUFU.LG2 (absolute error ~2^-22); the integer part
 // is recombined with a split constant (E*C_hi is exact), so the result carries 0.5 ulp(float) + ~1.4e-6 dB.
 // p == 0 -> 0 dB (__init__.py:241).  Branch-free.
-struct DbScale { int ke; float kf; double c; };     // ke = Ki - 1023
+struct DbScale { int ke; float kf; double c; float kif; };     // ke = Ki - 1023, kif = (float)Ki
 constexpr float kC = 3.01029995663981195f;
 constexpr float kC_hi = 6165.0f / 2048.0f;                                   // 13 significant bits
 constexpr float kC_lo = (float)(3.01029995663981195 - 6165.0 / 2048.0);
+
+// MUFU.LG2 alone: __log2f wraps it in a denormal rescue (FSETP + FMUL + FADD) that the inputs here never need
+__device__ __forceinline__ float lg2_raw(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ float db_combine(int E, float L) {
   const float Ef = __int_as_float(0x4b400000 + E) - 12582912.0f;             // exact int -> float, |E| < 2^22
@@ -164,7 +183,11 @@ __device__ __forceinline__ OutT db_out(double p, const DbScale &sc) {
   // mantissa fields; |X|^2 of int16 PCM lies in [1e-26, 1e21], inside the float range
   const float pf = __double2float_rn(p);
   const int b = __float_as_int(pf);
-  const float r = db_combine((b >> 23) + (sc.ke + 1023 - 127), __log2f(__int_as_float((b & 0x7fffff) | 0x3f800000)) + sc.kf);
+  // exponent and mantissa each through MUFU.LG2 (log2 of a power of two is exact): two mask instructions are all the
+  // integer pipe sees — K1 is bound by FP64 + integer pipe time, the MUFU pipe is idle
+  const float Ef = lg2_raw(__int_as_float(b & 0x7f800000)) + sc.kif;
+  const float L = lg2_raw(__int_as_float((b & 0x007fffff) | 0x3f800000)) + sc.kf;
+  const float r = fmaf(Ef, kC_hi, fmaf(Ef, kC_lo, L * kC));
   return (OutT)(pf == 0.f ? 0.f : r);
 }
 template <typename OutT>
@@ -282,7 +305,8 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
           c0p = c0; c1p = c1; c0 = ca0; c1 = ca1;
         }
         // x*(1 - cos) = 2*x*w: one FMA; the factor 2 is folded into the dB constant
-        const T s0 = sample_to_real<T>((int)(short)(w[a] & 0xffffu)), s1 = sample_to_real<T>((int)w[a] >> 16);
+        T s0, s1;
+        sample_pair<T>(w[a], s0, s1);
         xr[a] = fma(-s0, ca0, s0);
         xi[a] = fma(-s1, ca1, s1);
       }
@@ -486,6 +510,7 @@ static int launch(const StftLaunch &a, const StftTables<T> &tb, cudaStream_t s) 
     const double K = log2(sc);
     d.ke = (int)floor(K) - 1023;
     d.kf = (float)(K - floor(K));
+    d.kif = (float)floor(K);
     d.c = 10.0 * log10(sc);
     return d;
   };
