@@ -322,6 +322,12 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
       };
       auto mul = [](V2 a, V2 b) { V2 o; o.x = a.x * b.x - a.y * b.y; o.y = a.x * b.y + a.y * b.x; return o; };
       { V2 o; o.x = xr[0]; o.y = xi[0]; sbuf[t] = o; }
+#ifdef SIA_STFT_TWA_ALL
+      put(1, b1.x, b1.y); put(2, b2.x, b2.y); put(4, b4.x, b4.y); put(8, b8.x, b8.y);
+#pragma unroll
+      for (int ka = 3; ka < 16; ++ka)
+        if (ka & (ka - 1)) { const V2 w = __ldg(twA + ka * 128 + t); put(ka, w.x, w.y); }    // all 15 from the table
+#else
       put(1, b1.x, b1.y); put(2, b2.x, b2.y);
       { const V2 w3 = mul(b2, b1); put(3, w3.x, w3.y); }
       put(4, b4.x, b4.y);
@@ -334,6 +340,7 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
         const V2 w13 = mul(w12, b1); put(13, w13.x, w13.y);
         const V2 w14 = mul(w12, b2); put(14, w14.x, w14.y);
         const V2 w15 = mul(w14, b1); put(15, w15.x, w15.y); }
+#endif
     }
     __syncthreads();
     if (primed && g + 1 < g_end) fetch_half(trk, k + 2, slot);     // pass A has consumed this slot
@@ -384,15 +391,17 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
         }
       } else {
         OutT *__restrict__ row = out + g * (int64_t)SIA_F_STRIDE;
-        const V2 twp = __ldg(twP + t);                       // W4096^t
-        const T C1 = (T)0.92387953251128675613, S1 = (T)0.38268343236508977173, H = (T)0.70710678118654752440;
+        // W4096^(t + 256 j): j = 0..3 from the table (k <= 895), j = 4..7 by W^(k + 1024) = -i W^k — four loads,
+        // no products (K1 is bound by FP64 + integer pipe time, the load pipe has room)
+        V2 twj[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) twj[j] = __ldg(twP + t + 256 * j);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          // W4096^(t + 256 j) = W4096^t * W16^j
-          const T wr16 = j == 0 ? (T)1 : j == 1 ? C1 : j == 2 ? H : j == 3 ? S1 : j == 4 ? (T)0 : j == 5 ? -S1 : j == 6 ? -H : -C1;
-          const T wi16 = j == 0 ? (T)0 : j == 1 ? -S1 : j == 2 ? -H : j == 3 ? -C1 : j == 4 ? (T)-1 : j == 5 ? -C1 : j == 6 ? -H : -S1;
-          emit_pair<T, OutT>(row, yr[0][pos8(j)], yi[0][pos8(j)], yr[1][pos8(7 - j)], yi[1][pos8(7 - j)],
-                             twp.x * wr16 - twp.y * wi16, twp.x * wi16 + twp.y * wr16, t + 256 * j, sc_mid);
+          const T wr = j < 4 ? twj[j].x : twj[j - 4].y;
+          const T wi = j < 4 ? twj[j].y : -twj[j - 4].x;
+          emit_pair<T, OutT>(row, yr[0][pos8(j)], yi[0][pos8(j)], yr[1][pos8(7 - j)], yi[1][pos8(7 - j)], wr, wi,
+                             t + 256 * j, sc_mid);
         }
       }
     }
@@ -518,9 +527,11 @@ static int launch(const StftLaunch &a, const StftTables<T> &tb, cudaStream_t s) 
   const int G = a.frames_per_cta;
   const int64_t blocks = ceil_div(a.total_frames, G);
   if (blocks == 0) return SIA_OK;
-  // 4-5 resident CTAs x 44.5 KB of the SM's 228 KB: ask for the largest shared-memory carveout
-  SIA_CUDA(cudaFuncSetAttribute(stft_db_kernel<T, OutT>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                (int)cudaSharedmemCarveoutMaxShared));
+  // SIA_STFT_CARVEOUT: percent of the SM's 228 KB L1/shared storage asked for as shared memory.  Default 80 % =
+  // 182 KB: room for the 4 resident CTAs (4 x 44.5 KB) and ~70 KB of L1 for the twiddle / window tables, which the
+  // maximum carveout squeezes out (measured 38.3 ms at 100 %, 36.5 ms at 80 %)
+  const char *cv = getenv("SIA_STFT_CARVEOUT");
+  SIA_CUDA(cudaFuncSetAttribute(stft_db_kernel<T, OutT>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : 80));
   // SIA_STFT_PAD_KB: unused dynamic shared memory per CTA — an occupancy experiment knob
   const char *pad_env = getenv("SIA_STFT_PAD_KB");
   const size_t pad = pad_env ? (size_t)atoi(pad_env) * 1024 : 0;
