@@ -220,7 +220,7 @@ def main():
         for setting in args.vote_sweep.split(","):
             parts = setting.split(":")          # mode[:group tuples[:tuples per block[:bin slots per tuple[:filter 0/1]]]]
             os.environ["SIA_VOTE"] = parts[0]
-            for name, val in zip(("SIA_VOTE_GROUP_TUPLES", "SIA_VOTE_CHUNK", "SIA_VOTE_LOAD", "SIA_VOTE_FILTER", "SIA_VOTE_ROWS_LATE"), parts[1:] + [""] * 5):
+            for name, val in zip(("SIA_VOTE_GROUP_TUPLES", "SIA_VOTE_CHUNK", "SIA_VOTE_LOAD", "SIA_VOTE_FILTER"), parts[1:] + [""] * 4):
                 if val:
                     os.environ[name] = val
                 else:
@@ -231,7 +231,7 @@ def main():
                 step()
             torch.cuda.synchronize()
             sweep[setting] = round((time.perf_counter() - t0) / args.steps * 1e3, 2)
-        for name in ("SIA_VOTE", "SIA_VOTE_GROUP_TUPLES", "SIA_VOTE_CHUNK", "SIA_VOTE_LOAD", "SIA_VOTE_FILTER", "SIA_VOTE_ROWS_LATE"):
+        for name in ("SIA_VOTE", "SIA_VOTE_GROUP_TUPLES", "SIA_VOTE_CHUNK", "SIA_VOTE_LOAD", "SIA_VOTE_FILTER"):
             os.environ.pop(name, None)
 
     if rank == 0:

@@ -541,9 +541,6 @@ __device__ __forceinline__ uint32_t *filter_word(const QMeta &m, uint32_t song, 
 // MODE 0: every tuple is counted in the bin table.  MODE 1 / 2, the two-pass form that keeps the tables in L2:
 // pass 1 only marks each tuple's bucket in the query's duplicate filter (seen / seen twice); pass 2 counts a tuple in
 // the (then 4x smaller) bin table only if its bucket was seen twice — a tuple alone in its bucket is a bin of count 1.
-// MODE 3 = MODE 2 without the per-song row counts (one RED per tuple less: pass 2 runs at the L2's atomic rate);
-// MODE 4 then counts the rows of the <= 8 winners of every query only, after topn_hash_kernel has named them
-// (dedup_hashes[song] is reported for the top-n songs, recognizer.py:321-334).
 template <bool DENSE, int MODE>
 __global__ void __launch_bounds__(256)
 expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, const uint32_t *__restrict__ first,
@@ -552,8 +549,7 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
                    unsigned long long *__restrict__ bins, uint32_t *__restrict__ song_key,
                    uint32_t *__restrict__ song_rows, unsigned long long *__restrict__ song_best,
                    uint32_t *__restrict__ filter, unsigned long long *__restrict__ n_bins, int tuples_per_block,
-                   int32_t *__restrict__ overflow, const int32_t *__restrict__ out_song, int32_t *__restrict__ out_rows,
-                   const int32_t *__restrict__ out_nres, int topn, int qid_base) {
+                   int32_t *__restrict__ overflow) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per_warp = tuples_per_block >> 3;
   const int64_t j_lo = off[e0] + (int64_t)blockIdx.x * tuples_per_block + (int64_t)warp * per_warp;
@@ -570,17 +566,6 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
       const QMeta m = meta[e.y >> 40];
       const uint32_t qoff = (uint32_t)(e.x & kM24);
       const bool head = cnt_head[ei] != 0;                         // first entry of its (query, hash): rows count once
-      int32_t win[8];
-      int64_t win_base = 0;
-      if (MODE == 4) {
-        if (!head) continue;
-        const int64_t qg = (int64_t)(e.y >> 40) + qid_base;
-        const int nres = out_nres[qg];
-        if (nres == 0) continue;
-        win_base = qg * topn;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) win[r] = r < nres ? out_song[win_base + r] : -1;
-      }
       const ulonglong2 *__restrict__ run = rows + first[ei];
       const uint32_t k_hi = (uint32_t)(min(j_hi, o_next) - o_this);
       const uint32_t k_lo = (uint32_t)(max(j_lo, o_this) - o_this);
@@ -593,12 +578,6 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
         if (k + 32 < k_hi) r_next = run[k + 32];                   // the next step's posting is in flight during this one
         if (k >= k_hi) continue;
         const uint32_t song = (uint32_t)(r.x >> 24) & 0xffffffu;
-        if (MODE == 4) {
-#pragma unroll
-          for (int w = 0; w < 8; ++w)
-            if ((int32_t)song == win[w]) atomicAdd(&out_rows[win_base + w], 1);
-          continue;
-        }
         const uint32_t dbits = (uint32_t)(r.x & kM24) - qoff + SIA_DIFF_BIAS;    // db offset - query offset, biased
         if (MODE == 1) {
           uint32_t seen;
@@ -609,7 +588,7 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
         }
         unsigned long long count = 1;
         unsigned long long seen_best = 0;                          // a read of the song's best issued before the bin work
-        if (MODE == 2 || MODE == 3) {
+        if (MODE == 2) {
           uint32_t seen;
           const uint32_t *w = filter_word(m, song, dbits, filter, seen);
           const uint32_t fw = __ldcg(w);
@@ -621,7 +600,7 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
         }
         int64_t ss = -1;
         if (count) {
-          if ((MODE == 2 || MODE == 3) && DENSE) {
+          if (MODE == 2 && DENSE) {
             ss = m.song_base + song;
             const unsigned long long val = (count << kDiffBits) | (((1ull << kDiffBits) - 1) - dbits);
             if (seen_best < val) atomicMax(&song_best[ss], val);    // best only grows: a stale read that covers val is enough
@@ -629,12 +608,12 @@ expand_vote_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, co
             ss = song_update<DENSE>(m, song, dbits, count, song_key, song_best, overflow);
           }
         }
-        if (MODE != 3 && ss >= 0 && head) atomicAdd(&song_rows[ss], 1u);
+        if (ss >= 0 && head) atomicAdd(&song_rows[ss], 1u);
       }
       __syncwarp();
     }
   }
-  if (n_bins && MODE != 1 && MODE != 4) {
+  if (n_bins && MODE != 1) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
     if (lane == 0 && fresh) atomicAdd(n_bins, (unsigned long long)fresh);
@@ -800,13 +779,7 @@ topn_hash_kernel(const uint32_t *__restrict__ song_key, const uint32_t *__restri
     }
     if (got < kTopK) break;               // the table is exhausted
   }
-  if (threadIdx.x == 0) {
-    out_nres[q + qid_base] = nres;
-    for (int r = nres; r < topn; ++r) {       // unused slots read as zero whatever ran before
-      const int64_t o = ((int64_t)q + qid_base) * topn + r;
-      out_song[o] = 0; out_diff[o] = 0; out_count[o] = 0; out_rows[o] = 0;
-    }
-  }
+  if (threadIdx.x == 0) out_nres[q + qid_base] = nres;
 }
 
 inline unsigned grid_for(int64_t n, int threads = 256) {
@@ -1310,7 +1283,6 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
   // tuples per block of expand_vote_kernel: a multiple of 8 (every warp takes an eighth)
   const int vote_chunk = getenv("SIA_VOTE_CHUNK") ? std::max(256, atoi(getenv("SIA_VOTE_CHUNK")) & ~7) : kVoteTuplesDefault;
   const bool use_filter = !(getenv("SIA_VOTE_FILTER") && atoi(getenv("SIA_VOTE_FILTER")) == 0);
-  const bool rows_late = !(getenv("SIA_VOTE_ROWS_LATE") && atoi(getenv("SIA_VOTE_ROWS_LATE")) == 0);
   const int vote_mult = getenv("SIA_VOTE_LOAD") ? std::min(16, std::max(2, atoi(getenv("SIA_VOTE_LOAD")))) : 2;   // bin slots per tuple
   // tuples voted at once: sort path x ~70 B of scratch each; hash path x ~16 B of tables, one launch per group
   int64_t tuple_budget = use_hash ? hash_budget : (96ll << 20);
@@ -1447,20 +1419,15 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
       int32_t *fl = d_gflags + gi;
 #define SIA_EXPAND(D, M)                                                                                              \
       expand_vote_kernel<D, M><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->rows, dm, bins, \
-                                                      song_key, song_rows, song_best, filter, nbp, vote_chunk, fl,       \
-                                                      d_out_song, d_out_rows, d_out_nres, topn, (int)q0)
-      // rows of the winners only (MODE 3 + 4) when the winners fit the kernel's 8 registers
-      const bool late_rows = filt && topn <= 8 && rows_late;
+                                                      song_key, song_rows, song_best, filter, nbp, vote_chunk, fl)
       if (dense[gi]) {
-        if (filt) { SIA_EXPAND(true, 1); if (late_rows) { SIA_EXPAND(true, 3); } else { SIA_EXPAND(true, 2); } } else { SIA_EXPAND(true, 0); }
+        if (filt) { SIA_EXPAND(true, 1); SIA_EXPAND(true, 2); } else { SIA_EXPAND(true, 0); }
         topn_hash_kernel<true><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, dm, g.qa, (int)q0, topn,
                                                            d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
-        if (late_rows) { SIA_EXPAND(true, 4); }
       } else {
-        if (filt) { SIA_EXPAND(false, 1); if (late_rows) { SIA_EXPAND(false, 3); } else { SIA_EXPAND(false, 2); } } else { SIA_EXPAND(false, 0); }
+        if (filt) { SIA_EXPAND(false, 1); SIA_EXPAND(false, 2); } else { SIA_EXPAND(false, 0); }
         topn_hash_kernel<false><<<g.qb - g.qa, 256, 0, s>>>(song_key, song_rows, song_best, dm, g.qa, (int)q0, topn,
                                                             d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres);
-        if (late_rows) { SIA_EXPAND(false, 4); }
       }
 #undef SIA_EXPAND
       SIA_CHECK_LAUNCH();

@@ -465,9 +465,9 @@ def test_vote_hash_tables_equal_sorted_vote(gpudb, monkeypatch, id_stride, off_r
                 assert np.array_equal(a, b), ("vote_tuples", drop70, name, topn)
         # with the duplicate filter (two passes; these tie-heavy queries overflow the small bin table of most
         # groups, which are then redone without it) and without; any grouping of the queries
-        names = ("SIA_VOTE_GROUP_TUPLES", "SIA_VOTE_FILTER", "SIA_VOTE_CHUNK", "SIA_VOTE_ROWS_LATE")
-        for setting in ((None, None, None, None), ("1000", None, None, None), ("200000", None, "1001", None),
-                        (str(1 << 40), None, None, "0"), (None, "0", None, None), ("50000", "0", "300", None)):
+        names = ("SIA_VOTE_GROUP_TUPLES", "SIA_VOTE_FILTER", "SIA_VOTE_CHUNK")
+        for setting in ((None, None, None), ("1000", None, None), ("200000", None, "1001"), (str(1 << 40), None, None),
+                        (None, "0", None), ("50000", "0", "300")):
             for name, val in zip(names, setting):
                 if val is None:
                     monkeypatch.delenv(name, raising=False)
