@@ -779,7 +779,13 @@ topn_hash_kernel(const uint32_t *__restrict__ song_key, const uint32_t *__restri
     }
     if (got < kTopK) break;               // the table is exhausted
   }
-  if (threadIdx.x == 0) out_nres[q + qid_base] = nres;
+  if (threadIdx.x == 0) {
+    out_nres[q + qid_base] = nres;
+    for (int r = nres; r < topn; ++r) {       // unused slots read as zero whatever ran before (a redone group)
+      const int64_t o = ((int64_t)q + qid_base) * topn + r;
+      out_song[o] = 0; out_diff[o] = 0; out_count[o] = 0; out_rows[o] = 0;
+    }
+  }
 }
 
 inline unsigned grid_for(int64_t n, int threads = 256) {
