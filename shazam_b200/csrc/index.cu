@@ -861,9 +861,46 @@ int vote_sorted(Arena &ar, const uint64_t *bin_key, const int32_t *bin_count, in
 size_t vote_bytes(int64_t nbins) { return (size_t)nbins * (4 + 8 + 8 + 8) + scan_tmp_bytes(nbins) + 4096; }
 
 
+// Per-query sort of the packed entries in shared memory (sia_index_query_batch: the entries of a pass arrive grouped by
+// query, and all entries of a query share the query id in the top bits, so sorting each query's slice by the whole
+// 128 bits gives the (query, hash, offset) order of the global sort).  One CTA per query, bitonic network on 16-byte
+// keys, slices of up to kSmemSortMax entries (64 KB); a pass with a longer query takes the global LSD radix sort.
+constexpr int kSmemSortMax = 4096;
+constexpr int kSmemSortThreads = 512;
+
+__device__ __forceinline__ bool rec_less(const ulonglong2 &a, const ulonglong2 &b) {
+  return a.y < b.y || (a.y == b.y && a.x < b.x);
+}
+
+__global__ void __launch_bounds__(kSmemSortThreads)
+sort_queries_kernel(ulonglong2 *__restrict__ ent, const int64_t *__restrict__ query_starts, int64_t i0) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  ulonglong2 *key = reinterpret_cast<ulonglong2 *>(sort_smem);
+  const int64_t s0 = query_starts[blockIdx.x] - i0;
+  const int n = (int)(query_starts[blockIdx.x + 1] - i0 - s0);
+  if (n < 2) return;
+  int P = 2;
+  while (P < n) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += kSmemSortThreads) key[i] = i < n ? ent[s0 + i] : make_ulonglong2(~0ull, ~0ull);
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += kSmemSortThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // the lower index of the t-th pair at distance j
+        const int l = i | j;
+        const ulonglong2 a = key[i], b = key[l];
+        const bool up = (i & k) == 0;
+        if (rec_less(b, a) == up) { key[i] = b; key[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += kSmemSortThreads) ent[s0 + i] = key[i];
+}
+
 int lookup_pass(sia_index *ix, Arena &ar, const uint8_t *d_hash, const int32_t *d_qoff, const int32_t *d_qid,
                 const int64_t *d_query_starts, int n_queries, int qid_base, int64_t i0, int64_t n, Lookup &L,
-                cudaStream_t s) {
+                cudaStream_t s, int64_t max_query_entries = 0) {
   L = Lookup();
   L.n = n;
   if (n == 0) return SIA_OK;
@@ -880,8 +917,19 @@ int lookup_pass(sia_index *ix, Arena &ar, const uint8_t *d_hash, const int32_t *
                                                  ix->status);
   SIA_CHECK_LAUNCH();
   bool in_b = false;
-  int rc = radix_sort(a, b, n, 16, 0, 16, stmp, s, &in_b);
-  if (rc) return rc;
+  int rc = SIA_OK;
+  const bool smem_sort = d_query_starts && !d_qid && max_query_entries > 0 && max_query_entries <= kSmemSortMax &&
+                         !(getenv("SIA_QUERY_SORT") && std::string(getenv("SIA_QUERY_SORT")) == "radix");
+  if (smem_sort) {
+    int P = 2;
+    while (P < max_query_entries) P <<= 1;
+    const size_t smem = (size_t)P * sizeof(ulonglong2);
+    SIA_CUDA(cudaFuncSetAttribute(sort_queries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sort_queries_kernel<<<(unsigned)n_queries, kSmemSortThreads, smem, s>>>(a, d_query_starts, i0);
+    SIA_CHECK_LAUNCH();
+  } else if ((rc = radix_sort(a, b, n, 16, 0, 16, stmp, s, &in_b))) {
+    return rc;
+  }
   if (timing) cudaEventRecord(ev[1], s);
   L.ent = in_b ? b : a;
   lookup_kernel<<<grid_for(n), 256, 0, s>>>(L.ent, n, ix->rows, ix->dir, ix->dir_bits, ix->n_rows, first, c_all, c_head);
@@ -1311,7 +1359,9 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     const auto h0 = std::chrono::steady_clock::now();
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     if (timing) { for (auto &e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
-    if ((rc = lookup_pass(ix, ix->arena, d_hash, d_qoff, nullptr, d_qs, nq, 0, i0, n, L, s))) return rc;
+    int64_t max_entries = 0;
+    for (int q = 0; q < nq; ++q) max_entries = std::max(max_entries, h_query_starts[q0 + q + 1] - h_query_starts[q0 + q]);
+    if ((rc = lookup_pass(ix, ix->arena, d_hash, d_qoff, nullptr, d_qs, nq, 0, i0, n, L, s, max_entries))) return rc;
     if ((rc = check_status(ix, s, 2, "query: offset outside 0..2^24-1"))) return rc;
     if (timing) cudaEventRecord(ev[1], s);
     if (h_stats) { h_stats[1] += L.head_rows; h_stats[2] += L.tuples; }
