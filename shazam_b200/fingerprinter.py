@@ -277,7 +277,10 @@ class Fingerprinter:
         """All channels of one decoded file as one GPU batch: the interleaved samples are copied
         once, split on the device and fingerprinted channel by channel; digests stay in HBM (one track per
         channel), e.g. for ``ingest.union_channels_device``."""
-        x = torch.from_numpy(np.ascontiguousarray(pcm_interleaved, np.int16)).to(self.tdev)
+        host = np.ascontiguousarray(pcm_interleaved, np.int16)
+        if not host.flags.writeable:                    # np.frombuffer over the decoder's bytes: torch wants a writable array
+            host = host.copy()
+        x = torch.from_numpy(host).to(self.tdev)
         d_pcm, starts, lens = self.deinterleave(x, n_channels)
         p = self.params(Fs, fan_value, amp_min, connectivity, nbhd, compute)
         cap = self.default_cap(lens, fan_value)
