@@ -271,6 +271,7 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
   };
   int slot = 0;
   bool primed = false;
+  int64_t trk_end = frame_starts[trk + 1];            // first frame of the next track
 
   const int64_t g_first = g;
   for (; g < g_end; ++g) {
@@ -278,16 +279,17 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
     if (g > g_first && t >= 1 && t <= 9)
       emit_special<T, OutT>(out + (g - 1) * (int64_t)SIA_F_STRIDE, sspc[(g - 1) & 1][0], sspc[(g - 1) & 1][1], t - 1,
                             sc_mid, sc_edge);
-    while (g >= frame_starts[trk + 1]) ++trk;
-    const int64_t k = g - frame_starts[trk];
+    if (g >= trk_end) {                  // the run crosses into the next track(s)
+      do { ++trk; trk_end = frame_starts[trk + 1]; } while (g >= trk_end);
+    }
     if (!primed) {                       // first frame of the run or of a track: both half-blocks, synchronously
-      set_cursor(trk, k);
+      set_cursor(trk, g - frame_starts[trk]);
       fetch_half(slot);
       fetch_half(slot ^ 1);
       asm volatile("cp.async.wait_all;\n" ::: "memory");
       __syncthreads();
     }
-    primed = g + 1 < frame_starts[trk + 1];           // the next frame continues this track
+    primed = g + 1 < trk_end;                         // the next frame continues this track
     const uint32_t *__restrict__ h0 = spcm[slot], *__restrict__ h1 = spcm[slot ^ 1];
 
     T xr[16], xi[16];
