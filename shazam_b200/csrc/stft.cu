@@ -250,17 +250,24 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
   int trk = find_segment(frame_starts, n_tracks, g);
 
   const uint32_t spcm_base = (uint32_t)__cvta_generic_to_shared(&spcm[0][0]);
-  // copy half-block h of track `tr` into ring slot `slot` (2 x 16-byte chunks per thread)
-  auto fetch_half = [&](int tr, int64_t h, int slot) {
-    const int64_t valid = (track_len[tr] - h * SIA_HOP) * 2;          // bytes of this half-block inside the track
-    const char *src = reinterpret_cast<const char *>(pcm + track_starts[tr] + h * SIA_HOP);
+  // PCM cursor: this thread's first 16-byte chunk of the next half-block to stage and the bytes of the track left from
+  // there, clamped to +-2^30 (set at the start of every run / track, a run is a few frames: the clamp never bites)
+  const char *cur_src = nullptr;
+  int cur_rest = 0;
+  auto set_cursor = [&](int tr, int64_t h) {
+    const int64_t rest = (track_len[tr] - h * SIA_HOP) * 2 - 16 * t;
+    cur_rest = (int)max(min(rest, (int64_t)1 << 30), -((int64_t)1 << 30));
+    cur_src = reinterpret_cast<const char *>(pcm + track_starts[tr] + h * SIA_HOP) + 16 * t;
+  };
+  auto fetch_half = [&](int slot) {
 #pragma unroll
-    for (int c = t; c < 256; c += 128) {
-      const int64_t rest = valid - 16 * c;
-      const int nbytes = rest >= 16 ? 16 : (rest > 0 ? (int)rest : 0);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(spcm_base + (uint32_t)(slot * 4096 + 16 * c)),
-                   "l"(nbytes ? src + 16 * c : reinterpret_cast<const char *>(pcm)), "r"(nbytes));
+    for (int i = 0; i < 2; ++i) {
+      const int nbytes = min(max(cur_rest - 2048 * i, 0), 16);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(spcm_base + (uint32_t)(slot * 4096 + 16 * t + 2048 * i)),
+                   "l"(nbytes ? cur_src + 2048 * i : reinterpret_cast<const char *>(pcm)), "r"(nbytes));
     }
+    cur_src += 2 * SIA_HOP;
+    cur_rest -= 2 * SIA_HOP;
   };
   int slot = 0;
   bool primed = false;
@@ -274,8 +281,9 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
     while (g >= frame_starts[trk + 1]) ++trk;
     const int64_t k = g - frame_starts[trk];
     if (!primed) {                       // first frame of the run or of a track: both half-blocks, synchronously
-      fetch_half(trk, k, slot);
-      fetch_half(trk, k + 1, slot ^ 1);
+      set_cursor(trk, k);
+      fetch_half(slot);
+      fetch_half(slot ^ 1);
       asm volatile("cp.async.wait_all;\n" ::: "memory");
       __syncthreads();
     }
@@ -343,7 +351,7 @@ stft_db_kernel(const int16_t *__restrict__ pcm, const int64_t *__restrict__ trac
 #endif
     }
     __syncthreads();
-    if (primed && g + 1 < g_end) fetch_half(trk, k + 2, slot);     // pass A has consumed this slot
+    if (primed && g + 1 < g_end) fetch_half(slot);                 // half-block k+2; pass A has consumed this slot
     // ---- pass B: FFT16 over b -----------------------------------------------------------
     {
       const int ka = t >> 3, c = t & 7;
