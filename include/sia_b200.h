@@ -87,6 +87,12 @@ void sia_fp_params_default(sia_fp_params *p);
 int sia_ctx_create(int device, int64_t max_chunk_frames, sia_ctx **out);
 int sia_ctx_destroy(sia_ctx *ctx);
 
+/* K3 as a gather: build (enable != 0) or free the per-context table of sha1("f1|f2|dt")[:10] for EVERY message the
+ * pipeline can produce (f1, f2 in 0..2048, dt in 0..200: 8.4e8 entries of 16 bytes = 13.5 GB, filled once by the SHA-1
+ * kernel in ~50 ms).  With the table generate_hashes (__init__.py:198-208) costs one DRAM sector per hash instead of 80
+ * SHA-1 rounds; results are identical (the table IS the kernel's output).  Synchronous. */
+int sia_ctx_digest_table(sia_ctx *ctx, int enable);
+
 /* frames mlab.specgram yields for a track of n samples (short input -> 1 padded frame) */
 int64_t sia_num_frames(int64_t n_samples);
 
@@ -117,7 +123,9 @@ int sia_peaks(sia_ctx *ctx, const void *d_spec, int32_t in_type, const int64_t *
 
 /* K3. Replaces generate_hashes, __init__.py:179-210, on peaks already in (t, f) order.
  * Output order is the reference's list order (i major, j minor).  d_hash: [cap][10] bytes,
- * d_t1: [cap].  d_track_hash_starts: n_tracks+1 prefix offsets.  Overflow -> d_status[0]=2. */
+ * d_t1: [cap].  d_track_hash_starts: n_tracks+1 prefix offsets.  d_status[0] flags: 2 = output overflow, 4 = a peak
+ * bin outside 0..99999 (the message would not fit one SHA-1 block the way the kernel packs it; such rows are skipped
+ * and the caller must treat the call as failed). */
 int sia_pairs_sha1(sia_ctx *ctx, const int32_t *d_peak_t, const int32_t *d_peak_f,
                    const int64_t *d_track_peak_starts, int32_t n_tracks, int32_t fan_value,
                    uint8_t *d_hash, int32_t *d_t1, int64_t cap_hashes,
@@ -151,12 +159,17 @@ int sia_ctx_timing(sia_ctx *ctx, int enable, double *h_ms_out, int32_t *h_launch
 
 /* One shard of the `fingerprints` table (mysql_database.py:46-59): rows
  * (hash BINARY(10), song_id MEDIUMINT UNSIGNED (< 2^24), offset INT UNSIGNED (< 2^24 here)),
- * UNIQUE(song_id, offset, hash) -> set semantics (INSERT IGNORE, :62-68). */
+ * UNIQUE(song_id, offset, hash) -> set semantics (INSERT IGNORE, :62-68).
+ * Storage: every distinct hash once (16-byte key entry: hash + start of its posting run) and one packed 8-byte
+ * posting (song_id, offset) per row — 8 bytes per row + 16 per distinct hash, so the 100 000-track index of
+ * BASELINE.json configs[3] (8e9 rows) is 64 GB of postings and fits one B200.  capacity_rows postings are
+ * allocated up front; key table, directory and pending buffers grow on demand. */
 int sia_index_create(int device, int64_t capacity_rows, sia_index **out);
 int sia_index_destroy(sia_index *ix);
 
 /* insert_hashes(song_id, hashes), mysql_database.py:167-181.  Rows are appended to a
- * pending run; they become visible to queries after sia_index_finalize. */
+ * pending run; they become visible to queries after sia_index_finalize.  Stream-ordered on
+ * `stream` (any stream: finalize waits for the last insert). */
 int sia_index_insert(sia_index *ix, int32_t song_id, const uint8_t *d_hash, const int32_t *d_off,
                      int64_t n, void *stream);
 /* rows for many songs at once: d_song[n] gives each row's song id */
@@ -165,10 +178,14 @@ int sia_index_insert_rows(sia_index *ix, const int32_t *d_song, const uint8_t *d
 int sia_index_insert_host(sia_index *ix, int32_t song_id, const uint8_t *h_hash, const int32_t *h_off,
                           int64_t n);
 
-/* sort pending rows into the index, drop duplicates, rebuild the bucket directory.
- * *h_rows = rows now stored.  Synchronous. */
+/* Merge the pending rows into the table: sorts ONLY the pending rows, drops duplicates (of each other and of stored
+ * rows), and shifts the stored postings in place — the cost is O(pending log) + one pass over the part of the table
+ * behind the first inserted row, with scratch proportional to the pending rows (the reference commits per song,
+ * __init__.py:381-386).  *h_rows = rows now stored.  Synchronous; runs on the legacy default stream. */
 int sia_index_finalize(sia_index *ix, int64_t *h_rows);
 int64_t sia_index_rows(const sia_index *ix);
+int64_t sia_index_keys(const sia_index *ix);       /* distinct hashes stored */
+int32_t sia_index_max_song(const sia_index *ix);   /* largest song id inserted so far (as of the last finalize) */
 
 /* DELETE FROM songs WHERE ... with ON DELETE CASCADE on fingerprints (mysql_database.py:56-57,
  * 132-139): remove every stored row of the listed songs.  *h_rows = rows left.  Synchronous. */
@@ -196,8 +213,7 @@ int sia_index_select_host(sia_index *ix, const uint8_t *h_hash, int64_t n, int32
  *   out_rows             — dedup_hashes[song]: DB rows matched, counted once per row,
  *   out_nres[q]          — number of valid results (<= topn).
  * Equal counts order by ascending song id (stable sort, recognizer.py:307-310).
- * The vote uses per-query hash tables (no vote keys are written or sorted); a query of more than 32 767
- * (hash, offset) pairs is voted by sorting.  SIA_VOTE=sort forces the sort-based vote for every query.
+ * The vote uses per-query hash tables (no vote tuples are written or sorted; any query size).
  * h_stats (optional, 4 x int64): query (hash, offset) pairs, DB rows matched (the total of
  * dedup_hashes), (song, diff) tuples voted (len(results) of return_matches), distinct bins. */
 int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff,
@@ -205,41 +221,43 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
                           int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
                           int32_t *d_out_rows, int32_t *d_out_nres, int64_t *h_stats, void *stream);
 
-/* multi-GPU building blocks (hash-prefix sharding; the exchange itself is NCCL, driven by
- * the host layer).  Partial bins: per shard, the (query, song, diff) -> count histogram
- * and (query, song) -> rows histogram for the hashes this shard owns; merged by summing
- * equal keys, then voted with sia_vote_bins. */
-int sia_index_query_partial(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff,
-                            const int32_t *d_qid, int64_t n, uint64_t *d_bin_key, int32_t *d_bin_count,
-                            int64_t cap_bins, int64_t *h_nbins, uint64_t *d_row_key,
-                            int32_t *d_row_count, int64_t cap_rowbins, int64_t *h_nrowbins,
-                            void *stream);
-int sia_vote_bins(int device, const uint64_t *d_bin_key, const int32_t *d_bin_count, int64_t nbins,
-                  const uint64_t *d_row_key, const int32_t *d_row_count, int64_t nrowbins,
-                  int32_t n_queries, int32_t topn, int32_t *d_out_song, int32_t *d_out_diff,
-                  int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres, void *stream);
+/* Vote keys: what the (song_id, offset_difference) tuples of return_matches (recognizer.py:268) look like on the
+ * device — 64 bits: head (1) | query id (14) | song id (24) | offset difference + 2^24 (25).  head = 1 marks a tuple
+ * that also counts as one matched DB row (dedup_hashes, recognizer.py:259-264: the first query offset of its hash). */
+#define SIA_KEY_DIFF_BITS 25
+#define SIA_KEY_SONG_BITS 24
+#define SIA_KEY_QID_BITS  14
+#define SIA_DIFF_BIAS     (1 << 24)
 
-/* The same split one step earlier (the cheaper exchange: vote keys travel unsorted, the query's owner sorts
- * once).  sia_index_expand: for routed query hashes, the (query, song, diff) vote keys and the
- * (query, song) row keys of the postings this shard owns, grouped by ascending query id (ids < n_queries),
- * with per-query prefix offsets d_tuple_starts / d_row_starts [n_queries+1].  Passing NULL key buffers
- * only sizes (*h_ntuples, *h_nrows).  sia_vote_tuples: count + vote of concatenated keys with per-query hash
- * tables (a bin count beyond 15 bits falls back to sort + run lengths; the key buffers may be used as scratch). */
-int sia_index_expand(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff, const int32_t *d_qid, int64_t n,
-                     int32_t n_queries, uint64_t *d_tuple_key, int64_t cap_tuples, int64_t *h_ntuples,
-                     uint64_t *d_row_key, int64_t cap_rows, int64_t *h_nrows, int64_t *d_tuple_starts,
-                     int64_t *d_row_starts, void *stream);
-int sia_vote_tuples(int device, uint64_t *d_tuple_key, int64_t n_tuples, uint64_t *d_row_key, int64_t n_rows,
-                    int32_t n_queries, int32_t topn, int32_t *d_out_song, int32_t *d_out_diff,
-                    int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres, void *stream);
+/* The vote of align_matches (recognizer.py:303-310) over n_keys vote keys in any order: same outputs as
+ * sia_index_query_batch (out_rows counts the head keys of the winners).  n_queries <= 16384; song ids <= max_song. */
+int sia_vote_tuples(int device, const uint64_t *d_key, int64_t n_keys, int32_t n_queries, int32_t topn, int32_t max_song,
+                    int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count, int32_t *d_out_rows,
+                    int32_t *d_out_nres, void *stream);
 
-/* bin key layout (64 bits): query id (15 bits) | song id (24 bits) | offset difference + 2^24
- * (25 bits); row keys use the same layout with a zero difference field.  At most 32768 queries
- * per sia_index_query_partial / sia_vote_bins call (sia_index_query_batch splits internally). */
-#define SIA_BINKEY_DIFF_BITS 25
-#define SIA_BINKEY_SONG_BITS 24
-#define SIA_BINKEY_QID_BITS  15
-#define SIA_DIFF_BIAS        (1 << 24)
+/* ---- multi-GPU: hash-prefix sharding (the exchanges themselves are NCCL all-to-alls driven by the host layer) ----
+ * One query pass = sia_route_entries on the rank that owns the queries -> all-to-all of the entry slots ->
+ * sia_index_expand_slots on the shard that owns the hashes -> all-to-all of the key slots -> sia_vote_key_slots on
+ * the queries' owner.  A bin's count is the SUM over shards, so every vote key travels and the result equals the
+ * single-index result, tie-breaks included.  Slots have fixed capacities (equal-split all-to-alls, no size
+ * negotiation on the host); element 0 of a slot holds its count; overflow is reported, never silent.
+ *
+ * sia_route_entries: d_slots = world slots of slot_cap 16-byte entries; entry = (global query id = qid_base + local
+ * query, hash, query offset); destination = floor(prefix16(hash) * world / 65536).  d_status: int32 flags (2 = offset
+ * or query id out of range). */
+int sia_route_entries(int device, const uint8_t *d_hash, const int32_t *d_qoff, const int64_t *d_query_starts,
+                      int32_t n_queries, int64_t n, int32_t qid_base, int32_t world, int64_t slot_cap, void *d_slots,
+                      int32_t *d_status, void *stream);
+/* d_entry_slots: the world slots received from all ranks.  Rank r owns the global query ids
+ * [r * queries_per_rank, (r + 1) * queries_per_rank).  d_key_slots: world slots of key_cap vote keys (local query ids).
+ * d_info (4 x int64, accumulated — zero it before a pass): [0] flags (1 = a received entry slot had overflowed at its
+ * sender, 2 = a key slot overflowed), [1] largest key slot size needed, [2] largest entry slot size needed. */
+int sia_index_expand_slots(sia_index *ix, const void *d_entry_slots, int32_t world, int64_t entry_cap,
+                           int32_t queries_per_rank, uint64_t *d_key_slots, int64_t key_cap, int64_t *d_info,
+                           void *stream);
+int sia_vote_key_slots(int device, const uint64_t *d_key_slots, int32_t n_slots, int64_t key_cap, int32_t n_queries,
+                       int32_t topn, int32_t max_song, int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
+                       int32_t *d_out_rows, int32_t *d_out_nres, void *stream);
 
 #ifdef __cplusplus
 }

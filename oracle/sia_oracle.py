@@ -230,6 +230,42 @@ class FingerprintTable:
         return len(self._unique)
 
 
+class ArrayFingerprintTable(FingerprintTable):
+    """The same stand-in for tables too large for a dict of tuples: the ``fingerprints`` rows live in sorted numpy
+    arrays (the DB engine's index); ``select_multiple`` still hands the rows to the caller ONE BY ONE as
+    ``(HEXUPPER, song_id, offset)`` — the cursor iteration of ``recognizer.py:259`` whose Python loop is what the
+    reference spends its query time in."""
+
+    def __init__(self, digests, song_ids, offsets):
+        super().__init__()
+        d = np.ascontiguousarray(digests, np.uint8).reshape(-1, 10)
+        hi = d[:, :8].copy().view(">u8").reshape(-1).astype(np.uint64)
+        lo = d[:, 8:10].copy().view(">u2").reshape(-1).astype(np.uint64)
+        rec = np.empty(len(hi), dtype=[("hi", "<u8"), ("lo", "<u8"), ("s", "<i8"), ("o", "<i8")])
+        rec["hi"], rec["lo"], rec["s"], rec["o"] = hi, lo, np.asarray(song_ids, np.int64), np.asarray(offsets, np.int64)
+        rec = np.unique(rec)                      # UNIQUE(song_id, offset, hash) + (hash, song, offset) order
+        self._hi, self._lo = rec["hi"].copy(), rec["lo"].copy()
+        self._s, self._o = rec["s"].copy(), rec["o"].copy()
+
+    def insert_hashes(self, song_id, hashes, batch_size=1000):
+        raise NotImplementedError("ArrayFingerprintTable is built from arrays")
+
+    def select_multiple(self, hex_upper_list):
+        for h in hex_upper_list:
+            v = int(h, 16)
+            hi, lo = np.uint64(v >> 16), np.uint64(v & 0xffff)
+            a = int(np.searchsorted(self._hi, hi, "left"))
+            b = int(np.searchsorted(self._hi, hi, "right"))
+            if b > a:
+                lo_run = self._lo[a:b]
+                a, b = a + int(np.searchsorted(lo_run, lo, "left")), a + int(np.searchsorted(lo_run, lo, "right"))
+            for sid, off in zip(self._s[a:b].tolist(), self._o[a:b].tolist()):
+                yield h, sid, off
+
+    def num_rows(self):
+        return len(self._s)
+
+
 def return_matches(table: FingerprintTable, hashes, batch_size: int = 1000):
     """``recognizer.py:222-271``."""
     mapper = {}

@@ -45,6 +45,7 @@ SIGNATURES = {
     "sia_fp_params_default": (None, [C.POINTER(FpParams)]),
     "sia_ctx_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(_p)]),
     "sia_ctx_destroy": (C.c_int, [_p]),
+    "sia_ctx_digest_table": (C.c_int, [_p, C.c_int]),
     "sia_num_frames": (C.c_int64, [C.c_int64]),
     "sia_deinterleave_i16": (C.c_int, [_p, C.c_int64, C.c_int32, _p, C.c_int64, _p]),
     "sia_stft_db": (C.c_int, [_p, _p, _i64p, _i64p, C.c_int32, C.POINTER(FpParams), _p, C.c_int32, _i64p, _p]),
@@ -66,13 +67,13 @@ SIGNATURES = {
     "sia_index_export": (C.c_int, [_p, C.c_int64, C.c_int64, _p, _p, _p, _p]),
     "sia_index_select_host": (C.c_int, [_p, _p, C.c_int64, _p, _p, _p, C.c_int64, _i64p]),
     "sia_index_query_batch": (C.c_int, [_p, _p, _p, _i64p, C.c_int32, C.c_int32, _p, _p, _p, _p, _p, _i64p, _p]),
-    "sia_index_query_partial": (C.c_int, [_p, _p, _p, _p, C.c_int64, _p, _p, C.c_int64, _i64p, _p, _p, C.c_int64,
-                                          _i64p, _p]),
-    "sia_index_expand": (C.c_int, [_p, _p, _p, _p, C.c_int64, C.c_int32, _p, C.c_int64, _i64p, _p, C.c_int64, _i64p, _p,
-                                   _p, _p]),
-    "sia_vote_tuples": (C.c_int, [C.c_int, _p, C.c_int64, _p, C.c_int64, C.c_int32, C.c_int32, _p, _p, _p, _p, _p, _p]),
-    "sia_vote_bins": (C.c_int, [C.c_int, _p, _p, C.c_int64, _p, _p, C.c_int64, C.c_int32, C.c_int32, _p, _p, _p,
-                                _p, _p, _p]),
+    "sia_index_keys": (C.c_int64, [_p]),
+    "sia_index_max_song": (C.c_int32, [_p]),
+    "sia_vote_tuples": (C.c_int, [C.c_int, _p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p, _p, _p]),
+    "sia_route_entries": (C.c_int, [C.c_int, _p, _p, _p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _p, _p, _p]),
+    "sia_index_expand_slots": (C.c_int, [_p, _p, C.c_int32, C.c_int64, C.c_int32, _p, C.c_int64, _p, _p]),
+    "sia_vote_key_slots": (C.c_int, [C.c_int, _p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p,
+                                     _p, _p]),
 }
 
 _lib = None

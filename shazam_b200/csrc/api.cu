@@ -49,6 +49,7 @@ struct sia_ctx {
   void *scan_tmp = nullptr;
   int32_t *status = nullptr;      // device flag word
   int64_t *hash_base = nullptr;   // device scalar: running output offset
+  void *digest_table = nullptr;   // optional: sha1 of every (f1, f2, dt) the pipeline can produce (sia_ctx_digest_table)
   // batch metadata (grown on demand)
   int64_t *d_meta = nullptr;
   size_t d_meta_cap = 0;
@@ -269,7 +270,7 @@ int run_pairs(sia_ctx *c, const int32_t *d_peak_t, const int32_t *d_peak_f, cons
   {
     Timer t(c, s, T_PAIRS, 2);
     if ((rc = pairs_sha1_launch(d_peak_t, d_peak_f, d_track_peak_starts, nb, n_peaks_max, fan_value, c->pair_count,
-                                c->pair_off, hash_base_static, d_hash_base, d_hash, d_t1, cap_hashes,
+                                c->pair_off, hash_base_static, d_hash_base, c->digest_table, d_hash, d_t1, cap_hashes,
                                 d_track_hash_starts, d_status, s)))
       return rc;
   }
@@ -423,7 +424,7 @@ int sia_ctx_destroy(sia_ctx *c) {
   stft_tables_destroy(c->tf, c->td);
   void *ptrs[] = {c->spec, c->bitmap, c->row_count, c->row_off, c->peak_t, c->peak_f, c->pair_count, c->pair_off,
                   c->scan_tmp, c->status, c->hash_base, c->d_meta, c->pcm_stage[0], c->pcm_stage[1],
-                  c->hash_stage[0], c->hash_stage[1], c->t1_stage[0], c->t1_stage[1]};
+                  c->hash_stage[0], c->hash_stage[1], c->t1_stage[0], c->t1_stage[1], c->digest_table};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
@@ -433,6 +434,23 @@ int sia_ctx_destroy(sia_ctx *c) {
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   delete c;
   return SIA_OK;
+}
+
+int sia_ctx_digest_table(sia_ctx *c, int enable) {
+  SIA_REQUIRE(c != nullptr, SIA_E_INVALID, "ctx is NULL");
+  SIA_CUDA(cudaSetDevice(c->device));
+  SIA_CUDA(cudaDeviceSynchronize());
+  if (!enable) {
+    if (c->digest_table) cudaFree(c->digest_table);
+    c->digest_table = nullptr;
+    return SIA_OK;
+  }
+  if (c->digest_table) return SIA_OK;
+  SIA_CUDA(cudaMalloc(&c->digest_table, digest_table_bytes()));
+  int rc = digest_table_build(c->digest_table, nullptr);
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "digest table", __FILE__, __LINE__);
+  if (rc) { cudaFree(c->digest_table); c->digest_table = nullptr; }
+  return rc;
 }
 
 int sia_ctx_timing(sia_ctx *c, int enable, double *h_ms_out, int32_t *h_launches_out, int32_t n) {
@@ -652,11 +670,14 @@ int sia_fingerprint_batch_host(sia_ctx *c, const int16_t *h_pcm, const int64_t *
   SIA_CUDA(cudaMemcpyAsync(c->d_meta, h_meta_in, meta_total * sizeof(int64_t), cudaMemcpyHostToDevice, c->s_comp));
   SIA_CUDA(cudaMemsetAsync(c->status, 0, sizeof(int32_t), c->s_comp));
 
-  std::vector<cudaEvent_t> ev_h2d(nchunks), ev_comp(nchunks), ev_d2h(nchunks);
-  auto mkev = [&](cudaEvent_t &e) { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming); };
-  for (int i = 0; i < nchunks; ++i) { SIA_CUDA(mkev(ev_h2d[i])); SIA_CUDA(mkev(ev_comp[i])); SIA_CUDA(mkev(ev_d2h[i])); }
-  auto cleanup = [&]() {
-    for (int i = 0; i < nchunks; ++i) { cudaEventDestroy(ev_h2d[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_d2h[i]); }
+  // Every exit below goes through ONE epilogue that waits for the three streams (async copies into the caller's host
+  // buffers must not outlive the call, whatever failed) and destroys the events.
+  std::vector<cudaEvent_t> ev_h2d(nchunks, nullptr), ev_comp(nchunks, nullptr), ev_d2h(nchunks, nullptr);
+  auto epilogue = [&](int code) {
+    cudaStreamSynchronize(c->s_comp); cudaStreamSynchronize(c->s_d2h); cudaStreamSynchronize(c->s_h2d);
+    for (int i = 0; i < nchunks; ++i)
+      for (cudaEvent_t e : {ev_h2d[i], ev_comp[i], ev_d2h[i]}) if (e) cudaEventDestroy(e);
+    return code;
   };
 
   int64_t out_base = 0;   // rows already placed in h_hash
@@ -681,6 +702,9 @@ int sia_fingerprint_batch_host(sia_ctx *c, const int16_t *h_pcm, const int64_t *
     return SIA_OK;
   };
 
+  auto pipeline = [&]() -> int {
+  auto mkev = [&](cudaEvent_t &e) { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming); };
+  for (int i = 0; i < nchunks; ++i) { SIA_CUDA(mkev(ev_h2d[i])); SIA_CUDA(mkev(ev_comp[i])); SIA_CUDA(mkev(ev_d2h[i])); }
   for (int ci = 0; ci < nchunks; ++ci) {
     const Chunk &ch = chunks[ci];
     const int nb = ch.b1 - ch.b0;
@@ -693,12 +717,12 @@ int sia_fingerprint_batch_host(sia_ctx *c, const int16_t *h_pcm, const int64_t *
     // kernels of chunk ci: need its PCM, and the output staging[ci&1] drained (D2H of chunk ci-2)
     SIA_CUDA(cudaStreamWaitEvent(c->s_comp, ev_h2d[ci], 0));
     if (ci >= 2) {
-      if ((rc = drain(ci - 2))) { cleanup(); return rc; }
+      if ((rc = drain(ci - 2))) return rc;
       SIA_CUDA(cudaStreamWaitEvent(c->s_comp, ev_d2h[ci - 2], 0));
     }
     SIA_CUDA(cudaMemsetAsync(c->hash_base, 0, sizeof(int64_t), c->s_comp));
     if ((rc = run_chunk(c, c->pcm_stage[ci & 1], ch, p, c->hash_stage[ci & 1], c->t1_stage[ci & 1],
-                        c->cap_chunk_hashes, c->s_comp))) { cleanup(); return rc; }
+                        c->cap_chunk_hashes, c->s_comp))) return rc;
     MetaView dm(c->d_meta + ch.meta_off, nb);
     MetaView hm(h_meta_out + ch.meta_off, nb);
     SIA_CUDA(cudaMemcpyAsync(hm.track_hash_starts, dm.track_hash_starts, sizeof(int64_t) * (nb + 1),
@@ -707,12 +731,14 @@ int sia_fingerprint_batch_host(sia_ctx *c, const int16_t *h_pcm, const int64_t *
     SIA_CUDA(cudaEventRecord(ev_comp[ci], c->s_comp));
   }
   for (int ci = std::max(0, nchunks - 2); ci < nchunks; ++ci)
-    if ((rc = drain(ci))) { cleanup(); return rc; }
+    if ((rc = drain(ci))) return rc;
   SIA_CUDA(cudaMemcpyAsync(h_status, c->status, sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_comp));
   SIA_CUDA(cudaStreamSynchronize(c->s_comp));
   SIA_CUDA(cudaStreamSynchronize(c->s_d2h));
   SIA_CUDA(cudaStreamSynchronize(c->s_h2d));
-  cleanup();
+  return SIA_OK;
+  };
+  if ((rc = epilogue(pipeline()))) return rc;
   *h_total = out_base;
   if (h_track_hash_starts) h_track_hash_starts[n_tracks] = out_base;
   if (*h_status & 1) {

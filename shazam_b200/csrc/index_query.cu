@@ -1,0 +1,931 @@
+// K4, query side — the SELECT ... WHERE hash IN (...) lookup (recognizer.py:60-64, 252-259) and the vote inside
+// align_matches (recognizer.py:303-310) for a batch of queries, without materialising or sorting vote tuples.
+//
+// Lookup: the (hash, offset) pairs of the queries are packed into 16-byte entries, sorted by (query, hash, offset)
+// — duplicates drop out, equal hashes of one query become adjacent — and each is looked up: directory -> binary
+// search in the key table -> the run [start, next start) of 8-byte postings.
+//
+// Vote (per group of queries, every query owning zero-initialised sub-tables):
+//   pass 1  every vote tuple (query, song, db_offset - query_offset) marks a 2-bit bucket (seen / seen twice) of the
+//           query's duplicate filter with one atomicOr, and the tuples that landed in a twice-hit bucket are counted
+//           per query (exactly: the later arrivals + one for the bucket's first arrival);
+//   layout  the bin tables are sized from those counts on the device (2 slots per candidate tuple);
+//   pass 2  the tuples of twice-hit buckets — every bin of count >= 2 is among them — are counted in the bin table
+//           (open addressing, one 64-bit key word + a 32-bit count per slot) and keep the song's best
+//           (count << 25 | inverted diff: largest count, smallest difference on ties — Python's max() keeps the first
+//           maximum, recognizer.py:308) current with atomicMax; all other tuples are bins of count 1 and touch nothing;
+//   top-n   one block per query scans its song table: (count desc, song asc) — the stable sort of recognizer.py:307-310;
+//   singles a query whose n-th result has a count below 2 (or that has fewer than n results) needs the count-1 bins
+//           too: its tuples are voted again as (1, diff) and its top-n is redone (rare on a large index, the normal
+//           case on a tiny one);
+//   rows    dedup_hashes[song] (recognizer.py:259-264: DB rows matched, once per row) is counted for the winners only,
+//           in a last pass over the head postings.
+// The same passes run over vote keys that arrived from other shards (vote_key_slots, hash-prefix sharding).
+#include "index.cuh"
+
+#include <chrono>
+
+using namespace sia;
+
+namespace {
+
+constexpr int kQidBits = SIA_KEY_QID_BITS, kSongBits = SIA_KEY_SONG_BITS, kDiffBits = SIA_KEY_DIFF_BITS;
+constexpr int64_t kMaxQueriesPerPass = 1ll << kQidBits;
+constexpr uint64_t kDiffMask = (1ull << kDiffBits) - 1;
+constexpr int kTopK = 4;                  // results extracted per scan of a query's song table
+constexpr int kVoteTuples = 4096;         // vote tuples per block of the entry-walking kernels (512 per warp)
+
+struct QMeta {
+  int64_t bin_base, song_base, filt_base;   // first slot / word of the query's sub-tables inside the group's tables
+  uint32_t bin_cap, song_cap, filt_words, cand;   // cand: tuples in twice-hit buckets (pass 1), sizes the bin table
+};
+
+struct Tables {
+  unsigned long long *bins;       // [nb] key words ((song << 25 | biased diff) + 1; 0 = empty)
+  uint32_t *bin_cnt;              // [nb]
+  unsigned long long *song_best;  // [ns]
+  uint32_t *song_key;             // [ns] open addressing only (song + 1)
+  uint32_t *filter;               // [nf]
+};
+
+// ---- lookup ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_queries_kernel(const uint8_t *__restrict__ hash, const int32_t *__restrict__ qoff, const int32_t *__restrict__ qid_arr,
+                    const int64_t *__restrict__ query_starts, int n_queries, int64_t i0, int64_t n,
+                    ulonglong2 *__restrict__ out, int32_t *__restrict__ status) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + k;
+    uint64_t hi; uint32_t lo16;
+    load_digest(hash + i * SIA_HASH_BYTES, hi, lo16);
+    const int32_t q = qid_arr ? qid_arr[i] : find_segment(query_starts, n_queries, i);
+    const int32_t o = qoff[i];
+    if (o < 0 || o > (int32_t)kM24 || q < 0 || q >= (1 << 24)) atomicOr(status, 2);
+    out[k] = make_entry((uint32_t)q, hi, lo16, (uint32_t)o);
+  }
+}
+
+// Per-query sort of the packed entries in shared memory (the entries of a pass arrive grouped by query, and all entries
+// of a query share the query id in the top bits, so sorting each query's slice by the whole 128 bits gives the
+// (query, hash, offset) order of a global sort).  One CTA per query, bitonic network on 16-byte keys, slices of up to
+// kSmemSortMax entries (64 KB); a pass with a longer query takes the global LSD radix sort.
+constexpr int kSmemSortMax = 4096;
+constexpr int kSmemSortThreads = 512;
+
+__global__ void __launch_bounds__(kSmemSortThreads)
+sort_queries_kernel(ulonglong2 *__restrict__ ent, const int64_t *__restrict__ query_starts, int64_t i0) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  ulonglong2 *key = reinterpret_cast<ulonglong2 *>(sort_smem);
+  const int64_t s0 = query_starts[blockIdx.x] - i0;
+  const int n = (int)(query_starts[blockIdx.x + 1] - i0 - s0);
+  if (n < 2) return;
+  int P = 2;
+  while (P < n) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += kSmemSortThreads) key[i] = i < n ? ent[s0 + i] : make_ulonglong2(~0ull, ~0ull);
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += kSmemSortThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // the lower index of the t-th pair at distance j
+        const int l = i | j;
+        const ulonglong2 a = key[i], b = key[l];
+        const bool up = (i & k) == 0;
+        if (rec_less(b, a) == up) { key[i] = b; key[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += kSmemSortThreads) ent[s0 + i] = key[i];
+}
+
+// entry -> posting run.  An all-ones entry is padding (sorts last, matches nothing).
+__global__ void __launch_bounds__(256)
+lookup_kernel(const ulonglong2 *__restrict__ ent, int64_t n, const ulonglong2 *__restrict__ keys, int64_t n_keys,
+              const uint32_t *__restrict__ dir, int bits, int64_t *__restrict__ first, uint32_t *__restrict__ cnt_all,
+              uint32_t *__restrict__ cnt_head, int32_t *__restrict__ status) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const ulonglong2 e = ent[i];
+    bool dup = (e.x & e.y) == ~0ull, head = true;
+    if (i > 0) {
+      const ulonglong2 p = ent[i - 1];
+      dup = dup || rec_eq(e, p);
+      head = !(p.y == e.y && (p.x >> 24) == (e.x >> 24));   // same (qid, digest) as the previous entry?
+    }
+    int64_t f = 0;
+    uint32_t c = 0;
+    if (!dup && n_keys > 0) {
+      uint64_t khi; uint32_t klo16, qid, qoff;
+      entry_key(e, khi, klo16, qid, qoff);
+      const int64_t ki = hash_lower_bound_dir(keys, dir, bits, khi, klo16);
+      const ulonglong2 k = keys[ki];
+      if (ki < n_keys && k.y == khi && (uint32_t)(k.x >> 48) == klo16) {
+        f = (int64_t)(k.x & kM48);
+        const int64_t len = (int64_t)(keys[ki + 1].x & kM48) - f;
+        if (len > 0xffffffffll) atomicOr(status, 4);          // a run of 2^32 postings: not representable
+        c = (uint32_t)len;
+      }
+    }
+    first[i] = f;
+    cnt_all[i] = c;
+    cnt_head[i] = head ? c : 0u;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+select_rows_kernel(const ulonglong2 *__restrict__ ent, int64_t n, const int64_t *__restrict__ first,
+                   const int64_t *__restrict__ off, const uint64_t *__restrict__ post, int32_t *__restrict__ o_idx,
+                   int32_t *__restrict__ o_song, int32_t *__restrict__ o_off, int64_t cap) {
+  // entries here are packed with qoff = position of the hash in the caller's list
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = off[i], c = off[i + 1] - b;
+    for (int64_t k = 0; k < c; ++k) {
+      if (b + k >= cap) break;
+      const uint64_t r = post[first[i] + k];
+      o_idx[b + k] = (int32_t)(ent[i].x & kM24);
+      o_song[b + k] = (int32_t)((r >> 24) & kM24);
+      o_off[b + k] = (int32_t)(r & kM24);
+    }
+  }
+}
+
+__global__ void gather_offsets_kernel(const int64_t *__restrict__ off_all, const int64_t *__restrict__ off_head,
+                                      const int64_t *__restrict__ query_starts, int64_t i0, int nq,
+                                      int64_t *__restrict__ out) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q <= nq; q += gridDim.x * blockDim.x) {
+    const int64_t e = query_starts[q] - i0;
+    out[q] = off_all[e];
+    out[nq + 1 + q] = off_head[e];
+  }
+}
+
+// ---- vote tables ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t k) {
+  k ^= k >> 16; k *= 0x85ebca6bu; k ^= k >> 13; k *= 0xc2b2ae35u; k ^= k >> 16;
+  return k;
+}
+__device__ __forceinline__ uint32_t slot_of(uint32_t h, uint32_t cap) { return (uint32_t)(((uint64_t)h * cap) >> 32); }
+
+// song slot of `song` in query m's song table (dense: the id itself; else find-or-insert by open addressing)
+template <bool DENSE>
+__device__ __forceinline__ int64_t song_slot(const QMeta &m, uint32_t song, uint32_t *__restrict__ song_key) {
+  if (DENSE) return song < m.song_cap ? m.song_base + song : -1;
+  uint32_t t = slot_of(mix32(song), m.song_cap);
+  for (uint32_t probes = 0; probes < m.song_cap; ++probes) {     // bounded: a full table (inconsistent inputs) cannot hang
+    const uint32_t old = atomicCAS(&song_key[m.song_base + t], 0u, song + 1u);
+    if (old == 0u || old == song + 1u) return m.song_base + t;
+    if (++t == m.song_cap) t = 0;
+  }
+  return -1;
+}
+
+// count one vote tuple (song, biased diff) in query m's bin table; returns the bin's count including this tuple
+// (0 and flag 8 if the table is full, which the sizing rules out)
+__device__ __forceinline__ unsigned long long bin_count(const QMeta &m, uint32_t song, uint32_t dbits, const Tables &T,
+                                                        uint32_t &fresh, int32_t *__restrict__ flags) {
+  const unsigned long long key = (((unsigned long long)song << kDiffBits) | dbits) + 1ull;     // never 0
+  uint32_t s = slot_of(mix32(song * 0x9e3779b1u + dbits), m.bin_cap);
+  for (uint32_t probes = 0; probes < m.bin_cap; ++probes) {
+    const int64_t at = m.bin_base + s;
+    const unsigned long long old = atomicCAS(T.bins + at, 0ull, key);
+    if (old == 0ull) ++fresh;
+    if (old == 0ull || old == key) return (unsigned long long)atomicAdd(T.bin_cnt + at, 1u) + 1ull;
+    if (++s == m.bin_cap) s = 0;
+  }
+  atomicOr(flags, 8);
+  return 0;
+}
+
+// keep the song's best (count, smallest diff) current: best only grows, so a (possibly stale) read that already
+// covers the value makes the atomic unnecessary
+template <bool DENSE>
+__device__ __forceinline__ void song_update(const QMeta &m, uint32_t song, uint32_t dbits, unsigned long long count,
+                                            const Tables &T, int32_t *__restrict__ flags) {
+  const int64_t ss = song_slot<DENSE>(m, song, T.song_key);
+  if (ss < 0) { atomicOr(flags, 8); return; }
+  const unsigned long long val = (count << kDiffBits) | (kDiffMask - dbits);
+  if (__ldcg(&T.song_best[ss]) < val) atomicMax(&T.song_best[ss], val);
+}
+
+// duplicate filter: 2 bits per bucket (seen, seen twice), 16 buckets per 32-bit word, ~16 buckets per tuple
+__device__ __forceinline__ uint32_t *filter_word(const QMeta &m, uint32_t song, uint32_t dbits, uint32_t *__restrict__ filter,
+                                                 uint32_t &seen_bit) {
+  const uint32_t h = mix32(song * 0x85ebca6bu ^ (dbits * 0xc2b2ae35u + 0x27d4eb2fu));
+  seen_bit = 1u << (2 * (h & 15u));
+  return filter + m.filt_base + slot_of(h, m.filt_words);
+}
+
+// pass 1 of one tuple: mark the bucket; returns how many candidate tuples this arrival accounts for
+__device__ __forceinline__ uint32_t filter_mark(const QMeta &m, uint32_t song, uint32_t dbits, uint32_t *__restrict__ filter) {
+  uint32_t seen;
+  uint32_t *w = filter_word(m, song, dbits, filter, seen);
+  const uint32_t old = atomicOr(w, seen);
+  if (!(old & seen)) return 0;                      // first arrival in its bucket
+  if (old & (seen << 1)) return 1;                  // a later arrival of a bucket already known to be hit twice
+  return (atomicOr(w, seen << 1) & (seen << 1)) ? 1u : 2u;   // the arrival that marks "twice" also accounts for the first one
+}
+
+enum { PASS_MARK = 1, PASS_VOTE = 2, PASS_SINGLES = 3, PASS_ROWS = 4 };
+
+// The work of one vote tuple in each pass.  `wins`/`nwin`: the query's winners (PASS_ROWS).
+template <bool DENSE, int PASS>
+__device__ __forceinline__ void tuple_pass(const QMeta &m, uint32_t song, uint32_t dbits, bool head, const Tables &T,
+                                           uint32_t &acc, int32_t *__restrict__ flags) {
+  if (PASS == PASS_MARK) {
+    acc += filter_mark(m, song, dbits, T.filter);
+  } else if (PASS == PASS_VOTE) {
+    uint32_t seen;
+    const uint32_t *w = filter_word(m, song, dbits, T.filter, seen);
+    if (__ldcg(w) & (seen << 1)) {
+      const unsigned long long c = bin_count(m, song, dbits, T, acc, flags);
+      if (c) song_update<DENSE>(m, song, dbits, c, T, flags);
+    } else {
+      ++acc;                                        // alone in its bucket: a bin of its own, count 1
+    }
+  } else if (PASS == PASS_SINGLES) {
+    song_update<DENSE>(m, song, dbits, 1ull, T, flags);
+  }
+}
+
+// winners' rows: lanes whose posting belongs to winner r add up inside the warp, one atomic per warp and winner
+__device__ __forceinline__ void rows_pass(uint32_t active, bool mine, uint32_t song, const int32_t *__restrict__ win, int nwin,
+                                          int32_t *__restrict__ out_rows, int lane) {
+  for (int r = 0; r < nwin; ++r) {
+    const uint32_t hit = __ballot_sync(active, mine && song == (uint32_t)win[r]);
+    if (hit && lane == (__ffs(active) - 1)) atomicAdd(out_rows + r, __popc(hit));
+  }
+}
+
+// One block handles kVoteTuples consecutive vote tuples (postings of the entries [e0, e0+n), numbered by the exclusive
+// scan off[]), whatever entries they belong to: a heavy key's run is shared by many blocks.  Each warp takes an eighth
+// of the block's tuples and walks the entries they belong to: everything that depends on the entry (query tables,
+// query offset, head flag, first posting) is warp-uniform and loaded once per entry, the lanes then take the entry's
+// postings 32 at a time, the next step's posting in flight during this one.
+template <bool DENSE, int PASS>
+__global__ void __launch_bounds__(256)
+entries_pass_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, const int64_t *__restrict__ first,
+                    const int64_t *__restrict__ off, const uint32_t *__restrict__ cnt_head,
+                    const uint64_t *__restrict__ post, QMeta *__restrict__ meta, Tables T,
+                    const uint32_t *__restrict__ qflag, int qid_base, int topn, const int32_t *__restrict__ out_song,
+                    const int32_t *__restrict__ out_nres, int32_t *__restrict__ out_rows,
+                    unsigned long long *__restrict__ n_bins, int32_t *__restrict__ flags) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int per_warp = kVoteTuples >> 3;
+  const int64_t j_lo = off[e0] + (int64_t)blockIdx.x * kVoteTuples + (int64_t)warp * per_warp;
+  const int64_t j_hi = min(off[e0 + n], j_lo + per_warp);
+  if (j_lo >= j_hi) return;
+  uint32_t acc = 0;                        // PASS_MARK: candidate tuples of the current query; PASS_VOTE: new bins
+  uint32_t cur_q = 0xffffffffu;
+  int64_t ei = e0, hi = e0 + n;            // largest entry in [e0, e0+n) with off[ei] <= j_lo (warp-uniform search)
+  while (hi - ei > 1) { const int64_t mid = ei + ((hi - ei) >> 1); if (off[mid] <= j_lo) ei = mid; else hi = mid; }
+  for (; ei < e0 + n; ++ei) {
+    const int64_t o_this = off[ei], o_next = off[ei + 1];
+    if (o_this >= j_hi) break;
+    if (o_next == o_this) continue;                              // a hash without postings (or a duplicate pair)
+    const ulonglong2 e = ent[ei];
+    const uint32_t q = (uint32_t)(e.y >> 40);
+    const bool head = cnt_head[ei] != 0;                         // first entry of its (query, hash): rows count once
+    if (PASS == PASS_SINGLES && !qflag[q]) continue;
+    if (PASS == PASS_ROWS && !head) continue;
+    if (PASS == PASS_MARK && q != cur_q) {                       // flush the candidate count of the previous query
+#pragma unroll
+      for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+      if (lane == 0 && acc) atomicAdd(&meta[cur_q].cand, acc);
+      acc = 0; cur_q = q;
+    }
+    const QMeta m = meta[q];
+    const int nwin = PASS == PASS_ROWS ? out_nres[q + qid_base] : 0;
+    if (PASS == PASS_ROWS && nwin == 0) continue;
+    const int64_t obase = ((int64_t)q + qid_base) * topn;
+    const uint32_t qoff = (uint32_t)(e.x & kM24);
+    const uint64_t *__restrict__ run = post + first[ei];
+    const uint32_t k_hi = (uint32_t)(min(j_hi, o_next) - o_this);
+    const uint32_t k_lo = (uint32_t)(max(j_lo, o_this) - o_this);
+    uint64_t r_next = 0;
+    if (k_lo + lane < k_hi) r_next = run[k_lo + lane];
+    for (uint32_t kw = k_lo; kw < k_hi; kw += 32) {
+      __syncwarp();                                              // the probe loops below diverge
+      const uint32_t k = kw + lane;
+      const uint64_t r = r_next;
+      if (k + 32 < k_hi) r_next = run[k + 32];
+      const bool valid = k < k_hi;
+      const uint32_t song = (uint32_t)(r >> 24) & 0xffffffu;
+      if (PASS == PASS_ROWS) {
+        rows_pass(0xffffffffu, valid, song, out_song + obase, nwin, out_rows + obase, lane);
+        continue;
+      }
+      if (!valid) continue;
+      const uint32_t dbits = (uint32_t)(r & kM24) - qoff + SIA_DIFF_BIAS;      // db offset - query offset, biased
+      tuple_pass<DENSE, PASS>(m, song, dbits, head, T, acc, flags);
+    }
+    __syncwarp();
+  }
+  if (PASS == PASS_MARK || (PASS == PASS_VOTE && n_bins)) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0 && acc) {
+      if (PASS == PASS_MARK) atomicAdd(&meta[cur_q].cand, acc);
+      else atomicAdd(n_bins, (unsigned long long)acc);
+    }
+  }
+}
+
+// key i of a slotted key array: counts != NULL -> slot s holds counts[s] keys from its first element; counts == NULL ->
+// element 0 of every slot is its count and the keys follow (the exchanged layout, index_dist.cu)
+__device__ __forceinline__ bool load_slot_key(const uint64_t *__restrict__ keys, int64_t cap, const int64_t *__restrict__ counts,
+                                              int64_t i, uint64_t &k) {
+  const int64_t sl = i / cap, j = i - sl * cap;
+  if (counts) {
+    if (j >= min(counts[sl], cap)) return false;
+  } else {
+    if (j == 0 || j > min((int64_t)keys[sl * cap], cap - 1)) return false;
+  }
+  k = keys[i];
+  return true;
+}
+
+// The same passes over vote keys stored in slots (keys from other shards, or a caller's tuples).  Keys of one query are
+// mostly adjacent, so PASS_MARK aggregates the candidate counts per run inside the warp.
+template <bool DENSE, int PASS>
+__global__ void __launch_bounds__(256)
+keys_pass_kernel(const uint64_t *__restrict__ keys, int n_slots, int64_t cap, const int64_t *__restrict__ counts, int nq,
+                 QMeta *__restrict__ meta, Tables T, const uint32_t *__restrict__ qflag, int topn,
+                 const int32_t *__restrict__ out_song, const int32_t *__restrict__ out_nres, int32_t *__restrict__ out_rows,
+                 int32_t *__restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)n_slots * cap;
+  uint32_t dummy = 0;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < total; i0 += (int64_t)gridDim.x * blockDim.x) {
+    __syncwarp();
+    const int64_t i = i0 + threadIdx.x;
+    uint64_t k = 0;
+    bool valid = i < total && load_slot_key(keys, cap, counts, i, k);
+    const uint32_t q = (uint32_t)(k >> (kSongBits + kDiffBits)) & ((1u << kQidBits) - 1u);
+    if (valid && q >= (uint32_t)nq) { atomicOr(flags, 2); valid = false; }
+    const uint32_t song = (uint32_t)(k >> kDiffBits) & 0xffffffu;
+    const uint32_t dbits = (uint32_t)(k & kDiffMask);
+    const bool head = (k >> 63) != 0;
+    if (PASS == PASS_ROWS) {
+      // winners differ per query: handle the queries present in the warp one after the other
+      uint32_t todo = __ballot_sync(0xffffffffu, valid && head);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        const uint32_t qq = __shfl_sync(0xffffffffu, q, src);
+        const bool mine = valid && head && q == qq;
+        const int64_t obase = (int64_t)qq * topn;
+        rows_pass(0xffffffffu, mine, song, out_song + obase, out_nres[qq], out_rows + obase, lane);
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+      }
+      continue;
+    }
+    if (PASS == PASS_SINGLES && valid && !qflag[q]) valid = false;
+    uint32_t acc = 0;
+    if (valid) tuple_pass<DENSE, PASS>(meta[q], song, dbits, head, T, PASS == PASS_MARK ? acc : dummy, flags);
+    if (PASS == PASS_MARK) {
+      __syncwarp();
+      const uint32_t active = __ballot_sync(0xffffffffu, valid && acc);
+      if (valid && acc) {
+        const uint32_t peers = __match_any_sync(active, q);
+        uint32_t sum = 0;
+        for (uint32_t p = peers; p; p &= p - 1) sum += __shfl_sync(peers, acc, __ffs(p) - 1);
+        if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&meta[q].cand, sum);
+      }
+    }
+  }
+}
+
+// keys per query (keys arrive grouped by query: one atomic per run inside the warp)
+__global__ void __launch_bounds__(256)
+count_keys_kernel(const uint64_t *__restrict__ keys, int n_slots, int64_t cap, const int64_t *__restrict__ counts, int nq,
+                  uint32_t *__restrict__ cnt, int32_t *__restrict__ flags) {
+  const int64_t total = (int64_t)n_slots * cap;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < total; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    uint64_t k = 0;
+    bool valid = i < total && load_slot_key(keys, cap, counts, i, k);
+    const uint32_t q = (uint32_t)(k >> (kSongBits + kDiffBits)) & ((1u << kQidBits) - 1u);
+    if (valid && q >= (uint32_t)nq) { atomicOr(flags, 2); valid = false; }
+    const uint32_t active = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const uint32_t peers = __match_any_sync(active, q);
+      if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&cnt[q], (uint32_t)__popc(peers));
+    }
+  }
+}
+
+// single block: table layout of the keys path from the per-query key counts (filter, songs), cand zeroed
+__global__ void __launch_bounds__(1024)
+layout_keys_kernel(const uint32_t *__restrict__ cnt, int nq, int64_t dense_span, QMeta *__restrict__ meta) {
+  __shared__ int64_t s_f[1024], s_s[1024];
+  const int per = (nq + 1023) / 1024;
+  const int a = min(nq, (int)threadIdx.x * per), b = min(nq, a + per);
+  int64_t sf = 0, ss = 0;
+  for (int q = a; q < b; ++q) {
+    sf += (int64_t)cnt[q] + 1;
+    ss += dense_span > 0 ? dense_span : 2 * (int64_t)cnt[q] + 32;
+  }
+  s_f[threadIdx.x] = sf; s_s[threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t rf = 0, rs = 0;
+    for (int i = 0; i < 1024; ++i) { const int64_t x = s_f[i], y = s_s[i]; s_f[i] = rf; s_s[i] = rs; rf += x; rs += y; }
+  }
+  __syncthreads();
+  sf = s_f[threadIdx.x]; ss = s_s[threadIdx.x];
+  for (int q = a; q < b; ++q) {
+    QMeta m;
+    m.bin_base = 0; m.bin_cap = 0; m.cand = 0;
+    m.filt_base = sf; m.filt_words = cnt[q] + 1u;
+    m.song_base = ss; m.song_cap = dense_span > 0 ? (uint32_t)dense_span : 2u * cnt[q] + 32u;
+    meta[q] = m;
+    sf += m.filt_words; ss += m.song_cap;
+  }
+}
+
+// single block: bin tables from the candidate counts of pass 1 (2 slots per candidate tuple); *total = slots in use
+__global__ void __launch_bounds__(1024)
+layout_bins_kernel(QMeta *__restrict__ meta, int q_lo, int q_hi, int64_t *__restrict__ total) {
+  __shared__ int64_t s_b[1024];
+  const int nq = q_hi - q_lo;
+  const int per = (nq + 1023) / 1024;
+  const int a = q_lo + min(nq, (int)threadIdx.x * per), b = min(q_hi, a + per);
+  int64_t sb = 0;
+  for (int q = a; q < b; ++q) sb += 2 * (int64_t)meta[q].cand + 32;
+  s_b[threadIdx.x] = sb;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t rb = 0;
+    for (int i = 0; i < 1024; ++i) { const int64_t x = s_b[i]; s_b[i] = rb; rb += x; }
+    *total = rb;
+  }
+  __syncthreads();
+  sb = s_b[threadIdx.x];
+  for (int q = a; q < b; ++q) {
+    meta[q].bin_base = sb;
+    const int64_t c = 2 * (int64_t)meta[q].cand + 32;
+    meta[q].bin_cap = (uint32_t)c;
+    sb += c;
+  }
+}
+
+// zero the bin tables actually in use (the size is only known on the device)
+__global__ void __launch_bounds__(256)
+zero_bins_kernel(unsigned long long *__restrict__ bins, uint32_t *__restrict__ bin_cnt, const int64_t *__restrict__ total,
+                 int64_t cap, int32_t *__restrict__ flags) {
+  int64_t n = *total;
+  if (n > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(flags, 32); n = cap; }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    bins[i] = 0ull; bin_cnt[i] = 0u;
+  }
+}
+
+// one block per query: top-n songs by (count desc, song asc), kTopK results per scan of the query's song table.
+// Sets qflag[q] = 1 when the n-th result is not settled by the bins of count >= 2 (singles pass needed); with
+// ONLY_FLAGGED the kernel redoes just those queries.
+template <bool DENSE, bool ONLY_FLAGGED>
+__global__ void __launch_bounds__(256)
+topn_kernel(const Tables T, const QMeta *__restrict__ meta, int q_lo, int qid_base, int topn, uint32_t *__restrict__ qflag,
+            int32_t *__restrict__ out_song, int32_t *__restrict__ out_diff, int32_t *__restrict__ out_count,
+            int32_t *__restrict__ out_rows, int32_t *__restrict__ out_nres) {
+  __shared__ unsigned long long s_key[8];
+  __shared__ uint32_t s_slot[8];
+  __shared__ unsigned long long s_win;
+  const int q = (int)blockIdx.x + q_lo;
+  if (ONLY_FLAGGED && !qflag[q]) return;
+  const QMeta m = meta[q];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long prev = ~0ull;
+  int nres = 0;
+  unsigned long long last_count = 0;
+  while (nres < topn) {
+    // rank key: count (high) then inverted song id, so equal counts order by ascending song id
+    unsigned long long tk[kTopK];
+    uint32_t ts[kTopK];
+#pragma unroll
+    for (int i = 0; i < kTopK; ++i) { tk[i] = 0; ts[i] = 0; }
+    for (uint32_t s = threadIdx.x; s < m.song_cap; s += 256) {
+      const unsigned long long best = T.song_best[m.song_base + s];
+      if (best == 0ull) continue;          // empty slot / song without a match
+      const uint32_t song = DENSE ? s : T.song_key[m.song_base + s] - 1u;
+      unsigned long long k = ((best >> kDiffBits) << kSongBits) | (kM24 - song);
+      if (k >= prev || k <= tk[kTopK - 1]) continue;
+      uint32_t sl = s;
+#pragma unroll
+      for (int i = 0; i < kTopK; ++i)
+        if (k > tk[i]) { const unsigned long long a = tk[i]; const uint32_t b = ts[i]; tk[i] = k; ts[i] = sl; k = a; sl = b; }
+    }
+    int got = 0;
+    for (int r = 0; r < kTopK && nres < topn; ++r) {
+      unsigned long long bk = tk[0];
+      uint32_t bs = ts[0];
+#pragma unroll
+      for (int d = 16; d; d >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, d);
+        const uint32_t os = __shfl_xor_sync(0xffffffffu, bs, d);
+        if (ok > bk) { bk = ok; bs = os; }
+      }
+      if (lane == 0) { s_key[warp] = bk; s_slot[warp] = bs; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long w = 0; uint32_t ws = 0;
+        for (int i = 0; i < 8; ++i) if (s_key[i] > w) { w = s_key[i]; ws = s_slot[i]; }
+        s_win = w;
+        if (w) {
+          const unsigned long long v = T.song_best[m.song_base + ws];
+          const int64_t o = ((int64_t)q + qid_base) * topn + nres;
+          out_song[o] = (int32_t)(kM24 - (w & kM24));
+          out_count[o] = (int32_t)(v >> kDiffBits);
+          out_diff[o] = (int32_t)(kDiffMask - (v & kDiffMask)) - SIA_DIFF_BIAS;
+          out_rows[o] = 0;
+        }
+      }
+      __syncthreads();
+      const unsigned long long w = s_win;
+      if (w == 0) break;
+      if (tk[0] == w) {                   // the winner leaves its owner's list
+#pragma unroll
+        for (int i = 0; i + 1 < kTopK; ++i) { tk[i] = tk[i + 1]; ts[i] = ts[i + 1]; }
+        tk[kTopK - 1] = 0;
+      }
+      prev = w;
+      last_count = w >> kSongBits;
+      ++nres; ++got;
+      __syncthreads();
+    }
+    if (got < kTopK) break;               // the table is exhausted
+  }
+  if (threadIdx.x == 0) {
+    out_nres[q + qid_base] = nres;
+    for (int r = nres; r < topn; ++r) {       // unused slots read as zero whatever ran before
+      const int64_t o = ((int64_t)q + qid_base) * topn + r;
+      out_song[o] = 0; out_diff[o] = 0; out_count[o] = 0; out_rows[o] = 0;
+    }
+    if (!ONLY_FLAGGED) qflag[q] = (nres < topn || last_count < 2) ? 1u : 0u;
+  }
+}
+
+int set_device(const sia_index *ix) {
+  SIA_CUDA(cudaSetDevice(ix->device));
+  return SIA_OK;
+}
+
+// read-and-clear of selected status flags (other flags stay)
+__global__ void clear_flags_kernel(int32_t *status, int mask) { atomicAnd(status, ~mask); }
+
+int check_status(sia_index *ix, cudaStream_t s, int mask, const char *msg) {
+  int32_t st = 0;
+  SIA_CUDA(cudaMemcpyAsync(&st, ix->status, sizeof st, cudaMemcpyDeviceToHost, s));
+  SIA_CUDA(cudaStreamSynchronize(s));
+  if (st & mask) {
+    clear_flags_kernel<<<1, 1, 0, s>>>(ix->status, mask);
+    set_error(msg);
+    return SIA_E_INVALID;
+  }
+  return SIA_OK;
+}
+
+// scratch of the handle-less vote entry point, kept per device (cudaMalloc of GBs per call is slow)
+Arena g_vote_tables[64];
+
+}  // namespace
+
+namespace sia {
+
+size_t lookup_bytes(int64_t n) {
+  return (size_t)n * (16 * 2 + 8 + 4 * 2) + (size_t)(n + 1) * 16 + radix_sort_tmp_bytes(n) + 16384;
+}
+
+int lookup_sorted(::sia_index *ix, Arena &ar, ulonglong2 *a, ulonglong2 *b, int64_t n, const int64_t *d_query_starts,
+                  int64_t i0, int n_queries, int64_t max_query_entries, Lookup &L, cudaStream_t s) {
+  L = Lookup();
+  L.n = n;
+  if (n == 0) return SIA_OK;
+  void *stmp = ar.take<char>(radix_sort_tmp_bytes(n));
+  int64_t *first = ar.take<int64_t>(n);
+  uint32_t *c_all = ar.take<uint32_t>(n), *c_head = ar.take<uint32_t>(n);
+  int64_t *off_all = ar.take<int64_t>(n + 1), *off_head = ar.take<int64_t>(n + 1);
+  SIA_REQUIRE(stmp && first && c_all && c_head && off_all && off_head, SIA_E_NOMEM, "index scratch arena too small (lookup)");
+  bool in_b = false;
+  int rc = SIA_OK;
+  if (d_query_starts && max_query_entries > 0 && max_query_entries <= kSmemSortMax) {
+    int P = 2;
+    while (P < max_query_entries) P <<= 1;
+    const size_t smem = (size_t)P * sizeof(ulonglong2);
+    SIA_CUDA(cudaFuncSetAttribute(sort_queries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sort_queries_kernel<<<(unsigned)n_queries, kSmemSortThreads, smem, s>>>(a, d_query_starts, i0);
+    SIA_CHECK_LAUNCH();
+  } else if ((rc = radix_sort(a, b, n, 16, 0, 16, stmp, s, &in_b))) {
+    return rc;
+  }
+  L.ent = in_b ? b : a;
+  lookup_kernel<<<grid_for(n), 256, 0, s>>>(L.ent, n, ix->keys[ix->cur], ix->n_keys, ix->dir, ix->dir_bits, first, c_all,
+                                           c_head, ix->status);
+  SIA_CHECK_LAUNCH();
+  if ((rc = exclusive_scan_u32(c_all, off_all, n, stmp, s))) return rc;
+  if ((rc = exclusive_scan_u32(c_head, off_head, n, stmp, s))) return rc;
+  int64_t tot[2];
+  SIA_CUDA(cudaMemcpyAsync(&tot[0], off_all + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  SIA_CUDA(cudaMemcpyAsync(&tot[1], off_head + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  SIA_CUDA(cudaStreamSynchronize(s));
+  L.first = first; L.cnt_head = c_head; L.off_all = off_all; L.off_head = off_head; L.tuples = tot[0]; L.head_rows = tot[1];
+  return SIA_OK;
+}
+
+// bytes of vote tables for `tuples` tuples over nq queries: filter + worst-case bins (every tuple a candidate) + songs
+static size_t vote_table_bytes(int64_t tuples, int64_t nq, int64_t song_slots, bool dense) {
+  return (size_t)(tuples + nq) * 4 + (size_t)(2 * tuples + 32 * nq) * 12 + (size_t)song_slots * (dense ? 8 : 12) + 4096;
+}
+
+int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap, const int64_t *d_counts, int32_t n_queries,
+                   int32_t topn, int32_t max_song, int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
+                   int32_t *d_out_rows, int32_t *d_out_nres, cudaStream_t s) {
+  SIA_REQUIRE(n_queries >= 0 && n_queries <= kMaxQueriesPerPass && topn >= 1, SIA_E_INVALID,
+              "vote: 0..16384 queries per call, topn >= 1");
+  SIA_REQUIRE(n_slots >= 1 && cap >= 0 && max_song >= 0 && max_song <= (int32_t)kM24, SIA_E_INVALID, "vote: bad sizes");
+  if (n_queries == 0) return SIA_OK;
+  SIA_REQUIRE(d_out_song && d_out_diff && d_out_count && d_out_rows && d_out_nres, SIA_E_INVALID, "NULL output");
+  SIA_REQUIRE(device >= 0 && device < 64, SIA_E_INVALID, "device index");
+  SIA_CUDA(cudaSetDevice(device));
+  const int64_t T = (int64_t)n_slots * cap;             // upper bound of the keys
+  SIA_REQUIRE(T < (1ll << 31), SIA_E_UNSUPPORTED, "vote: more than 2^31 key slots in one call");
+  const int nq = n_queries;
+  Arena &ar = g_vote_tables[device];
+  // song tables: dense (slot = song id) when that is the smaller layout, else open addressing
+  const int64_t span = (int64_t)max_song + 1;
+  const int64_t ns_hashed = 2 * T + 32ll * nq;
+  const bool dense = span * nq * 8 <= ns_hashed * 12;
+  const int64_t ns = dense ? span * nq : ns_hashed;
+  const int64_t nb_cap = 2 * T + 32ll * nq, nf = T + nq;
+  int rc = ar.reserve(vote_table_bytes(T, nq, ns, dense) + (size_t)nq * (sizeof(QMeta) + 8) + 65536);
+  if (rc) return rc;
+  QMeta *meta = ar.take<QMeta>(nq);
+  uint32_t *cnt = ar.take<uint32_t>(nq), *qflag = ar.take<uint32_t>(nq);
+  int64_t *total = ar.take<int64_t>(1);
+  int32_t *flags = ar.take<int32_t>(1);
+  Tables Tb;
+  Tb.filter = ar.take<uint32_t>(nf);
+  Tb.song_best = ar.take<unsigned long long>(ns);
+  Tb.song_key = dense ? nullptr : ar.take<uint32_t>(ns);
+  Tb.bins = ar.take<unsigned long long>(nb_cap);
+  Tb.bin_cnt = ar.take<uint32_t>(nb_cap);
+  SIA_REQUIRE(meta && cnt && qflag && total && flags && Tb.filter && Tb.song_best && Tb.bins && Tb.bin_cnt &&
+              (dense || Tb.song_key), SIA_E_NOMEM, "vote: scratch");
+  SIA_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * nq, s));
+  SIA_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t), s));
+  SIA_CUDA(cudaMemsetAsync(Tb.filter, 0, sizeof(uint32_t) * nf, s));
+  SIA_CUDA(cudaMemsetAsync(Tb.song_best, 0, sizeof(unsigned long long) * ns, s));
+  if (!dense) SIA_CUDA(cudaMemsetAsync(Tb.song_key, 0, sizeof(uint32_t) * ns, s));
+  const unsigned grid = grid_for(T);
+  count_keys_kernel<<<grid, 256, 0, s>>>(d_keys, n_slots, cap, d_counts, nq, cnt, flags);
+  layout_keys_kernel<<<1, 1024, 0, s>>>(cnt, nq, dense ? span : 0, meta);
+#define SIA_KEYS_PASS(D, P)                                                                                            \
+  keys_pass_kernel<D, P><<<grid, 256, 0, s>>>(d_keys, n_slots, cap, d_counts, nq, meta, Tb, qflag, topn, d_out_song,   \
+                                              d_out_nres, d_out_rows, flags)
+#define SIA_KEYS_VOTE(D)                                                                                               \
+  do {                                                                                                                 \
+    SIA_KEYS_PASS(D, PASS_MARK);                                                                                       \
+    layout_bins_kernel<<<1, 1024, 0, s>>>(meta, 0, nq, total);                                                         \
+    zero_bins_kernel<<<kNumSMs * 8, 256, 0, s>>>(Tb.bins, Tb.bin_cnt, total, nb_cap, flags);                           \
+    SIA_KEYS_PASS(D, PASS_VOTE);                                                                                       \
+    topn_kernel<D, false><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, d_out_song, d_out_diff, d_out_count,         \
+                                             d_out_rows, d_out_nres);                                                  \
+    SIA_KEYS_PASS(D, PASS_SINGLES);                                                                                    \
+    topn_kernel<D, true><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, d_out_song, d_out_diff, d_out_count,          \
+                                            d_out_rows, d_out_nres);                                                   \
+    SIA_KEYS_PASS(D, PASS_ROWS);                                                                                       \
+  } while (0)
+  if (dense) SIA_KEYS_VOTE(true); else SIA_KEYS_VOTE(false);
+#undef SIA_KEYS_VOTE
+#undef SIA_KEYS_PASS
+  SIA_CHECK_LAUNCH();
+  int32_t h_flags = 0;
+  SIA_CUDA(cudaMemcpyAsync(&h_flags, flags, sizeof h_flags, cudaMemcpyDeviceToHost, s));
+  SIA_CUDA(cudaStreamSynchronize(s));
+  SIA_REQUIRE(!(h_flags & 2), SIA_E_INVALID, "vote: query id outside 0..n_queries-1");
+  SIA_REQUIRE(!(h_flags & (8 | 32)), SIA_E_CUDA, "vote: table overflow (internal error, or song id above max_song)");
+  return SIA_OK;
+}
+
+}  // namespace sia
+
+extern "C" {
+
+int sia_index_select_host(sia_index *ix, const uint8_t *h_hash, int64_t n, int32_t *h_row_hashidx, int32_t *h_row_song,
+                          int32_t *h_row_off, int64_t cap, int64_t *h_nrows) {
+  SIA_REQUIRE(ix && h_nrows, SIA_E_INVALID, "NULL argument");
+  SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
+  *h_nrows = 0;
+  if (n == 0) return SIA_OK;
+  SIA_REQUIRE(h_hash && n > 0 && n <= (int64_t)kM24, SIA_E_INVALID, "select: 1..2^24-1 hashes per call");
+  int rc = set_device(ix);
+  if (rc) return rc;
+  cudaStream_t s = nullptr;
+  SIA_CUDA(cudaDeviceSynchronize());
+  // position of each hash rides in the qoff field, qid = 0 -> sorted by (digest, position)
+  std::vector<int32_t> pos(n);
+  for (int64_t i = 0; i < n; ++i) pos[i] = (int32_t)i;
+  const size_t in_bytes = (size_t)n * (SIA_HASH_BYTES + 4 + 4) + 4096;
+  if ((rc = ix->arena.reserve(in_bytes + lookup_bytes(n) + (size_t)cap * 12 + 4096))) return rc;
+  uint8_t *dh = ix->arena.take<uint8_t>((size_t)n * SIA_HASH_BYTES);
+  int32_t *dpos = ix->arena.take<int32_t>(n), *dq = ix->arena.take<int32_t>(n);
+  ulonglong2 *a = ix->arena.take<ulonglong2>(n), *b = ix->arena.take<ulonglong2>(n);
+  SIA_REQUIRE(dh && dpos && dq && a && b, SIA_E_NOMEM, "index scratch arena too small (select)");
+  SIA_CUDA(cudaMemcpyAsync(dh, h_hash, (size_t)n * SIA_HASH_BYTES, cudaMemcpyHostToDevice, s));
+  SIA_CUDA(cudaMemcpyAsync(dpos, pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  SIA_CUDA(cudaMemsetAsync(dq, 0, (size_t)n * 4, s));
+  pack_queries_kernel<<<grid_for(n), 256, 0, s>>>(dh, dpos, dq, nullptr, 1, 0, n, a, ix->status);
+  SIA_CHECK_LAUNCH();
+  Lookup L;
+  if ((rc = lookup_sorted(ix, ix->arena, a, b, n, nullptr, 0, 1, 0, L, s))) return rc;
+  *h_nrows = L.tuples;
+  const int64_t m = std::min(L.tuples, cap);
+  if (m > 0) {
+    SIA_REQUIRE(h_row_hashidx && h_row_song && h_row_off, SIA_E_INVALID, "NULL output");
+    int32_t *o1 = ix->arena.take<int32_t>(m), *o2 = ix->arena.take<int32_t>(m), *o3 = ix->arena.take<int32_t>(m);
+    SIA_REQUIRE(o1 && o2 && o3, SIA_E_NOMEM, "index scratch arena too small (select)");
+    select_rows_kernel<<<grid_for(n), 256, 0, s>>>(L.ent, n, L.first, L.off_all, ix->post, o1, o2, o3, m);
+    SIA_CHECK_LAUNCH();
+    SIA_CUDA(cudaMemcpyAsync(h_row_hashidx, o1, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    SIA_CUDA(cudaMemcpyAsync(h_row_song, o2, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    SIA_CUDA(cudaMemcpyAsync(h_row_off, o3, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+  }
+  SIA_CUDA(cudaStreamSynchronize(s));
+  return SIA_OK;
+}
+
+int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff, const int64_t *h_query_starts,
+                          int32_t n_queries, int32_t topn, int32_t *d_out_song, int32_t *d_out_diff,
+                          int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres, int64_t *h_stats, void *stream) {
+  SIA_REQUIRE(ix && h_query_starts, SIA_E_INVALID, "NULL argument");
+  SIA_REQUIRE(n_queries >= 0 && topn >= 1, SIA_E_INVALID, "n_queries >= 0 and topn >= 1 required");
+  SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
+  if (h_stats) h_stats[0] = h_stats[1] = h_stats[2] = h_stats[3] = 0;
+  if (n_queries == 0) return SIA_OK;
+  SIA_REQUIRE(d_out_song && d_out_diff && d_out_count && d_out_rows && d_out_nres, SIA_E_INVALID, "NULL output");
+  int rc = set_device(ix);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int q = 0; q < n_queries; ++q)
+    SIA_REQUIRE(h_query_starts[q] <= h_query_starts[q + 1], SIA_E_INVALID, "query_starts must be non-decreasing");
+  SIA_REQUIRE(h_query_starts[n_queries] == h_query_starts[0] || (d_hash && d_qoff), SIA_E_INVALID, "NULL input");
+  SIA_CUDA(cudaMemsetAsync(d_out_nres, 0, sizeof(int32_t) * n_queries, s));
+  for (int32_t *o : {d_out_song, d_out_diff, d_out_count, d_out_rows})
+    SIA_CUDA(cudaMemsetAsync(o, 0, sizeof(int32_t) * (size_t)n_queries * topn, s));
+
+  // vote tuples per group of queries (one set of launches per group): bounded by what the device has left
+  int64_t tuple_budget = getenv("SIA_VOTE_GROUP_TUPLES") ? std::max(1ll, atoll(getenv("SIA_VOTE_GROUP_TUPLES"))) : (256ll << 20);
+  {
+    size_t free_b = 0, total_b = 0;
+    SIA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    tuple_budget = std::max<int64_t>(1 << 20, std::min<int64_t>(tuple_budget, (int64_t)((free_b + ix->arena3.cap) * 0.6 / 40)));
+  }
+  const bool timing = getenv("SIA_QUERY_TIMING") != nullptr;       // stage times of every pass on stderr
+  const int64_t span = (int64_t)ix->max_song + 1;
+  for (int64_t q0 = 0; q0 < n_queries; q0 += kMaxQueriesPerPass) {
+    const int nq = (int)std::min<int64_t>(kMaxQueriesPerPass, n_queries - q0);
+    const int64_t i0 = h_query_starts[q0], n = h_query_starts[q0 + nq] - i0;
+    if (h_stats) h_stats[0] += n;
+    if (n == 0) continue;    // out_nres is already 0 for these queries
+    if ((rc = ix->arena.reserve((size_t)(nq + 1) * 8 * 3 + (size_t)n * 32 + lookup_bytes(n) + (1 << 20)))) return rc;
+    int64_t *d_qs = ix->arena.take<int64_t>(nq + 1);
+    int64_t *d_goff = ix->arena.take<int64_t>(2 * (size_t)(nq + 1));
+    ulonglong2 *ea = ix->arena.take<ulonglong2>(n), *eb = ix->arena.take<ulonglong2>(n);
+    SIA_REQUIRE(d_qs && d_goff && ea && eb, SIA_E_NOMEM, "index scratch arena too small (query)");
+    SIA_CUDA(cudaMemcpyAsync(d_qs, h_query_starts + q0, sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, s));
+    const auto h0 = std::chrono::steady_clock::now();
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (timing) { for (auto &e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
+    int64_t max_entries = 0;
+    for (int q = 0; q < nq; ++q) max_entries = std::max(max_entries, h_query_starts[q0 + q + 1] - h_query_starts[q0 + q]);
+    pack_queries_kernel<<<grid_for(n), 256, 0, s>>>(d_hash, d_qoff, nullptr, d_qs, nq, i0, n, ea, ix->status);
+    SIA_CHECK_LAUNCH();
+    Lookup L;
+    if ((rc = lookup_sorted(ix, ix->arena, ea, eb, n, d_qs, i0, nq, max_entries, L, s))) return rc;
+    if ((rc = check_status(ix, s, 2 | 4, "query: offset outside 0..2^24-1 (or a posting run of 2^32 rows)"))) return rc;
+    if (timing) cudaEventRecord(ev[1], s);
+    if (h_stats) { h_stats[1] += L.head_rows; h_stats[2] += L.tuples; }
+    // After the sort query q still owns entries [starts[q]-i0, starts[q+1]-i0) (duplicates stay, with no
+    // postings), so the scanned offsets at those positions split the pass into groups that fit the budget.
+    std::vector<int64_t> h_goff(2 * (size_t)(nq + 1));
+    gather_offsets_kernel<<<grid_for(nq + 1), 256, 0, s>>>(L.off_all, L.off_head, d_qs, i0, nq, d_goff);
+    SIA_CHECK_LAUNCH();
+    SIA_CUDA(cudaMemcpyAsync(h_goff.data(), d_goff, h_goff.size() * 8, cudaMemcpyDeviceToHost, s));
+    SIA_CUDA(cudaStreamSynchronize(s));
+    const int64_t *h_off_all = h_goff.data(), *h_off_head = h_goff.data() + nq + 1;
+    struct Group { int qa, qb; bool dense; int64_t nf, ns; };
+    std::vector<Group> groups;
+    std::vector<QMeta> h_meta(nq);
+    size_t max_bytes = 0;
+    for (int qa = 0; qa < nq;) {
+      int qb = qa + 1;
+      while (qb < nq && h_off_all[qb + 1] - h_off_all[qa] <= tuple_budget) ++qb;
+      Group g{qa, qb, false, 0, 0};
+      const int64_t t_all = h_off_all[qb] - h_off_all[qa], h_all = h_off_head[qb] - h_off_head[qa];
+      SIA_REQUIRE(t_all < (1ll << 31), SIA_E_UNSUPPORTED, "query_batch: more than 2^31 vote tuples in one query");
+      const int64_t ns_hashed = 2 * h_all + 32ll * (qb - qa);
+      g.dense = span * (qb - qa) * 8 <= ns_hashed * 12 * 2;
+      int64_t fb = 0, sb = 0;
+      for (int q = qa; q < qb; ++q) {
+        const int64_t t = h_off_all[q + 1] - h_off_all[q], h = h_off_head[q + 1] - h_off_head[q];
+        QMeta &m = h_meta[q];
+        m.bin_base = 0; m.bin_cap = 0; m.cand = 0;
+        m.filt_base = fb; m.filt_words = (uint32_t)(t + 1);
+        m.song_base = sb; m.song_cap = g.dense ? (uint32_t)span : (uint32_t)(2 * h + 32);
+        fb += m.filt_words; sb += m.song_cap;
+      }
+      g.nf = fb; g.ns = sb;
+      max_bytes = std::max(max_bytes, vote_table_bytes(t_all, qb - qa, sb, g.dense));
+      groups.push_back(g);
+      qa = qb;
+    }
+    if ((rc = ix->arena3.reserve(max_bytes + (size_t)nq * (sizeof(QMeta) + 4) + 65536))) return rc;
+    QMeta *d_meta = ix->arena3.take<QMeta>(nq);
+    uint32_t *qflag = ix->arena3.take<uint32_t>(nq);
+    int64_t *d_total = ix->arena3.take<int64_t>(1);
+    unsigned long long *d_nbins = ix->arena3.take<unsigned long long>(1);
+    int32_t *d_flags = ix->arena3.take<int32_t>(1);
+    const size_t fixed = ix->arena3.used;
+    SIA_REQUIRE(d_meta && qflag && d_total && d_nbins && d_flags, SIA_E_NOMEM, "index scratch arena too small (vote)");
+    SIA_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(QMeta) * nq, cudaMemcpyHostToDevice, s));
+    SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long), s));
+    SIA_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t), s));
+    for (const Group &g : groups) {
+      const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
+      const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa];
+      if (tuples == 0) continue;           // out_nres is already 0 for these queries
+      ix->arena3.used = fixed;
+      const int64_t nb_cap = 2 * tuples + 32ll * (g.qb - g.qa);
+      Tables Tb;
+      Tb.filter = ix->arena3.take<uint32_t>(g.nf);
+      Tb.song_best = ix->arena3.take<unsigned long long>(g.ns);
+      Tb.song_key = g.dense ? nullptr : ix->arena3.take<uint32_t>(g.ns);
+      Tb.bins = ix->arena3.take<unsigned long long>(nb_cap);
+      Tb.bin_cnt = ix->arena3.take<uint32_t>(nb_cap);
+      SIA_REQUIRE(Tb.filter && Tb.song_best && Tb.bins && Tb.bin_cnt && (g.dense || Tb.song_key), SIA_E_NOMEM,
+                  "index scratch arena too small (vote tables)");
+      SIA_CUDA(cudaMemsetAsync(Tb.filter, 0, sizeof(uint32_t) * g.nf, s));
+      SIA_CUDA(cudaMemsetAsync(Tb.song_best, 0, sizeof(unsigned long long) * g.ns, s));
+      if (!g.dense) SIA_CUDA(cudaMemsetAsync(Tb.song_key, 0, sizeof(uint32_t) * g.ns, s));
+      const unsigned blocks = (unsigned)ceil_div(tuples, kVoteTuples);
+      const int gq = g.qb - g.qa;
+#define SIA_ENT_PASS(D, P)                                                                                              \
+      entries_pass_kernel<D, P><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->post, d_meta, Tb,  \
+                                                       qflag, (int)q0, topn, d_out_song, d_out_nres, d_out_rows, d_nbins,    \
+                                                       d_flags)
+#define SIA_ENT_VOTE(D)                                                                                                 \
+      do {                                                                                                              \
+        SIA_ENT_PASS(D, PASS_MARK);                                                                                     \
+        layout_bins_kernel<<<1, 1024, 0, s>>>(d_meta, g.qa, g.qb, d_total);                                             \
+        zero_bins_kernel<<<kNumSMs * 8, 256, 0, s>>>(Tb.bins, Tb.bin_cnt, d_total, nb_cap, d_flags);                    \
+        SIA_ENT_PASS(D, PASS_VOTE);                                                                                     \
+        topn_kernel<D, false><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_out_song, d_out_diff,        \
+                                                 d_out_count, d_out_rows, d_out_nres);                                  \
+        SIA_ENT_PASS(D, PASS_SINGLES);                                                                                  \
+        topn_kernel<D, true><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_out_song, d_out_diff,         \
+                                                d_out_count, d_out_rows, d_out_nres);                                   \
+        SIA_ENT_PASS(D, PASS_ROWS);                                                                                     \
+      } while (0)
+      if (g.dense) SIA_ENT_VOTE(true); else SIA_ENT_VOTE(false);
+#undef SIA_ENT_VOTE
+#undef SIA_ENT_PASS
+      SIA_CHECK_LAUNCH();
+    }
+    int32_t h_flags = 0;
+    unsigned long long h_nb = 0;
+    SIA_CUDA(cudaMemcpyAsync(&h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, s));
+    SIA_CUDA(cudaMemcpyAsync(&h_nb, d_nbins, sizeof h_nb, cudaMemcpyDeviceToHost, s));
+    if (timing) cudaEventRecord(ev[2], s);
+    SIA_CUDA(cudaStreamSynchronize(s));      // the lookup scratch and the tables are reused by the next pass / call
+    SIA_REQUIRE(!(h_flags & (8 | 32)), SIA_E_CUDA, "query: vote table overflow (internal error)");
+    if (h_stats) h_stats[3] += (int64_t)h_nb;
+    if (timing) {
+      float t_lookup = 0, t_vote = 0;
+      cudaEventElapsedTime(&t_lookup, ev[0], ev[1]); cudaEventElapsedTime(&t_vote, ev[1], ev[2]);
+      const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+      fprintf(stderr, "[sia] query pass: %d queries, %lld entries, %lld tuples, %zu groups: lookup %.2f ms, vote %.2f ms, host wall %.2f ms\n",
+              nq, (long long)n, (long long)L.tuples, groups.size(), t_lookup, t_vote, host_ms);
+      for (auto &e : ev) cudaEventDestroy(e);
+    }
+  }
+  return SIA_OK;
+}
+
+int sia_vote_tuples(int device, const uint64_t *d_key, int64_t n_keys, int32_t n_queries, int32_t topn, int32_t max_song,
+                    int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count, int32_t *d_out_rows,
+                    int32_t *d_out_nres, void *stream) {
+  SIA_REQUIRE(n_keys >= 0, SIA_E_INVALID, "negative size");
+  SIA_REQUIRE(device >= 0 && device < 64, SIA_E_INVALID, "device index");
+  SIA_CUDA(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  static int64_t *d_count[64] = {nullptr};                      // one device scalar per device
+  if (!d_count[device]) SIA_CUDA(cudaMalloc(&d_count[device], sizeof(int64_t)));
+  SIA_CUDA(cudaMemcpyAsync(d_count[device], &n_keys, sizeof n_keys, cudaMemcpyHostToDevice, s));
+  SIA_CUDA(cudaStreamSynchronize(s));                           // n_keys is a stack variable
+  if (n_queries > 0 && d_out_nres) {
+    SIA_CUDA(cudaMemsetAsync(d_out_nres, 0, sizeof(int32_t) * n_queries, s));
+    for (int32_t *o : {d_out_song, d_out_diff, d_out_count, d_out_rows})
+      if (o) SIA_CUDA(cudaMemsetAsync(o, 0, sizeof(int32_t) * (size_t)n_queries * topn, s));
+  }
+  return vote_key_slots(device, d_key, 1, std::max<int64_t>(n_keys, 1), d_count[device], n_queries, topn, max_song, d_out_song,
+                        d_out_diff, d_out_count, d_out_rows, d_out_nres, s);
+}
+
+}  // extern "C"

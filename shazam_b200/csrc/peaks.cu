@@ -730,8 +730,10 @@ extract_kernel(const uint32_t *__restrict__ bitmap, const int64_t *__restrict__ 
   const int k = (int)(g - frame_starts[trk]);
   int64_t base = row_off[g] + peak_base;
   if (lane == 0) {
-    if (k == 0) track_peak_starts[trk] = base;
-    if (g == total_frames - 1) track_peak_starts[n_tracks] = row_off[total_frames] + peak_base;
+    // prefix offsets never point past the workspace: the peaks beyond `cap` are dropped (status bit 1), and the
+    // kernels that follow (pair counting, scans, SHA-1) read these counts from the device
+    if (k == 0) track_peak_starts[trk] = min(base, cap);
+    if (g == total_frames - 1) track_peak_starts[n_tracks] = min(row_off[total_frames] + peak_base, cap);
   }
   const uint32_t *row = bitmap + g * kBitmapRowWords;
   bool overflow = false;

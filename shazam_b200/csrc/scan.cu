@@ -48,7 +48,7 @@ __device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t *total)
 __global__ void __launch_bounds__(kScanThreads)
 scan_reduce_kernel(const uint32_t *__restrict__ in, const int64_t *__restrict__ d_n, int64_t n_static,
                    uint64_t *__restrict__ block_sums) {
-  const int64_t n = d_n ? *d_n : n_static;
+  const int64_t n = d_n ? min(*d_n, n_static) : n_static;   // a device-side count never exceeds the buffers
   const int64_t base = (int64_t)blockIdx.x * kScanTile;
   uint64_t s = 0;
 #pragma unroll
@@ -64,7 +64,7 @@ scan_reduce_kernel(const uint32_t *__restrict__ in, const int64_t *__restrict__ 
 __global__ void __launch_bounds__(1024)
 scan_block_sums_kernel(uint64_t *__restrict__ block_sums, int64_t nblocks_max, const int64_t *__restrict__ d_n,
                        int64_t n_static, int64_t *__restrict__ out) {
-  const int64_t n = d_n ? *d_n : n_static;
+  const int64_t n = d_n ? min(*d_n, n_static) : n_static;   // a device-side count never exceeds the buffers
   int64_t nblocks = (n + kScanTile - 1) / kScanTile;
   if (nblocks > nblocks_max) nblocks = nblocks_max;
   uint64_t carry = 0;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kScanThreads)
 scan_tiles_kernel(const uint32_t *__restrict__ in, const int64_t *__restrict__ d_n, int64_t n_static,
                   const uint64_t *__restrict__ block_sums, int64_t *__restrict__ out) {
   __shared__ uint32_t tile[kScanTile];
-  const int64_t n = d_n ? *d_n : n_static;
+  const int64_t n = d_n ? min(*d_n, n_static) : n_static;   // a device-side count never exceeds the buffers
   const int64_t base = (int64_t)blockIdx.x * kScanTile;
   if (base >= n) return;
 #pragma unroll

@@ -67,7 +67,10 @@ int pairs_count_launch(const int32_t *d_peak_t, const int64_t *d_track_peak_star
 int pairs_sha1_launch(const int32_t *d_peak_t, const int32_t *d_peak_f, const int64_t *d_track_peak_starts,
                       int n_tracks, int64_t n_peaks_max, int fan_value, const uint32_t *d_pair_count,
                       const int64_t *d_pair_off, int64_t hash_base_static, const int64_t *d_hash_base,
-                      uint8_t *d_hash, int32_t *d_t1, int64_t cap_hashes, int64_t *d_track_hash_starts,
-                      int32_t *d_status, cudaStream_t s);
+                      const void *d_digest_table, uint8_t *d_hash, int32_t *d_t1, int64_t cap_hashes,
+                      int64_t *d_track_hash_starts, int32_t *d_status, cudaStream_t s);
+// optional digest table of the whole pre-image space (pairs_sha1.cu): NULL = compute every digest
+size_t digest_table_bytes();
+int digest_table_build(void *d_table, cudaStream_t s);
 
 }  // namespace sia

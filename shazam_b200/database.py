@@ -101,7 +101,6 @@ class FingerprintIndex:
             assert d.dtype == torch.uint8 and d.shape == (n, N.HASH_BYTES)
             N.check(self.lib.sia_index_insert(self._h, int(song_id), C.c_void_p(d.data_ptr()),
                                               C.c_void_p(o.data_ptr()), n, self._stream()))
-            torch.cuda.current_stream(self.tdev).synchronize()   # d/o may be temporaries
         else:
             d = np.ascontiguousarray(digests, np.uint8).reshape(n, N.HASH_BYTES)
             o = np.ascontiguousarray(offsets, np.int32)
@@ -119,7 +118,6 @@ class FingerprintIndex:
         o = offsets.to(torch.int32).contiguous()
         N.check(self.lib.sia_index_insert_rows(self._h, C.c_void_p(s.data_ptr()), C.c_void_p(d.data_ptr()),
                                                C.c_void_p(o.data_ptr()), n, self._stream()))
-        torch.cuda.current_stream(self.tdev).synchronize()
         self._dirty = True
 
     def finalize(self) -> int:
@@ -193,92 +191,79 @@ class FingerprintIndex:
             return (*outs, nres, list(stats))
         return (*outs, nres)
 
-    def expand_size(self, digests: torch.Tensor, qoffsets: torch.Tensor, qids: torch.Tensor, n_queries: int) -> int:
-        """Vote keys ``expand`` would produce for these inputs (the lookup is cached for the following call)."""
+    @property
+    def keys(self) -> int:
+        """Distinct hashes stored (one 16-byte key entry each; postings are 8 bytes per row)."""
         self.finalize()
-        self._exp_args = (digests.contiguous(), qoffsets.to(torch.int32).contiguous(), qids.to(torch.int32).contiguous())
-        d, o, q = self._exp_args
-        nt = C.c_int64(); nr = C.c_int64()
-        N.check(self.lib.sia_index_expand(self._h, C.c_void_p(d.data_ptr()), C.c_void_p(o.data_ptr()),
-                                          C.c_void_p(q.data_ptr()), o.numel(), int(n_queries), None, 0, C.byref(nt),
-                                          None, 0, C.byref(nr), None, None, self._stream()))
-        return int(nt.value)
+        return int(self.lib.sia_index_keys(self._h))
 
-    def expand(self, digests: torch.Tensor, qoffsets: torch.Tensor, qids: torch.Tensor, n_queries: int):
-        """Vote keys of the postings this shard owns for routed query hashes (multi-GPU path, before the
-        sort): (tuple_key i64[T], row_key i64[R], tuple_starts i64[n_queries+1], row_starts i64[n_queries+1]),
-        keys grouped by ascending query id."""
+    @property
+    def max_song(self) -> int:
+        """Largest song id ever inserted (sizes the dense per-query song tables of the vote)."""
         self.finalize()
-        n = qoffsets.numel()
-        prev = getattr(self, "_exp_args", None)          # same tensors as the sizing call -> same device pointers
-        if prev is not None and prev[1].numel() == n and digests.data_ptr() == prev[0].data_ptr():
-            d, o, q = prev
-        else:
-            d = digests.contiguous(); o = qoffsets.to(torch.int32).contiguous(); q = qids.to(torch.int32).contiguous()
-        self._exp_args = None
-        ts = torch.zeros(n_queries + 1, dtype=torch.int64, device=self.tdev)
-        rs = torch.zeros(n_queries + 1, dtype=torch.int64, device=self.tdev)
-        nt = C.c_int64(); nr = C.c_int64()
-        args = (self._h, C.c_void_p(d.data_ptr()), C.c_void_p(o.data_ptr()), C.c_void_p(q.data_ptr()), n, int(n_queries))
-        N.check(self.lib.sia_index_expand(*args, None, 0, C.byref(nt), None, 0, C.byref(nr), None, None, self._stream()))
-        tk = torch.empty(nt.value, dtype=torch.int64, device=self.tdev)
-        rk = torch.empty(nr.value, dtype=torch.int64, device=self.tdev)
-        N.check(self.lib.sia_index_expand(*args, C.c_void_p(tk.data_ptr()), tk.numel(), C.byref(nt),
-                                          C.c_void_p(rk.data_ptr()), rk.numel(), C.byref(nr),
-                                          C.c_void_p(ts.data_ptr()), C.c_void_p(rs.data_ptr()), self._stream()))
-        return tk, rk, ts, rs
+        return int(self.lib.sia_index_max_song(self._h))
 
-    def query_partial(self, digests: torch.Tensor, qoffsets: torch.Tensor, qids: torch.Tensor):
-        """Partial vote histograms of this shard for routed query hashes (multi-GPU path).
-        Returns (bin_key u64, bin_count i32, row_key u64, row_count i32) CUDA tensors."""
+    # ---- hash-prefix sharding: the device steps around the two all-to-alls (distributed.ShardedIndex) ------------
+    def expand_slots(self, entry_slots: torch.Tensor, world: int, queries_per_rank: int, key_cap: int,
+                     info: torch.Tensor) -> torch.Tensor:
+        """Received entry slots (int64[world, entry_cap, 2]) -> vote-key slots int64[world, key_cap] for the
+        ranks that own the queries; ``info`` (int64[4], zeroed per pass) accumulates overflow flags and sizes."""
         self.finalize()
-        n = qoffsets.numel()
-        d = digests.contiguous(); o = qoffsets.to(torch.int32).contiguous(); q = qids.to(torch.int32).contiguous()
-        cap = max(1024, 4 * n)
-        while True:
-            bk = torch.empty(cap, dtype=torch.int64, device=self.tdev); bc = torch.empty(cap, dtype=torch.int32, device=self.tdev)
-            rk = torch.empty(cap, dtype=torch.int64, device=self.tdev); rc_ = torch.empty(cap, dtype=torch.int32, device=self.tdev)
-            nb = C.c_int64(); nr = C.c_int64()
-            rc = self.lib.sia_index_query_partial(self._h, C.c_void_p(d.data_ptr()), C.c_void_p(o.data_ptr()),
-                                                  C.c_void_p(q.data_ptr()), n, C.c_void_p(bk.data_ptr()),
-                                                  C.c_void_p(bc.data_ptr()), cap, C.byref(nb), C.c_void_p(rk.data_ptr()),
-                                                  C.c_void_p(rc_.data_ptr()), cap, C.byref(nr), self._stream())
-            if rc == N.E_CAPACITY and max(nb.value, nr.value) > cap:
-                cap = int(max(nb.value, nr.value))
-                continue
-            N.check(rc)
-            return bk[:nb.value], bc[:nb.value], rk[:nr.value], rc_[:nr.value]
+        assert entry_slots.is_cuda and entry_slots.dtype == torch.int64 and entry_slots.is_contiguous()
+        entry_cap = entry_slots.shape[1]
+        out = torch.empty((world, int(key_cap)), dtype=torch.int64, device=self.tdev)
+        N.check(self.lib.sia_index_expand_slots(self._h, C.c_void_p(entry_slots.data_ptr()), int(world), int(entry_cap),
+                                                int(queries_per_rank), C.c_void_p(out.data_ptr()), int(key_cap),
+                                                C.c_void_p(info.data_ptr()), self._stream()))
+        return out
 
 
-def vote_tuples(device: int, tuple_key: torch.Tensor, row_key: torch.Tensor, n_queries: int, topn: int):
-    """Sort, count and vote concatenated (query, song, diff) keys (+ (query, song) row keys).  The key
-    tensors are used as scratch.  CUDA tensors in and out."""
+def route_entries(device: int, digests: torch.Tensor, qoffsets: torch.Tensor, query_starts: torch.Tensor, qid_base: int,
+                  world: int, slot_cap: int, status: torch.Tensor) -> torch.Tensor:
+    """(hash, offset) pairs of this rank's queries -> one slot of packed entries per destination shard
+    (int64[world, slot_cap, 2]; element 0 of a slot is its count).  ``query_starts``: int64[Q+1] on the device."""
     lib = N.lib()
     tdev = torch.device("cuda", device)
+    d = digests.contiguous(); o = qoffsets.to(torch.int32).contiguous()
+    n = o.numel()
+    nq = query_starts.numel() - 1
+    slots = torch.empty((world, int(slot_cap), 2), dtype=torch.int64, device=tdev)
+    N.check(lib.sia_route_entries(device, C.c_void_p(d.data_ptr()), C.c_void_p(o.data_ptr()),
+                                  C.c_void_p(query_starts.data_ptr()), nq, n, int(qid_base), int(world), int(slot_cap),
+                                  C.c_void_p(slots.data_ptr()), C.c_void_p(status.data_ptr()),
+                                  C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)))
+    return slots
+
+
+def _vote_outputs(tdev, n_queries, topn):
     outs = [torch.zeros((n_queries, topn), dtype=torch.int32, device=tdev) for _ in range(4)]
-    nres = torch.zeros(n_queries, dtype=torch.int32, device=tdev)
-    tk = tuple_key.contiguous(); rk = row_key.contiguous()
-    N.check(lib.sia_vote_tuples(device, C.c_void_p(tk.data_ptr()), tk.numel(), C.c_void_p(rk.data_ptr()), rk.numel(),
-                                n_queries, int(topn), C.c_void_p(outs[0].data_ptr()), C.c_void_p(outs[1].data_ptr()),
-                                C.c_void_p(outs[2].data_ptr()), C.c_void_p(outs[3].data_ptr()),
-                                C.c_void_p(nres.data_ptr()), C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)))
+    return outs, torch.zeros(n_queries, dtype=torch.int32, device=tdev)
+
+
+def vote_key_slots(device: int, key_slots: torch.Tensor, n_queries: int, topn: int, max_song: int):
+    """Vote the key slots received from every shard (int64[world, key_cap], element 0 of a slot = its count)."""
+    lib = N.lib()
+    tdev = torch.device("cuda", device)
+    outs, nres = _vote_outputs(tdev, n_queries, topn)
+    ks = key_slots.contiguous()
+    N.check(lib.sia_vote_key_slots(device, C.c_void_p(ks.data_ptr()), ks.shape[0], ks.shape[1], n_queries, int(topn),
+                                   int(max_song), C.c_void_p(outs[0].data_ptr()), C.c_void_p(outs[1].data_ptr()),
+                                   C.c_void_p(outs[2].data_ptr()), C.c_void_p(outs[3].data_ptr()),
+                                   C.c_void_p(nres.data_ptr()), C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)))
     return (*outs, nres)
 
 
-def vote_bins(device: int, bin_key: torch.Tensor, bin_count: torch.Tensor, row_key: torch.Tensor,
-              row_count: torch.Tensor, n_queries: int, topn: int):
-    """Sum equal keys of (possibly several shards') partial bins and vote.  CUDA tensors in and out."""
+def vote_tuples(device: int, keys: torch.Tensor, n_queries: int, topn: int, max_song: int):
+    """The align_matches vote over vote keys in any order (head | query | song | diff + 2^24, ``sia_b200.h``).
+    CUDA tensors in and out."""
     lib = N.lib()
     tdev = torch.device("cuda", device)
-    outs = [torch.zeros((n_queries, topn), dtype=torch.int32, device=tdev) for _ in range(4)]
-    nres = torch.zeros(n_queries, dtype=torch.int32, device=tdev)
-    bk = bin_key.contiguous(); bc = bin_count.to(torch.int32).contiguous()
-    rk = row_key.contiguous(); rc_ = row_count.to(torch.int32).contiguous()
-    N.check(lib.sia_vote_bins(device, C.c_void_p(bk.data_ptr()), C.c_void_p(bc.data_ptr()), bk.numel(),
-                              C.c_void_p(rk.data_ptr()), C.c_void_p(rc_.data_ptr()), rk.numel(), n_queries, int(topn),
-                              C.c_void_p(outs[0].data_ptr()), C.c_void_p(outs[1].data_ptr()),
-                              C.c_void_p(outs[2].data_ptr()), C.c_void_p(outs[3].data_ptr()),
-                              C.c_void_p(nres.data_ptr()), C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)))
+    outs, nres = _vote_outputs(tdev, n_queries, topn)
+    k = keys.contiguous()
+    N.check(lib.sia_vote_tuples(device, C.c_void_p(k.data_ptr()), k.numel(), n_queries, int(topn), int(max_song),
+                                C.c_void_p(outs[0].data_ptr()), C.c_void_p(outs[1].data_ptr()),
+                                C.c_void_p(outs[2].data_ptr()), C.c_void_p(outs[3].data_ptr()),
+                                C.c_void_p(nres.data_ptr()), C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)))
     return (*outs, nres)
 
 
@@ -341,7 +326,7 @@ class GPUDatabase:
     def __init__(self, device: Optional[int] = None, capacity_rows: int = 1 << 24, metadata: Optional[dict] = None,
                  **options):
         # host/user/password/database of config["database"] (__init__.py:29-37) are accepted and ignored
-        self._options = dict(options, device=device, capacity_rows=capacity_rows)
+        self._options = dict(options, device=device, capacity_rows=capacity_rows, metadata=metadata)
         dev = torch.cuda.current_device() if device is None and torch.cuda.is_available() else (device or 0)
         self.index = FingerprintIndex(dev, capacity_rows)
         self.songs = {}           # song_id -> dict(song_name, file_sha1, total_hashes, fingerprinted, date_created)
@@ -489,4 +474,11 @@ class GPUDatabase:
         return db
 
     def __getstate__(self):
+        """``mysql_database.py:202-204``: only the constructor options travel — the index lives in this process's GPU
+        memory; the other side gets an EMPTY database with the same options (use ``dump``/``load`` to move rows)."""
         return (self._options,)
+
+    def __setstate__(self, state):
+        """``mysql_database.py:206-207``."""
+        (options,) = state
+        self.__init__(**options)

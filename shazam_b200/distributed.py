@@ -5,14 +5,21 @@
 * The index shards BY HASH PREFIX: ``owner = floor(prefix16(hash) * world / 65536)``.
   - build: fingerprints are produced track-sharded, so rows are exchanged once
     (``all_to_all``) to their owning shard;
-  - query: exchange #1 routes every query hash (+ its query offset and query id) to the
-    shard that owns it; each shard computes PARTIAL vote histograms
-    ``(query, song, diff) -> count`` and ``(query, song) -> rows``.  A bin's true count is
-    the SUM over shards, so exchange #2 sends the partial bins to the rank that owns the
-    query, which sums equal keys and votes (``sia_vote_bins``); results can then be
-    gathered.  This keeps results identical to the single-GPU index, tie-breaks included.
+  - query, per pass of at most 16 384 queries per rank, two equal-split NCCL all-to-alls with the
+    device steps of ``csrc/index_dist.cu`` around them:
+      ``sia_route_entries``       (query owner)  entries -> one fixed-size slot per hash shard
+      all-to-all #1               16-byte (query, hash, offset) entries
+      ``sia_index_expand_slots``  (hash owner)   sort, lookup, posting runs -> vote keys, one slot per query owner
+      all-to-all #2               8-byte vote keys (head | query | song | offset difference)
+      ``sia_vote_key_slots``      (query owner)  the exact vote over the keys of ALL shards.
+    A bin's true count is the SUM over shards (finding 3), so the vote keys travel, not local
+    winners: results equal the single-GPU index, tie-breaks included.  Slots have fixed capacities (no
+    host-side size negotiation, no per-buffer collectives); an overflowing slot is reported by the device
+    and the pass is redone with the capacity it asked for (a steady-state pass never retries).
+  Why not a threshold top-k (local top-k -> bound tau -> bins >= tau/G)?  With the reference's TOPN of 2/3/5 and
+  one true match per query, ranks 2..n are noise songs whose best bin holds 2-4 matches spread over different
+  shards, so tau <= G and the threshold degenerates to "send every bin"; bench.py reports the measured n-th counts.
 
-The exchanges are NCCL all-to-alls over NVLink/NVSwitch; the path has no other collective.
 Everything here is host-side orchestration over a ``ShardBackend`` — the CUDA one wraps
 ``FingerprintIndex``; tests inject a CPU stand-in to exercise the routing under gloo.
 """
@@ -27,8 +34,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-QID_BITS, SONG_BITS, DIFF_BITS = 15, 24, 25
-MAX_QUERIES_PER_PASS = 1 << QID_BITS
+QID_BITS, SONG_BITS, DIFF_BITS = 14, 24, 25
+MAX_QUERIES_PER_PASS = 1 << QID_BITS       # per rank
 
 
 def shard_tracks(n_tracks: int, rank: int, world: int) -> np.ndarray:
@@ -46,7 +53,7 @@ def hash_owner(digests: torch.Tensor, world: int) -> torch.Tensor:
 
 def exchange(buffers: Sequence[torch.Tensor], dest: torch.Tensor, world: int, group=None) -> List[torch.Tensor]:
     """Send row i of every buffer to rank ``dest[i]``; returns what this rank receives,
-    ordered by source rank (stable within a source)."""
+    ordered by source rank (stable within a source).  Used by the index BUILD (once per batch of rows)."""
     if world == 1:
         return [b for b in buffers]
     order = torch.argsort(dest, stable=True)
@@ -65,26 +72,6 @@ def exchange(buffers: Sequence[torch.Tensor], dest: torch.Tensor, world: int, gr
     return out
 
 
-def exchange_grouped(buffers: Sequence[torch.Tensor], send_counts: Sequence[int], world: int, group=None):
-    """Like ``exchange`` for rows that are ALREADY grouped by destination rank (``send_counts[r]`` rows for
-    rank r, in order): no reordering, just the all-to-all."""
-    if world == 1:
-        return [b for b in buffers]
-    dev = buffers[0].device
-    counts = torch.tensor(list(send_counts), dtype=torch.int64, device=dev)
-    recv_counts = torch.empty_like(counts)
-    dist.all_to_all_single(recv_counts, counts, group=group)
-    out_split = recv_counts.tolist()
-    total = int(sum(out_split))
-    out = []
-    for b in buffers:
-        recv = b.new_empty((total,) + tuple(b.shape[1:]))
-        dist.all_to_all_single(recv, b.contiguous(), output_split_sizes=out_split, input_split_sizes=list(send_counts),
-                               group=group)
-        out.append(recv)
-    return out
-
-
 class ShardBackend:
     """What the orchestration needs from one shard."""
 
@@ -96,20 +83,16 @@ class ShardBackend:
     def finalize(self) -> int:
         raise NotImplementedError
 
-    def query_partial(self, digests, qoffsets, qids) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    def max_song(self) -> int:
         raise NotImplementedError
 
-    def vote(self, bin_key, bin_count, row_key, row_count, n_queries: int, topn: int):
+    def route_entries(self, digests, qoffsets, query_starts, qid_base: int, world: int, slot_cap: int, status):
         raise NotImplementedError
 
-    def expand(self, digests, qoffsets, qids, n_queries: int):
+    def expand_slots(self, entry_slots, world: int, queries_per_rank: int, key_cap: int, info):
         raise NotImplementedError
 
-    def expand_size(self, digests, qoffsets, qids, n_queries: int) -> int:
-        """Number of vote keys ``expand`` would produce (sizing only)."""
-        raise NotImplementedError
-
-    def vote_tuples(self, tuple_key, row_key, n_queries: int, topn: int):
+    def vote_key_slots(self, key_slots, n_queries: int, topn: int, max_song: int):
         raise NotImplementedError
 
     def query_batch(self, digests, qoffsets, query_starts, topn: int):
@@ -131,22 +114,19 @@ class CudaShard(ShardBackend):
     def finalize(self) -> int:
         return self.index.finalize()
 
-    def query_partial(self, digests, qoffsets, qids):
-        return self.index.query_partial(digests, qoffsets, qids)
+    def max_song(self) -> int:
+        return self.index.max_song
 
-    def vote(self, bin_key, bin_count, row_key, row_count, n_queries, topn):
-        from .database import vote_bins
-        return vote_bins(self._dev_index, bin_key, bin_count, row_key, row_count, n_queries, topn)
+    def route_entries(self, digests, qoffsets, query_starts, qid_base, world, slot_cap, status):
+        from .database import route_entries
+        return route_entries(self._dev_index, digests, qoffsets, query_starts, qid_base, world, slot_cap, status)
 
-    def expand(self, digests, qoffsets, qids, n_queries):
-        return self.index.expand(digests, qoffsets, qids, n_queries)
+    def expand_slots(self, entry_slots, world, queries_per_rank, key_cap, info):
+        return self.index.expand_slots(entry_slots, world, queries_per_rank, key_cap, info)
 
-    def expand_size(self, digests, qoffsets, qids, n_queries):
-        return self.index.expand_size(digests, qoffsets, qids, n_queries)
-
-    def vote_tuples(self, tuple_key, row_key, n_queries, topn):
-        from .database import vote_tuples
-        return vote_tuples(self._dev_index, tuple_key, row_key, n_queries, topn)
+    def vote_key_slots(self, key_slots, n_queries, topn, max_song):
+        from .database import vote_key_slots
+        return vote_key_slots(self._dev_index, key_slots, n_queries, topn, max_song)
 
     def query_batch(self, digests, qoffsets, query_starts, topn):
         return self.index.query_batch(digests, qoffsets, query_starts, topn)
@@ -159,16 +139,16 @@ class ShardedIndex:
     """The hash-prefix-sharded fingerprints table over ``world`` ranks."""
 
     def __init__(self, backend: ShardBackend, rank: Optional[int] = None, world: Optional[int] = None, group=None,
-                 exchange: str = "tuples"):
-        """``exchange``: what travels to the query's owner in the second all-to-all — ``"tuples"`` (unsorted
-        vote keys; the owner sorts once: the default) or ``"bins"`` (each shard sorts and run-length counts
-        first; the owner re-sorts and sums).  Both are exact."""
-        assert exchange in ("tuples", "bins")
-        self.exchange_mode = exchange
+                 key_cap: int = 1 << 16):
         self.backend = backend
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
+        self.entry_cap = 0          # slot capacities, kept between calls (grown when the device reports an overflow)
+        self.key_cap = max(2, int(key_cap))
+        self.retries = 0            # passes redone because a slot overflowed (0 in steady state)
+        self._max_song = 0
+        self.last_pass_ms = None    # stage times of the last pass on this rank (SIA_DIST_TIMING=1)
 
     # ---- build ---------------------------------------------------------------------------
     def insert(self, songs: torch.Tensor, digests: torch.Tensor, offsets: torch.Tensor) -> None:
@@ -180,104 +160,95 @@ class ShardedIndex:
 
     def finalize(self) -> int:
         """Collective.  Returns the total number of stored rows over all shards."""
-        n = torch.tensor([self.backend.finalize()], dtype=torch.int64, device=self.backend.device)
+        n = torch.tensor([self.backend.finalize(), 0], dtype=torch.int64, device=self.backend.device)
+        m = torch.tensor([self.backend.max_song()], dtype=torch.int64, device=self.backend.device)
         if self.world > 1:
             dist.all_reduce(n, group=self.group)
-        return int(n.item())
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+        self._max_song = int(m.item())      # the query owner sizes its song tables for songs of ALL shards
+        return int(n[0].item())
 
     # ---- query ---------------------------------------------------------------------------
     def query(self, digests: torch.Tensor, qoffsets: torch.Tensor, query_starts: np.ndarray, topn: int,
-              queries_per_pass: int = 4096, tuple_budget: int = 1_000_000_000):
+              queries_per_pass: int = 4096):
         """Collective.  Each rank submits ITS queries (``query_starts`` local, int64[Q_r+1]) and gets
         their results back: int32 tensors (song[Q_r,topn], diff, count, rows, nres[Q_r])."""
         dev = self.backend.device
         qs = np.asarray(query_starts, np.int64)
+        if self.world == 1:
+            return self.backend.query_batch(digests, qoffsets, qs, topn)
         q_local = len(qs) - 1
-        counts = torch.tensor([q_local], dtype=torch.int64, device=dev)
+        qp = max(1, min(MAX_QUERIES_PER_PASS, int(queries_per_pass)))
+        # one small collective per call: the number of passes and the largest per-pass entry count of any rank
+        pass_entries = [int(qs[min(lo + qp, q_local)] - qs[lo]) for lo in range(0, max(q_local, 1), qp)] or [0]
+        meta = torch.tensor([q_local, max(pass_entries)], dtype=torch.int64, device=dev)
         if self.world > 1:
-            allc = [torch.zeros_like(counts) for _ in range(self.world)]
-            dist.all_gather(allc, counts, group=self.group)
-            per_rank = [int(c.item()) for c in allc]
-        else:
-            per_rank = [q_local]
-        max_q = max(per_rank) if per_rank else 0
+            dist.all_reduce(meta, op=dist.ReduceOp.MAX, group=self.group)
+        max_q, max_entries = (int(x) for x in meta.tolist())
+        # hashes spread uniformly over the shards: 25 % + 64 entries of head-room per slot
+        self.entry_cap = max(self.entry_cap, int(max_entries / self.world * 1.25) + 66)
         outs = [torch.zeros((q_local, topn), dtype=torch.int32, device=dev) for _ in range(4)]
         nres = torch.zeros(q_local, dtype=torch.int32, device=dev)
-        # passes of at most 32768 queries in total: every rank contributes the same local range per pass
-        # (and at most queries_per_pass per rank).  A pass whose vote keys would exceed `tuple_budget` on some
-        # shard is retried with half the queries — decided collectively, so all ranks stay in step.
-        step = max(1, min(MAX_QUERIES_PER_PASS // self.world, int(queries_per_pass)))
+        qs_dev = torch.as_tensor(qs, dtype=torch.int64, device=dev)
         lo = 0
         while lo < max_q:
-            a, b = min(lo, q_local), min(lo + step, q_local)
-            sizes = [max(0, min(lo + step, c) - min(lo, c)) for c in per_rank]
-            base = int(sum(sizes[: self.rank]))
-            res = self._query_pass(digests[qs[a]:qs[b]], qoffsets[qs[a]:qs[b]], qs[a:b + 1] - qs[a], sizes, base, topn,
-                                   tuple_budget if step > 1 else None)
-            if res is None:
-                step = max(1, step // 2)
+            a, b = min(lo, q_local), min(lo + qp, q_local)
+            e0, e1 = int(qs[a]), int(qs[b])
+            res = self._query_pass(digests[e0:e1], qoffsets[e0:e1], qs_dev[a:b + 1] - e0, b - a, qp, topn)
+            if res is None:              # a slot overflowed somewhere: capacities were raised, redo the pass
+                self.retries += 1
                 continue
             for o, r in zip(outs, res[:4]):
                 o[a:b] = r
             nres[a:b] = res[4]
-            lo += step
+            lo += qp
         return (*outs, nres)
 
-    def _query_pass(self, digests, qoffsets, qs, sizes, base, topn, tuple_budget=None):
-        dev = self.backend.device
-        nq = len(qs) - 1
-        timing = os.environ.get("SIA_DIST_TIMING") and self.rank == 0
+    def _query_pass(self, digests, qoffsets, qs_dev, nq, qp, topn):
+        """One pass over nq of this rank's queries (``qs_dev``: their entry offsets into ``digests``, int64[nq+1] on the
+        device, starting at 0)."""
+        be, dev, G = self.backend, self.backend.device, self.world
+        timing = bool(os.environ.get("SIA_DIST_TIMING"))
         marks = []
 
         def mark(name):
             if timing:
-                torch.cuda.synchronize(dev)
+                if dev.type == "cuda":
+                    torch.cuda.synchronize(dev)
                 marks.append((name, time.perf_counter()))
         mark("start")
-        lens = torch.as_tensor(np.diff(qs), dtype=torch.int64, device=dev)
-        qid = torch.repeat_interleave(torch.arange(nq, dtype=torch.int64, device=dev), lens) + base   # pass-global ids
-        # exchange #1: query hashes to their owning shard
-        dest = hash_owner(digests, self.world)
-        d, o, q = exchange([digests, qoffsets.to(torch.int32), qid.to(torch.int32)], dest, self.world, self.group)
-        mark("route hashes")
-        shift = SONG_BITS + DIFF_BITS
-        if self.exchange_mode == "tuples":
-            total_q = int(sum(sizes))
-            if tuple_budget is not None and self.world > 1:
-                need = torch.tensor([self.backend.expand_size(d, o, q, total_q)], dtype=torch.int64, device=dev)
-                dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
-                if int(need.item()) > tuple_budget:
-                    return None
-            mark("lookup (sizing)")
-            tk, rk, ts, rs = self.backend.expand(d, o, q, total_q)
-            mark("expand")
-            # keys are grouped by ascending query id = by ascending owner rank: split points from the offsets
-            cuts = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64, device=ts.device)
-            tcut = ts[cuts].cpu().numpy()
-            rcut = rs[cuts].cpu().numpy()
-            (tk2,) = exchange_grouped([tk], np.diff(tcut).tolist(), self.world, self.group)
-            (rk2,) = exchange_grouped([rk], np.diff(rcut).tolist(), self.world, self.group)
-            mark("exchange vote keys")
-            tk2 = tk2 - (base << shift)
-            rk2 = rk2 - (base << shift)
-            mark("rebase")
-            res = self.backend.vote_tuples(tk2, rk2, nq, topn)
-            mark("vote")
-            if timing:
-                print("[sia dist] pass: %d local queries, %d vote keys out, %d in: " % (nq, tk.numel(), tk2.numel()) +
-                      ", ".join("%s %.1f ms" % (n, (t - marks[i][1]) * 1e3) for i, (n, t) in enumerate(marks[1:])),
-                      file=sys.stderr)
-            return res
-        bk, bc, rk, rc = self.backend.query_partial(d, o, q)
-        # exchange #2: partial bins to the rank that owns the query (sum-by-key happens there)
-        bounds = torch.as_tensor(np.cumsum(sizes), dtype=torch.int64, device=dev)
-        qmask = (1 << QID_BITS) - 1          # keys are uint64 carried in int64 tensors
-        bk2, bc2 = exchange([bk, bc], torch.bucketize((bk >> shift) & qmask, bounds, right=True), self.world, self.group)
-        rk2, rc2 = exchange([rk, rc], torch.bucketize((rk >> shift) & qmask, bounds, right=True), self.world, self.group)
-        # local query ids for the vote
-        bk2 = bk2 - (base << shift)
-        rk2 = rk2 - (base << shift)
-        return self.backend.vote(bk2, bc2, rk2, rc2, nq, topn)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        info = torch.zeros(4, dtype=torch.int64, device=dev)
+        send_e = be.route_entries(digests, qoffsets, qs_dev, self.rank * qp, G, self.entry_cap, status)
+        mark("route")
+        recv_e = torch.empty_like(send_e)
+        dist.all_to_all_single(recv_e, send_e, group=self.group)
+        mark("all-to-all entries")
+        send_k = be.expand_slots(recv_e, G, qp, self.key_cap, info)
+        mark("lookup + expand")
+        recv_k = torch.empty_like(send_k)
+        dist.all_to_all_single(recv_k, send_k, group=self.group)
+        mark("all-to-all keys")
+        # did any slot overflow anywhere?  (max over ranks: flags, key slot needed, entry slot needed, status)
+        chk = torch.cat([info[:3], status.to(torch.int64)])
+        dist.all_reduce(chk, op=dist.ReduceOp.MAX, group=self.group)
+        flags, need_k, need_e, st = (int(x) for x in chk.tolist())
+        if st & 2:
+            raise ValueError("query: offset outside 0..2^24-1 or more than 2^24 queries in one pass")
+        if flags & 3:
+            if flags & 1:
+                self.entry_cap = int(need_e * 1.25) + 64
+            if flags & 2:
+                self.key_cap = int(need_k * 1.25) + 64
+            return None
+        res = be.vote_key_slots(recv_k, nq, topn, self._max_song)
+        mark("vote")
+        if timing:
+            self.last_pass_ms = {n: (t - marks[i][1]) * 1e3 for i, (n, t) in enumerate(marks[1:])}
+            if self.rank == 0:
+                print("[sia dist] pass: %d local queries, key slots %d x %d: " % (nq, G, self.key_cap) +
+                      ", ".join("%s %.1f ms" % kv for kv in self.last_pass_ms.items()), file=sys.stderr)
+        return res
 
 
 class TrackShardedIndex:
@@ -318,6 +289,7 @@ class TrackShardedIndex:
         meta = torch.tensor([len(qs) - 1, int(qs[-1])], dtype=torch.int64, device=dev)
         metas = [torch.zeros_like(meta) for _ in range(self.world)]
         dist.all_gather(metas, meta, group=self.group)
+        metas = torch.stack(metas).cpu().numpy()
         nq = [int(m[0]) for m in metas]
         nh = [int(m[1]) for m in metas]
         all_d = self._all_gather_ragged(digests, nh)
@@ -343,7 +315,10 @@ class TrackShardedIndex:
         o_cnt = pick(c_cnt)
         ok = o_cnt >= 0
         z = lambda x: torch.where(ok, pick(x).to(torch.int32), torch.zeros_like(o_cnt, dtype=torch.int32))
-        return z(c_song), z(c_diff), z(c_cnt), z(c_rows), ok.sum(1).to(torch.int32)
+        res = [z(c_song), z(c_diff), z(c_cnt), z(c_rows)]
+        if res[0].shape[1] < topn:      # fewer candidates than topn (tiny worlds): pad to the contract's shape
+            res = [torch.nn.functional.pad(r, (0, topn - r.shape[1])) for r in res]
+        return (*res, ok.sum(1).to(torch.int32))
 
 
 def gather_results(results, group=None, dst: int = 0):

@@ -112,6 +112,11 @@ class Fingerprinter:
         self._h = h
         self.max_chunk_frames = int(max_chunk_frames)
 
+    def digest_table(self, enable: bool = True) -> None:
+        """Build (or free) the 13.5 GB table of every sha1("f1|f2|dt")[:10] the pipeline can produce: K3 becomes a
+        gather.  Identical results; worth it when many tracks are fingerprinted with this context."""
+        N.check(self.lib.sia_ctx_digest_table(self._h, 1 if enable else 0))
+
     def close(self):
         if getattr(self, "_h", None):
             self.lib.sia_ctx_destroy(self._h)
@@ -201,7 +206,10 @@ class Fingerprinter:
                                         C.c_void_p(hsh.data_ptr()), C.c_void_p(t1.data_ptr()), cap,
                                         C.c_void_p(ths.data_ptr()), C.c_void_p(status.data_ptr()), self._stream()))
         ths_h = ths.cpu().numpy()
-        if int(status.item()) & 2:
+        st = int(status.item())
+        if st & 4:
+            raise N.SiaError(N.E_INVALID, "generate_hashes: peak frequency bins must be in 0..99999")
+        if st & 2:
             raise N.CapacityError(N.E_CAPACITY, f"hash capacity {cap} exceeded ({int(ths_h[-1])} hashes)")
         n = int(ths_h[-1])
         return hsh[:n], t1[:n], ths

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .database import GPUDatabase, vote_bins
+from .database import GPUDatabase, vote_tuples
 from .fingerprinter import hex_to_digests
 
 # result-dict keys and constants, recognizer.py:30-68
@@ -90,20 +90,16 @@ def _result_dict(song_id: int, offset: int, hashes_matched: int, queried_hashes:
 
 def align_matches(matches, dedup_hashes, queried_hashes, topn: int = TOPN):
     """``recognizer.py:289-338``.  The vote (sort, run-length count, per-song first maximum,
-    stable descending sort) runs on the GPU: the tuples are uploaded as unit-weight bins."""
+    stable descending sort) runs on the GPU: the tuples are uploaded as vote keys (``sia_vote_tuples``)."""
     if len(matches) == 0:
         return []
     m = np.asarray(matches, dtype=np.int64).reshape(-1, 2)
     sid, diff = m[:, 0], m[:, 1]
     if sid.min() < 0 or sid.max() >= 1 << 24 or np.abs(diff).max() >= 1 << 24:
         raise N.SiaError(N.E_INVALID, "song ids / offset differences outside the 24-bit range")
-    dev = db.index.device
-    key = (sid << 25) | (diff + (1 << 24))
-    bk = torch.from_numpy(key).to(db.index.tdev)
-    bc = torch.ones(len(key), dtype=torch.int32, device=db.index.tdev)
-    empty_k = torch.empty(0, dtype=torch.int64, device=db.index.tdev)
-    empty_c = torch.empty(0, dtype=torch.int32, device=db.index.tdev)
-    song, dif, cnt, rows, nres = vote_bins(dev, bk, bc, empty_k, empty_c, 1, int(topn))
+    # vote keys of query 0 without the head flag (dedup_hashes comes from the caller's dict), sia_b200.h
+    key = torch.from_numpy((sid << 25) | (diff + (1 << 24))).to(db.index.tdev)
+    song, dif, cnt, rows, nres = vote_tuples(db.index.device, key, 1, int(topn), int(sid.max()))
     k = int(nres[0].item())
     song = song[0, :k].cpu().tolist()
     dif = dif[0, :k].cpu().tolist()

@@ -1,5 +1,5 @@
-"""world_size-2 gloo tests of the multi-GPU host logic (track sharding, hash-prefix routing, the exact
-partial-vote merge) with a CPU stand-in shard.  The CUDA shard is covered by tests/test_index_gpu.py."""
+"""world_size-2 gloo tests of the multi-GPU host logic (track sharding, hash-prefix routing through fixed-size slots,
+overflow retries, the exact vote over the keys of all shards) with a CPU stand-in shard.  The CUDA shard is covered by tests/test_index_gpu.py."""
 import hashlib
 import os
 import socket
@@ -44,7 +44,7 @@ def _oracle_results(songs, queries, topn):
     return out, table.num_rows()
 
 
-def _worker(rank, world, port, topn, mode="tuples"):
+def _worker(rank, world, port, topn, mode="hash"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -52,7 +52,7 @@ def _worker(rank, world, port, topn, mode="tuples"):
         from tests.dist_helpers import CpuShard
         songs, queries = _world()
         want, nrows = _oracle_results(songs, queries, topn)
-        ix = TrackShardedIndex(CpuShard()) if mode == "track" else ShardedIndex(CpuShard(), exchange=mode)
+        ix = TrackShardedIndex(CpuShard()) if mode == "track" else ShardedIndex(CpuShard(), key_cap=8)
         mine = shard_tracks(len(songs), rank, world)            # tracks fingerprinted by this rank
         assert sorted(np.concatenate([shard_tracks(len(songs), r, world) for r in range(world)]).tolist()) == list(range(len(songs)))
         sid = torch.tensor([songs[i][0] for i in mine for _ in songs[i][1]], dtype=torch.int32)
@@ -70,8 +70,15 @@ def _worker(rank, world, port, topn, mode="tuples"):
         D = np.array([np.frombuffer(h, np.uint8) for qi in myq for h, _ in queries[qi]], np.uint8).reshape(-1, 10)
         Oq = np.array([o for qi in myq for _, o in queries[qi]], np.int32)
         starts = np.cumsum([0] + [len(queries[qi]) for qi in myq])
-        kw = dict(queries_per_pass=3, tuple_budget=40) if mode == "tuples" else {}      # forces split passes + retries
+        kw = dict(queries_per_pass=3) if mode == "hash" else {}      # forces split passes; tiny first slots force retries
         res = ix.query(torch.from_numpy(D), torch.from_numpy(Oq), starts, topn, **kw)
+        if mode == "hash":
+            assert ix.retries >= 1                              # the first pass outgrew the initial key slots
+            before = ix.retries
+            res2 = ix.query(torch.from_numpy(D), torch.from_numpy(Oq), starts, topn, **kw)
+            assert ix.retries == before                         # steady state: capacities are kept, no retry
+            for a, b in zip(res, res2):
+                assert torch.equal(a, b)
         song, diff, cnt, rows, nres = [t.numpy() for t in res]
         for k, qi in enumerate(myq):
             got = [(int(song[k, r]), int(diff[k, r]), int(cnt[k, r]), int(rows[k, r])) for r in range(nres[k])]
@@ -91,7 +98,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("topn,mode", [(1, "tuples"), (3, "tuples"), (3, "bins"), (2, "track")])
+@pytest.mark.parametrize("topn,mode", [(1, "hash"), (3, "hash"), (2, "track")])
 def test_sharded_index_world2_gloo(topn, mode):
     mp.spawn(_worker, args=(2, _free_port(), topn, mode), nprocs=2, join=True)
 

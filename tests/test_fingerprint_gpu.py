@@ -68,6 +68,10 @@ def test_k1_spectrogram_synth_cases(fpr, synth_cases):
         assert got.shape == ref.shape, kind
         e = _check_spec(got, ref, floor_db=200.0)
         assert e < 5e-5, (kind, e)
+        # north_star's bound on EVERY bin, no floor (the deepest bins of these cases sit 206 dB under their frame's
+        # maximum); exact zeros (silence, gaps) are reproduced exactly
+        assert np.abs(got - ref).max() < DB_TOL, (kind, float(np.abs(got - ref).max()))
+        assert np.array_equal(got == 0, ref == 0), kind
 
 
 def test_k1_batch_layout(fpr):
@@ -83,6 +87,7 @@ def test_k1_batch_layout(fpr):
         ref = O.spectrogram_db(t, 44100)
         got = spec[row:row + ref.shape[1], :2049].T
         assert _check_spec(got, ref, floor_db=200.0) < 5e-5
+        assert np.abs(got - ref).max() < DB_TOL              # every bin
         row += ref.shape[1]
     assert row == spec.shape[0]
 
@@ -309,6 +314,71 @@ def test_capacity_error_is_reported(fpr):
         fpr.fingerprint_host(pcm, starts, lens, fpr.params(fan_value=15), cap_hashes=10)
 
 
+def test_peak_workspace_overflow_fails_cleanly(native_lib, monkeypatch):
+    """A chunk with more peaks than the workspace holds (here: a 1-peak-per-frame workspace) must come back as
+    SIA_E_CAPACITY with every device-side count clamped to the buffers — no out-of-bounds access, the device stays
+    usable and a correctly sized context gives the right answer afterwards."""
+    import torch
+    from shazam_b200 import _native as N
+    from shazam_b200.fingerprinter import Fingerprinter
+    track = O.synth_track(77, 5 * 44100)
+    monkeypatch.setenv("SIA_PEAKS_PER_FRAME_CAP", "1")
+    tiny = Fingerprinter(0, max_chunk_frames=256)
+    try:
+        with pytest.raises(N.CapacityError, match="peak workspace"):
+            tiny.fingerprint_tracks([track], fan_value=15)
+        torch.cuda.synchronize()                                  # no sticky CUDA error
+        with pytest.raises(N.CapacityError, match="peak workspace"):
+            tiny.fingerprint_tracks([track, track[:50000]], fan_value=5)
+    finally:
+        tiny.close()
+    monkeypatch.delenv("SIA_PEAKS_PER_FRAME_CAP")
+    ok = Fingerprinter(0, max_chunk_frames=256)
+    try:
+        h, t1 = ok.fingerprint_tracks([track], fan_value=15).track(0)
+        oh, ot = O.fingerprint_arrays(track, 44100, 15)
+        assert np.array_equal(h, oh) and np.array_equal(t1, ot)
+    finally:
+        ok.close()
+
+
+def test_digest_table_is_the_sha1_kernel(native_lib, synth_cases, wav_fixture):
+    """K3 as a gather (sia_ctx_digest_table): the table of every sha1("f1|f2|dt")[:10] gives the same digests as
+    hashing — golden vectors of the reference's generate_hashes — and inputs outside the kernel's message packing
+    fail loudly instead of producing a wrong digest."""
+    import torch
+    from shazam_b200 import _native as N, compat
+    from shazam_b200.fingerprinter import Fingerprinter
+    fp = Fingerprinter(0, max_chunk_frames=4096)
+    try:
+        fp.digest_table(True)
+        g = synth_cases
+        tracks = [g[f"{k}_pcm"] for k in g["kinds"]]
+        b = fp.fingerprint_tracks(tracks, Fs=44100, fan_value=15, amp_min=10)
+        for i, kind in enumerate(g["kinds"]):
+            h, t = b.track(i)
+            assert np.array_equal(h, g[f"{kind}_hash_fan15_amp10"]) and np.array_equal(t, g[f"{kind}_t1_fan15_amp10"]), kind
+        w = fp.fingerprint_tracks([wav_fixture["pcm"]], Fs=22050, fan_value=5)
+        assert np.array_equal(w.hash, wav_fixture["hash_c2_fan5_fs22050"])
+        # corners of the table and values outside it (computed): KATs of SURVEY §8a-5 through the public function
+        compat.set_fingerprinter(fp)
+        kat = compat.generate_hashes([(253, 0), (422, 0), (577, 0)], 3)
+        assert kat[0] == ("987a1bcc49e707cb9e6a", 0) and kat[1] == ("0f34024f21634bf6fbb0", 0)
+        assert compat.generate_hashes([(2048, 0), (0, 200)], 2) == [("a8b1bf935e7453ba6aef", 0)]
+        assert compat.generate_hashes([(0, 5), (0, 5)], 2) == [("bcd8195eb61a41102f4c", 5)]
+        import hashlib
+        big = compat.generate_hashes([(99999, 1), (54321, 200)], 2)          # 15-byte message: the one-block limit
+        assert big == [(hashlib.sha1(b"99999|54321|199").hexdigest()[:20], 1)]
+        for bad in ([(100000, 0), (5, 1)], [(-1, 0), (5, 1)]):
+            with pytest.raises(N.SiaError):
+                compat.generate_hashes(bad, 2)
+        fp.digest_table(False)
+        assert compat.generate_hashes([(2048, 0), (0, 200)], 2) == [("a8b1bf935e7453ba6aef", 0)]
+    finally:
+        compat.set_fingerprinter(None)
+        fp.close()
+
+
 def test_full_size_track_properties(fpr):
     """BASELINE configs[1] size (3-min tracks): size-independent properties + oracle on one track."""
     import torch
@@ -327,7 +397,12 @@ def test_full_size_track_properties(fpr):
     oh, ot = O.fingerprint_arrays(t0, 44100, 15)
     sa = set(zip(map(bytes, h0), t10.tolist())); sb = set(zip(map(bytes, oh), ot.tolist()))
     jacc = len(sa & sb) / len(sa | sb)
-    assert jacc >= 0.99, jacc
+    # Not bit-exact end to end at this size, as north_star allows (>= 0.99): K2 compares the float32-stored dB, and
+    # rounding to float32 creates ties (or breaks near-ties) between neighbouring bins that the float64 reference does
+    # not have, so a few peaks — and the <= 2 * (fan - 1) hashes each takes part in — differ.  Print how many.
+    print(f"full-size track: {len(sa)} GPU / {len(sb)} oracle hashes, {len(sa - sb)} only GPU, {len(sb - sa)} only oracle, "
+          f"Jaccard {jacc:.5f}")
+    assert jacc >= 0.99, (jacc, len(sa - sb), len(sb - sa))
     assert len(h0) == len(oh) or jacc < 1.0
 
 
