@@ -187,6 +187,10 @@ int64_t sia_index_rows(const sia_index *ix);
 int64_t sia_index_keys(const sia_index *ix);       /* distinct hashes stored */
 int32_t sia_index_max_song(const sia_index *ix);   /* largest song id inserted so far (as of the last finalize) */
 
+/* Give back everything that is not the table itself: pending buffers, the second key buffer, build / lookup / vote
+ * scratch (all of it is re-allocated on demand by the next insert, finalize or query).  Synchronous. */
+int sia_index_trim(sia_index *ix);
+
 /* DELETE FROM songs WHERE ... with ON DELETE CASCADE on fingerprints (mysql_database.py:56-57,
  * 132-139): remove every stored row of the listed songs.  *h_rows = rows left.  Synchronous. */
 int sia_index_delete_songs(sia_index *ix, const int32_t *h_song_ids, int32_t n, int64_t *h_rows);
@@ -198,8 +202,9 @@ int sia_index_export(sia_index *ix, int64_t first_row, int64_t n, uint8_t *d_has
                      void *stream);
 
 /* SELECT HEX(hash), song_id, offset WHERE hash IN (...) (recognizer.py:60-64, 252-259):
- * every stored row whose hash is in the list of n DISTINCT hashes.  Row order: by
- * position in h_hash, then (song_id, offset).  Fills up to cap rows; *h_nrows = total. */
+ * every stored row whose hash is in the list of n DISTINCT hashes.  Row order: by hash
+ * (h_row_hashidx gives the position of the row's hash in h_hash), then (song_id, offset); the host
+ * layer re-orders to IN-list order.  Fills up to cap rows; *h_nrows = total. */
 int sia_index_select_host(sia_index *ix, const uint8_t *h_hash, int64_t n, int32_t *h_row_hashidx,
                           int32_t *h_row_song, int32_t *h_row_off, int64_t cap, int64_t *h_nrows);
 
@@ -220,6 +225,10 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
                           const int64_t *h_query_starts, int32_t n_queries, int32_t topn,
                           int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
                           int32_t *d_out_rows, int32_t *d_out_nres, int64_t *h_stats, void *stream);
+
+/* device time (ms, CUDA events on the call's stream) of the last sia_index_query_batch: [0] pack + sort + lookup,
+ * [1] vote (all passes of the call) */
+int sia_index_query_timing(const sia_index *ix, double *h_ms2);
 
 /* Vote keys: what the (song_id, offset_difference) tuples of return_matches (recognizer.py:268) look like on the
  * device — 64 bits: head (1) | query id (14) | song id (24) | offset difference + 2^24 (25).  head = 1 marks a tuple

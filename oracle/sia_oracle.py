@@ -247,6 +247,18 @@ class ArrayFingerprintTable(FingerprintTable):
         self._hi, self._lo = rec["hi"].copy(), rec["lo"].copy()
         self._s, self._o = rec["s"].copy(), rec["o"].copy()
 
+    @classmethod
+    def from_sorted(cls, hi, lo, song_ids, offsets):
+        """Rows that are already unique and in (hash, song_id, offset) order (hi: first 8 digest bytes as big-endian
+        uint64, lo: last 2 as an integer) — e.g. an export of the GPU index — without the sort of the constructor."""
+        t = cls.__new__(cls)
+        FingerprintTable.__init__(t)
+        t._hi = np.ascontiguousarray(hi, np.uint64)
+        t._lo = np.ascontiguousarray(lo, np.uint64)
+        t._s = np.ascontiguousarray(song_ids, np.int64)
+        t._o = np.ascontiguousarray(offsets, np.int64)
+        return t
+
     def insert_hashes(self, song_id, hashes, batch_size=1000):
         raise NotImplementedError("ArrayFingerprintTable is built from arrays")
 

@@ -143,6 +143,9 @@ int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap,
                    int32_t topn, int32_t max_song, int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
                    int32_t *d_out_rows, int32_t *d_out_nres, cudaStream_t s);
 
+// frees the per-device scratch of vote_key_slots
+void vote_scratch_release(int device);
+
 }  // namespace sia
 
 struct sia_index {
@@ -164,6 +167,8 @@ struct sia_index {
   cudaEvent_t insert_done = nullptr;   // recorded after every insert's pack kernel (inserts may run on any stream)
   sia::Arena arena;                 // build / lookup scratch
   sia::Arena arena3;                // vote tables
+  cudaEvent_t ev_q[3] = {nullptr, nullptr, nullptr};   // start / after lookup / end of a query pass
+  double last_lookup_ms = 0, last_vote_ms = 0;          // device time of the last sia_index_query_batch call
   uint64_t *stage = nullptr;        // staging chunk of the in-place posting moves
   int64_t stage_cap = 0;
 

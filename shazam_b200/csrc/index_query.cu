@@ -269,6 +269,7 @@ entries_pass_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, c
                     unsigned long long *__restrict__ n_bins, int32_t *__restrict__ flags) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int per_warp = kVoteTuples >> 3;
+  if (PASS == PASS_VOTE && (*flags & 32)) return;    // the bin tables did not fit their reservation: the host redoes the group
   const int64_t j_lo = off[e0] + (int64_t)blockIdx.x * kVoteTuples + (int64_t)warp * per_warp;
   const int64_t j_hi = min(off[e0 + n], j_lo + per_warp);
   if (j_lo >= j_hi) return;
@@ -353,6 +354,7 @@ keys_pass_kernel(const uint64_t *__restrict__ keys, int n_slots, int64_t cap, co
   const int lane = threadIdx.x & 31;
   const int64_t total = (int64_t)n_slots * cap;
   uint32_t dummy = 0;
+  if (PASS == PASS_VOTE && (*flags & 32)) return;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < total; i0 += (int64_t)gridDim.x * blockDim.x) {
     __syncwarp();
     const int64_t i = i0 + threadIdx.x;
@@ -630,8 +632,17 @@ int lookup_sorted(::sia_index *ix, Arena &ar, ulonglong2 *a, ulonglong2 *b, int6
 }
 
 // bytes of vote tables for `tuples` tuples over nq queries: filter + worst-case bins (every tuple a candidate) + songs
-static size_t vote_table_bytes(int64_t tuples, int64_t nq, int64_t song_slots, bool dense) {
-  return (size_t)(tuples + nq) * 4 + (size_t)(2 * tuples + 32 * nq) * 12 + (size_t)song_slots * (dense ? 8 : 12) + 4096;
+static size_t vote_table_bytes(int64_t tuples, int64_t nq, int64_t bin_slots, int64_t song_slots, bool dense) {
+  return (size_t)(tuples + nq) * 4 + (size_t)bin_slots * 12 + (size_t)song_slots * (dense ? 8 : 12) + 4096;
+}
+// bin slots reserved for `tuples` tuples over nq queries: first for up to a quarter of the tuples landing in twice-hit
+// buckets (12 % on the benchmark's index), then — if pass 1 counted more — for all of them
+static int64_t bin_slots_for(int64_t tuples, int64_t nq, int attempt) {
+  return (attempt == 0 ? tuples / 2 : 2 * tuples) + 32 * nq;
+}
+
+void vote_scratch_release(int device) {
+  if (device >= 0 && device < 64) g_vote_tables[device].release();
 }
 
 int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap, const int64_t *d_counts, int32_t n_queries,
@@ -653,8 +664,10 @@ int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap,
   const int64_t ns_hashed = 2 * T + 32ll * nq;
   const bool dense = span * nq * 8 <= ns_hashed * 12;
   const int64_t ns = dense ? span * nq : ns_hashed;
-  const int64_t nb_cap = 2 * T + 32ll * nq, nf = T + nq;
-  int rc = ar.reserve(vote_table_bytes(T, nq, ns, dense) + (size_t)nq * (sizeof(QMeta) + 8) + 65536);
+  const int64_t nf = T + nq;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+  const int64_t nb_cap = bin_slots_for(T, nq, attempt);
+  int rc = ar.reserve(vote_table_bytes(T, nq, nb_cap, ns, dense) + (size_t)nq * (sizeof(QMeta) + 8) + 65536);
   if (rc) return rc;
   QMeta *meta = ar.take<QMeta>(nq);
   uint32_t *cnt = ar.take<uint32_t>(nq), *qflag = ar.take<uint32_t>(nq);
@@ -700,7 +713,10 @@ int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap,
   SIA_CUDA(cudaMemcpyAsync(&h_flags, flags, sizeof h_flags, cudaMemcpyDeviceToHost, s));
   SIA_CUDA(cudaStreamSynchronize(s));
   SIA_REQUIRE(!(h_flags & 2), SIA_E_INVALID, "vote: query id outside 0..n_queries-1");
-  SIA_REQUIRE(!(h_flags & (8 | 32)), SIA_E_CUDA, "vote: table overflow (internal error, or song id above max_song)");
+  SIA_REQUIRE(!(h_flags & 8), SIA_E_CUDA, "vote: table overflow (internal error, or song id above max_song)");
+  if (!(h_flags & 32)) return SIA_OK;
+  SIA_REQUIRE(attempt == 0, SIA_E_CUDA, "vote: bin table overflow (internal error)");
+  }
   return SIA_OK;
 }
 
@@ -778,6 +794,8 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     tuple_budget = std::max<int64_t>(1 << 20, std::min<int64_t>(tuple_budget, (int64_t)((free_b + ix->arena3.cap) * 0.6 / 40)));
   }
   const bool timing = getenv("SIA_QUERY_TIMING") != nullptr;       // stage times of every pass on stderr
+  ix->last_lookup_ms = ix->last_vote_ms = 0;
+  for (auto &e : ix->ev_q) if (!e) SIA_CUDA(cudaEventCreate(&e));
   const int64_t span = (int64_t)ix->max_song + 1;
   for (int64_t q0 = 0; q0 < n_queries; q0 += kMaxQueriesPerPass) {
     const int nq = (int)std::min<int64_t>(kMaxQueriesPerPass, n_queries - q0);
@@ -791,8 +809,7 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     SIA_REQUIRE(d_qs && d_goff && ea && eb, SIA_E_NOMEM, "index scratch arena too small (query)");
     SIA_CUDA(cudaMemcpyAsync(d_qs, h_query_starts + q0, sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, s));
     const auto h0 = std::chrono::steady_clock::now();
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    if (timing) { for (auto &e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
+    SIA_CUDA(cudaEventRecord(ix->ev_q[0], s));
     int64_t max_entries = 0;
     for (int q = 0; q < nq; ++q) max_entries = std::max(max_entries, h_query_starts[q0 + q + 1] - h_query_starts[q0 + q]);
     pack_queries_kernel<<<grid_for(n), 256, 0, s>>>(d_hash, d_qoff, nullptr, d_qs, nq, i0, n, ea, ix->status);
@@ -800,7 +817,7 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     Lookup L;
     if ((rc = lookup_sorted(ix, ix->arena, ea, eb, n, d_qs, i0, nq, max_entries, L, s))) return rc;
     if ((rc = check_status(ix, s, 2 | 4, "query: offset outside 0..2^24-1 (or a posting run of 2^32 rows)"))) return rc;
-    if (timing) cudaEventRecord(ev[1], s);
+    SIA_CUDA(cudaEventRecord(ix->ev_q[1], s));
     if (h_stats) { h_stats[1] += L.head_rows; h_stats[2] += L.tuples; }
     // After the sort query q still owns entries [starts[q]-i0, starts[q+1]-i0) (duplicates stay, with no
     // postings), so the scanned offsets at those positions split the pass into groups that fit the budget.
@@ -813,7 +830,6 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     struct Group { int qa, qb; bool dense; int64_t nf, ns; };
     std::vector<Group> groups;
     std::vector<QMeta> h_meta(nq);
-    size_t max_bytes = 0;
     for (int qa = 0; qa < nq;) {
       int qb = qa + 1;
       while (qb < nq && h_off_all[qb + 1] - h_off_all[qa] <= tuple_budget) ++qb;
@@ -832,79 +848,97 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
         fb += m.filt_words; sb += m.song_cap;
       }
       g.nf = fb; g.ns = sb;
-      max_bytes = std::max(max_bytes, vote_table_bytes(t_all, qb - qa, sb, g.dense));
       groups.push_back(g);
       qa = qb;
     }
-    if ((rc = ix->arena3.reserve(max_bytes + (size_t)nq * (sizeof(QMeta) + 4) + 65536))) return rc;
-    QMeta *d_meta = ix->arena3.take<QMeta>(nq);
-    uint32_t *qflag = ix->arena3.take<uint32_t>(nq);
-    int64_t *d_total = ix->arena3.take<int64_t>(1);
-    unsigned long long *d_nbins = ix->arena3.take<unsigned long long>(1);
-    int32_t *d_flags = ix->arena3.take<int32_t>(1);
-    const size_t fixed = ix->arena3.used;
-    SIA_REQUIRE(d_meta && qflag && d_total && d_nbins && d_flags, SIA_E_NOMEM, "index scratch arena too small (vote)");
-    SIA_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(QMeta) * nq, cudaMemcpyHostToDevice, s));
-    SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long), s));
-    SIA_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t), s));
-    for (const Group &g : groups) {
-      const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
-      const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa];
-      if (tuples == 0) continue;           // out_nres is already 0 for these queries
-      ix->arena3.used = fixed;
-      const int64_t nb_cap = 2 * tuples + 32ll * (g.qb - g.qa);
-      Tables Tb;
-      Tb.filter = ix->arena3.take<uint32_t>(g.nf);
-      Tb.song_best = ix->arena3.take<unsigned long long>(g.ns);
-      Tb.song_key = g.dense ? nullptr : ix->arena3.take<uint32_t>(g.ns);
-      Tb.bins = ix->arena3.take<unsigned long long>(nb_cap);
-      Tb.bin_cnt = ix->arena3.take<uint32_t>(nb_cap);
-      SIA_REQUIRE(Tb.filter && Tb.song_best && Tb.bins && Tb.bin_cnt && (g.dense || Tb.song_key), SIA_E_NOMEM,
-                  "index scratch arena too small (vote tables)");
-      SIA_CUDA(cudaMemsetAsync(Tb.filter, 0, sizeof(uint32_t) * g.nf, s));
-      SIA_CUDA(cudaMemsetAsync(Tb.song_best, 0, sizeof(unsigned long long) * g.ns, s));
-      if (!g.dense) SIA_CUDA(cudaMemsetAsync(Tb.song_key, 0, sizeof(uint32_t) * g.ns, s));
-      const unsigned blocks = (unsigned)ceil_div(tuples, kVoteTuples);
-      const int gq = g.qb - g.qa;
-#define SIA_ENT_PASS(D, P)                                                                                              \
-      entries_pass_kernel<D, P><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->post, d_meta, Tb,  \
-                                                       qflag, (int)q0, topn, d_out_song, d_out_nres, d_out_rows, d_nbins,    \
-                                                       d_flags)
-#define SIA_ENT_VOTE(D)                                                                                                 \
-      do {                                                                                                              \
-        SIA_ENT_PASS(D, PASS_MARK);                                                                                     \
-        layout_bins_kernel<<<1, 1024, 0, s>>>(d_meta, g.qa, g.qb, d_total);                                             \
-        zero_bins_kernel<<<kNumSMs * 8, 256, 0, s>>>(Tb.bins, Tb.bin_cnt, d_total, nb_cap, d_flags);                    \
-        SIA_ENT_PASS(D, PASS_VOTE);                                                                                     \
-        topn_kernel<D, false><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_out_song, d_out_diff,        \
-                                                 d_out_count, d_out_rows, d_out_nres);                                  \
-        SIA_ENT_PASS(D, PASS_SINGLES);                                                                                  \
-        topn_kernel<D, true><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_out_song, d_out_diff,         \
-                                                d_out_count, d_out_rows, d_out_nres);                                   \
-        SIA_ENT_PASS(D, PASS_ROWS);                                                                                     \
-      } while (0)
-      if (g.dense) SIA_ENT_VOTE(true); else SIA_ENT_VOTE(false);
-#undef SIA_ENT_VOTE
-#undef SIA_ENT_PASS
-      SIA_CHECK_LAUNCH();
-    }
     int32_t h_flags = 0;
     unsigned long long h_nb = 0;
-    SIA_CUDA(cudaMemcpyAsync(&h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, s));
-    SIA_CUDA(cudaMemcpyAsync(&h_nb, d_nbins, sizeof h_nb, cudaMemcpyDeviceToHost, s));
-    if (timing) cudaEventRecord(ev[2], s);
-    SIA_CUDA(cudaStreamSynchronize(s));      // the lookup scratch and the tables are reused by the next pass / call
-    SIA_REQUIRE(!(h_flags & (8 | 32)), SIA_E_CUDA, "query: vote table overflow (internal error)");
-    if (h_stats) h_stats[3] += (int64_t)h_nb;
-    if (timing) {
-      float t_lookup = 0, t_vote = 0;
-      cudaEventElapsedTime(&t_lookup, ev[0], ev[1]); cudaEventElapsedTime(&t_vote, ev[1], ev[2]);
-      const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
-      fprintf(stderr, "[sia] query pass: %d queries, %lld entries, %lld tuples, %zu groups: lookup %.2f ms, vote %.2f ms, host wall %.2f ms\n",
-              nq, (long long)n, (long long)L.tuples, groups.size(), t_lookup, t_vote, host_ms);
-      for (auto &e : ev) cudaEventDestroy(e);
+    // attempt 0 reserves bin slots for a quarter of the tuples being candidates; if pass 1 counts more in some group
+    // (tie-heavy queries) the device flags it and the pass is voted again with room for all of them
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      size_t max_bytes = 0;
+      for (const Group &g : groups)
+        max_bytes = std::max(max_bytes, vote_table_bytes(h_off_all[g.qb] - h_off_all[g.qa], g.qb - g.qa,
+                                                         bin_slots_for(h_off_all[g.qb] - h_off_all[g.qa], g.qb - g.qa, attempt),
+                                                         g.ns, g.dense));
+      if ((rc = ix->arena3.reserve(max_bytes + (size_t)nq * (sizeof(QMeta) + 4) + 65536))) return rc;
+      QMeta *d_meta = ix->arena3.take<QMeta>(nq);
+      uint32_t *qflag = ix->arena3.take<uint32_t>(nq);
+      int64_t *d_total = ix->arena3.take<int64_t>(1);
+      unsigned long long *d_nbins = ix->arena3.take<unsigned long long>(1);
+      int32_t *d_flags = ix->arena3.take<int32_t>(1);
+      const size_t fixed = ix->arena3.used;
+      SIA_REQUIRE(d_meta && qflag && d_total && d_nbins && d_flags, SIA_E_NOMEM, "index scratch arena too small (vote)");
+      SIA_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(QMeta) * nq, cudaMemcpyHostToDevice, s));
+      SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long), s));
+      SIA_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t), s));
+      for (const Group &g : groups) {
+        const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
+        const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa];
+        if (tuples == 0) continue;           // out_nres is already 0 for these queries
+        ix->arena3.used = fixed;
+        const int64_t nb_cap = bin_slots_for(tuples, g.qb - g.qa, attempt);
+        Tables Tb;
+        Tb.filter = ix->arena3.take<uint32_t>(g.nf);
+        Tb.song_best = ix->arena3.take<unsigned long long>(g.ns);
+        Tb.song_key = g.dense ? nullptr : ix->arena3.take<uint32_t>(g.ns);
+        Tb.bins = ix->arena3.take<unsigned long long>(nb_cap);
+        Tb.bin_cnt = ix->arena3.take<uint32_t>(nb_cap);
+        SIA_REQUIRE(Tb.filter && Tb.song_best && Tb.bins && Tb.bin_cnt && (g.dense || Tb.song_key), SIA_E_NOMEM,
+                    "index scratch arena too small (vote tables)");
+        SIA_CUDA(cudaMemsetAsync(Tb.filter, 0, sizeof(uint32_t) * g.nf, s));
+        SIA_CUDA(cudaMemsetAsync(Tb.song_best, 0, sizeof(unsigned long long) * g.ns, s));
+        if (!g.dense) SIA_CUDA(cudaMemsetAsync(Tb.song_key, 0, sizeof(uint32_t) * g.ns, s));
+        const unsigned blocks = (unsigned)ceil_div(tuples, kVoteTuples);
+        const int gq = g.qb - g.qa;
+#define SIA_ENT_PASS(D, P)                                                                                              \
+        entries_pass_kernel<D, P><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->post, d_meta, Tb,  \
+                                                         qflag, (int)q0, topn, d_out_song, d_out_nres, d_out_rows, d_nbins,    \
+                                                         d_flags)
+#define SIA_ENT_VOTE(D)                                                                                                 \
+        do {                                                                                                            \
+          SIA_ENT_PASS(D, PASS_MARK);                                                                                   \
+          layout_bins_kernel<<<1, 1024, 0, s>>>(d_meta, g.qa, g.qb, d_total);                                           \
+          zero_bins_kernel<<<kNumSMs * 8, 256, 0, s>>>(Tb.bins, Tb.bin_cnt, d_total, nb_cap, d_flags);                  \
+          SIA_ENT_PASS(D, PASS_VOTE);                                                                                   \
+          topn_kernel<D, false><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_out_song, d_out_diff,      \
+                                                   d_out_count, d_out_rows, d_out_nres);                                \
+          SIA_ENT_PASS(D, PASS_SINGLES);                                                                                \
+          topn_kernel<D, true><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_out_song, d_out_diff,       \
+                                                  d_out_count, d_out_rows, d_out_nres);                                 \
+          SIA_ENT_PASS(D, PASS_ROWS);                                                                                   \
+        } while (0)
+        if (g.dense) SIA_ENT_VOTE(true); else SIA_ENT_VOTE(false);
+#undef SIA_ENT_VOTE
+#undef SIA_ENT_PASS
+        SIA_CHECK_LAUNCH();
+      }
+      SIA_CUDA(cudaMemcpyAsync(&h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, s));
+      SIA_CUDA(cudaMemcpyAsync(&h_nb, d_nbins, sizeof h_nb, cudaMemcpyDeviceToHost, s));
+      SIA_CUDA(cudaEventRecord(ix->ev_q[2], s));
+      SIA_CUDA(cudaStreamSynchronize(s));      // the lookup scratch and the tables are reused by the next pass / call
+      SIA_REQUIRE(!(h_flags & 8), SIA_E_CUDA, "query: vote table overflow (internal error)");
+      if (!(h_flags & 32)) break;
+      SIA_REQUIRE(attempt == 0, SIA_E_CUDA, "query: bin table overflow (internal error)");
     }
+    {
+      float t_lookup = 0, t_vote = 0;
+      cudaEventElapsedTime(&t_lookup, ix->ev_q[0], ix->ev_q[1]); cudaEventElapsedTime(&t_vote, ix->ev_q[1], ix->ev_q[2]);
+      ix->last_lookup_ms += t_lookup; ix->last_vote_ms += t_vote;
+      if (timing) {
+        const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+        fprintf(stderr, "[sia] query pass: %d queries, %lld entries, %lld tuples, %zu groups: lookup %.2f ms, vote %.2f ms, host wall %.2f ms\n",
+                nq, (long long)n, (long long)L.tuples, groups.size(), t_lookup, t_vote, host_ms);
+      }
+    }
+    if (h_stats) h_stats[3] += (int64_t)h_nb;
   }
+  return SIA_OK;
+}
+
+int sia_index_query_timing(const sia_index *ix, double *h_ms2) {
+  SIA_REQUIRE(ix && h_ms2, SIA_E_INVALID, "NULL argument");
+  h_ms2[0] = ix->last_lookup_ms; h_ms2[1] = ix->last_vote_ms;
   return SIA_OK;
 }
 

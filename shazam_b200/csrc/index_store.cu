@@ -438,6 +438,7 @@ int sia_index_destroy(sia_index *ix) {
   if (ix->status) cudaFree(ix->status);
   if (ix->stage) cudaFree(ix->stage);
   if (ix->insert_done) cudaEventDestroy(ix->insert_done);
+  for (cudaEvent_t e : ix->ev_q) if (e) cudaEventDestroy(e);
   ix->arena.release();
   ix->arena3.release();
   delete ix;
@@ -566,6 +567,25 @@ int sia_index_delete_songs(sia_index *ix, const int32_t *h_song_ids, int32_t n, 
   if ((rc = rebuild_dir(ix, s))) return rc;
   SIA_CUDA(cudaStreamSynchronize(s));
   if (h_rows) *h_rows = ix->n_rows;
+  return SIA_OK;
+}
+
+int sia_index_trim(sia_index *ix) {
+  SIA_REQUIRE(ix != nullptr, SIA_E_INVALID, "index is NULL");
+  SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
+  int rc = set_device(ix);
+  if (rc) return rc;
+  SIA_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < 2; ++k) { if (ix->pend[k]) cudaFree(ix->pend[k]); ix->pend[k] = nullptr; }
+  ix->pend_cap = 0;
+  const int other = ix->cur ^ 1;
+  if (ix->keys[other]) cudaFree(ix->keys[other]);
+  ix->keys[other] = nullptr; ix->keys_cap[other] = 0;
+  if (ix->stage) cudaFree(ix->stage);
+  ix->stage = nullptr; ix->stage_cap = 0;
+  ix->arena.release();
+  ix->arena3.release();
+  vote_scratch_release(ix->device);
   return SIA_OK;
 }
 

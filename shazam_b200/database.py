@@ -163,7 +163,8 @@ class FingerprintIndex:
                                                    C.byref(nr)))
             if nr.value <= cap:
                 m = nr.value
-                return idx[:m], sid[:m], off[:m]
+                order = np.argsort(idx[:m], kind="stable")      # the device answers in hash order: back to IN-list order
+                return idx[:m][order], sid[:m][order], off[:m][order]
             cap = int(nr.value)
 
     def query_batch(self, digests: torch.Tensor, qoffsets: torch.Tensor, query_starts: np.ndarray, topn: int,
@@ -190,6 +191,17 @@ class FingerprintIndex:
         if want_stats:
             return (*outs, nres, list(stats))
         return (*outs, nres)
+
+    def trim(self) -> None:
+        """Release build / lookup / vote scratch (re-allocated on demand); the table stays."""
+        self.finalize()
+        N.check(self.lib.sia_index_trim(self._h))
+
+    def query_timing(self):
+        """(lookup ms, vote ms): device time of the last ``query_batch`` call (CUDA events on its stream)."""
+        ms = (C.c_double * 2)()
+        N.check(self.lib.sia_index_query_timing(self._h, ms))
+        return float(ms[0]), float(ms[1])
 
     @property
     def keys(self) -> int:

@@ -1,7 +1,7 @@
 """Multi-GPU check (launch under torchrun on N >= 2 GPUs of one node):
   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/run_dist_gpu.py
 Track-sharded fingerprinting -> hash-prefix-sharded index (NCCL all-to-all) -> routed queries with the
-exact partial-vote merge; every rank's results must equal a single-GPU index built from all rows."""
+exact vote over the exchanged keys; every rank's results must equal a single-GPU index built from all rows."""
 import os
 import sys
 
@@ -48,12 +48,11 @@ def main():
     qb = fp.fingerprint_tracks([clips[i] for i in myq], fan_value=15)
     D, Oq = torch.from_numpy(qb.hash).to(dev), torch.from_numpy(qb.t1).to(dev)
     want = single.query_batch(D, Oq, qb.starts, 3)
-    for name in ("tuples", "bins", "track"):
+    for name in ("hash", "hash small passes", "track"):
         if name == "track":
             got = by_track.query(D, Oq, qb.starts, 3)
         else:
-            sharded.exchange_mode = name
-            got = sharded.query(D, Oq, qb.starts, 3)
+            got = sharded.query(D, Oq, qb.starts, 3, queries_per_pass=4096 if name == "hash" else 3)
         for a, w in zip(got, want):
             assert torch.equal(a, w), (name, rank, a, w)
     top = got[0][:, 0].cpu().tolist()

@@ -222,7 +222,7 @@ def test_hash_prefix_slots_equal_single_index(gpudb):
         ref = db.index.query_batch(D, Oq, starts, 3)
         max_song = db.index.max_song
         owners = [(0, QP), (QP, len(queries))]          # query ranges of the two query-owning ranks
-        ecap, kcap = 400, 12000
+        ecap, kcap = 800, 12000
         for attempt in range(2):
             sent = []
             for r, (a, b) in enumerate(owners):
