@@ -155,6 +155,16 @@ int sia_fingerprint_batch_host(sia_ctx *ctx, const int16_t *h_pcm, const int64_t
  * last reset; order: stft, peaks(bitmap), peaks(compact), pairs+sha1, scans.  n <= 8. */
 int sia_ctx_timing(sia_ctx *ctx, int enable, double *h_ms_out, int32_t *h_launches_out, int32_t n);
 
+/* ---- noise-robustness harness -------------------------------------------------------------------- */
+/* get_noise_from_sound + the mix (recognizer_test.py:426-435, 554) for a batch of clips: clip c reads n_samples int16
+ * at d_signal + c * signal_stride and n_samples float noise samples at d_noise + c * noise_stride, and writes
+ * round(signal + noise * RMS_n / RMS_noise), RMS_n = RMS_signal / 10^(SNR/20), saturated to int16, at d_out + c *
+ * out_stride (a multiple of 8 keeps the clips aligned for K1).  d_scale_out (optional, n_clips doubles): the factor
+ * applied to each clip's noise.  Stream-ordered. */
+int sia_mix_noise(int device, const int16_t *d_signal, int64_t signal_stride, const float *d_noise, int64_t noise_stride,
+                  int32_t n_clips, int64_t n_samples, double snr_db, int16_t *d_out, int64_t out_stride,
+                  double *d_scale_out, void *stream);
+
 /* ---- index (replaces the fingerprints table + SELECT_MULTIPLE + align_matches) --------- */
 
 /* One shard of the `fingerprints` table (mysql_database.py:46-59): rows

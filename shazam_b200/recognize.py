@@ -42,16 +42,23 @@ def set_database(database: GPUDatabase) -> None:
     db = database
 
 
-def return_matches(hashes, batch_size: int = 1000):
+def return_matches(hashes, batch_size: int = 1000, apriori: bool = False):
     """``recognizer.py:222-271``: ``(results, dedup_hashes)`` with ``results`` a list of
     ``(song_id, db_offset - query_offset)`` and ``dedup_hashes[song_id]`` the number of DB rows
-    matched (each row once, however many query offsets share its hash)."""
+    matched (each row once, however many query offsets share its hash).
+
+    ``apriori=True`` is the early exit of ``recognizer_apriori.py:297-308``: after every batch of
+    ``batch_size`` distinct hashes the matches so far are aligned, and the lookup stops as soon as the best song has
+    more than twice the matched hashes of the runner-up.  It changes ``hashes_matched`` (fewer batches are read), so
+    it is off by default and outside the parity tests; the return value then has the reference's third element,
+    the aligned results at the point of exit (``[]`` if the exit never triggered)."""
     mapper = {}
     for hsh, offset in hashes:
         mapper.setdefault(hsh.upper(), []).append(offset)
     values = list(mapper.keys())
     dedup_hashes = {}
     results = []
+    songs_arr = []
     with db.cursor() as cur:
         for index in range(0, len(values), batch_size):
             batch = values[index: index + batch_size]
@@ -60,6 +67,13 @@ def return_matches(hashes, batch_size: int = 1000):
                 dedup_hashes[sid] = dedup_hashes.get(sid, 0) + 1
                 for song_sampled_offset in mapper[hsh]:
                     results.append((sid, offset - song_sampled_offset))
+            if apriori:
+                songs_arr = align_matches(results, dedup_hashes, len(hashes))
+                if len(songs_arr) > 1 and songs_arr[0][HASHES_MATCHED] / 2 > songs_arr[1][HASHES_MATCHED]:
+                    break
+                songs_arr = []
+    if apriori:
+        return results, dedup_hashes, songs_arr
     return results, dedup_hashes
 
 
