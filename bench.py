@@ -71,7 +71,7 @@ def parse():
     ap.add_argument("--match-topn", type=int, default=3)
     ap.add_argument("--match-gen-batch", type=int, default=500, help="tracks generated per batch")
     ap.add_argument("--match-flush-rows", type=int, default=250_000_000, help="pending rows per finalize (merge)")
-    ap.add_argument("--match-pass-keys", type=int, default=400_000_000, help="N>1: vote keys a rank receives per pass")
+    ap.add_argument("--match-pass-keys", type=int, default=1_000_000_000, help="N>1: vote keys a rank receives per pass")
     ap.add_argument("--match-check-queries", type=int, default=256, help="N>1: subsample checked against one full index")
     ap.add_argument("--match-cpu-tracks", type=int, default=2714, help="index size of the CPU baseline (configs[2])")
     return ap.parse_args()

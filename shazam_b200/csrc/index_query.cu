@@ -33,7 +33,7 @@ constexpr int kQidBits = SIA_KEY_QID_BITS, kSongBits = SIA_KEY_SONG_BITS, kDiffB
 constexpr int64_t kMaxQueriesPerPass = 1ll << kQidBits;
 constexpr uint64_t kDiffMask = (1ull << kDiffBits) - 1;
 constexpr int kTopK = 4;                  // results extracted per scan of a query's song table
-constexpr int kVoteTuples = 4096;         // vote tuples per block of the entry-walking kernels (512 per warp)
+constexpr int kVoteTuples = 16384;        // vote tuples per block of the entry-walking kernels (2048 per warp)
 
 struct QMeta {
   int64_t bin_base, song_base, filt_base;   // first slot / word of the query's sub-tables inside the group's tables
@@ -213,11 +213,9 @@ __device__ __forceinline__ uint32_t *filter_word(const QMeta &m, uint32_t song, 
   return filter + m.filt_base + slot_of(h, m.filt_words);
 }
 
-// pass 1 of one tuple: mark the bucket; returns how many candidate tuples this arrival accounts for
-__device__ __forceinline__ uint32_t filter_mark(const QMeta &m, uint32_t song, uint32_t dbits, uint32_t *__restrict__ filter) {
-  uint32_t seen;
-  uint32_t *w = filter_word(m, song, dbits, filter, seen);
-  const uint32_t old = atomicOr(w, seen);
+// pass 1 of one tuple, second half: `old` is what the atomicOr of the bucket's seen bit returned; returns how many
+// candidate tuples this arrival accounts for
+__device__ __forceinline__ uint32_t mark_finish(uint32_t *__restrict__ w, uint32_t seen, uint32_t old) {
   if (!(old & seen)) return 0;                      // first arrival in its bucket
   if (old & (seen << 1)) return 1;                  // a later arrival of a bucket already known to be hit twice
   return (atomicOr(w, seen << 1) & (seen << 1)) ? 1u : 2u;   // the arrival that marks "twice" also accounts for the first one
@@ -225,23 +223,41 @@ __device__ __forceinline__ uint32_t filter_mark(const QMeta &m, uint32_t song, u
 
 enum { PASS_MARK = 1, PASS_VOTE = 2, PASS_SINGLES = 3, PASS_ROWS = 4 };
 
-// The work of one vote tuple in each pass.  `wins`/`nwin`: the query's winners (PASS_ROWS).
+// pass 2 of one tuple, second half: fw is the tuple's filter word
+template <bool DENSE>
+__device__ __forceinline__ void vote_finish(const QMeta &m, uint32_t song, uint32_t dbits, uint32_t fw, uint32_t seen,
+                                            const Tables &T, uint32_t &fresh, int32_t *__restrict__ flags) {
+  if (fw & (seen << 1)) {
+    const unsigned long long c = bin_count(m, song, dbits, T, fresh, flags);
+    if (c) song_update<DENSE>(m, song, dbits, c, T, flags);
+  } else {
+    ++fresh;                                        // alone in its bucket: a bin of its own, count 1
+  }
+}
+
+// Two vote tuples per lane and step, so that the two L2 round trips (the atomicOr of pass 1, the filter read of
+// pass 2) of a step are in flight together.
 template <bool DENSE, int PASS>
-__device__ __forceinline__ void tuple_pass(const QMeta &m, uint32_t song, uint32_t dbits, bool head, const Tables &T,
-                                           uint32_t &acc, int32_t *__restrict__ flags) {
+__device__ __forceinline__ void tuple_pair_pass(const QMeta &m, bool va, uint32_t song_a, uint32_t db_a, bool vb, uint32_t song_b,
+                                                uint32_t db_b, const Tables &T, uint32_t &acc, int32_t *__restrict__ flags) {
+  if (PASS == PASS_SINGLES) {
+    if (va) song_update<DENSE>(m, song_a, db_a, 1ull, T, flags);
+    if (vb) song_update<DENSE>(m, song_b, db_b, 1ull, T, flags);
+    return;
+  }
+  uint32_t sa, sb;
+  uint32_t *wa = filter_word(m, song_a, db_a, T.filter, sa);
+  uint32_t *wb = filter_word(m, song_b, db_b, T.filter, sb);
   if (PASS == PASS_MARK) {
-    acc += filter_mark(m, song, dbits, T.filter);
-  } else if (PASS == PASS_VOTE) {
-    uint32_t seen;
-    const uint32_t *w = filter_word(m, song, dbits, T.filter, seen);
-    if (__ldcg(w) & (seen << 1)) {
-      const unsigned long long c = bin_count(m, song, dbits, T, acc, flags);
-      if (c) song_update<DENSE>(m, song, dbits, c, T, flags);
-    } else {
-      ++acc;                                        // alone in its bucket: a bin of its own, count 1
-    }
-  } else if (PASS == PASS_SINGLES) {
-    song_update<DENSE>(m, song, dbits, 1ull, T, flags);
+    const uint32_t oa = va ? atomicOr(wa, sa) : 0u;
+    const uint32_t ob = vb ? atomicOr(wb, sb) : 0u;
+    if (va) acc += mark_finish(wa, sa, oa);
+    if (vb) acc += mark_finish(wb, sb, ob);
+  } else {
+    const uint32_t fa = va ? __ldcg(wa) : 0u;
+    const uint32_t fb = vb ? __ldcg(wb) : 0u;
+    if (va) vote_finish<DENSE>(m, song_a, db_a, fa, sa, T, acc, flags);
+    if (vb) vote_finish<DENSE>(m, song_b, db_b, fb, sb, T, acc, flags);
   }
 }
 
@@ -257,19 +273,18 @@ __device__ __forceinline__ void rows_pass(uint32_t active, bool mine, uint32_t s
 // One block handles kVoteTuples consecutive vote tuples (postings of the entries [e0, e0+n), numbered by the exclusive
 // scan off[]), whatever entries they belong to: a heavy key's run is shared by many blocks.  Each warp takes an eighth
 // of the block's tuples and walks the entries they belong to: everything that depends on the entry (query tables,
-// query offset, head flag, first posting) is warp-uniform and loaded once per entry, the lanes then take the entry's
-// postings 32 at a time, the next step's posting in flight during this one.
+// query offset, first posting) is warp-uniform and loaded once per entry, the lanes then take the entry's
+// postings 64 at a time (two per lane), the next step's postings in flight during this one.
 template <bool DENSE, int PASS>
 __global__ void __launch_bounds__(256)
 entries_pass_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, const int64_t *__restrict__ first,
-                    const int64_t *__restrict__ off, const uint32_t *__restrict__ cnt_head,
-                    const uint64_t *__restrict__ post, QMeta *__restrict__ meta, Tables T,
-                    const uint32_t *__restrict__ qflag, int qid_base, int topn, const int32_t *__restrict__ out_song,
-                    const int32_t *__restrict__ out_nres, int32_t *__restrict__ out_rows,
+                    const int64_t *__restrict__ off, const uint64_t *__restrict__ post, QMeta *__restrict__ meta, Tables T,
+                    const uint32_t *__restrict__ qflag, const int32_t *__restrict__ n_flagged,
                     unsigned long long *__restrict__ n_bins, int32_t *__restrict__ flags) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int per_warp = kVoteTuples >> 3;
   if (PASS == PASS_VOTE && (*flags & 32)) return;    // the bin tables did not fit their reservation: the host redoes the group
+  if (PASS == PASS_SINGLES && *n_flagged == 0) return;            // every query was settled by its bins of count >= 2
   const int64_t j_lo = off[e0] + (int64_t)blockIdx.x * kVoteTuples + (int64_t)warp * per_warp;
   const int64_t j_hi = min(off[e0 + n], j_lo + per_warp);
   if (j_lo >= j_hi) return;
@@ -283,9 +298,7 @@ entries_pass_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, c
     if (o_next == o_this) continue;                              // a hash without postings (or a duplicate pair)
     const ulonglong2 e = ent[ei];
     const uint32_t q = (uint32_t)(e.y >> 40);
-    const bool head = cnt_head[ei] != 0;                         // first entry of its (query, hash): rows count once
     if (PASS == PASS_SINGLES && !qflag[q]) continue;
-    if (PASS == PASS_ROWS && !head) continue;
     if (PASS == PASS_MARK && q != cur_q) {                       // flush the candidate count of the previous query
 #pragma unroll
       for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
@@ -293,29 +306,23 @@ entries_pass_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, c
       acc = 0; cur_q = q;
     }
     const QMeta m = meta[q];
-    const int nwin = PASS == PASS_ROWS ? out_nres[q + qid_base] : 0;
-    if (PASS == PASS_ROWS && nwin == 0) continue;
-    const int64_t obase = ((int64_t)q + qid_base) * topn;
     const uint32_t qoff = (uint32_t)(e.x & kM24);
     const uint64_t *__restrict__ run = post + first[ei];
     const uint32_t k_hi = (uint32_t)(min(j_hi, o_next) - o_this);
     const uint32_t k_lo = (uint32_t)(max(j_lo, o_this) - o_this);
-    uint64_t r_next = 0;
-    if (k_lo + lane < k_hi) r_next = run[k_lo + lane];
-    for (uint32_t kw = k_lo; kw < k_hi; kw += 32) {
+    uint64_t na = 0, nb = 0;
+    if (k_lo + lane < k_hi) na = run[k_lo + lane];
+    if (k_lo + 32 + lane < k_hi) nb = run[k_lo + 32 + lane];
+    for (uint32_t kw = k_lo; kw < k_hi; kw += 64) {
       __syncwarp();                                              // the probe loops below diverge
-      const uint32_t k = kw + lane;
-      const uint64_t r = r_next;
-      if (k + 32 < k_hi) r_next = run[k + 32];
-      const bool valid = k < k_hi;
-      const uint32_t song = (uint32_t)(r >> 24) & 0xffffffu;
-      if (PASS == PASS_ROWS) {
-        rows_pass(0xffffffffu, valid, song, out_song + obase, nwin, out_rows + obase, lane);
-        continue;
-      }
-      if (!valid) continue;
-      const uint32_t dbits = (uint32_t)(r & kM24) - qoff + SIA_DIFF_BIAS;      // db offset - query offset, biased
-      tuple_pass<DENSE, PASS>(m, song, dbits, head, T, acc, flags);
+      const uint32_t ka = kw + lane, kb = ka + 32;
+      const uint64_t ra = na, rb = nb;
+      if (ka + 64 < k_hi) na = run[ka + 64];
+      if (kb + 64 < k_hi) nb = run[kb + 64];
+      // db offset - query offset, biased
+      tuple_pair_pass<DENSE, PASS>(m, ka < k_hi, (uint32_t)(ra >> 24) & 0xffffffu, (uint32_t)(ra & kM24) - qoff + SIA_DIFF_BIAS,
+                                   kb < k_hi, (uint32_t)(rb >> 24) & 0xffffffu, (uint32_t)(rb & kM24) - qoff + SIA_DIFF_BIAS,
+                                   T, acc, flags);
     }
     __syncwarp();
   }
@@ -329,66 +336,125 @@ entries_pass_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, c
   }
 }
 
-// key i of a slotted key array: counts != NULL -> slot s holds counts[s] keys from its first element; counts == NULL ->
-// element 0 of every slot is its count and the keys follow (the exchanged layout, index_dist.cu)
-__device__ __forceinline__ bool load_slot_key(const uint64_t *__restrict__ keys, int64_t cap, const int64_t *__restrict__ counts,
-                                              int64_t i, uint64_t &k) {
-  const int64_t sl = i / cap, j = i - sl * cap;
-  if (counts) {
-    if (j >= min(counts[sl], cap)) return false;
-  } else {
-    if (j == 0 || j > min((int64_t)keys[sl * cap], cap - 1)) return false;
+// dedup_hashes of the winners (recognizer.py:259-264): one warp per head entry.  A run is sorted by (song, offset), so a
+// long run is not read at all: two binary searches per winner bracket its rows (lanes 2r, 2r+1); short runs are read.
+__global__ void __launch_bounds__(256)
+entries_rows_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, const int64_t *__restrict__ first,
+                    const uint32_t *__restrict__ cnt_head, const uint64_t *__restrict__ post, int qid_base, int topn,
+                    const int32_t *__restrict__ out_song, const int32_t *__restrict__ out_nres, int32_t *__restrict__ out_rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+    const int64_t ei = e0 + i;
+    const uint32_t c = cnt_head[ei];                              // 0: not the first entry of its (query, hash), or no postings
+    if (c == 0) continue;
+    const uint32_t q = (uint32_t)(ent[ei].y >> 40);
+    const int nwin = out_nres[q + qid_base];
+    if (nwin == 0) continue;
+    const int64_t obase = ((int64_t)q + qid_base) * topn;
+    const uint64_t *__restrict__ run = post + first[ei];
+    if (c <= 64) {
+      for (uint32_t kw = 0; kw < c; kw += 32) {
+        const uint32_t k = kw + lane;
+        const uint32_t song = k < c ? (uint32_t)(run[k] >> 24) & 0xffffffu : 0xffffffffu;
+        rows_pass(0xffffffffu, k < c, song, out_song + obase, nwin, out_rows + obase, lane);
+      }
+    } else {
+      for (int r0 = 0; r0 < nwin; r0 += 16) {
+        const int r = r0 + (lane >> 1);
+        int64_t pos = 0;
+        if (r < nwin) pos = lower_bound_u64(run, 0, (int64_t)c, ((uint64_t)(uint32_t)out_song[obase + r] + (lane & 1)) << 24);
+        const int64_t lo = __shfl_sync(0xffffffffu, pos, lane & ~1), hi = __shfl_sync(0xffffffffu, pos, lane | 1);
+        if (!(lane & 1) && r < nwin && hi > lo) atomicAdd(out_rows + obase + r, (int32_t)(hi - lo));
+      }
+    }
   }
-  k = keys[i];
-  return true;
 }
 
-// The same passes over vote keys stored in slots (keys from other shards, or a caller's tuples).  Keys of one query are
-// mostly adjacent, so PASS_MARK aggregates the candidate counts per run inside the warp.
+// keys of slot `sl` of a slotted key array: counts != NULL -> slot s holds counts[s] keys from its first element;
+// counts == NULL -> element 0 of every slot is its count and the keys follow (the exchanged layout, index_dist.cu)
+__device__ __forceinline__ const uint64_t *slot_keys(const uint64_t *__restrict__ keys, int64_t cap,
+                                                     const int64_t *__restrict__ counts, int sl, int64_t &n) {
+  const uint64_t *base = keys + (int64_t)sl * cap;
+  if (counts) { n = min(counts[sl], cap); return base; }
+  n = min((int64_t)base[0], cap - 1);
+  return base + 1;
+}
+
+// The same passes over vote keys stored in slots (keys from other shards, or a caller's tuples): blockIdx.y = slot, the
+// slot's keys are spread over blockIdx.x with two keys per thread and step.  Keys of one query are mostly adjacent, so
+// PASS_MARK aggregates the candidate counts per run inside the warp.
 template <bool DENSE, int PASS>
 __global__ void __launch_bounds__(256)
-keys_pass_kernel(const uint64_t *__restrict__ keys, int n_slots, int64_t cap, const int64_t *__restrict__ counts, int nq,
-                 QMeta *__restrict__ meta, Tables T, const uint32_t *__restrict__ qflag, int topn,
-                 const int32_t *__restrict__ out_song, const int32_t *__restrict__ out_nres, int32_t *__restrict__ out_rows,
-                 int32_t *__restrict__ flags) {
+keys_pass_kernel(const uint64_t *__restrict__ keys, int64_t cap, const int64_t *__restrict__ counts, int nq,
+                 QMeta *__restrict__ meta, Tables T, const uint32_t *__restrict__ qflag, const int32_t *__restrict__ n_flagged,
+                 int topn, const int32_t *__restrict__ out_song, const int32_t *__restrict__ out_nres,
+                 int32_t *__restrict__ out_rows, int32_t *__restrict__ flags) {
   const int lane = threadIdx.x & 31;
-  const int64_t total = (int64_t)n_slots * cap;
   uint32_t dummy = 0;
   if (PASS == PASS_VOTE && (*flags & 32)) return;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < total; i0 += (int64_t)gridDim.x * blockDim.x) {
+  if (PASS == PASS_SINGLES && *n_flagged == 0) return;
+  int64_t n;
+  const uint64_t *__restrict__ kk = slot_keys(keys, cap, counts, blockIdx.y, n);
+  const uint32_t qmask = (1u << kQidBits) - 1u;
+  for (int64_t i0 = (int64_t)blockIdx.x * 512; i0 < n; i0 += (int64_t)gridDim.x * 512) {
     __syncwarp();
-    const int64_t i = i0 + threadIdx.x;
-    uint64_t k = 0;
-    bool valid = i < total && load_slot_key(keys, cap, counts, i, k);
-    const uint32_t q = (uint32_t)(k >> (kSongBits + kDiffBits)) & ((1u << kQidBits) - 1u);
-    if (valid && q >= (uint32_t)nq) { atomicOr(flags, 2); valid = false; }
-    const uint32_t song = (uint32_t)(k >> kDiffBits) & 0xffffffu;
-    const uint32_t dbits = (uint32_t)(k & kDiffMask);
-    const bool head = (k >> 63) != 0;
+    // a warp takes 64 consecutive keys: lane l the keys l and l + 32
+    const int64_t ia = i0 + (threadIdx.x >> 5) * 64 + lane, ib = ia + 32;
+    bool va = ia < n, vb = ib < n;
+    const uint64_t ka = va ? kk[ia] : 0, kb = vb ? kk[ib] : 0;
+    const uint32_t qa = (uint32_t)(ka >> (kSongBits + kDiffBits)) & qmask, qb = (uint32_t)(kb >> (kSongBits + kDiffBits)) & qmask;
+    if (va && qa >= (uint32_t)nq) { atomicOr(flags, 2); va = false; }
+    if (vb && qb >= (uint32_t)nq) { atomicOr(flags, 2); vb = false; }
+    const uint32_t song_a = (uint32_t)(ka >> kDiffBits) & 0xffffffu, song_b = (uint32_t)(kb >> kDiffBits) & 0xffffffu;
+    const uint32_t db_a = (uint32_t)(ka & kDiffMask), db_b = (uint32_t)(kb & kDiffMask);
     if (PASS == PASS_ROWS) {
       // winners differ per query: handle the queries present in the warp one after the other
-      uint32_t todo = __ballot_sync(0xffffffffu, valid && head);
-      while (todo) {
-        const int src = __ffs(todo) - 1;
-        const uint32_t qq = __shfl_sync(0xffffffffu, q, src);
-        const bool mine = valid && head && q == qq;
-        const int64_t obase = (int64_t)qq * topn;
-        rows_pass(0xffffffffu, mine, song, out_song + obase, out_nres[qq], out_rows + obase, lane);
-        todo &= ~__ballot_sync(0xffffffffu, mine);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const bool v = half ? vb : va;
+        const uint64_t k = half ? kb : ka;
+        const uint32_t q = half ? qb : qa, song = half ? song_b : song_a;
+        const bool head = (k >> 63) != 0;
+        uint32_t todo = __ballot_sync(0xffffffffu, v && head);
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          const uint32_t qq = __shfl_sync(0xffffffffu, q, src);
+          const bool mine = v && head && q == qq;
+          const int64_t obase = (int64_t)qq * topn;
+          rows_pass(0xffffffffu, mine, song, out_song + obase, out_nres[qq], out_rows + obase, lane);
+          todo &= ~__ballot_sync(0xffffffffu, mine);
+        }
       }
       continue;
     }
-    if (PASS == PASS_SINGLES && valid && !qflag[q]) valid = false;
-    uint32_t acc = 0;
-    if (valid) tuple_pass<DENSE, PASS>(meta[q], song, dbits, head, T, PASS == PASS_MARK ? acc : dummy, flags);
+    if (PASS == PASS_SINGLES) {
+      if (va && !qflag[qa]) va = false;
+      if (vb && !qflag[qb]) vb = false;
+    }
+    uint32_t acc_a = 0, acc_b = 0;
+    if (qa == qb || !vb || !va) {                       // the common case: both keys belong to one query
+      const uint32_t q = va ? qa : qb;
+      if (va || vb) tuple_pair_pass<DENSE, PASS>(meta[q], va, song_a, db_a, vb, song_b, db_b, T, PASS == PASS_MARK ? acc_a : dummy, flags);
+      if (!va) { acc_b = acc_a; acc_a = 0; }
+    } else {
+      tuple_pair_pass<DENSE, PASS>(meta[qa], true, song_a, db_a, false, 0u, 0u, T, PASS == PASS_MARK ? acc_a : dummy, flags);
+      tuple_pair_pass<DENSE, PASS>(meta[qb], true, song_b, db_b, false, 0u, 0u, T, PASS == PASS_MARK ? acc_b : dummy, flags);
+    }
     if (PASS == PASS_MARK) {
       __syncwarp();
-      const uint32_t active = __ballot_sync(0xffffffffu, valid && acc);
-      if (valid && acc) {
-        const uint32_t peers = __match_any_sync(active, q);
-        uint32_t sum = 0;
-        for (uint32_t p = peers; p; p &= p - 1) sum += __shfl_sync(peers, acc, __ffs(p) - 1);
-        if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&meta[q].cand, sum);
+      // candidate counts: when both keys are one query's, acc_a holds their sum
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t acc = half ? acc_b : acc_a;
+        const uint32_t q = half ? qb : (va ? qa : qb);
+        const uint32_t active = __ballot_sync(0xffffffffu, acc != 0);
+        if (acc) {
+          const uint32_t peers = __match_any_sync(active, q);
+          uint32_t sum = 0;
+          for (uint32_t p = peers; p; p &= p - 1) sum += __shfl_sync(peers, acc, __ffs(p) - 1);
+          if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&meta[q].cand, sum);
+        }
       }
     }
   }
@@ -396,13 +462,14 @@ keys_pass_kernel(const uint64_t *__restrict__ keys, int n_slots, int64_t cap, co
 
 // keys per query (keys arrive grouped by query: one atomic per run inside the warp)
 __global__ void __launch_bounds__(256)
-count_keys_kernel(const uint64_t *__restrict__ keys, int n_slots, int64_t cap, const int64_t *__restrict__ counts, int nq,
+count_keys_kernel(const uint64_t *__restrict__ keys, int64_t cap, const int64_t *__restrict__ counts, int nq,
                   uint32_t *__restrict__ cnt, int32_t *__restrict__ flags) {
-  const int64_t total = (int64_t)n_slots * cap;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < total; i0 += (int64_t)gridDim.x * blockDim.x) {
+  int64_t n;
+  const uint64_t *__restrict__ kk = slot_keys(keys, cap, counts, blockIdx.y, n);
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = i0 + threadIdx.x;
-    uint64_t k = 0;
-    bool valid = i < total && load_slot_key(keys, cap, counts, i, k);
+    bool valid = i < n;
+    const uint64_t k = valid ? kk[i] : 0;
     const uint32_t q = (uint32_t)(k >> (kSongBits + kDiffBits)) & ((1u << kQidBits) - 1u);
     if (valid && q >= (uint32_t)nq) { atomicOr(flags, 2); valid = false; }
     const uint32_t active = __ballot_sync(0xffffffffu, valid);
@@ -485,13 +552,13 @@ zero_bins_kernel(unsigned long long *__restrict__ bins, uint32_t *__restrict__ b
 template <bool DENSE, bool ONLY_FLAGGED>
 __global__ void __launch_bounds__(256)
 topn_kernel(const Tables T, const QMeta *__restrict__ meta, int q_lo, int qid_base, int topn, uint32_t *__restrict__ qflag,
-            int32_t *__restrict__ out_song, int32_t *__restrict__ out_diff, int32_t *__restrict__ out_count,
+            int32_t *__restrict__ n_flagged, int32_t *__restrict__ out_song, int32_t *__restrict__ out_diff, int32_t *__restrict__ out_count,
             int32_t *__restrict__ out_rows, int32_t *__restrict__ out_nres) {
   __shared__ unsigned long long s_key[8];
   __shared__ uint32_t s_slot[8];
   __shared__ unsigned long long s_win;
   const int q = (int)blockIdx.x + q_lo;
-  if (ONLY_FLAGGED && !qflag[q]) return;
+  if (ONLY_FLAGGED && (*n_flagged == 0 || !qflag[q])) return;
   const QMeta m = meta[q];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long prev = ~0ull;
@@ -560,7 +627,11 @@ topn_kernel(const Tables T, const QMeta *__restrict__ meta, int q_lo, int qid_ba
       const int64_t o = ((int64_t)q + qid_base) * topn + r;
       out_song[o] = 0; out_diff[o] = 0; out_count[o] = 0; out_rows[o] = 0;
     }
-    if (!ONLY_FLAGGED) qflag[q] = (nres < topn || last_count < 2) ? 1u : 0u;
+    if (!ONLY_FLAGGED) {
+      const bool f = m.filt_words > 1 && (nres < topn || last_count < 2);    // a query without tuples has nothing to add
+      qflag[q] = f ? 1u : 0u;
+      if (f) atomicAdd(n_flagged, 1);
+    }
   }
 }
 
@@ -672,7 +743,8 @@ int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap,
   QMeta *meta = ar.take<QMeta>(nq);
   uint32_t *cnt = ar.take<uint32_t>(nq), *qflag = ar.take<uint32_t>(nq);
   int64_t *total = ar.take<int64_t>(1);
-  int32_t *flags = ar.take<int32_t>(1);
+  int32_t *flags = ar.take<int32_t>(2);          // [0] flags, [1] queries that need the singles pass
+  int32_t *nflag = flags + 1;
   Tables Tb;
   Tb.filter = ar.take<uint32_t>(nf);
   Tb.song_best = ar.take<unsigned long long>(ns);
@@ -682,26 +754,27 @@ int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap,
   SIA_REQUIRE(meta && cnt && qflag && total && flags && Tb.filter && Tb.song_best && Tb.bins && Tb.bin_cnt &&
               (dense || Tb.song_key), SIA_E_NOMEM, "vote: scratch");
   SIA_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * nq, s));
-  SIA_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t), s));
+  SIA_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), s));
   SIA_CUDA(cudaMemsetAsync(Tb.filter, 0, sizeof(uint32_t) * nf, s));
   SIA_CUDA(cudaMemsetAsync(Tb.song_best, 0, sizeof(unsigned long long) * ns, s));
   if (!dense) SIA_CUDA(cudaMemsetAsync(Tb.song_key, 0, sizeof(uint32_t) * ns, s));
-  const unsigned grid = grid_for(T);
-  count_keys_kernel<<<grid, 256, 0, s>>>(d_keys, n_slots, cap, d_counts, nq, cnt, flags);
+  // blockIdx.y = slot; the x blocks of a slot stride over its keys (~32 resident blocks per SM in all)
+  const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(cap, 512), (kNumSMs * 32) / n_slots + 1)), (unsigned)n_slots);
+  count_keys_kernel<<<grid, 256, 0, s>>>(d_keys, cap, d_counts, nq, cnt, flags);
   layout_keys_kernel<<<1, 1024, 0, s>>>(cnt, nq, dense ? span : 0, meta);
 #define SIA_KEYS_PASS(D, P)                                                                                            \
-  keys_pass_kernel<D, P><<<grid, 256, 0, s>>>(d_keys, n_slots, cap, d_counts, nq, meta, Tb, qflag, topn, d_out_song,   \
-                                              d_out_nres, d_out_rows, flags)
+  keys_pass_kernel<D, P><<<grid, 256, 0, s>>>(d_keys, cap, d_counts, nq, meta, Tb, qflag, nflag, topn,                 \
+                                              d_out_song, d_out_nres, d_out_rows, flags)
 #define SIA_KEYS_VOTE(D)                                                                                               \
   do {                                                                                                                 \
     SIA_KEYS_PASS(D, PASS_MARK);                                                                                       \
     layout_bins_kernel<<<1, 1024, 0, s>>>(meta, 0, nq, total);                                                         \
     zero_bins_kernel<<<kNumSMs * 8, 256, 0, s>>>(Tb.bins, Tb.bin_cnt, total, nb_cap, flags);                           \
     SIA_KEYS_PASS(D, PASS_VOTE);                                                                                       \
-    topn_kernel<D, false><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, d_out_song, d_out_diff, d_out_count,         \
+    topn_kernel<D, false><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, nflag, d_out_song, d_out_diff, d_out_count,  \
                                              d_out_rows, d_out_nres);                                                  \
     SIA_KEYS_PASS(D, PASS_SINGLES);                                                                                    \
-    topn_kernel<D, true><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, d_out_song, d_out_diff, d_out_count,          \
+    topn_kernel<D, true><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, nflag, d_out_song, d_out_diff, d_out_count,   \
                                             d_out_rows, d_out_nres);                                                   \
     SIA_KEYS_PASS(D, PASS_ROWS);                                                                                       \
   } while (0)
@@ -866,12 +939,13 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
       uint32_t *qflag = ix->arena3.take<uint32_t>(nq);
       int64_t *d_total = ix->arena3.take<int64_t>(1);
       unsigned long long *d_nbins = ix->arena3.take<unsigned long long>(1);
-      int32_t *d_flags = ix->arena3.take<int32_t>(1);
+      int32_t *d_flags = ix->arena3.take<int32_t>(2);     // [0] flags, [1] queries of the group that need the singles pass
+      int32_t *d_nflag = d_flags + 1;
       const size_t fixed = ix->arena3.used;
       SIA_REQUIRE(d_meta && qflag && d_total && d_nbins && d_flags, SIA_E_NOMEM, "index scratch arena too small (vote)");
       SIA_CUDA(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(QMeta) * nq, cudaMemcpyHostToDevice, s));
       SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long), s));
-      SIA_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t), s));
+      SIA_CUDA(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int32_t), s));
       for (const Group &g : groups) {
         const int64_t e0 = h_query_starts[q0 + g.qa] - i0, ne = h_query_starts[q0 + g.qb] - i0 - e0;
         const int64_t tuples = h_off_all[g.qb] - h_off_all[g.qa];
@@ -892,23 +966,24 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
         const unsigned blocks = (unsigned)ceil_div(tuples, kVoteTuples);
         const int gq = g.qb - g.qa;
 #define SIA_ENT_PASS(D, P)                                                                                              \
-        entries_pass_kernel<D, P><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, L.cnt_head, ix->post, d_meta, Tb,  \
-                                                         qflag, (int)q0, topn, d_out_song, d_out_nres, d_out_rows, d_nbins,    \
-                                                         d_flags)
+        entries_pass_kernel<D, P><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, ix->post, d_meta, Tb, qflag,       \
+                                                         d_nflag, d_nbins, d_flags)
 #define SIA_ENT_VOTE(D)                                                                                                 \
         do {                                                                                                            \
           SIA_ENT_PASS(D, PASS_MARK);                                                                                   \
           layout_bins_kernel<<<1, 1024, 0, s>>>(d_meta, g.qa, g.qb, d_total);                                           \
           zero_bins_kernel<<<kNumSMs * 8, 256, 0, s>>>(Tb.bins, Tb.bin_cnt, d_total, nb_cap, d_flags);                  \
           SIA_ENT_PASS(D, PASS_VOTE);                                                                                   \
-          topn_kernel<D, false><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_out_song, d_out_diff,      \
-                                                   d_out_count, d_out_rows, d_out_nres);                                \
+          topn_kernel<D, false><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_nflag, d_out_song,         \
+                                                   d_out_diff, d_out_count, d_out_rows, d_out_nres);                    \
           SIA_ENT_PASS(D, PASS_SINGLES);                                                                                \
-          topn_kernel<D, true><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_out_song, d_out_diff,       \
-                                                  d_out_count, d_out_rows, d_out_nres);                                 \
-          SIA_ENT_PASS(D, PASS_ROWS);                                                                                   \
+          topn_kernel<D, true><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_nflag, d_out_song,          \
+                                                  d_out_diff, d_out_count, d_out_rows, d_out_nres);                     \
         } while (0)
+        SIA_CUDA(cudaMemsetAsync(d_nflag, 0, sizeof(int32_t), s));
         if (g.dense) SIA_ENT_VOTE(true); else SIA_ENT_VOTE(false);
+        entries_rows_kernel<<<grid_for(ne * 32), 256, 0, s>>>(L.ent, e0, ne, L.first, L.cnt_head, ix->post, (int)q0, topn,
+                                                             d_out_song, d_out_nres, d_out_rows);
 #undef SIA_ENT_VOTE
 #undef SIA_ENT_PASS
         SIA_CHECK_LAUNCH();
