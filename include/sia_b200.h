@@ -274,9 +274,13 @@ int sia_route_entries(int device, const uint8_t *d_hash, const int32_t *d_qoff, 
 int sia_index_expand_slots(sia_index *ix, const void *d_entry_slots, int32_t world, int64_t entry_cap,
                            int32_t queries_per_rank, uint64_t *d_key_slots, int64_t key_cap, int64_t *d_info,
                            void *stream);
+/* defer != 0: return as soon as everything is enqueued on `stream` (the host can then prepare the next pass on another
+ * stream while this vote runs); sia_vote_finish(device) waits for it and completes the call — one vote in flight per
+ * device, key slots and outputs must stay alive until then. */
 int sia_vote_key_slots(int device, const uint64_t *d_key_slots, int32_t n_slots, int64_t key_cap, int32_t n_queries,
                        int32_t topn, int32_t max_song, int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
-                       int32_t *d_out_rows, int32_t *d_out_nres, void *stream);
+                       int32_t *d_out_rows, int32_t *d_out_nres, int32_t defer, void *stream);
+int sia_vote_finish(int device);
 
 #ifdef __cplusplus
 }

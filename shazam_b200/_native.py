@@ -76,7 +76,8 @@ SIGNATURES = {
     "sia_route_entries": (C.c_int, [C.c_int, _p, _p, _p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _p, _p, _p]),
     "sia_index_expand_slots": (C.c_int, [_p, _p, C.c_int32, C.c_int64, C.c_int32, _p, C.c_int64, _p, _p]),
     "sia_vote_key_slots": (C.c_int, [C.c_int, _p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p,
-                                     _p, _p]),
+                                     _p, C.c_int32, _p]),
+    "sia_vote_finish": (C.c_int, [C.c_int]),
 }
 
 _lib = None

@@ -141,7 +141,8 @@ size_t lookup_bytes(int64_t n);
 // d_counts[i] valid keys (a header-less layout; d_counts on the device)
 int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap, const int64_t *d_counts, int32_t n_queries,
                    int32_t topn, int32_t max_song, int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
-                   int32_t *d_out_rows, int32_t *d_out_nres, cudaStream_t s);
+                   int32_t *d_out_rows, int32_t *d_out_nres, cudaStream_t s, int defer);
+int vote_key_slots_finish(int device);
 
 // frees the per-device scratch of vote_key_slots
 void vote_scratch_release(int device);

@@ -175,7 +175,7 @@ int sia_index_expand_slots(sia_index *ix, const void *d_entry_slots, int32_t wor
 
 int sia_vote_key_slots(int device, const uint64_t *d_key_slots, int32_t n_slots, int64_t key_cap, int32_t n_queries,
                        int32_t topn, int32_t max_song, int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
-                       int32_t *d_out_rows, int32_t *d_out_nres, void *stream) {
+                       int32_t *d_out_rows, int32_t *d_out_nres, int32_t defer, void *stream) {
   SIA_REQUIRE(d_key_slots && key_cap >= 2, SIA_E_INVALID, "vote_key_slots: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   SIA_CUDA(cudaSetDevice(device));
@@ -185,7 +185,9 @@ int sia_vote_key_slots(int device, const uint64_t *d_key_slots, int32_t n_slots,
       if (o) SIA_CUDA(cudaMemsetAsync(o, 0, sizeof(int32_t) * (size_t)n_queries * topn, s));
   }
   return vote_key_slots(device, d_key_slots, n_slots, key_cap, nullptr, n_queries, topn, max_song, d_out_song, d_out_diff,
-                        d_out_count, d_out_rows, d_out_nres, s);
+                        d_out_count, d_out_rows, d_out_nres, s, defer);
 }
+
+int sia_vote_finish(int device) { return vote_key_slots_finish(device); }
 
 }  // extern "C"

@@ -716,27 +716,37 @@ void vote_scratch_release(int device) {
   if (device >= 0 && device < 64) g_vote_tables[device].release();
 }
 
-int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap, const int64_t *d_counts, int32_t n_queries,
-                   int32_t topn, int32_t max_song, int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
-                   int32_t *d_out_rows, int32_t *d_out_nres, cudaStream_t s) {
-  SIA_REQUIRE(n_queries >= 0 && n_queries <= kMaxQueriesPerPass && topn >= 1, SIA_E_INVALID,
-              "vote: 0..16384 queries per call, topn >= 1");
-  SIA_REQUIRE(n_slots >= 1 && cap >= 0 && max_song >= 0 && max_song <= (int32_t)kM24, SIA_E_INVALID, "vote: bad sizes");
-  if (n_queries == 0) return SIA_OK;
-  SIA_REQUIRE(d_out_song && d_out_diff && d_out_count && d_out_rows && d_out_nres, SIA_E_INVALID, "NULL output");
-  SIA_REQUIRE(device >= 0 && device < 64, SIA_E_INVALID, "device index");
-  SIA_CUDA(cudaSetDevice(device));
+// one vote over slotted keys: everything a retry or a deferred completion needs
+struct KeyVote {
+  bool pending = false;
+  int device = 0;
+  const uint64_t *d_keys = nullptr;
+  int n_slots = 0;
+  int64_t cap = 0;
+  const int64_t *d_counts = nullptr;
+  int32_t n_queries = 0, topn = 0, max_song = 0;
+  int32_t *o_song = nullptr, *o_diff = nullptr, *o_count = nullptr, *o_rows = nullptr, *o_nres = nullptr;
+  cudaStream_t s = nullptr;
+  int32_t *d_flags = nullptr;      // device flags of the attempt in flight
+};
+static KeyVote g_key_vote[64];
+
+// enqueue every launch of one attempt (0: bin slots for a quarter of the keys being candidates; 1: for all of them)
+static int key_vote_enqueue(KeyVote &v, int attempt) {
+  const int nq = v.n_queries, n_slots = v.n_slots, topn = v.topn;
+  const int64_t cap = v.cap;
+  const uint64_t *d_keys = v.d_keys;
+  const int64_t *d_counts = v.d_counts;
+  int32_t *d_out_song = v.o_song, *d_out_diff = v.o_diff, *d_out_count = v.o_count, *d_out_rows = v.o_rows, *d_out_nres = v.o_nres;
+  cudaStream_t s = v.s;
   const int64_t T = (int64_t)n_slots * cap;             // upper bound of the keys
-  SIA_REQUIRE(T < (1ll << 31), SIA_E_UNSUPPORTED, "vote: more than 2^31 key slots in one call");
-  const int nq = n_queries;
-  Arena &ar = g_vote_tables[device];
+  Arena &ar = g_vote_tables[v.device];
   // song tables: dense (slot = song id) when that is the smaller layout, else open addressing
-  const int64_t span = (int64_t)max_song + 1;
+  const int64_t span = (int64_t)v.max_song + 1;
   const int64_t ns_hashed = 2 * T + 32ll * nq;
   const bool dense = span * nq * 8 <= ns_hashed * 12;
   const int64_t ns = dense ? span * nq : ns_hashed;
   const int64_t nf = T + nq;
-  for (int attempt = 0; attempt < 2; ++attempt) {
   const int64_t nb_cap = bin_slots_for(T, nq, attempt);
   int rc = ar.reserve(vote_table_bytes(T, nq, nb_cap, ns, dense) + (size_t)nq * (sizeof(QMeta) + 8) + 65536);
   if (rc) return rc;
@@ -753,6 +763,7 @@ int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap,
   Tb.bin_cnt = ar.take<uint32_t>(nb_cap);
   SIA_REQUIRE(meta && cnt && qflag && total && flags && Tb.filter && Tb.song_best && Tb.bins && Tb.bin_cnt &&
               (dense || Tb.song_key), SIA_E_NOMEM, "vote: scratch");
+  v.d_flags = flags;
   SIA_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * nq, s));
   SIA_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), s));
   SIA_CUDA(cudaMemsetAsync(Tb.filter, 0, sizeof(uint32_t) * nf, s));
@@ -782,15 +793,53 @@ int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap,
 #undef SIA_KEYS_VOTE
 #undef SIA_KEYS_PASS
   SIA_CHECK_LAUNCH();
-  int32_t h_flags = 0;
-  SIA_CUDA(cudaMemcpyAsync(&h_flags, flags, sizeof h_flags, cudaMemcpyDeviceToHost, s));
-  SIA_CUDA(cudaStreamSynchronize(s));
-  SIA_REQUIRE(!(h_flags & 2), SIA_E_INVALID, "vote: query id outside 0..n_queries-1");
-  SIA_REQUIRE(!(h_flags & 8), SIA_E_CUDA, "vote: table overflow (internal error, or song id above max_song)");
-  if (!(h_flags & 32)) return SIA_OK;
-  SIA_REQUIRE(attempt == 0, SIA_E_CUDA, "vote: bin table overflow (internal error)");
+  return SIA_OK;
+}
+
+// wait for the vote in flight on this device, check its flags, redo it with the larger bin reservation if it asked
+int vote_key_slots_finish(int device) {
+  SIA_REQUIRE(device >= 0 && device < 64, SIA_E_INVALID, "device index");
+  KeyVote &v = g_key_vote[device];
+  if (!v.pending) return SIA_OK;
+  v.pending = false;
+  SIA_CUDA(cudaSetDevice(device));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    int32_t h_flags = 0;
+    SIA_CUDA(cudaMemcpyAsync(&h_flags, v.d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, v.s));
+    SIA_CUDA(cudaStreamSynchronize(v.s));
+    SIA_REQUIRE(!(h_flags & 2), SIA_E_INVALID, "vote: query id outside 0..n_queries-1");
+    SIA_REQUIRE(!(h_flags & 8), SIA_E_CUDA, "vote: table overflow (internal error, or song id above max_song)");
+    if (!(h_flags & 32)) return SIA_OK;
+    SIA_REQUIRE(attempt == 0, SIA_E_CUDA, "vote: bin table overflow (internal error)");
+    int rc = key_vote_enqueue(v, 1);
+    if (rc) return rc;
   }
   return SIA_OK;
+}
+
+// defer != 0: return once everything is enqueued; vote_key_slots_finish(device) completes the call (one vote in flight
+// per device; the key slots and outputs must stay alive until then)
+int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap, const int64_t *d_counts, int32_t n_queries,
+                   int32_t topn, int32_t max_song, int32_t *d_out_song, int32_t *d_out_diff, int32_t *d_out_count,
+                   int32_t *d_out_rows, int32_t *d_out_nres, cudaStream_t s, int defer) {
+  SIA_REQUIRE(n_queries >= 0 && n_queries <= kMaxQueriesPerPass && topn >= 1, SIA_E_INVALID,
+              "vote: 0..16384 queries per call, topn >= 1");
+  SIA_REQUIRE(n_slots >= 1 && cap >= 0 && max_song >= 0 && max_song <= (int32_t)kM24, SIA_E_INVALID, "vote: bad sizes");
+  if (n_queries == 0) return SIA_OK;
+  SIA_REQUIRE(d_out_song && d_out_diff && d_out_count && d_out_rows && d_out_nres, SIA_E_INVALID, "NULL output");
+  SIA_REQUIRE(device >= 0 && device < 64, SIA_E_INVALID, "device index");
+  SIA_CUDA(cudaSetDevice(device));
+  SIA_REQUIRE((int64_t)n_slots * cap < (1ll << 31), SIA_E_UNSUPPORTED, "vote: more than 2^31 key slots in one call");
+  int rc = vote_key_slots_finish(device);               // a vote left in flight by the caller
+  if (rc) return rc;
+  KeyVote &v = g_key_vote[device];
+  v.device = device; v.d_keys = d_keys; v.n_slots = n_slots; v.cap = cap; v.d_counts = d_counts;
+  v.n_queries = n_queries; v.topn = topn; v.max_song = max_song;
+  v.o_song = d_out_song; v.o_diff = d_out_diff; v.o_count = d_out_count; v.o_rows = d_out_rows; v.o_nres = d_out_nres;
+  v.s = s;
+  if ((rc = key_vote_enqueue(v, 0))) return rc;
+  v.pending = true;
+  return defer ? SIA_OK : vote_key_slots_finish(device);
 }
 
 }  // namespace sia
@@ -869,6 +918,8 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
   const bool timing = getenv("SIA_QUERY_TIMING") != nullptr;       // stage times of every pass on stderr
   ix->last_lookup_ms = ix->last_vote_ms = 0;
   for (auto &e : ix->ev_q) if (!e) SIA_CUDA(cudaEventCreate(&e));
+  static cudaEvent_t stage_ev[8] = {nullptr};          // SIA_QUERY_TIMING only: per-kernel times of the vote
+  double stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
   const int64_t span = (int64_t)ix->max_song + 1;
   for (int64_t q0 = 0; q0 < n_queries; q0 += kMaxQueriesPerPass) {
     const int nq = (int)std::min<int64_t>(kMaxQueriesPerPass, n_queries - q0);
@@ -968,22 +1019,38 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
 #define SIA_ENT_PASS(D, P)                                                                                              \
         entries_pass_kernel<D, P><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, ix->post, d_meta, Tb, qflag,       \
                                                          d_nflag, d_nbins, d_flags)
+#define SIA_STAGE(k) do { if (timing) cudaEventRecord(stage_ev[k], s); } while (0)
 #define SIA_ENT_VOTE(D)                                                                                                 \
         do {                                                                                                            \
+          SIA_STAGE(0);                                                                                                 \
           SIA_ENT_PASS(D, PASS_MARK);                                                                                   \
+          SIA_STAGE(1);                                                                                                 \
           layout_bins_kernel<<<1, 1024, 0, s>>>(d_meta, g.qa, g.qb, d_total);                                           \
           zero_bins_kernel<<<kNumSMs * 8, 256, 0, s>>>(Tb.bins, Tb.bin_cnt, d_total, nb_cap, d_flags);                  \
+          SIA_STAGE(2);                                                                                                 \
           SIA_ENT_PASS(D, PASS_VOTE);                                                                                   \
+          SIA_STAGE(3);                                                                                                 \
           topn_kernel<D, false><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_nflag, d_out_song,         \
                                                    d_out_diff, d_out_count, d_out_rows, d_out_nres);                    \
+          SIA_STAGE(4);                                                                                                 \
           SIA_ENT_PASS(D, PASS_SINGLES);                                                                                \
           topn_kernel<D, true><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_nflag, d_out_song,          \
                                                   d_out_diff, d_out_count, d_out_rows, d_out_nres);                     \
+          SIA_STAGE(5);                                                                                                 \
         } while (0)
         SIA_CUDA(cudaMemsetAsync(d_nflag, 0, sizeof(int32_t), s));
+        if (timing) { if (!stage_ev[0]) for (auto &e : stage_ev) cudaEventCreate(&e); cudaEventRecord(stage_ev[7], s); }
         if (g.dense) SIA_ENT_VOTE(true); else SIA_ENT_VOTE(false);
         entries_rows_kernel<<<grid_for(ne * 32), 256, 0, s>>>(L.ent, e0, ne, L.first, L.cnt_head, ix->post, (int)q0, topn,
                                                              d_out_song, d_out_nres, d_out_rows);
+        SIA_STAGE(6);
+        if (timing) {
+          cudaEventSynchronize(stage_ev[6]);
+          float t;
+          cudaEventElapsedTime(&t, stage_ev[7], stage_ev[0]); stage_ms[0] += t;      // memsets of the tables
+          for (int k = 0; k < 6; ++k) { cudaEventElapsedTime(&t, stage_ev[k], stage_ev[k + 1]); stage_ms[k + 1] += t; }
+        }
+#undef SIA_STAGE
 #undef SIA_ENT_VOTE
 #undef SIA_ENT_PASS
         SIA_CHECK_LAUNCH();
@@ -1004,6 +1071,9 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
         const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
         fprintf(stderr, "[sia] query pass: %d queries, %lld entries, %lld tuples, %zu groups: lookup %.2f ms, vote %.2f ms, host wall %.2f ms\n",
                 nq, (long long)n, (long long)L.tuples, groups.size(), t_lookup, t_vote, host_ms);
+        fprintf(stderr, "[sia]   vote stages (ms): table memsets %.2f, mark %.2f, bin layout + zero %.2f, vote %.2f, topn %.2f, "
+                "singles + topn %.2f, rows %.2f\n", stage_ms[0], stage_ms[1], stage_ms[2], stage_ms[3], stage_ms[4], stage_ms[5],
+                stage_ms[6]);
       }
     }
     if (h_stats) h_stats[3] += (int64_t)h_nb;
@@ -1034,7 +1104,7 @@ int sia_vote_tuples(int device, const uint64_t *d_key, int64_t n_keys, int32_t n
       if (o) SIA_CUDA(cudaMemsetAsync(o, 0, sizeof(int32_t) * (size_t)n_queries * topn, s));
   }
   return vote_key_slots(device, d_key, 1, std::max<int64_t>(n_keys, 1), d_count[device], n_queries, topn, max_song, d_out_song,
-                        d_out_diff, d_out_count, d_out_rows, d_out_nres, s);
+                        d_out_diff, d_out_count, d_out_rows, d_out_nres, s, 0);
 }
 
 }  // extern "C"

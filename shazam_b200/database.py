@@ -252,8 +252,10 @@ def _vote_outputs(tdev, n_queries, topn):
     return outs, torch.zeros(n_queries, dtype=torch.int32, device=tdev)
 
 
-def vote_key_slots(device: int, key_slots: torch.Tensor, n_queries: int, topn: int, max_song: int):
-    """Vote the key slots received from every shard (int64[world, key_cap], element 0 of a slot = its count)."""
+def vote_key_slots(device: int, key_slots: torch.Tensor, n_queries: int, topn: int, max_song: int, defer: bool = False):
+    """Vote the key slots received from every shard (int64[world, key_cap], element 0 of a slot = its count).
+    ``defer=True`` returns once the work is enqueued on the current stream; ``vote_finish(device)`` completes it (keep
+    ``key_slots`` and the returned tensors alive until then)."""
     lib = N.lib()
     tdev = torch.device("cuda", device)
     outs, nres = _vote_outputs(tdev, n_queries, topn)
@@ -261,8 +263,13 @@ def vote_key_slots(device: int, key_slots: torch.Tensor, n_queries: int, topn: i
     N.check(lib.sia_vote_key_slots(device, C.c_void_p(ks.data_ptr()), ks.shape[0], ks.shape[1], n_queries, int(topn),
                                    int(max_song), C.c_void_p(outs[0].data_ptr()), C.c_void_p(outs[1].data_ptr()),
                                    C.c_void_p(outs[2].data_ptr()), C.c_void_p(outs[3].data_ptr()),
-                                   C.c_void_p(nres.data_ptr()), C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)))
+                                   C.c_void_p(nres.data_ptr()), 1 if defer else 0,
+                                   C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)))
     return (*outs, nres)
+
+
+def vote_finish(device: int) -> None:
+    N.check(N.lib().sia_vote_finish(device))
 
 
 def vote_tuples(device: int, keys: torch.Tensor, n_queries: int, topn: int, max_song: int):

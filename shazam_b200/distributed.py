@@ -92,7 +92,11 @@ class ShardBackend:
     def expand_slots(self, entry_slots, world: int, queries_per_rank: int, key_cap: int, info):
         raise NotImplementedError
 
-    def vote_key_slots(self, key_slots, n_queries: int, topn: int, max_song: int):
+    def vote_key_slots(self, key_slots, n_queries: int, topn: int, max_song: int, defer: bool = False):
+        raise NotImplementedError
+
+    def vote_finish(self) -> None:
+        """Completes a ``vote_key_slots(..., defer=True)``."""
         raise NotImplementedError
 
     def query_batch(self, digests, qoffsets, query_starts, topn: int):
@@ -124,9 +128,13 @@ class CudaShard(ShardBackend):
     def expand_slots(self, entry_slots, world, queries_per_rank, key_cap, info):
         return self.index.expand_slots(entry_slots, world, queries_per_rank, key_cap, info)
 
-    def vote_key_slots(self, key_slots, n_queries, topn, max_song):
+    def vote_key_slots(self, key_slots, n_queries, topn, max_song, defer=False):
         from .database import vote_key_slots
-        return vote_key_slots(self._dev_index, key_slots, n_queries, topn, max_song)
+        return vote_key_slots(self._dev_index, key_slots, n_queries, topn, max_song, defer)
+
+    def vote_finish(self):
+        from .database import vote_finish
+        vote_finish(self._dev_index)
 
     def query_batch(self, digests, qoffsets, query_starts, topn):
         return self.index.query_batch(digests, qoffsets, query_starts, topn)
@@ -148,7 +156,8 @@ class ShardedIndex:
         self.key_cap = max(2, int(key_cap))
         self.retries = 0            # passes redone because a slot overflowed (0 in steady state)
         self._max_song = 0
-        self.last_pass_ms = None    # stage times of the last pass on this rank (SIA_DIST_TIMING=1)
+        self.last_pass_ms = None    # stage times of the last pass on this rank (SIA_DIST_TIMING=1: synchronises)
+        self._side = None           # second CUDA stream: pass i+1 is prepared while pass i is voted
 
     # ---- build ---------------------------------------------------------------------------
     def insert(self, songs: torch.Tensor, digests: torch.Tensor, offsets: torch.Tensor) -> None:
@@ -190,23 +199,47 @@ class ShardedIndex:
         outs = [torch.zeros((q_local, topn), dtype=torch.int32, device=dev) for _ in range(4)]
         nres = torch.zeros(q_local, dtype=torch.int32, device=dev)
         qs_dev = torch.as_tensor(qs, dtype=torch.int64, device=dev)
-        lo = 0
-        while lo < max_q:
-            a, b = min(lo, q_local), min(lo + qp, q_local)
+        passes = [(min(lo, q_local), min(lo + qp, q_local)) for lo in range(0, max_q, qp)]
+        # Software pipeline over the passes: while the vote of pass i runs on the caller's stream, the routing, lookup,
+        # expansion and both all-to-alls of pass i+1 run on a second (high-priority) stream.
+        cuda = dev.type == "cuda"
+        if cuda and self._side is None:
+            self._side = torch.cuda.Stream(dev, priority=-1)
+        main = torch.cuda.current_stream(dev) if cuda else None
+        if cuda:
+            self._side.wait_stream(main)           # the query tensors were produced on the caller's stream
+
+        def prepare(pi):
+            a, b = passes[pi]
             e0, e1 = int(qs[a]), int(qs[b])
-            res = self._query_pass(digests[e0:e1], qoffsets[e0:e1], qs_dev[a:b + 1] - e0, b - a, qp, topn)
-            if res is None:              # a slot overflowed somewhere: capacities were raised, redo the pass
-                self.retries += 1
-                continue
+            while True:
+                if cuda:
+                    with torch.cuda.stream(self._side):
+                        keys = self._prepare_pass(digests[e0:e1], qoffsets[e0:e1], qs_dev[a:b + 1] - e0, qp)
+                else:
+                    keys = self._prepare_pass(digests[e0:e1], qoffsets[e0:e1], qs_dev[a:b + 1] - e0, qp)
+                if keys is not None:
+                    return keys
+                self.retries += 1                  # a slot overflowed somewhere: capacities were raised, redo the pass
+
+        nxt = prepare(0) if passes else None
+        for pi, (a, b) in enumerate(passes):
+            keys = nxt
+            if cuda:
+                main.wait_stream(self._side)       # the keys of this pass have arrived
+            res = self.backend.vote_key_slots(keys, b - a, topn, self._max_song, defer=True)
+            nxt = prepare(pi + 1) if pi + 1 < len(passes) else None
+            self.backend.vote_finish()
             for o, r in zip(outs, res[:4]):
                 o[a:b] = r
             nres[a:b] = res[4]
-            lo += qp
+            del keys
         return (*outs, nres)
 
-    def _query_pass(self, digests, qoffsets, qs_dev, nq, qp, topn):
-        """One pass over nq of this rank's queries (``qs_dev``: their entry offsets into ``digests``, int64[nq+1] on the
-        device, starting at 0)."""
+    def _prepare_pass(self, digests, qoffsets, qs_dev, qp):
+        """Everything of one pass up to the vote: this rank's queries (``qs_dev``: their entry offsets into ``digests``,
+        int64[nq+1] on the device, starting at 0) -> the key slots this rank received, or None if a slot overflowed
+        on some rank (capacities are then raised — identically on every rank — and the caller redoes the pass)."""
         be, dev, G = self.backend, self.backend.device, self.world
         timing = bool(os.environ.get("SIA_DIST_TIMING"))
         marks = []
@@ -233,6 +266,8 @@ class ShardedIndex:
         chk = torch.cat([info[:3], status.to(torch.int64)])
         dist.all_reduce(chk, op=dist.ReduceOp.MAX, group=self.group)
         flags, need_k, need_e, st = (int(x) for x in chk.tolist())
+        if timing:
+            self.last_pass_ms = {n: (t - marks[i][1]) * 1e3 for i, (n, t) in enumerate(marks[1:])}
         if st & 2:
             raise ValueError("query: offset outside 0..2^24-1 or more than 2^24 queries in one pass")
         if flags & 3:
@@ -241,14 +276,7 @@ class ShardedIndex:
             if flags & 2:
                 self.key_cap = int(need_k * 1.25) + 64
             return None
-        res = be.vote_key_slots(recv_k, nq, topn, self._max_song)
-        mark("vote")
-        if timing:
-            self.last_pass_ms = {n: (t - marks[i][1]) * 1e3 for i, (n, t) in enumerate(marks[1:])}
-            if self.rank == 0:
-                print("[sia dist] pass: %d local queries, key slots %d x %d: " % (nq, G, self.key_cap) +
-                      ", ".join("%s %.1f ms" % kv for kv in self.last_pass_ms.items()), file=sys.stderr)
-        return res
+        return recv_k
 
 
 class TrackShardedIndex:

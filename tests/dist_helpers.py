@@ -99,7 +99,10 @@ class CpuShard(ShardBackend):
                 info[0] |= 2
         return out
 
-    def vote_key_slots(self, key_slots, n_queries, topn, max_song):
+    def vote_finish(self):
+        pass
+
+    def vote_key_slots(self, key_slots, n_queries, topn, max_song, defer=False):
         keys = []
         cap = key_slots.shape[1]
         for s in range(key_slots.shape[0]):

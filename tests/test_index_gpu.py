@@ -195,7 +195,7 @@ def test_hash_prefix_slots_equal_single_index(gpudb):
     expansion into key slots -> vote over the keys of all shards, csrc/index_dist.cu) give the results of one index and of
     the oracle; slot overflow is reported, never silent."""
     import torch
-    from shazam_b200.database import FingerprintIndex, route_entries, vote_key_slots, vote_tuples
+    from shazam_b200.database import FingerprintIndex, route_entries, vote_finish, vote_key_slots, vote_tuples
     from shazam_b200.fingerprinter import hex_to_digests
     rng = np.random.default_rng(21)
     table, rows = _random_table(rng, 30, 300, 800)
@@ -245,7 +245,9 @@ def test_hash_prefix_slots_equal_single_index(gpudb):
             # "all-to-all #2": owner r receives slot r of every shard
             for r, (a, b) in enumerate(owners):
                 recv = torch.stack([keys[g][r] for g in range(G)])
-                got = vote_key_slots(0, recv, b - a, 3, max_song)
+                got = vote_key_slots(0, recv, b - a, 3, max_song, defer=attempt == 1)
+                if attempt == 1:
+                    vote_finish(0)                          # the deferred form: enqueue, then complete
                 for x, y in zip(ref, got):
                     assert torch.equal(x[a:b], y), (attempt, r)
             if attempt == 0:                            # the same keys, unslotted, through the plain key vote
