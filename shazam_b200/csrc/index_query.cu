@@ -33,11 +33,14 @@ constexpr int kQidBits = SIA_KEY_QID_BITS, kSongBits = SIA_KEY_SONG_BITS, kDiffB
 constexpr int64_t kMaxQueriesPerPass = 1ll << kQidBits;
 constexpr uint64_t kDiffMask = (1ull << kDiffBits) - 1;
 constexpr int kTopK = 4;                  // results extracted per scan of a query's song table
-constexpr int kVoteTuples = 16384;        // vote tuples per block of the entry-walking kernels (2048 per warp)
+constexpr int kVoteTuples = 4096;         // vote tuples per block of the entry-walking kernels (512 per warp): the tuples
+                                          // in flight on the whole GPU then belong to 2-3 queries, whose filters stay in L2
 
 struct QMeta {
   int64_t bin_base, song_base, filt_base;   // first slot / word of the query's sub-tables inside the group's tables
+  int64_t cand_base;                        // first entry of the query's candidate list
   uint32_t bin_cap, song_cap, filt_words, cand;   // cand: tuples in twice-hit buckets (pass 1), sizes the bin table
+  uint32_t cursor, pad_;                    // candidates collected so far (pass 2)
 };
 
 struct Tables {
@@ -46,6 +49,7 @@ struct Tables {
   unsigned long long *song_best;  // [ns]
   uint32_t *song_key;             // [ns] open addressing only (song + 1)
   uint32_t *filter;               // [nf]
+  unsigned long long *cand;       // [nb / 2] candidate vote keys (query | song | biased diff), per-query lists
 };
 
 // ---- lookup ---------------------------------------------------------------------------------------------------
@@ -223,23 +227,45 @@ __device__ __forceinline__ uint32_t mark_finish(uint32_t *__restrict__ w, uint32
 
 enum { PASS_MARK = 1, PASS_VOTE = 2, PASS_SINGLES = 3, PASS_ROWS = 4 };
 
-// pass 2 of one tuple, second half: fw is the tuple's filter word
-template <bool DENSE>
-__device__ __forceinline__ void vote_finish(const QMeta &m, uint32_t song, uint32_t dbits, uint32_t fw, uint32_t seen,
-                                            const Tables &T, uint32_t &fresh, int32_t *__restrict__ flags) {
-  if (fw & (seen << 1)) {
-    const unsigned long long c = bin_count(m, song, dbits, T, fresh, flags);
-    if (c) song_update<DENSE>(m, song, dbits, c, T, flags);
-  } else {
-    ++fresh;                                        // alone in its bucket: a bin of its own, count 1
+constexpr int kCandBuf = 320;             // candidate keys a warp buffers in shared memory before it flushes them
+
+// write a warp's buffered candidate keys (all of query q) to q's candidate list: one atomic per flush
+__device__ __forceinline__ void cand_flush(unsigned long long *__restrict__ buf, int &n, uint32_t q, QMeta *__restrict__ meta,
+                                           unsigned long long *__restrict__ cand, int lane, int32_t *__restrict__ flags) {
+  if (n == 0) return;                                // warp-uniform
+  __syncwarp();
+  unsigned long long base = 0;
+  if (lane == 0) {
+    const uint32_t at = atomicAdd(&meta[q].cursor, (uint32_t)n);
+    if (at + (uint32_t)n > meta[q].cand) { atomicOr(flags, 8); base = ~0ull; }     // cannot happen: pass 1 counted them
+    else base = (unsigned long long)meta[q].cand_base + at;
   }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (base != ~0ull)
+    for (int i = lane; i < n; i += 32) cand[base + i] = buf[i];
+  __syncwarp();
+  n = 0;
+}
+
+// append the candidates among (a, b) of every lane to the warp's buffer (lane order)
+__device__ __forceinline__ void cand_push(unsigned long long *__restrict__ buf, int &n, bool ca, unsigned long long ka, bool cb,
+                                          unsigned long long kb, int lane) {
+  const uint32_t ma = __ballot_sync(0xffffffffu, ca), mb = __ballot_sync(0xffffffffu, cb);
+  const uint32_t lt = (1u << lane) - 1u;
+  if (ca) buf[n + __popc(ma & lt)] = ka;
+  if (cb) buf[n + __popc(ma) + __popc(mb & lt)] = kb;
+  n += __popc(ma) + __popc(mb);
 }
 
 // Two vote tuples per lane and step, so that the two L2 round trips (the atomicOr of pass 1, the filter read of
-// pass 2) of a step are in flight together.
+// pass 2) of a step are in flight together.  PASS_MARK: acc += candidate tuples accounted for.  PASS_VOTE: tuples alone
+// in their bucket are bins of count 1 (acc += 1 each, nothing else to do); the others — every bin of count >= 2 is among
+// them — are only COLLECTED here (ca / cb), and voted by cand_vote_kernel with all lanes busy.
 template <bool DENSE, int PASS>
 __device__ __forceinline__ void tuple_pair_pass(const QMeta &m, bool va, uint32_t song_a, uint32_t db_a, bool vb, uint32_t song_b,
-                                                uint32_t db_b, const Tables &T, uint32_t &acc, int32_t *__restrict__ flags) {
+                                                uint32_t db_b, const Tables &T, uint32_t &acc, bool &ca, bool &cb,
+                                                int32_t *__restrict__ flags) {
+  ca = cb = false;
   if (PASS == PASS_SINGLES) {
     if (va) song_update<DENSE>(m, song_a, db_a, 1ull, T, flags);
     if (vb) song_update<DENSE>(m, song_b, db_b, 1ull, T, flags);
@@ -256,8 +282,44 @@ __device__ __forceinline__ void tuple_pair_pass(const QMeta &m, bool va, uint32_
   } else {
     const uint32_t fa = va ? __ldcg(wa) : 0u;
     const uint32_t fb = vb ? __ldcg(wb) : 0u;
-    if (va) vote_finish<DENSE>(m, song_a, db_a, fa, sa, T, acc, flags);
-    if (vb) vote_finish<DENSE>(m, song_b, db_b, fb, sb, T, acc, flags);
+    ca = va && (fa & (sa << 1));
+    cb = vb && (fb & (sb << 1));
+    acc += (uint32_t)(va && !ca) + (uint32_t)(vb && !cb);
+  }
+}
+
+__device__ __forceinline__ unsigned long long cand_key(uint32_t q, uint32_t song, uint32_t dbits) {
+  return ((unsigned long long)q << (kSongBits + kDiffBits)) | ((unsigned long long)song << kDiffBits) | dbits;
+}
+
+// Pass 2b: the collected candidates, densely — bin table (CAS the key word, bump the count) and the song's best; two
+// keys per thread so that their L2 round trips overlap.
+template <bool DENSE>
+__global__ void __launch_bounds__(256)
+cand_vote_kernel(const unsigned long long *__restrict__ cand, const QMeta *__restrict__ meta, int q_lo, int q_hi, Tables T,
+                 unsigned long long *__restrict__ n_bins, int32_t *__restrict__ flags) {
+  if (*flags & 32) return;
+  const int64_t lo = meta[q_lo].cand_base, total = meta[q_hi - 1].cand_base + meta[q_hi - 1].cand - lo;
+  uint32_t fresh = 0;
+  const uint32_t qmask = (1u << kQidBits) - 1u;
+  for (int64_t i0 = (int64_t)blockIdx.x * 512; i0 < total; i0 += (int64_t)gridDim.x * 512) {
+    __syncwarp();
+    const int64_t ia = i0 + threadIdx.x, ib = ia + 256;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int64_t i = half ? ib : ia;
+      if (i >= total) continue;
+      const unsigned long long k = cand[lo + i];
+      const QMeta m = meta[(uint32_t)(k >> (kSongBits + kDiffBits)) & qmask];
+      const uint32_t song = (uint32_t)(k >> kDiffBits) & 0xffffffu, dbits = (uint32_t)(k & kDiffMask);
+      const unsigned long long c = bin_count(m, song, dbits, T, fresh, flags);
+      if (c) song_update<DENSE>(m, song, dbits, c, T, flags);
+    }
+  }
+  if (n_bins) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
+    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(n_bins, (unsigned long long)fresh);
   }
 }
 
@@ -275,10 +337,23 @@ __device__ __forceinline__ void rows_pass(uint32_t active, bool mine, uint32_t s
 // of the block's tuples and walks the entries they belong to: everything that depends on the entry (query tables,
 // query offset, first posting) is warp-uniform and loaded once per entry, the lanes then take the entry's
 // postings 64 at a time (two per lane), the next step's postings in flight during this one.
+// entry in which every warp's piece of kVoteTuples / 8 tuples starts (relative to e0): computed once per group, read by
+// all passes instead of a 24-step binary search at the start of every warp of every pass
+__global__ void __launch_bounds__(256)
+piece_entries_kernel(const int64_t *__restrict__ off, int64_t e0, int64_t n, int64_t n_pieces, uint32_t *__restrict__ piece_ent) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pieces; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = off[e0] + p * (kVoteTuples >> 3);
+    int64_t ei = e0, hi = e0 + n;            // largest entry in [e0, e0+n) with off[ei] <= j
+    while (hi - ei > 1) { const int64_t mid = ei + ((hi - ei) >> 1); if (off[mid] <= j) ei = mid; else hi = mid; }
+    piece_ent[p] = (uint32_t)(ei - e0);
+  }
+}
+
 template <bool DENSE, int PASS>
 __global__ void __launch_bounds__(256)
 entries_pass_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, const int64_t *__restrict__ first,
-                    const int64_t *__restrict__ off, const uint64_t *__restrict__ post, QMeta *__restrict__ meta, Tables T,
+                    const int64_t *__restrict__ off, const uint32_t *__restrict__ piece_ent,
+                    const uint64_t *__restrict__ post, QMeta *__restrict__ meta, Tables T,
                     const uint32_t *__restrict__ qflag, const int32_t *__restrict__ n_flagged,
                     unsigned long long *__restrict__ n_bins, int32_t *__restrict__ flags) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -288,10 +363,12 @@ entries_pass_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, c
   const int64_t j_lo = off[e0] + (int64_t)blockIdx.x * kVoteTuples + (int64_t)warp * per_warp;
   const int64_t j_hi = min(off[e0 + n], j_lo + per_warp);
   if (j_lo >= j_hi) return;
-  uint32_t acc = 0;                        // PASS_MARK: candidate tuples of the current query; PASS_VOTE: new bins
+  uint32_t acc = 0;                        // PASS_MARK: candidate tuples of the current query; PASS_VOTE: bins of count 1
   uint32_t cur_q = 0xffffffffu;
-  int64_t ei = e0, hi = e0 + n;            // largest entry in [e0, e0+n) with off[ei] <= j_lo (warp-uniform search)
-  while (hi - ei > 1) { const int64_t mid = ei + ((hi - ei) >> 1); if (off[mid] <= j_lo) ei = mid; else hi = mid; }
+  __shared__ unsigned long long s_cand[PASS == PASS_VOTE ? 8 * kCandBuf : 1];
+  unsigned long long *cbuf = s_cand + (PASS == PASS_VOTE ? warp * kCandBuf : 0);
+  int ncand = 0;                           // PASS_VOTE: candidate keys of query cur_q waiting in cbuf (warp-uniform)
+  int64_t ei = e0 + piece_ent[(int64_t)blockIdx.x * 8 + warp];    // the entry this warp's first tuple belongs to
   for (; ei < e0 + n; ++ei) {
     const int64_t o_this = off[ei], o_next = off[ei + 1];
     if (o_this >= j_hi) break;
@@ -305,27 +382,37 @@ entries_pass_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, c
       if (lane == 0 && acc) atomicAdd(&meta[cur_q].cand, acc);
       acc = 0; cur_q = q;
     }
+    if (PASS == PASS_VOTE && q != cur_q) {                       // the buffer holds one query's candidates
+      cand_flush(cbuf, ncand, cur_q, meta, T.cand, lane, flags);
+      cur_q = q;
+    }
     const QMeta m = meta[q];
     const uint32_t qoff = (uint32_t)(e.x & kM24);
     const uint64_t *__restrict__ run = post + first[ei];
     const uint32_t k_hi = (uint32_t)(min(j_hi, o_next) - o_this);
     const uint32_t k_lo = (uint32_t)(max(j_lo, o_this) - o_this);
-    uint64_t na = 0, nb = 0;
-    if (k_lo + lane < k_hi) na = run[k_lo + lane];
-    if (k_lo + 32 + lane < k_hi) nb = run[k_lo + 32 + lane];
+    uint64_t na = 0, nb = 0;                                     // streaming loads: the postings pass through, the filters
+    if (k_lo + lane < k_hi) na = __ldcs(run + k_lo + lane);      // and tables are what should stay in L2
+    if (k_lo + 32 + lane < k_hi) nb = __ldcs(run + k_lo + 32 + lane);
     for (uint32_t kw = k_lo; kw < k_hi; kw += 64) {
       __syncwarp();                                              // the probe loops below diverge
       const uint32_t ka = kw + lane, kb = ka + 32;
       const uint64_t ra = na, rb = nb;
-      if (ka + 64 < k_hi) na = run[ka + 64];
-      if (kb + 64 < k_hi) nb = run[kb + 64];
+      if (ka + 64 < k_hi) na = __ldcs(run + ka + 64);
+      if (kb + 64 < k_hi) nb = __ldcs(run + kb + 64);
       // db offset - query offset, biased
-      tuple_pair_pass<DENSE, PASS>(m, ka < k_hi, (uint32_t)(ra >> 24) & 0xffffffu, (uint32_t)(ra & kM24) - qoff + SIA_DIFF_BIAS,
-                                   kb < k_hi, (uint32_t)(rb >> 24) & 0xffffffu, (uint32_t)(rb & kM24) - qoff + SIA_DIFF_BIAS,
-                                   T, acc, flags);
+      const uint32_t song_a = (uint32_t)(ra >> 24) & 0xffffffu, db_a = (uint32_t)(ra & kM24) - qoff + SIA_DIFF_BIAS;
+      const uint32_t song_b = (uint32_t)(rb >> 24) & 0xffffffu, db_b = (uint32_t)(rb & kM24) - qoff + SIA_DIFF_BIAS;
+      bool ca, cb;
+      tuple_pair_pass<DENSE, PASS>(m, ka < k_hi, song_a, db_a, kb < k_hi, song_b, db_b, T, acc, ca, cb, flags);
+      if (PASS == PASS_VOTE) {
+        if (ncand > kCandBuf - 64) cand_flush(cbuf, ncand, q, meta, T.cand, lane, flags);
+        cand_push(cbuf, ncand, ca, cand_key(q, song_a, db_a), cb, cand_key(q, song_b, db_b), lane);
+      }
     }
     __syncwarp();
   }
+  if (PASS == PASS_VOTE) cand_flush(cbuf, ncand, cur_q, meta, T.cand, lane, flags);
   if (PASS == PASS_MARK || (PASS == PASS_VOTE && n_bins)) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
@@ -381,82 +468,80 @@ __device__ __forceinline__ const uint64_t *slot_keys(const uint64_t *__restrict_
   return base + 1;
 }
 
-// The same passes over vote keys stored in slots (keys from other shards, or a caller's tuples): blockIdx.y = slot, the
-// slot's keys are spread over blockIdx.x with two keys per thread and step.  Keys of one query are mostly adjacent, so
-// PASS_MARK aggregates the candidate counts per run inside the warp.
+// The same passes over vote keys stored in slots (keys from other shards, or a caller's tuples): blockIdx.y = slot, every
+// warp takes pieces of 512 consecutive keys of the slot, two keys per lane and step.  Keys of one query are adjacent
+// (the shards emit them in query order), so a step normally belongs to one query; the few steps that straddle queries
+// are handled one query after the other.
 template <bool DENSE, int PASS>
 __global__ void __launch_bounds__(256)
 keys_pass_kernel(const uint64_t *__restrict__ keys, int64_t cap, const int64_t *__restrict__ counts, int nq,
                  QMeta *__restrict__ meta, Tables T, const uint32_t *__restrict__ qflag, const int32_t *__restrict__ n_flagged,
                  int topn, const int32_t *__restrict__ out_song, const int32_t *__restrict__ out_nres,
                  int32_t *__restrict__ out_rows, int32_t *__restrict__ flags) {
-  const int lane = threadIdx.x & 31;
-  uint32_t dummy = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (PASS == PASS_VOTE && (*flags & 32)) return;
   if (PASS == PASS_SINGLES && *n_flagged == 0) return;
   int64_t n;
   const uint64_t *__restrict__ kk = slot_keys(keys, cap, counts, blockIdx.y, n);
   const uint32_t qmask = (1u << kQidBits) - 1u;
-  for (int64_t i0 = (int64_t)blockIdx.x * 512; i0 < n; i0 += (int64_t)gridDim.x * 512) {
-    __syncwarp();
-    // a warp takes 64 consecutive keys: lane l the keys l and l + 32
-    const int64_t ia = i0 + (threadIdx.x >> 5) * 64 + lane, ib = ia + 32;
-    bool va = ia < n, vb = ib < n;
-    const uint64_t ka = va ? kk[ia] : 0, kb = vb ? kk[ib] : 0;
-    const uint32_t qa = (uint32_t)(ka >> (kSongBits + kDiffBits)) & qmask, qb = (uint32_t)(kb >> (kSongBits + kDiffBits)) & qmask;
-    if (va && qa >= (uint32_t)nq) { atomicOr(flags, 2); va = false; }
-    if (vb && qb >= (uint32_t)nq) { atomicOr(flags, 2); vb = false; }
-    const uint32_t song_a = (uint32_t)(ka >> kDiffBits) & 0xffffffu, song_b = (uint32_t)(kb >> kDiffBits) & 0xffffffu;
-    const uint32_t db_a = (uint32_t)(ka & kDiffMask), db_b = (uint32_t)(kb & kDiffMask);
-    if (PASS == PASS_ROWS) {
-      // winners differ per query: handle the queries present in the warp one after the other
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const bool v = half ? vb : va;
-        const uint64_t k = half ? kb : ka;
-        const uint32_t q = half ? qb : qa, song = half ? song_b : song_a;
-        const bool head = (k >> 63) != 0;
-        uint32_t todo = __ballot_sync(0xffffffffu, v && head);
-        while (todo) {
-          const int src = __ffs(todo) - 1;
-          const uint32_t qq = __shfl_sync(0xffffffffu, q, src);
-          const bool mine = v && head && q == qq;
+  __shared__ unsigned long long s_cand[PASS == PASS_VOTE ? 8 * kCandBuf : 1];
+  unsigned long long *cbuf = s_cand + (PASS == PASS_VOTE ? warp * kCandBuf : 0);
+  const int64_t n_pieces = (n + 511) >> 9;
+  for (int64_t piece = (int64_t)blockIdx.x * 8 + warp; piece < n_pieces; piece += (int64_t)gridDim.x * 8) {
+    const int64_t i_lo = piece << 9, i_hi = min(n, i_lo + 512);
+    uint32_t cur_q = 0xffffffffu, acc = 0;
+    int ncand = 0;
+    for (int64_t i0 = i_lo; i0 < i_hi; i0 += 64) {
+      __syncwarp();
+      const int64_t ia = i0 + lane, ib = ia + 32;
+      bool va = ia < i_hi, vb = ib < i_hi;
+      const uint64_t ka = va ? __ldcs(kk + ia) : 0, kb = vb ? __ldcs(kk + ib) : 0;
+      const uint32_t qa = (uint32_t)(ka >> (kSongBits + kDiffBits)) & qmask, qb = (uint32_t)(kb >> (kSongBits + kDiffBits)) & qmask;
+      if (va && qa >= (uint32_t)nq) { atomicOr(flags, 2); va = false; }
+      if (vb && qb >= (uint32_t)nq) { atomicOr(flags, 2); vb = false; }
+      const uint32_t song_a = (uint32_t)(ka >> kDiffBits) & 0xffffffu, song_b = (uint32_t)(kb >> kDiffBits) & 0xffffffu;
+      const uint32_t db_a = (uint32_t)(ka & kDiffMask), db_b = (uint32_t)(kb & kDiffMask);
+      if (PASS == PASS_ROWS) { va = va && (ka >> 63); vb = vb && (kb >> 63); }      // head keys count as matched rows
+      uint32_t todo_a = __ballot_sync(0xffffffffu, va), todo_b = __ballot_sync(0xffffffffu, vb);
+      while (todo_a | todo_b) {                          // one iteration per query present in the step (normally one)
+        const uint32_t qq = todo_a ? __shfl_sync(0xffffffffu, qa, __ffs(todo_a) - 1) : __shfl_sync(0xffffffffu, qb, __ffs(todo_b) - 1);
+        const bool ma = va && qa == qq, mb = vb && qb == qq;
+        todo_a &= ~__ballot_sync(0xffffffffu, ma);
+        todo_b &= ~__ballot_sync(0xffffffffu, mb);
+        if (PASS == PASS_ROWS) {
           const int64_t obase = (int64_t)qq * topn;
-          rows_pass(0xffffffffu, mine, song, out_song + obase, out_nres[qq], out_rows + obase, lane);
-          todo &= ~__ballot_sync(0xffffffffu, mine);
+          const int nwin = out_nres[qq];
+          rows_pass(0xffffffffu, ma, song_a, out_song + obase, nwin, out_rows + obase, lane);
+          rows_pass(0xffffffffu, mb, song_b, out_song + obase, nwin, out_rows + obase, lane);
+          continue;
         }
+        if (PASS == PASS_SINGLES && !qflag[qq]) continue;
+        if (qq != cur_q) {
+          if (PASS == PASS_MARK) {                       // flush the candidate count of the previous query
+#pragma unroll
+            for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            if (lane == 0 && acc) atomicAdd(&meta[cur_q].cand, acc);
+            acc = 0;
+          }
+          if (PASS == PASS_VOTE) cand_flush(cbuf, ncand, cur_q, meta, T.cand, lane, flags);
+          cur_q = qq;
+        }
+        const QMeta m = meta[qq];
+        bool ca, cb;
+        tuple_pair_pass<DENSE, PASS>(m, ma, song_a, db_a, mb, song_b, db_b, T, acc, ca, cb, flags);
+        if (PASS == PASS_VOTE) {
+          if (ncand > kCandBuf - 64) cand_flush(cbuf, ncand, qq, meta, T.cand, lane, flags);
+          cand_push(cbuf, ncand, ca, cand_key(qq, song_a, db_a), cb, cand_key(qq, song_b, db_b), lane);
+        }
+        __syncwarp();
       }
-      continue;
-    }
-    if (PASS == PASS_SINGLES) {
-      if (va && !qflag[qa]) va = false;
-      if (vb && !qflag[qb]) vb = false;
-    }
-    uint32_t acc_a = 0, acc_b = 0;
-    if (qa == qb || !vb || !va) {                       // the common case: both keys belong to one query
-      const uint32_t q = va ? qa : qb;
-      if (va || vb) tuple_pair_pass<DENSE, PASS>(meta[q], va, song_a, db_a, vb, song_b, db_b, T, PASS == PASS_MARK ? acc_a : dummy, flags);
-      if (!va) { acc_b = acc_a; acc_a = 0; }
-    } else {
-      tuple_pair_pass<DENSE, PASS>(meta[qa], true, song_a, db_a, false, 0u, 0u, T, PASS == PASS_MARK ? acc_a : dummy, flags);
-      tuple_pair_pass<DENSE, PASS>(meta[qb], true, song_b, db_b, false, 0u, 0u, T, PASS == PASS_MARK ? acc_b : dummy, flags);
     }
     if (PASS == PASS_MARK) {
-      __syncwarp();
-      // candidate counts: when both keys are one query's, acc_a holds their sum
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t acc = half ? acc_b : acc_a;
-        const uint32_t q = half ? qb : (va ? qa : qb);
-        const uint32_t active = __ballot_sync(0xffffffffu, acc != 0);
-        if (acc) {
-          const uint32_t peers = __match_any_sync(active, q);
-          uint32_t sum = 0;
-          for (uint32_t p = peers; p; p &= p - 1) sum += __shfl_sync(peers, acc, __ffs(p) - 1);
-          if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&meta[q].cand, sum);
-        }
-      }
+      for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+      if (lane == 0 && acc) atomicAdd(&meta[cur_q].cand, acc);
     }
+    if (PASS == PASS_VOTE) cand_flush(cbuf, ncand, cur_q, meta, T.cand, lane, flags);
   }
 }
 
@@ -501,7 +586,7 @@ layout_keys_kernel(const uint32_t *__restrict__ cnt, int nq, int64_t dense_span,
   sf = s_f[threadIdx.x]; ss = s_s[threadIdx.x];
   for (int q = a; q < b; ++q) {
     QMeta m;
-    m.bin_base = 0; m.bin_cap = 0; m.cand = 0;
+    m.bin_base = 0; m.bin_cap = 0; m.cand = 0; m.cand_base = 0; m.cursor = 0; m.pad_ = 0;
     m.filt_base = sf; m.filt_words = cnt[q] + 1u;
     m.song_base = ss; m.song_cap = dense_span > 0 ? (uint32_t)dense_span : 2u * cnt[q] + 32u;
     meta[q] = m;
@@ -529,6 +614,9 @@ layout_bins_kernel(QMeta *__restrict__ meta, int q_lo, int q_hi, int64_t *__rest
   sb = s_b[threadIdx.x];
   for (int q = a; q < b; ++q) {
     meta[q].bin_base = sb;
+    // the candidate lists follow the same scan: slots before this query = 2 * candidates + 32 per query
+    meta[q].cand_base = (sb - 32ll * (q - q_lo)) >> 1;
+    meta[q].cursor = 0;
     const int64_t c = 2 * (int64_t)meta[q].cand + 32;
     meta[q].bin_cap = (uint32_t)c;
     sb += c;
@@ -704,7 +792,8 @@ int lookup_sorted(::sia_index *ix, Arena &ar, ulonglong2 *a, ulonglong2 *b, int6
 
 // bytes of vote tables for `tuples` tuples over nq queries: filter + worst-case bins (every tuple a candidate) + songs
 static size_t vote_table_bytes(int64_t tuples, int64_t nq, int64_t bin_slots, int64_t song_slots, bool dense) {
-  return (size_t)(tuples + nq) * 4 + (size_t)bin_slots * 12 + (size_t)song_slots * (dense ? 8 : 12) + 4096;
+  return (size_t)(tuples + nq) * 4 + (size_t)bin_slots * 16 + (size_t)song_slots * (dense ? 8 : 12) +
+         (size_t)(tuples / (kVoteTuples >> 3) + 16) * 4 + 8192;
 }
 // bin slots reserved for `tuples` tuples over nq queries: first for up to a quarter of the tuples landing in twice-hit
 // buckets (12 % on the benchmark's index), then — if pass 1 counted more — for all of them
@@ -728,6 +817,8 @@ struct KeyVote {
   int32_t *o_song = nullptr, *o_diff = nullptr, *o_count = nullptr, *o_rows = nullptr, *o_nres = nullptr;
   cudaStream_t s = nullptr;
   int32_t *d_flags = nullptr;      // device flags of the attempt in flight
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SIA_QUERY_TIMING only
+  bool timed = false;
 };
 static KeyVote g_key_vote[64];
 
@@ -761,9 +852,12 @@ static int key_vote_enqueue(KeyVote &v, int attempt) {
   Tb.song_key = dense ? nullptr : ar.take<uint32_t>(ns);
   Tb.bins = ar.take<unsigned long long>(nb_cap);
   Tb.bin_cnt = ar.take<uint32_t>(nb_cap);
-  SIA_REQUIRE(meta && cnt && qflag && total && flags && Tb.filter && Tb.song_best && Tb.bins && Tb.bin_cnt &&
+  Tb.cand = ar.take<unsigned long long>(nb_cap / 2 + 16);
+  SIA_REQUIRE(meta && cnt && qflag && total && flags && Tb.filter && Tb.song_best && Tb.bins && Tb.bin_cnt && Tb.cand &&
               (dense || Tb.song_key), SIA_E_NOMEM, "vote: scratch");
   v.d_flags = flags;
+  v.timed = getenv("SIA_QUERY_TIMING") != nullptr;
+  if (v.timed) { for (auto &e : v.ev) if (!e) cudaEventCreate(&e); cudaEventRecord(v.ev[0], s); }
   SIA_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * nq, s));
   SIA_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), s));
   SIA_CUDA(cudaMemsetAsync(Tb.filter, 0, sizeof(uint32_t) * nf, s));
@@ -776,22 +870,31 @@ static int key_vote_enqueue(KeyVote &v, int attempt) {
 #define SIA_KEYS_PASS(D, P)                                                                                            \
   keys_pass_kernel<D, P><<<grid, 256, 0, s>>>(d_keys, cap, d_counts, nq, meta, Tb, qflag, nflag, topn,                 \
                                               d_out_song, d_out_nres, d_out_rows, flags)
+#define SIA_KSTAGE(k) do { if (v.timed) cudaEventRecord(v.ev[k], s); } while (0)
 #define SIA_KEYS_VOTE(D)                                                                                               \
   do {                                                                                                                 \
+    SIA_KSTAGE(1);                                                                                                     \
     SIA_KEYS_PASS(D, PASS_MARK);                                                                                       \
+    SIA_KSTAGE(2);                                                                                                     \
     layout_bins_kernel<<<1, 1024, 0, s>>>(meta, 0, nq, total);                                                         \
     zero_bins_kernel<<<kNumSMs * 8, 256, 0, s>>>(Tb.bins, Tb.bin_cnt, total, nb_cap, flags);                           \
     SIA_KEYS_PASS(D, PASS_VOTE);                                                                                       \
+    SIA_KSTAGE(3);                                                                                                     \
+    cand_vote_kernel<D><<<kNumSMs * 8, 256, 0, s>>>(Tb.cand, meta, 0, nq, Tb, nullptr, flags);                         \
+    SIA_KSTAGE(4);                                                                                                     \
     topn_kernel<D, false><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, nflag, d_out_song, d_out_diff, d_out_count,  \
                                              d_out_rows, d_out_nres);                                                  \
     SIA_KEYS_PASS(D, PASS_SINGLES);                                                                                    \
     topn_kernel<D, true><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, nflag, d_out_song, d_out_diff, d_out_count,   \
                                             d_out_rows, d_out_nres);                                                   \
+    SIA_KSTAGE(5);                                                                                                     \
     SIA_KEYS_PASS(D, PASS_ROWS);                                                                                       \
+    SIA_KSTAGE(6);                                                                                                     \
   } while (0)
   if (dense) SIA_KEYS_VOTE(true); else SIA_KEYS_VOTE(false);
 #undef SIA_KEYS_VOTE
 #undef SIA_KEYS_PASS
+#undef SIA_KSTAGE
   SIA_CHECK_LAUNCH();
   return SIA_OK;
 }
@@ -809,6 +912,13 @@ int vote_key_slots_finish(int device) {
     SIA_CUDA(cudaStreamSynchronize(v.s));
     SIA_REQUIRE(!(h_flags & 2), SIA_E_INVALID, "vote: query id outside 0..n_queries-1");
     SIA_REQUIRE(!(h_flags & 8), SIA_E_CUDA, "vote: table overflow (internal error, or song id above max_song)");
+    if (v.timed) {
+      float t[6];
+      for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], v.ev[k], v.ev[k + 1]);
+      fprintf(stderr, "[sia] key vote: %d queries, %d slots x %lld: memsets + count + layout %.2f ms, mark %.2f, bin layout + collect %.2f, "
+              "candidate vote %.2f, topn + singles %.2f, rows %.2f\n", v.n_queries, v.n_slots, (long long)v.cap, t[0], t[1], t[2], t[3],
+              t[4], t[5]);
+    }
     if (!(h_flags & 32)) return SIA_OK;
     SIA_REQUIRE(attempt == 0, SIA_E_CUDA, "vote: bin table overflow (internal error)");
     int rc = key_vote_enqueue(v, 1);
@@ -918,8 +1028,8 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
   const bool timing = getenv("SIA_QUERY_TIMING") != nullptr;       // stage times of every pass on stderr
   ix->last_lookup_ms = ix->last_vote_ms = 0;
   for (auto &e : ix->ev_q) if (!e) SIA_CUDA(cudaEventCreate(&e));
-  static cudaEvent_t stage_ev[8] = {nullptr};          // SIA_QUERY_TIMING only: per-kernel times of the vote
-  double stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+  static cudaEvent_t stage_ev[9] = {nullptr};          // SIA_QUERY_TIMING only: per-kernel times of the vote
+  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int64_t span = (int64_t)ix->max_song + 1;
   for (int64_t q0 = 0; q0 < n_queries; q0 += kMaxQueriesPerPass) {
     const int nq = (int)std::min<int64_t>(kMaxQueriesPerPass, n_queries - q0);
@@ -966,7 +1076,7 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
       for (int q = qa; q < qb; ++q) {
         const int64_t t = h_off_all[q + 1] - h_off_all[q], h = h_off_head[q + 1] - h_off_head[q];
         QMeta &m = h_meta[q];
-        m.bin_base = 0; m.bin_cap = 0; m.cand = 0;
+        m.bin_base = 0; m.bin_cap = 0; m.cand = 0; m.cand_base = 0; m.cursor = 0; m.pad_ = 0;
         m.filt_base = fb; m.filt_words = (uint32_t)(t + 1);
         m.song_base = sb; m.song_cap = g.dense ? (uint32_t)span : (uint32_t)(2 * h + 32);
         fb += m.filt_words; sb += m.song_cap;
@@ -1009,16 +1119,21 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
         Tb.song_key = g.dense ? nullptr : ix->arena3.take<uint32_t>(g.ns);
         Tb.bins = ix->arena3.take<unsigned long long>(nb_cap);
         Tb.bin_cnt = ix->arena3.take<uint32_t>(nb_cap);
-        SIA_REQUIRE(Tb.filter && Tb.song_best && Tb.bins && Tb.bin_cnt && (g.dense || Tb.song_key), SIA_E_NOMEM,
+        Tb.cand = ix->arena3.take<unsigned long long>(nb_cap / 2 + 16);
+        SIA_REQUIRE(Tb.filter && Tb.song_best && Tb.bins && Tb.bin_cnt && Tb.cand && (g.dense || Tb.song_key), SIA_E_NOMEM,
                     "index scratch arena too small (vote tables)");
         SIA_CUDA(cudaMemsetAsync(Tb.filter, 0, sizeof(uint32_t) * g.nf, s));
         SIA_CUDA(cudaMemsetAsync(Tb.song_best, 0, sizeof(unsigned long long) * g.ns, s));
         if (!g.dense) SIA_CUDA(cudaMemsetAsync(Tb.song_key, 0, sizeof(uint32_t) * g.ns, s));
         const unsigned blocks = (unsigned)ceil_div(tuples, kVoteTuples);
         const int gq = g.qb - g.qa;
+        const int64_t n_pieces = (int64_t)blocks * 8;
+        uint32_t *piece_ent = ix->arena3.take<uint32_t>(n_pieces);
+        SIA_REQUIRE(piece_ent != nullptr, SIA_E_NOMEM, "index scratch arena too small (vote pieces)");
+        piece_entries_kernel<<<grid_for(n_pieces), 256, 0, s>>>(L.off_all, e0, ne, n_pieces, piece_ent);
 #define SIA_ENT_PASS(D, P)                                                                                              \
-        entries_pass_kernel<D, P><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, ix->post, d_meta, Tb, qflag,       \
-                                                         d_nflag, d_nbins, d_flags)
+        entries_pass_kernel<D, P><<<blocks, 256, 0, s>>>(L.ent, e0, ne, L.first, L.off_all, piece_ent, ix->post, d_meta, Tb,   \
+                                                         qflag, d_nflag, d_nbins, d_flags)
 #define SIA_STAGE(k) do { if (timing) cudaEventRecord(stage_ev[k], s); } while (0)
 #define SIA_ENT_VOTE(D)                                                                                                 \
         do {                                                                                                            \
@@ -1029,6 +1144,8 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
           zero_bins_kernel<<<kNumSMs * 8, 256, 0, s>>>(Tb.bins, Tb.bin_cnt, d_total, nb_cap, d_flags);                  \
           SIA_STAGE(2);                                                                                                 \
           SIA_ENT_PASS(D, PASS_VOTE);                                                                                   \
+          SIA_STAGE(8);                                                                                                 \
+          cand_vote_kernel<D><<<kNumSMs * 8, 256, 0, s>>>(Tb.cand, d_meta, g.qa, g.qb, Tb, d_nbins, d_flags);           \
           SIA_STAGE(3);                                                                                                 \
           topn_kernel<D, false><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_nflag, d_out_song,         \
                                                    d_out_diff, d_out_count, d_out_rows, d_out_nres);                    \
@@ -1049,6 +1166,7 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
           float t;
           cudaEventElapsedTime(&t, stage_ev[7], stage_ev[0]); stage_ms[0] += t;      // memsets of the tables
           for (int k = 0; k < 6; ++k) { cudaEventElapsedTime(&t, stage_ev[k], stage_ev[k + 1]); stage_ms[k + 1] += t; }
+          cudaEventElapsedTime(&t, stage_ev[8], stage_ev[3]); stage_ms[7] += t;        // the dense candidate vote inside "vote"
         }
 #undef SIA_STAGE
 #undef SIA_ENT_VOTE
@@ -1071,9 +1189,9 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
         const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
         fprintf(stderr, "[sia] query pass: %d queries, %lld entries, %lld tuples, %zu groups: lookup %.2f ms, vote %.2f ms, host wall %.2f ms\n",
                 nq, (long long)n, (long long)L.tuples, groups.size(), t_lookup, t_vote, host_ms);
-        fprintf(stderr, "[sia]   vote stages (ms): table memsets %.2f, mark %.2f, bin layout + zero %.2f, vote %.2f, topn %.2f, "
-                "singles + topn %.2f, rows %.2f\n", stage_ms[0], stage_ms[1], stage_ms[2], stage_ms[3], stage_ms[4], stage_ms[5],
-                stage_ms[6]);
+        fprintf(stderr, "[sia]   vote stages (ms): table memsets %.2f, mark %.2f, bin layout + zero %.2f, collect + candidate vote %.2f "
+                "(candidate vote %.2f), topn %.2f, singles + topn %.2f, rows %.2f\n", stage_ms[0], stage_ms[1], stage_ms[2],
+                stage_ms[3], stage_ms[7], stage_ms[4], stage_ms[5], stage_ms[6]);
       }
     }
     if (h_stats) h_stats[3] += (int64_t)h_nb;
