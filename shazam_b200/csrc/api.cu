@@ -216,8 +216,7 @@ int run_stft(sia_ctx *c, const int16_t *d_pcm, const MetaView &m, int nb, int64_
   StftLaunch a;
   a.d_pcm = d_pcm; a.d_track_starts = m.track_starts; a.d_track_len = m.track_len; a.d_frame_starts = m.frame_starts;
   a.n_tracks = nb; a.total_frames = frames; a.d_spec = d_spec; a.out_type = out_type;
-  // run length per CTA; capped: K1's PCM cursor keeps a clamped 32-bit remainder that is only exact over short runs
-  a.frames_per_cta = (int)std::min<int64_t>(4096, std::max<int64_t>(1, env_i64("SIA_STFT_FRAMES_PER_CTA", 8)));
+  a.frames_per_cta = 8;      // frames per CTA run (K1's PCM cursor keeps a clamped 32-bit remainder: runs stay short)
   a.compute = p->compute; a.Fs = p->Fs;
   Timer t(c, s, T_STFT, 1);
   return stft_db_launch(a, c->tf, c->td, s);

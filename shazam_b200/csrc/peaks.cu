@@ -263,78 +263,7 @@ __device__ __forceinline__ void warp_tile_peaks(const float4 *__restrict__ A, ui
   }
 }
 
-template <bool TMA>
-__global__ void __launch_bounds__(kW2Threads, 3)
-peaks_square_warp_kernel(const float *__restrict__ spec, const int64_t *__restrict__ frame_starts,
-                         const int64_t *__restrict__ ttile_starts, int n_tracks, float amp_lo,
-                         uint32_t *__restrict__ bitmap, const __grid_constant__ CUtensorMap tmap) {
-  __shared__ __align__(128) float4 A[kW2TileRows * kW2Cols4];       // 40 320 B
-  __shared__ __align__(8) unsigned long long tma_bar;
-  const int64_t tt = blockIdx.x / kW2Strips;
-  const int strip = (int)(blockIdx.x - tt * kW2Strips);
-  const int f0 = strip * kW2Bins;
-  const int trk = find_segment(ttile_starts, n_tracks, tt);
-  const int64_t row_lo = frame_starts[trk], row_hi = frame_starts[trk + 1];
-  const int64_t r0 = row_lo + (tt - ttile_starts[trk]) * kW2Rows;
-
-  const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(A);
-  if (TMA) {
-    // Stage the 84 x 120 halo tile with ONE bulk tensor copy (TMA): the tensor is [frames][2049 bins] with a row
-    // pitch of 2080 floats, so bins < 0 or > 2048 (including the unwritten row padding) and frames outside the
-    // chunk arrive as zeros.  Frames of the neighbouring tracks are zeroed below.  With amp_min >= 0 a zero can
-    // neither exceed nor equal a candidate (> amp_min), so it is as good as -inf here.
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
-      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
-                   "r"((uint32_t)(sizeof(float4) * kW2TileRows * kW2Cols4)) : "memory");
-      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
-                   ::"r"(a_base), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(f0 - 12), "r"((int)(r0 - 10)), "r"(bar)
-                   : "memory");
-    }
-    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n"
-                 ::"r"(bar) : "memory");
-    const int64_t g_first = r0 - 10;
-    if (g_first < row_lo || g_first + kW2TileRows > row_hi) {      // first / last tiles of a track
-      for (int i = threadIdx.x; i < kW2TileRows * kW2Cols4; i += kW2Threads) {
-        const int64_t g = g_first + i / kW2Cols4;
-        if (g < row_lo || g >= row_hi) A[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      __syncthreads();
-    }
-  } else {
-  // Stage the halo tile with cp.async (16-byte LDGSTS, no register round trip, ~20 requests in flight per
-  // thread).  Out-of-track frames and out-of-range bins are ZERO-filled (src-size 0).
-  if (threadIdx.x < 4 * kW2Cols4) {                     // 120 loader threads: fixed column, rows rs, rs+4, ...
-    const int j = threadIdx.x % kW2Cols4, rs = threadIdx.x / kW2Cols4;
-    const int f = f0 - 12 + 4 * j;
-    const bool col_in = f >= 0 && f < SIA_NBINS;
-    const bool edge = f == SIA_NBINS - 1;               // bin 2048 shares its float4 with row padding: patch it
-    int64_t g = r0 - 10 + rs;
-    const float *gp = spec + g * SIA_F_STRIDE + f;
-    uint32_t sa = a_base + (uint32_t)(rs * kW2Cols4 + j) * 16u;
-#pragma unroll 3
-    for (int r = rs; r < kW2TileRows; r += 4, g += 4, gp += 4 * SIA_F_STRIDE, sa += 4 * kW2Cols4 * 16) {
-      const bool in = col_in && g >= row_lo && g < row_hi;
-      if (edge) {
-        A[r * kW2Cols4 + j] = make_float4(in ? __ldg(gp) : 0.f, 0.f, 0.f, 0.f);
-      } else {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(in ? gp : spec), "r"(in ? 16 : 0));
-      }
-    }
-  }
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
-  __syncthreads();
-  }
-
-  warp_tile_peaks(A, a_base, r0, row_hi, strip, f0, amp_lo, bitmap);
-}
-
-// Persistent form of the kernel above: 2 CTAs per SM walk the tiles with a stride of the grid, two tile buffers
+// Persistent kernel: 2 CTAs per SM walk the tiles with a stride of the grid, two tile buffers
 // each; the TMA copy of the next tile is in flight while the current one is filtered, so no warp ever waits for
 // the tile it is about to read (the copy engine does the staging, the 128 threads only compute).
 constexpr size_t kW2TileBytes = sizeof(float4) * kW2TileRows * kW2Cols4;
@@ -422,203 +351,14 @@ int launch_square_warp(const PeaksLaunch &a, cudaStream_t s) {
   float amp_lo = (float)a.amp_min;
   if ((double)amp_lo > a.amp_min) amp_lo = nextafterf(amp_lo, -INFINITY);
   const int64_t blocks = a.total_ttiles * kW2Strips;
-  // SIA_PEAKS_STAGING=cpasync keeps the LDGSTS tile staging (A/B checks); default: one TMA tensor copy per tile
-  const char *st = getenv("SIA_PEAKS_STAGING");
   alignas(64) CUtensorMap tm;
   memset(&tm, 0, sizeof tm);
-  if (st && std::string(st) == "cpasync") {
-    peaks_square_warp_kernel<false><<<(unsigned)blocks, kW2Threads, 0, s>>>((const float *)a.d_spec, a.d_frame_starts,
-                                                                            a.d_ttile_starts, a.n_tracks, amp_lo, a.d_bitmap, tm);
-  } else {
-    int rc = make_spec_tensor_map((const float *)a.d_spec, a.total_frames, &tm);
-    if (rc) return rc;
-    if (st && std::string(st) == "tma1") {            // one tile per CTA
-      peaks_square_warp_kernel<true><<<(unsigned)blocks, kW2Threads, 0, s>>>((const float *)a.d_spec, a.d_frame_starts,
-                                                                             a.d_ttile_starts, a.n_tracks, amp_lo, a.d_bitmap, tm);
-    } else {
-      SIA_CUDA(cudaFuncSetAttribute(peaks_square_warp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kW2PersistSmem));
-      const unsigned grid = (unsigned)std::min<int64_t>(blocks, 2 * kNumSMs);
-      peaks_square_warp_tma_kernel<<<grid, kW2Threads, kW2PersistSmem, s>>>(a.d_frame_starts, a.d_ttile_starts, a.n_tracks, blocks,
-                                                                            amp_lo, a.d_bitmap, tm);
-    }
-  }
-  SIA_CHECK_LAUNCH();
-  return SIA_OK;
-}
-
-// ---- alternative path: candidate pruning (float32, square 21x21, amp_min >= 0; SIA_PEAKS_KERNEL=prune) -----
-// A peak is the maximum of its 21x21 window, so it is also the maximum of any block of elements that lies inside
-// that window — in particular of the aligned 8-frame x 4-bin block that contains it.  One CTA stages a
-// 64-frame x 128-bin tile plus halo (88 x 152 floats, cp.async, zero fill outside the track / the 2049 bins:
-// with amp_min >= 0 a zero can neither exceed nor equal a candidate) and then
-//   P1  takes the maximum of every 8x4 block (one thread per block: 8 conflict-free 128-bit loads, 31 max);
-//   P2  visits only blocks whose maximum exceeds amp_min: the elements equal to the block maximum are the
-//       candidates.  A candidate is checked against the maxima of the ~24 blocks its window touches: a block
-//       entirely inside the window with a larger maximum rejects it at once, a partially covered one has the
-//       covered elements compared one by one, everything else is skipped.  Ties keep every tied element
-//       (maximum_filter(A) == A, __init__.py:143).
-// Cost is ~1 instruction per element plus work proportional to the number of block maxima above the
-// threshold, instead of a full separable max filter over every element.  Plain bitmap layout.
-constexpr int kP_Rows = kPeakTileT;                  // 64 output frames
-constexpr int kP_Cols = 128;                         // output bins (the last strip also owns bin 2048)
-constexpr int kP_Strips = (SIA_NBINS - 1) / kP_Cols; // 16
-constexpr int kP_TileRows = 88;                      // 10 + 64 + 10, rounded up to a multiple of 8
-constexpr int kP_C4 = 38;                            // float4 columns: 12 + 129 + 10 -> 152 floats
-constexpr int kP_TileCols = 4 * kP_C4;
-constexpr int kP_BlockRows = kP_TileRows / 8;        // 11
-constexpr int kP_Blocks = kP_BlockRows * kP_C4;      // 418 blocks of 8 x 4
-constexpr int kP_Threads = 256;
-static_assert(SIA_NBINS == kP_Strips * kP_Cols + 1, "strip layout assumes 2049 bins");
-
-constexpr int kP_MaxCand = 1024;
-
-// candidate (rt, ct) of value m (tile coordinates): is it the maximum of its window?  Serial version.
-__device__ __forceinline__ bool peak_window_serial(const float *__restrict__ A, const float *__restrict__ Bm, int rt, int ct,
-                                                   float m) {
-  const int wr0 = rt - 10, wr1 = rt + 10, wc0 = ct - 10, wc1 = ct + 10;
-  for (int bR = wr0 >> 3; bR <= (wr1 >> 3); ++bR) {
-    const int rr0 = max(wr0, 8 * bR), rr1 = min(wr1, 8 * bR + 7);
-    for (int bC = wc0 >> 2; bC <= (wc1 >> 2); ++bC) {
-      if (!(Bm[bR * kP_C4 + bC] > m)) continue;
-      const int cc0 = max(wc0, 4 * bC), cc1 = min(wc1, 4 * bC + 3);
-      if (rr1 - rr0 == 7 && cc1 - cc0 == 3) return false;      // the larger element is inside the window
-      for (int r = rr0; r <= rr1; ++r)
-        for (int c = cc0; c <= cc1; ++c)
-          if (A[r * kP_TileCols + c] > m) return false;
-    }
-  }
-  return true;
-}
-
-__global__ void __launch_bounds__(kP_Threads, 3)
-peaks_square_prune_kernel(const float *__restrict__ spec, const int64_t *__restrict__ frame_starts,
-                          const int64_t *__restrict__ ttile_starts, int n_tracks, float amp_lo,
-                          uint32_t *__restrict__ bitmap) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];       // 53 504 B tile + block maxima + tile bitmap
-  float4 *A4 = reinterpret_cast<float4 *>(smem_raw);
-  float *Bm = reinterpret_cast<float *>(A4 + kP_TileRows * kP_C4);
-  uint32_t *sbits = reinterpret_cast<uint32_t *>(Bm + kP_Blocks + 2);
-  uint16_t *cand = reinterpret_cast<uint16_t *>(sbits + kP_Rows * 5);
-  int *ncand = reinterpret_cast<int *>(cand + kP_MaxCand);
-  const float *A = reinterpret_cast<const float *>(A4);
-  const int64_t tt = blockIdx.x / kP_Strips;
-  const int strip = (int)(blockIdx.x - tt * kP_Strips);
-  const int f0 = strip * kP_Cols;
-  const int ncols = strip == kP_Strips - 1 ? kP_Cols + 1 : kP_Cols;
-  const int trk = find_segment(ttile_starts, n_tracks, tt);
-  const int64_t row_lo = frame_starts[trk], row_hi = frame_starts[trk + 1];
-  const int64_t r0 = row_lo + (tt - ttile_starts[trk]) * kP_Rows;
-  const int nvalid = (int)min((int64_t)kP_Rows, row_hi - r0);       // output frames of this tile inside the track
-
-  const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(A4);
-  if (threadIdx.x < 6 * kP_C4) {                        // 228 loader threads: fixed column, rows rs, rs+6, ...
-    const int j = threadIdx.x % kP_C4, rs = threadIdx.x / kP_C4;
-    const int f = f0 - 12 + 4 * j;
-    // bin 2048 shares its float4 with the (unwritten) row padding: copy 4 bytes, zero-fill the rest
-    const int col_bytes = f < 0 || f >= SIA_NBINS ? 0 : (f == SIA_NBINS - 1 ? 4 : 16);
-    int64_t g = r0 - 10 + rs;
-    const float *gp = spec + g * SIA_F_STRIDE + f;
-    uint32_t sa = a_base + (uint32_t)(rs * kP_C4 + j) * 16u;
-#pragma unroll 5
-    for (int r = rs; r < kP_TileRows; r += 6, g += 6, gp += 6 * SIA_F_STRIDE, sa += 6 * kP_C4 * 16) {
-      const int nbytes = g >= row_lo && g < row_hi ? col_bytes : 0;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(nbytes ? gp : spec), "r"(nbytes));
-    }
-  }
-  for (int i = threadIdx.x; i < kP_Rows * 5; i += kP_Threads) sbits[i] = 0;
-  if (threadIdx.x == 0) *ncand = 0;
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
-  __syncthreads();
-
-  // P1: block maxima
-  for (int b = threadIdx.x; b < kP_Blocks; b += kP_Threads) {
-    const int br = b / kP_C4, c4 = b - br * kP_C4;
-    float m = 0.f;                                        // every candidate is > amp_min >= 0
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 v = A4[(8 * br + k) * kP_C4 + c4];
-      m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-    }
-    Bm[b] = m;
-  }
-  __syncthreads();
-
-  // P2a: blocks above the threshold list their candidates (the elements equal to the block maximum).  The two
-  // column neighbours of a block lie inside the window of every element of the block: a larger maximum there
-  // rules the whole block out.
-  for (int b = threadIdx.x; b < kP_Blocks; b += kP_Threads) {
-    const float m = Bm[b];
-    if (!(m > amp_lo)) continue;
-    const int br = b / kP_C4, c4 = b - br * kP_C4;
-    const int ra = max(8 * br, 10), rb = min(8 * br + 7, 10 + nvalid - 1);   // inside the output region of this tile
-    const int ca = max(4 * c4, 12), cb = min(4 * c4 + 3, 12 + ncols - 1);
-    if (ra > rb || ca > cb) continue;
-    if (Bm[b - 1] > m || Bm[b + 1] > m) continue;        // c4 is in 3..35 here: both neighbours exist
-    for (int rt = ra; rt <= rb; ++rt) {
-      const float4 v = A4[rt * kP_C4 + c4];
-      const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int ct = 4 * c4 + k;
-        if (e[k] != m || ct < ca || ct > cb) continue;
-        const int slot = atomicAdd(ncand, 1);
-        if (slot < kP_MaxCand) cand[slot] = (uint16_t)(rt << 8 | ct);
-        else if (peak_window_serial(A, Bm, rt, ct, m))       // list full (wide plateaus): check it here
-          atomicOr(&sbits[(rt - 10) * 5 + ((ct - 12) >> 5)], 1u << ((ct - 12) & 31));
-      }
-    }
-  }
-  __syncthreads();
-
-  // P2b: one warp per candidate; lane l takes one of the <= 4 x 7 blocks the window touches
-  {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = min(*ncand, kP_MaxCand);
-    for (int i = warp; i < n; i += kP_Threads / 32) {
-      const int rt = cand[i] >> 8, ct = cand[i] & 0xff;
-      const float m = A[rt * kP_TileCols + ct];
-      const int wr0 = rt - 10, wr1 = rt + 10, wc0 = ct - 10, wc1 = ct + 10;
-      const int bR0 = wr0 >> 3, nR = (wr1 >> 3) - bR0 + 1, bC0 = wc0 >> 2, nC = (wc1 >> 2) - bC0 + 1;   // nR <= 4, nC <= 7
-      const int lr = lane / nC, bR = bR0 + lr, bC = bC0 + (lane - lr * nC);
-      bool bigger = false, inside = false;
-      int rr0 = 0, rr1 = -1, cc0 = 0, cc1 = -1;
-      if (lr < nR && Bm[bR * kP_C4 + bC] > m) {
-        bigger = true;
-        rr0 = max(wr0, 8 * bR); rr1 = min(wr1, 8 * bR + 7);
-        cc0 = max(wc0, 4 * bC); cc1 = min(wc1, 4 * bC + 3);
-        inside = rr1 - rr0 == 7 && cc1 - cc0 == 3;       // the larger element certainly lies in the window
-      }
-      if (__any_sync(0xffffffffu, inside)) continue;
-      bool found = false;
-      if (bigger) {
-        for (int r = rr0; r <= rr1 && !found; ++r)
-          for (int c = cc0; c <= cc1; ++c)
-            if (A[r * kP_TileCols + c] > m) { found = true; break; }
-      }
-      if (!__any_sync(0xffffffffu, found) && lane == 0)
-        atomicOr(&sbits[(rt - 10) * 5 + ((ct - 12) >> 5)], 1u << ((ct - 12) & 31));
-    }
-  }
-  __syncthreads();
-
-  // plain layout: word w of a row, bit b <-> bin 32 w + b; this strip owns words 4*strip .. 4*strip+3 (+ word 64)
-  for (int i = threadIdx.x; i < kP_Rows * 5; i += kP_Threads) {
-    const int row = i / 5, w = i - row * 5;
-    if (row < nvalid && (w < 4 || strip == kP_Strips - 1)) bitmap[(r0 + row) * kBitmapRowWords + 4 * strip + w] = sbits[i];
-  }
-}
-
-int launch_square_prune(const PeaksLaunch &a, cudaStream_t s) {
-  // float c > (double) amp_min  <=>  c > amp_lo with amp_lo = amp_min rounded DOWN to float
-  float amp_lo = (float)a.amp_min;
-  if ((double)amp_lo > a.amp_min) amp_lo = nextafterf(amp_lo, -INFINITY);
-  const int64_t blocks = a.total_ttiles * kP_Strips;
-  const size_t smem = sizeof(float4) * kP_TileRows * kP_C4 + sizeof(float) * (kP_Blocks + 2) + sizeof(uint32_t) * kP_Rows * 5 +
-                      sizeof(uint16_t) * kP_MaxCand + 16;
-  SIA_CUDA(cudaFuncSetAttribute(peaks_square_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  peaks_square_prune_kernel<<<(unsigned)blocks, kP_Threads, smem, s>>>((const float *)a.d_spec, a.d_frame_starts,
-                                                                    a.d_ttile_starts, a.n_tracks, amp_lo, a.d_bitmap);
+  int rc = make_spec_tensor_map((const float *)a.d_spec, a.total_frames, &tm);
+  if (rc) return rc;
+  SIA_CUDA(cudaFuncSetAttribute(peaks_square_warp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kW2PersistSmem));
+  const unsigned grid = (unsigned)std::min<int64_t>(blocks, 2 * kNumSMs);
+  peaks_square_warp_tma_kernel<<<grid, kW2Threads, kW2PersistSmem, s>>>(a.d_frame_starts, a.d_ttile_starts, a.n_tracks, blocks,
+                                                                        amp_lo, a.d_bitmap, tm);
   SIA_CHECK_LAUNCH();
   return SIA_OK;
 }
@@ -797,10 +537,6 @@ int peaks_bitmap_launch(const PeaksLaunch &a, cudaStream_t s, bool *striped) {
     // (double + erosion would need 255 KB of shared memory: it takes the generic kernel)
     if (a.in_type == SIA_F64 && !erosion) return launch_square<double, 10, false>(a, s);
     if (a.in_type == SIA_F32 && !erosion) {
-      // SIA_PEAKS_KERNEL=prune selects the candidate-pruning kernel: faster on sparse spectrograms (few block
-      // maxima above amp_min), slower on dense ones (22.9 vs 16.0 ms per 1000 benchmark tracks) — not the default
-      const char *k = getenv("SIA_PEAKS_KERNEL");
-      if (k && std::string(k) == "prune") return launch_square_prune(a, s);
       *striped = true;
       return launch_square_warp(a, s);
     }

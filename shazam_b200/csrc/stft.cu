@@ -535,16 +535,11 @@ static int launch(const StftLaunch &a, const StftTables<T> &tb, cudaStream_t s) 
   const int G = a.frames_per_cta;
   const int64_t blocks = ceil_div(a.total_frames, G);
   if (blocks == 0) return SIA_OK;
-  // SIA_STFT_CARVEOUT: percent of the SM's 228 KB L1/shared storage asked for as shared memory.  Default 80 % =
-  // 182 KB: room for the 4 resident CTAs (4 x 44.5 KB) and ~70 KB of L1 for the twiddle / window tables, which the
-  // maximum carveout squeezes out (measured 38.3 ms at 100 %, 36.5 ms at 80 %)
-  const char *cv = getenv("SIA_STFT_CARVEOUT");
-  SIA_CUDA(cudaFuncSetAttribute(stft_db_kernel<T, OutT>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : 80));
-  // SIA_STFT_PAD_KB: unused dynamic shared memory per CTA — an occupancy experiment knob
-  const char *pad_env = getenv("SIA_STFT_PAD_KB");
-  const size_t pad = pad_env ? (size_t)atoi(pad_env) * 1024 : 0;
-  if (pad) SIA_CUDA(cudaFuncSetAttribute(stft_db_kernel<T, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
-  stft_db_kernel<T, OutT><<<(unsigned)blocks, 128, pad, s>>>(
+  // 80 % of the SM's 228 KB L1/shared storage as shared memory = 182 KB: room for the 4 resident CTAs (4 x 44.5 KB) and
+  // ~70 KB of L1 for the twiddle / window tables, which the maximum carveout squeezes out (measured 38.3 ms at 100 %,
+  // 36.5 ms at 80 %)
+  SIA_CUDA(cudaFuncSetAttribute(stft_db_kernel<T, OutT>, cudaFuncAttributePreferredSharedMemoryCarveout, 80));
+  stft_db_kernel<T, OutT><<<(unsigned)blocks, 128, 0, s>>>(
       a.d_pcm, a.d_track_starts, a.d_track_len, a.d_frame_starts, a.n_tracks, a.total_frames, G, (OutT *)a.d_spec,
       sc_mid, sc_edge, (const V2 *)tb.win2, (const V2 *)tb.twA, (const V2 *)tb.twB, (const V2 *)tb.twP);
   SIA_CHECK_LAUNCH();
