@@ -147,6 +147,38 @@ int vote_key_slots_finish(int device);
 // frees the per-device scratch of vote_key_slots
 void vote_scratch_release(int device);
 
+// keys of slot `sl` of a slotted key array: counts != NULL -> slot s holds counts[s] keys from its first element;
+// counts == NULL -> element 0 of every slot is its count and the keys follow (the exchanged layout, index_dist.cu)
+__device__ __forceinline__ const uint64_t *slot_keys(const uint64_t *__restrict__ keys, int64_t cap,
+                                                     const int64_t *__restrict__ counts, int sl, int64_t &n) {
+  const uint64_t *base = keys + (int64_t)sl * cap;
+  if (counts) { n = min(counts[sl], cap); return base; }
+  n = min((int64_t)base[0], cap - 1);
+  return base + 1;
+}
+
+// ---- partitioned vote (index_pvote.cu) ------------------------------------------------------------------------
+// The vote tuples of every query are split by a hash of the SONG into partitions small enough for an exact hash table
+// in shared memory: one scatter pass (posting runs / received vote keys -> per-(query, partition) regions, staged and
+// sorted by partition in shared memory so that the global writes are contiguous runs), one count pass (one CTA per
+// region: bins counted in shared memory, the region's top-n songs), one merge (top-n over a query's regions: a song
+// lives in exactly one partition, so the merge of per-partition top-n lists is exact).  Queries whose partitions do
+// not fit (a bin of > 6144 matches, > 2048 * 6144 tuples) are flagged in d_qover and left to the table vote.
+constexpr int kPvMaxTopn = 32;
+struct PvOut { int32_t *song, *diff, *count, *rows, *nres; };
+// scratch bytes for `tuples` vote tuples of nq queries arriving from n_src sources (worst case)
+size_t pvote_bytes(int64_t tuples, int64_t nq, int n_src, int topn);
+// entries of the queries [qa, qb) of a lookup.  d_qs: entry offsets of the pass's queries (absolute, i0 = first);
+// d_goff / h_goff: tuple offsets (off_all) at the queries' first entries, [nq_pass + 1].  Rows are NOT counted here.
+int pvote_entries(Arena &ar, const Lookup &L, const uint64_t *post, const int64_t *d_qs, int64_t i0, const int64_t *d_goff,
+                  const int64_t *h_goff, int qa, int qb, int qid_base, int topn, const PvOut &out, uint32_t *d_qover,
+                  unsigned long long *d_nbins, cudaStream_t s);
+// slotted vote keys, each slot sorted by query id (else *d_unsorted is set and nothing is written); rows counted.
+// d_over_count: incremented once per flagged query.
+int pvote_key_slots(Arena &ar, const uint64_t *d_keys, int n_slots, int64_t cap, const int64_t *d_counts, int nq, int topn,
+                    const PvOut &out, uint32_t *d_qover, uint32_t *d_flags2 /* [0] unsorted, [1] flagged queries */,
+                    cudaStream_t s);
+
 }  // namespace sia
 
 struct sia_index {

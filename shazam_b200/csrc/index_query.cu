@@ -24,6 +24,7 @@
 #include "index.cuh"
 
 #include <chrono>
+#include <cstring>
 
 using namespace sia;
 
@@ -458,16 +459,6 @@ entries_rows_kernel(const ulonglong2 *__restrict__ ent, int64_t e0, int64_t n, c
   }
 }
 
-// keys of slot `sl` of a slotted key array: counts != NULL -> slot s holds counts[s] keys from its first element;
-// counts == NULL -> element 0 of every slot is its count and the keys follow (the exchanged layout, index_dist.cu)
-__device__ __forceinline__ const uint64_t *slot_keys(const uint64_t *__restrict__ keys, int64_t cap,
-                                                     const int64_t *__restrict__ counts, int sl, int64_t &n) {
-  const uint64_t *base = keys + (int64_t)sl * cap;
-  if (counts) { n = min(counts[sl], cap); return base; }
-  n = min((int64_t)base[0], cap - 1);
-  return base + 1;
-}
-
 // The same passes over vote keys stored in slots (keys from other shards, or a caller's tuples): blockIdx.y = slot, every
 // warp takes pieces of 512 consecutive keys of the slot, two keys per lane and step.  Keys of one query are adjacent
 // (the shards emit them in query order), so a step normally belongs to one query; the few steps that straddle queries
@@ -476,7 +467,7 @@ template <bool DENSE, int PASS>
 __global__ void __launch_bounds__(256)
 keys_pass_kernel(const uint64_t *__restrict__ keys, int64_t cap, const int64_t *__restrict__ counts, int nq,
                  QMeta *__restrict__ meta, Tables T, const uint32_t *__restrict__ qflag, const int32_t *__restrict__ n_flagged,
-                 int topn, const int32_t *__restrict__ out_song, const int32_t *__restrict__ out_nres,
+                 const uint32_t *__restrict__ qsel, int topn, const int32_t *__restrict__ out_song, const int32_t *__restrict__ out_nres,
                  int32_t *__restrict__ out_rows, int32_t *__restrict__ flags) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (PASS == PASS_VOTE && (*flags & 32)) return;
@@ -508,6 +499,7 @@ keys_pass_kernel(const uint64_t *__restrict__ keys, int64_t cap, const int64_t *
         const bool ma = va && qa == qq, mb = vb && qb == qq;
         todo_a &= ~__ballot_sync(0xffffffffu, ma);
         todo_b &= ~__ballot_sync(0xffffffffu, mb);
+        if (qsel && !qsel[qq]) continue;                 // only the queries the partitioned vote left over
         if (PASS == PASS_ROWS) {
           const int64_t obase = (int64_t)qq * topn;
           const int nwin = out_nres[qq];
@@ -548,7 +540,7 @@ keys_pass_kernel(const uint64_t *__restrict__ keys, int64_t cap, const int64_t *
 // keys per query (keys arrive grouped by query: one atomic per run inside the warp)
 __global__ void __launch_bounds__(256)
 count_keys_kernel(const uint64_t *__restrict__ keys, int64_t cap, const int64_t *__restrict__ counts, int nq,
-                  uint32_t *__restrict__ cnt, int32_t *__restrict__ flags) {
+                  const uint32_t *__restrict__ qsel, uint32_t *__restrict__ cnt, int32_t *__restrict__ flags) {
   int64_t n;
   const uint64_t *__restrict__ kk = slot_keys(keys, cap, counts, blockIdx.y, n);
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
@@ -557,6 +549,7 @@ count_keys_kernel(const uint64_t *__restrict__ keys, int64_t cap, const int64_t 
     const uint64_t k = valid ? kk[i] : 0;
     const uint32_t q = (uint32_t)(k >> (kSongBits + kDiffBits)) & ((1u << kQidBits) - 1u);
     if (valid && q >= (uint32_t)nq) { atomicOr(flags, 2); valid = false; }
+    if (valid && qsel && !qsel[q]) valid = false;
     const uint32_t active = __ballot_sync(0xffffffffu, valid);
     if (valid) {
       const uint32_t peers = __match_any_sync(active, q);
@@ -567,14 +560,15 @@ count_keys_kernel(const uint64_t *__restrict__ keys, int64_t cap, const int64_t 
 
 // single block: table layout of the keys path from the per-query key counts (filter, songs), cand zeroed
 __global__ void __launch_bounds__(1024)
-layout_keys_kernel(const uint32_t *__restrict__ cnt, int nq, int64_t dense_span, QMeta *__restrict__ meta) {
+layout_keys_kernel(const uint32_t *__restrict__ cnt, int nq, int64_t dense_span, const uint32_t *__restrict__ qsel,
+                   QMeta *__restrict__ meta) {
   __shared__ int64_t s_f[1024], s_s[1024];
   const int per = (nq + 1023) / 1024;
   const int a = min(nq, (int)threadIdx.x * per), b = min(nq, a + per);
   int64_t sf = 0, ss = 0;
   for (int q = a; q < b; ++q) {
     sf += (int64_t)cnt[q] + 1;
-    ss += dense_span > 0 ? dense_span : 2 * (int64_t)cnt[q] + 32;
+    ss += (qsel && !qsel[q]) ? 0 : dense_span > 0 ? dense_span : 2 * (int64_t)cnt[q] + 32;
   }
   s_f[threadIdx.x] = sf; s_s[threadIdx.x] = ss;
   __syncthreads();
@@ -588,7 +582,7 @@ layout_keys_kernel(const uint32_t *__restrict__ cnt, int nq, int64_t dense_span,
     QMeta m;
     m.bin_base = 0; m.bin_cap = 0; m.cand = 0; m.cand_base = 0; m.cursor = 0; m.pad_ = 0;
     m.filt_base = sf; m.filt_words = cnt[q] + 1u;
-    m.song_base = ss; m.song_cap = dense_span > 0 ? (uint32_t)dense_span : 2u * cnt[q] + 32u;
+    m.song_base = ss; m.song_cap = (qsel && !qsel[q]) ? 0u : dense_span > 0 ? (uint32_t)dense_span : 2u * cnt[q] + 32u;
     meta[q] = m;
     sf += m.filt_words; ss += m.song_cap;
   }
@@ -640,13 +634,14 @@ zero_bins_kernel(unsigned long long *__restrict__ bins, uint32_t *__restrict__ b
 template <bool DENSE, bool ONLY_FLAGGED>
 __global__ void __launch_bounds__(256)
 topn_kernel(const Tables T, const QMeta *__restrict__ meta, int q_lo, int qid_base, int topn, uint32_t *__restrict__ qflag,
-            int32_t *__restrict__ n_flagged, int32_t *__restrict__ out_song, int32_t *__restrict__ out_diff, int32_t *__restrict__ out_count,
+            int32_t *__restrict__ n_flagged, const uint32_t *__restrict__ qsel, int32_t *__restrict__ out_song, int32_t *__restrict__ out_diff, int32_t *__restrict__ out_count,
             int32_t *__restrict__ out_rows, int32_t *__restrict__ out_nres) {
   __shared__ unsigned long long s_key[8];
   __shared__ uint32_t s_slot[8];
   __shared__ unsigned long long s_win;
   const int q = (int)blockIdx.x + q_lo;
   if (ONLY_FLAGGED && (*n_flagged == 0 || !qflag[q])) return;
+  if (qsel && !qsel[q]) return;           // the partitioned vote settled this query
   const QMeta m = meta[q];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long prev = ~0ull;
@@ -817,6 +812,9 @@ struct KeyVote {
   int32_t *o_song = nullptr, *o_diff = nullptr, *o_count = nullptr, *o_rows = nullptr, *o_nres = nullptr;
   cudaStream_t s = nullptr;
   int32_t *d_flags = nullptr;      // device flags of the attempt in flight
+  int stage = 1;                   // 0: the partitioned vote is in flight; 1: the table vote
+  uint32_t *d_small = nullptr;     // per device, allocated once: [0] unsorted, [1] flagged queries, [64..] per-query flags
+  const uint32_t *qsel = nullptr;  // table vote: only these queries (the ones the partitioned vote left over)
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SIA_QUERY_TIMING only
   bool timed = false;
 };
@@ -824,6 +822,7 @@ static KeyVote g_key_vote[64];
 
 // enqueue every launch of one attempt (0: bin slots for a quarter of the keys being candidates; 1: for all of them)
 static int key_vote_enqueue(KeyVote &v, int attempt) {
+  const uint32_t *qsel = v.qsel;
   const int nq = v.n_queries, n_slots = v.n_slots, topn = v.topn;
   const int64_t cap = v.cap;
   const uint64_t *d_keys = v.d_keys;
@@ -865,10 +864,10 @@ static int key_vote_enqueue(KeyVote &v, int attempt) {
   if (!dense) SIA_CUDA(cudaMemsetAsync(Tb.song_key, 0, sizeof(uint32_t) * ns, s));
   // blockIdx.y = slot; the x blocks of a slot stride over its keys (~32 resident blocks per SM in all)
   const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(cap, 512), (kNumSMs * 32) / n_slots + 1)), (unsigned)n_slots);
-  count_keys_kernel<<<grid, 256, 0, s>>>(d_keys, cap, d_counts, nq, cnt, flags);
-  layout_keys_kernel<<<1, 1024, 0, s>>>(cnt, nq, dense ? span : 0, meta);
+  count_keys_kernel<<<grid, 256, 0, s>>>(d_keys, cap, d_counts, nq, qsel, cnt, flags);
+  layout_keys_kernel<<<1, 1024, 0, s>>>(cnt, nq, dense ? span : 0, qsel, meta);
 #define SIA_KEYS_PASS(D, P)                                                                                            \
-  keys_pass_kernel<D, P><<<grid, 256, 0, s>>>(d_keys, cap, d_counts, nq, meta, Tb, qflag, nflag, topn,                 \
+  keys_pass_kernel<D, P><<<grid, 256, 0, s>>>(d_keys, cap, d_counts, nq, meta, Tb, qflag, nflag, qsel, topn,           \
                                               d_out_song, d_out_nres, d_out_rows, flags)
 #define SIA_KSTAGE(k) do { if (v.timed) cudaEventRecord(v.ev[k], s); } while (0)
 #define SIA_KEYS_VOTE(D)                                                                                               \
@@ -882,11 +881,11 @@ static int key_vote_enqueue(KeyVote &v, int attempt) {
     SIA_KSTAGE(3);                                                                                                     \
     cand_vote_kernel<D><<<kNumSMs * 8, 256, 0, s>>>(Tb.cand, meta, 0, nq, Tb, nullptr, flags);                         \
     SIA_KSTAGE(4);                                                                                                     \
-    topn_kernel<D, false><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, nflag, d_out_song, d_out_diff, d_out_count,  \
-                                             d_out_rows, d_out_nres);                                                  \
+    topn_kernel<D, false><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, nflag, qsel, d_out_song, d_out_diff,         \
+                                             d_out_count, d_out_rows, d_out_nres);                                     \
     SIA_KEYS_PASS(D, PASS_SINGLES);                                                                                    \
-    topn_kernel<D, true><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, nflag, d_out_song, d_out_diff, d_out_count,   \
-                                            d_out_rows, d_out_nres);                                                   \
+    topn_kernel<D, true><<<nq, 256, 0, s>>>(Tb, meta, 0, 0, topn, qflag, nflag, qsel, d_out_song, d_out_diff,          \
+                                            d_out_count, d_out_rows, d_out_nres);                                      \
     SIA_KSTAGE(5);                                                                                                     \
     SIA_KEYS_PASS(D, PASS_ROWS);                                                                                       \
     SIA_KSTAGE(6);                                                                                                     \
@@ -899,6 +898,21 @@ static int key_vote_enqueue(KeyVote &v, int attempt) {
   return SIA_OK;
 }
 
+// the partitioned vote of the keys (index_pvote.cu): shared-memory tables, streaming traffic only
+static int key_pvote_enqueue(KeyVote &v) {
+  if (!v.d_small) SIA_CUDA(cudaMalloc(&v.d_small, sizeof(uint32_t) * (64 + kMaxQueriesPerPass)));
+  Arena &ar = g_vote_tables[v.device];
+  int rc = ar.reserve(pvote_bytes((int64_t)v.n_slots * v.cap, v.n_queries, v.n_slots, v.topn) + 65536);
+  if (rc) return rc;
+  SIA_CUDA(cudaMemsetAsync(v.d_small, 0, sizeof(uint32_t) * (64 + (size_t)v.n_queries), v.s));
+  v.timed = getenv("SIA_QUERY_TIMING") != nullptr;
+  if (v.timed) { for (auto &e : v.ev) if (!e) cudaEventCreate(&e); cudaEventRecord(v.ev[0], v.s); }
+  const PvOut po{v.o_song, v.o_diff, v.o_count, v.o_rows, v.o_nres};
+  rc = pvote_key_slots(ar, v.d_keys, v.n_slots, v.cap, v.d_counts, v.n_queries, v.topn, po, v.d_small + 64, v.d_small, v.s);
+  if (v.timed) cudaEventRecord(v.ev[1], v.s);
+  return rc;
+}
+
 // wait for the vote in flight on this device, check its flags, redo it with the larger bin reservation if it asked
 int vote_key_slots_finish(int device) {
   SIA_REQUIRE(device >= 0 && device < 64, SIA_E_INVALID, "device index");
@@ -906,6 +920,23 @@ int vote_key_slots_finish(int device) {
   if (!v.pending) return SIA_OK;
   v.pending = false;
   SIA_CUDA(cudaSetDevice(device));
+  if (v.stage == 0) {
+    uint32_t h2[2] = {0, 0};
+    SIA_CUDA(cudaMemcpyAsync(h2, v.d_small, sizeof h2, cudaMemcpyDeviceToHost, v.s));
+    SIA_CUDA(cudaStreamSynchronize(v.s));
+    if (v.timed) {
+      float t = 0;
+      cudaEventElapsedTime(&t, v.ev[0], v.ev[1]);
+      fprintf(stderr, "[sia] key vote (partitioned): %d queries, %d slots x %lld: %.2f ms, unsorted %u, flagged queries %u\n",
+              v.n_queries, v.n_slots, (long long)v.cap, t, h2[0], h2[1]);
+    }
+    if (!h2[0] && !h2[1]) return SIA_OK;
+    // keys not grouped by query (any order is allowed): everything goes to the table vote; else only the flagged queries
+    v.qsel = h2[0] ? nullptr : v.d_small + 64;
+    v.stage = 1;
+    int rc = key_vote_enqueue(v, 0);
+    if (rc) return rc;
+  }
   for (int attempt = 0; attempt < 2; ++attempt) {
     int32_t h_flags = 0;
     SIA_CUDA(cudaMemcpyAsync(&h_flags, v.d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, v.s));
@@ -947,7 +978,16 @@ int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap,
   v.n_queries = n_queries; v.topn = topn; v.max_song = max_song;
   v.o_song = d_out_song; v.o_diff = d_out_diff; v.o_count = d_out_count; v.o_rows = d_out_rows; v.o_nres = d_out_nres;
   v.s = s;
-  if ((rc = key_vote_enqueue(v, 0))) return rc;
+  v.qsel = nullptr;
+  const char *vote_env = getenv("SIA_VOTE");             // "tables": the table vote for every query (A/B tests)
+  if (topn <= kPvMaxTopn && !(vote_env && !strcmp(vote_env, "tables"))) {
+    v.stage = 0;
+    rc = key_pvote_enqueue(v);
+  } else {
+    v.stage = 1;
+    rc = key_vote_enqueue(v, 0);
+  }
+  if (rc) return rc;
   v.pending = true;
   return defer ? SIA_OK : vote_key_slots_finish(device);
 }
@@ -1026,6 +1066,8 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     tuple_budget = std::max<int64_t>(1 << 20, std::min<int64_t>(tuple_budget, (int64_t)((free_b + ix->arena3.cap) * 0.6 / 40)));
   }
   const bool timing = getenv("SIA_QUERY_TIMING") != nullptr;       // stage times of every pass on stderr
+  const char *vote_env = getenv("SIA_VOTE");                       // "tables": the table vote for every query (A/B tests)
+  const bool use_pvote = topn <= kPvMaxTopn && !(vote_env && !strcmp(vote_env, "tables"));
   ix->last_lookup_ms = ix->last_vote_ms = 0;
   for (auto &e : ix->ev_q) if (!e) SIA_CUDA(cudaEventCreate(&e));
   static cudaEvent_t stage_ev[9] = {nullptr};          // SIA_QUERY_TIMING only: per-kernel times of the vote
@@ -1062,14 +1104,11 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     SIA_CUDA(cudaStreamSynchronize(s));
     const int64_t *h_off_all = h_goff.data(), *h_off_head = h_goff.data() + nq + 1;
     struct Group { int qa, qb; bool dense; int64_t nf, ns; };
-    std::vector<Group> groups;
     std::vector<QMeta> h_meta(nq);
-    for (int qa = 0; qa < nq;) {
-      int qb = qa + 1;
-      while (qb < nq && h_off_all[qb + 1] - h_off_all[qa] <= tuple_budget) ++qb;
+    // queries [qa, qb) as one group of the table vote: sub-table layout of its queries
+    auto make_group = [&](int qa, int qb) {
       Group g{qa, qb, false, 0, 0};
-      const int64_t t_all = h_off_all[qb] - h_off_all[qa], h_all = h_off_head[qb] - h_off_head[qa];
-      SIA_REQUIRE(t_all < (1ll << 31), SIA_E_UNSUPPORTED, "query_batch: more than 2^31 vote tuples in one query");
+      const int64_t h_all = h_off_head[qb] - h_off_head[qa];
       const int64_t ns_hashed = 2 * h_all + 32ll * (qb - qa);
       g.dense = span * (qb - qa) * 8 <= ns_hashed * 12 * 2;
       int64_t fb = 0, sb = 0;
@@ -1082,14 +1121,68 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
         fb += m.filt_words; sb += m.song_cap;
       }
       g.nf = fb; g.ns = sb;
-      groups.push_back(g);
-      qa = qb;
+      return g;
+    };
+    for (int q = 0; q < nq; ++q)
+      SIA_REQUIRE(h_off_all[q + 1] - h_off_all[q] < (1ll << 31), SIA_E_UNSUPPORTED, "query_batch: more than 2^31 vote tuples in one query");
+    std::vector<Group> groups;               // what the table vote has to do
+    unsigned long long h_nb_total = 0;
+    if (use_pvote) {
+      // ---- partitioned vote (index_pvote.cu): shared-memory tables, streaming traffic only --------------------------
+      std::vector<std::pair<int, int>> pg;
+      size_t max_bytes = 0;
+      for (int qa = 0; qa < nq;) {
+        int qb = qa + 1;
+        while (qb < nq && h_off_all[qb + 1] - h_off_all[qa] <= tuple_budget) ++qb;
+        pg.emplace_back(qa, qb);
+        max_bytes = std::max(max_bytes, pvote_bytes(h_off_all[qb] - h_off_all[qa], qb - qa, 1, topn));
+        qa = qb;
+      }
+      if ((rc = ix->arena3.reserve(max_bytes + (size_t)nq * 4 + 65536))) return rc;
+      uint32_t *d_qover = ix->arena3.take<uint32_t>(nq);
+      unsigned long long *d_nbins = ix->arena3.take<unsigned long long>(1);
+      SIA_REQUIRE(d_qover && d_nbins, SIA_E_NOMEM, "index scratch arena too small (vote)");
+      const size_t fixed = ix->arena3.used;
+      SIA_CUDA(cudaMemsetAsync(d_qover, 0, sizeof(uint32_t) * nq, s));
+      SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long), s));
+      const PvOut po{d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres};
+      for (const auto &g : pg) {
+        if (h_off_all[g.second] == h_off_all[g.first]) continue;
+        ix->arena3.used = fixed;
+        if ((rc = pvote_entries(ix->arena3, L, ix->post, d_qs, i0, d_goff, h_off_all, g.first, g.second, (int)q0, topn, po, d_qover,
+                                h_stats ? d_nbins : nullptr, s)))
+          return rc;
+        const int64_t e0 = h_query_starts[q0 + g.first] - i0, ne = h_query_starts[q0 + g.second] - i0 - e0;
+        entries_rows_kernel<<<grid_for(ne * 32), 256, 0, s>>>(L.ent, e0, ne, L.first, L.cnt_head, ix->post, (int)q0, topn,
+                                                             d_out_song, d_out_nres, d_out_rows);
+        SIA_CHECK_LAUNCH();
+      }
+      std::vector<uint32_t> h_qover(nq);
+      SIA_CUDA(cudaMemcpyAsync(h_qover.data(), d_qover, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s));
+      SIA_CUDA(cudaMemcpyAsync(&h_nb_total, d_nbins, sizeof h_nb_total, cudaMemcpyDeviceToHost, s));
+      SIA_CUDA(cudaStreamSynchronize(s));
+      // queries that did not fit their partitions (a bin of thousands of matches, > 2048 partitions): table vote
+      for (int qa = 0; qa < nq;) {
+        if (!h_qover[qa]) { ++qa; continue; }
+        int qb = qa + 1;
+        while (qb < nq && h_qover[qb] && h_off_all[qb + 1] - h_off_all[qa] <= tuple_budget) ++qb;
+        groups.push_back(make_group(qa, qb));
+        qa = qb;
+      }
+      if (timing && !groups.empty()) fprintf(stderr, "[sia]   partitioned vote: %zu group(s) of flagged queries go to the table vote\n", groups.size());
+    } else {
+      for (int qa = 0; qa < nq;) {
+        int qb = qa + 1;
+        while (qb < nq && h_off_all[qb + 1] - h_off_all[qa] <= tuple_budget) ++qb;
+        groups.push_back(make_group(qa, qb));
+        qa = qb;
+      }
     }
     int32_t h_flags = 0;
     unsigned long long h_nb = 0;
     // attempt 0 reserves bin slots for a quarter of the tuples being candidates; if pass 1 counts more in some group
     // (tie-heavy queries) the device flags it and the pass is voted again with room for all of them
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 2 && !groups.empty(); ++attempt) {
       size_t max_bytes = 0;
       for (const Group &g : groups)
         max_bytes = std::max(max_bytes, vote_table_bytes(h_off_all[g.qb] - h_off_all[g.qa], g.qb - g.qa,
@@ -1147,11 +1240,11 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
           SIA_STAGE(8);                                                                                                 \
           cand_vote_kernel<D><<<kNumSMs * 8, 256, 0, s>>>(Tb.cand, d_meta, g.qa, g.qb, Tb, d_nbins, d_flags);           \
           SIA_STAGE(3);                                                                                                 \
-          topn_kernel<D, false><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_nflag, d_out_song,         \
+          topn_kernel<D, false><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_nflag, nullptr, d_out_song, \
                                                    d_out_diff, d_out_count, d_out_rows, d_out_nres);                    \
           SIA_STAGE(4);                                                                                                 \
           SIA_ENT_PASS(D, PASS_SINGLES);                                                                                \
-          topn_kernel<D, true><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_nflag, d_out_song,          \
+          topn_kernel<D, true><<<gq, 256, 0, s>>>(Tb, d_meta, g.qa, (int)q0, topn, qflag, d_nflag, nullptr, d_out_song,  \
                                                   d_out_diff, d_out_count, d_out_rows, d_out_nres);                     \
           SIA_STAGE(5);                                                                                                 \
         } while (0)
@@ -1175,12 +1268,14 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
       }
       SIA_CUDA(cudaMemcpyAsync(&h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, s));
       SIA_CUDA(cudaMemcpyAsync(&h_nb, d_nbins, sizeof h_nb, cudaMemcpyDeviceToHost, s));
-      SIA_CUDA(cudaEventRecord(ix->ev_q[2], s));
       SIA_CUDA(cudaStreamSynchronize(s));      // the lookup scratch and the tables are reused by the next pass / call
       SIA_REQUIRE(!(h_flags & 8), SIA_E_CUDA, "query: vote table overflow (internal error)");
       if (!(h_flags & 32)) break;
       SIA_REQUIRE(attempt == 0, SIA_E_CUDA, "query: bin table overflow (internal error)");
     }
+    h_nb += h_nb_total;
+    SIA_CUDA(cudaEventRecord(ix->ev_q[2], s));
+    SIA_CUDA(cudaStreamSynchronize(s));
     {
       float t_lookup = 0, t_vote = 0;
       cudaEventElapsedTime(&t_lookup, ix->ev_q[0], ix->ev_q[1]); cudaEventElapsedTime(&t_vote, ix->ev_q[1], ix->ev_q[2]);

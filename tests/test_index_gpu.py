@@ -572,8 +572,12 @@ def test_vote_large_table_vs_oracle(gpudb, monkeypatch, id_stride, off_range):
             best = O.best_offsets(m, topn)
             assert [tuple(b) for b in best] == [(int(want[0][q, r]), int(want[1][q, r]), int(want[2][q, r])) for r in range(want[4][q])]
             assert [dd[b[0]] for b in best] == [int(want[3][q, r]) for r in range(want[4][q])]
-        names = ("SIA_VOTE_GROUP_TUPLES",)
-        for setting in ((None,), ("1000",), ("200000",), (str(1 << 40),)):
+        # default = the partitioned vote (shared-memory tables; query 70's bin of 33000 matches does not fit a region and
+        # goes to the table vote); SIA_PVOTE_CAP: small regions, so that most queries are split or handed over;
+        # SIA_VOTE=tables: the table vote for every query
+        names = ("SIA_VOTE_GROUP_TUPLES", "SIA_PVOTE_CAP", "SIA_VOTE")
+        for setting in ((None, None, None), ("1000", None, None), ("200000", None, None), (str(1 << 40), None, None),
+                        (None, "64", None), ("200000", "1024", None), (None, None, "tables"), ("200000", None, "tables")):
             for name, val in zip(names, setting):
                 if val is None:
                     monkeypatch.delenv(name, raising=False)
@@ -588,7 +592,14 @@ def test_vote_large_table_vs_oracle(gpudb, monkeypatch, id_stride, off_range):
             monkeypatch.delenv(name, raising=False)
         # the same tuples as vote keys in random order (the exchanged-keys vote of hash-prefix sharding); query ids < 2^14
         key = (head.astype(np.int64) << 63) | (t_q << 49) | (t_song << 25) | (t_diff + (1 << 24))
-        tk = torch.from_numpy(key[rng.permutation(len(key))]).to(dev)
-        got = [t.cpu().numpy() for t in vote_tuples(0, tk, nq, topn, int(song.max()))]
-        for a, b, name in zip(got, want, ("song", "diff", "count", "rows", "nres")):
-            assert np.array_equal(a, b), ("vote_tuples", name, topn)
+        perm = key[rng.permutation(len(key))]
+        by_query = perm[np.argsort((perm >> 49) & 0x3fff, kind="stable")]      # grouped by query: the partitioned vote
+        for label, arr, cap in (("any order", perm, None), ("by query", by_query, None), ("by query, small regions", by_query, "512")):
+            if cap is None:
+                monkeypatch.delenv("SIA_PVOTE_CAP", raising=False)
+            else:
+                monkeypatch.setenv("SIA_PVOTE_CAP", cap)
+            got = [t.cpu().numpy() for t in vote_tuples(0, torch.from_numpy(arr).to(dev), nq, topn, int(song.max()))]
+            for a, b, name in zip(got, want, ("song", "diff", "count", "rows", "nres")):
+                assert np.array_equal(a, b), ("vote_tuples", label, name, topn, np.argwhere(a != b)[:5])
+        monkeypatch.delenv("SIA_PVOTE_CAP", raising=False)
