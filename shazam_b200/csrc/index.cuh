@@ -168,11 +168,14 @@ constexpr int kPvMaxTopn = 32;
 struct PvOut { int32_t *song, *diff, *count, *rows, *nres; };
 // scratch bytes for `tuples` vote tuples of nq queries arriving from n_src sources (worst case)
 size_t pvote_bytes(int64_t tuples, int64_t nq, int n_src, int topn);
+// per entry of a lookup what the scatter walk reads (once per pass): d_info[L.n] (16 B each), d_qh[L.n]
+int pvote_entry_info(const Lookup &L, longlong2 *d_info, uint32_t *d_qh, cudaStream_t s);
 // entries of the queries [qa, qb) of a lookup.  d_qs: entry offsets of the pass's queries (absolute, i0 = first);
 // d_goff / h_goff: tuple offsets (off_all) at the queries' first entries, [nq_pass + 1].  Rows are NOT counted here.
-int pvote_entries(Arena &ar, const Lookup &L, const uint64_t *post, const int64_t *d_qs, int64_t i0, const int64_t *d_goff,
-                  const int64_t *h_goff, int qa, int qb, int qid_base, int topn, const PvOut &out, uint32_t *d_qover,
-                  unsigned long long *d_nbins, cudaStream_t s);
+int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uint32_t *d_qh, const uint64_t *post, const int64_t *d_qs,
+                  int64_t i0, const int64_t *d_goff, const int64_t *h_goff, int qa, int qb, int qid_base, int topn, const PvOut &out,
+                  uint32_t *d_qover, unsigned long long *d_nbins, cudaStream_t s,
+                  double *stage_ms /* NULL, or += {layout, scatter, count + merge} */);
 // slotted vote keys, each slot sorted by query id (else *d_unsorted is set and nothing is written); rows counted.
 // d_over_count: incremented once per flagged query.
 int pvote_key_slots(Arena &ar, const uint64_t *d_keys, int n_slots, int64_t cap, const int64_t *d_counts, int nq, int topn,

@@ -66,7 +66,23 @@ __device__ __forceinline__ uint32_t mix32(uint32_t k) {
   k ^= k >> 16; k *= 0x85ebca6bu; k ^= k >> 13; k *= 0xc2b2ae35u; k ^= k >> 16;
   return k;
 }
-__device__ __forceinline__ uint32_t pv_part(uint32_t song, uint32_t np) { return (uint32_t)(((uint64_t)mix32(song) * np) >> 32); }
+// partition of a song: multiplicative hash (song ids are dense integers: the top bits of id * phi are equidistributed)
+__device__ __forceinline__ uint32_t pv_part(uint32_t song, uint32_t np) { return (((song * 0x9e3779b1u) >> 16) * np) >> 16; }
+
+// largest i in [lo, hi) with a[i] <= x, given a[lo] <= x and a non-decreasing; the 32 lanes of a warp call it with the
+// same arguments and probe 32 positions per round (3 dependent loads for 2 000 elements instead of 11)
+template <typename T, typename X>
+__device__ __forceinline__ int64_t warp_search(const T *__restrict__ a, int64_t lo, int64_t hi, X x, int lane) {
+  while (hi - lo > 1) {
+    const int64_t step = (hi - lo + 31) >> 5;
+    const int64_t pos = lo + (int64_t)(lane + 1) * step;
+    const bool le = pos < hi && (X)a[pos] <= x;
+    const int c = __popc(__ballot_sync(0xffffffffu, le));
+    lo += (int64_t)c * step;
+    hi = min(hi, lo + step);
+  }
+  return lo;
+}
 
 // ---- layout ---------------------------------------------------------------------------------------------------
 // segments: (query, source) -> a range of tuples / keys.  Entries variant: one source, the query's slice of off_all.
@@ -75,6 +91,17 @@ __global__ void pv_segs_entries_kernel(const int64_t *__restrict__ goff, int qa,
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
     seg_lo[q] = goff[qa + q];
     seg_cnt[q] = (uint32_t)(goff[qa + q + 1] - goff[qa + q]);
+  }
+}
+
+// per entry what the scatter walk needs, in two loads: {end of the entry's tuples, first posting - first tuple} and
+// query offset << 1 | head
+__global__ void __launch_bounds__(256)
+pv_entry_info_kernel(const ulonglong2 *__restrict__ ent, const int64_t *__restrict__ first, const int64_t *__restrict__ off,
+                     const uint32_t *__restrict__ cnt_head, int64_t n, longlong2 *__restrict__ info, uint32_t *__restrict__ qh) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    info[e] = make_longlong2(off[e + 1], first[e] - off[e]);
+    qh[e] = ((uint32_t)(ent[e].x & kM24) << 1) | (cnt_head[e] != 0 ? 1u : 0u);
   }
 }
 
@@ -155,19 +182,34 @@ pv_layout_kernel(const uint32_t *__restrict__ seg_cnt, int nq, int G, PvTune tun
   }
 }
 
+// scatter block -> segment and region -> query, so that the big kernels start with one load instead of a search
+__global__ void __launch_bounds__(256)
+pv_maps_kernel(const uint32_t *__restrict__ seg_blk0, int n_seg, const uint32_t *__restrict__ q_ridx0, int nq,
+               const uint32_t *__restrict__ tot, uint32_t *__restrict__ blk_seg, uint32_t *__restrict__ reg_q) {
+  const uint32_t n_reg = tot[0], n_blk = tot[1];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_reg + n_blk; i += gridDim.x * blockDim.x) {
+    if (i < n_blk) blk_seg[i] = (uint32_t)find_segment(seg_blk0, n_seg, i);
+    else reg_q[i - n_blk] = (uint32_t)find_segment(q_ridx0, nq, i - n_blk);
+  }
+}
+
 // ---- scatter --------------------------------------------------------------------------------------------------
 struct ScatterArgs {
-  const uint32_t *seg_blk0; const int64_t *seg_lo; const uint32_t *seg_cnt; int n_seg, G;
+  const uint32_t *seg_blk0, *blk_seg; const int64_t *seg_lo; const uint32_t *seg_cnt; int G;
   const PvQuery *pq; const uint32_t *tot;
   uint64_t *regions; uint32_t *fill; uint32_t *qover; int q_lo;
   // source 0: posting runs of the query's entries
-  const ulonglong2 *ent; const int64_t *first; const int64_t *off; const uint32_t *cnt_head; const uint64_t *post;
+  const int64_t *off; const longlong2 *info; const uint32_t *qh; const uint64_t *post;
   const int64_t *q_ent; int64_t i0;
   // source 1: vote keys in slots
   const uint64_t *keys; int64_t key_cap; const int64_t *counts; uint32_t *unsorted;
 };
 
 constexpr size_t kScatterSmem = (size_t)kBlk * 8 + (size_t)kBlk * 2 + (size_t)(2 * kMaxParts + 1) * 4;
+
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
+}
 
 template <int SRC>
 __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const ScatterArgs a) {
@@ -180,7 +222,7 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
   const uint32_t b = blockIdx.x;
   if (b >= a.tot[1]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int s = find_segment(a.seg_blk0, a.n_seg, b);
+  const int s = (int)a.blk_seg[b];
   const int ql = s / a.G, g = s - ql * a.G;
   const PvQuery m = a.pq[ql];
   const int64_t lo = a.seg_lo[s];
@@ -188,86 +230,67 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
   const int n = (int)min((int64_t)kBlk, lo + (int64_t)a.seg_cnt[s] - j0);
   const uint32_t np = m.np;
   for (uint32_t p = tid; p <= np; p += kScThreads) hist[p] = 0;
-  __syncthreads();
 
-  uint32_t pr[kTpt];                       // partition << 13 | rank inside the partition (this block)
+  uint32_t pr[kTpt];                       // first the entry's (query offset, head), then partition << 13 | rank
   const int iw = warp * (kBlk / (kScThreads / 32));
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+  // the raw postings / keys of the block go straight to the staging buffer (cp.async: all 16 loads of a thread in flight)
   if (SRC == 0) {
-    int64_t e = 0, onext = 0, adj = 0;
-    uint32_t qh = 0;
-    bool fresh = true;
     if (iw < n) {
-      // entry of the warp's first tuple: largest e in the query's entries with off[e] <= j0 + iw
-      const int64_t jw = j0 + iw;
-      e = a.q_ent[a.q_lo + ql] - a.i0;
-      int64_t hi = a.q_ent[a.q_lo + ql + 1] - a.i0;
-      while (hi - e > 1) { const int64_t mid = e + ((hi - e) >> 1); if (a.off[mid] <= jw) e = mid; else hi = mid; }
-      onext = a.off[e + 1];
-    }
+      // entry of the warp's first tuple, then every lane walks on from there by itself
+      int64_t e = warp_search(a.off, a.q_ent[a.q_lo + ql] - a.i0, a.q_ent[a.q_lo + ql + 1] - a.i0, j0 + iw, lane);
+      longlong2 inf = a.info[e];
+      uint32_t qh = a.qh[e];
 #pragma unroll
-    for (int k0 = 0; k0 < kTpt; k0 += 4) {
-      uint64_t r[4];
-      uint32_t q4[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = iw + (k0 + u) * 32 + lane;
-        r[u] = 0; q4[u] = 0;
+      for (int k = 0; k < kTpt; ++k) {
+        const int i = iw + k * 32 + lane;
+        pr[k] = 0;
         if (i < n) {
           const int64_t j = j0 + i;
-          while (onext <= j) { ++e; onext = a.off[e + 1]; fresh = true; }
-          if (fresh) {
-            adj = a.first[e] - a.off[e];
-            qh = ((uint32_t)(a.ent[e].x & kM24) << 1) | (a.cnt_head[e] != 0 ? 1u : 0u);
-            fresh = false;
+          if (inf.x <= j) {
+            do { ++e; inf = a.info[e]; } while (inf.x <= j);
+            qh = a.qh[e];
           }
-          r[u] = __ldcs(a.post + adj + j);
-          q4[u] = qh;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = iw + (k0 + u) * 32 + lane;
-        pr[k0 + u] = 0;
-        if (i < n) {
-          const uint32_t song = (uint32_t)(r[u] >> 24) & 0xffffffu;
-          const uint32_t dbits = ((uint32_t)(r[u] & kM24) - (q4[u] >> 1) + SIA_DIFF_BIAS) & (uint32_t)kDiffMask;
-          const uint32_t p = pv_part(song, np);
-          const uint32_t rk = atomicAdd(&hist[p], 1u);
-          stage[i] = ((uint64_t)song << (kDiffBits + 1)) | ((uint64_t)dbits << 1) | (q4[u] & 1u);
-          pr[k0 + u] = (p << 13) | rk;
+          cp_async8(stage_s + (uint32_t)i * 8u, a.post + inf.y + j);
+          pr[k] = qh;
         }
       }
     }
   } else {
     int64_t nk;
     const uint64_t *__restrict__ kk = slot_keys(a.keys, a.key_cap, a.counts, g, nk);
-    const uint32_t qmask = (1u << kQidBits) - 1u;
-    bool bad = false;
 #pragma unroll
-    for (int k0 = 0; k0 < kTpt; k0 += 4) {
-      uint64_t r[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = iw + (k0 + u) * 32 + lane;
-        r[u] = i < n ? __ldcs(kk + j0 + i) : 0ull;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = iw + (k0 + u) * 32 + lane;
-        pr[k0 + u] = 0;
-        if (i < n) {
-          const uint64_t key = r[u];
-          bad = bad || ((uint32_t)(key >> (kSongBits + kDiffBits)) & qmask) != (uint32_t)ql;
-          const uint32_t song = (uint32_t)(key >> kDiffBits) & 0xffffffu;
-          const uint32_t p = pv_part(song, np);
-          const uint32_t rk = atomicAdd(&hist[p], 1u);
-          stage[i] = ((uint64_t)song << (kDiffBits + 1)) | ((key & kDiffMask) << 1) | (key >> 63);
-          pr[k0 + u] = (p << 13) | rk;
-        }
-      }
+    for (int k = 0; k < kTpt; ++k) {
+      const int i = iw + k * 32 + lane;
+      if (i < n) cp_async8(stage_s + (uint32_t)i * 8u, kk + j0 + i);
     }
-    if (bad) atomicOr(a.unsorted, 1u);
   }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();                         // the histogram is zero (every thread reads only its own staged words)
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < kTpt; ++k) {
+    const int i = iw + k * 32 + lane;
+    if (i < n) {
+      const uint64_t r = stage[i];
+      uint32_t song;
+      uint64_t tup;
+      if (SRC == 0) {
+        song = (uint32_t)(r >> 24) & 0xffffffu;
+        const uint32_t dbits = ((uint32_t)(r & kM24) - (pr[k] >> 1) + SIA_DIFF_BIAS) & (uint32_t)kDiffMask;
+        tup = ((uint64_t)song << (kDiffBits + 1)) | ((uint64_t)dbits << 1) | (pr[k] & 1u);
+      } else {
+        bad = bad || ((uint32_t)(r >> (kSongBits + kDiffBits)) & ((1u << kQidBits) - 1u)) != (uint32_t)ql;
+        song = (uint32_t)(r >> kDiffBits) & 0xffffffu;
+        tup = ((uint64_t)song << (kDiffBits + 1)) | ((r & kDiffMask) << 1) | (r >> 63);
+      }
+      const uint32_t p = pv_part(song, np);
+      const uint32_t rk = atomicAdd(&hist[p], 1u);
+      stage[i] = tup;
+      pr[k] = (p << 13) | rk;
+    }
+  }
+  if (SRC == 1 && bad) atomicOr(a.unsorted, 1u);
   __syncthreads();
 
   // exclusive scan of the histogram (4 partitions per thread), room reserved in the regions
@@ -329,65 +352,65 @@ __device__ __forceinline__ uint64_t pv_rank(uint64_t slot) {          // count d
   return ((slot & 0x7fffull) << 49) | ((kM24 - (key >> kDiffBits)) << kDiffBits) | (kDiffMask - (key & kDiffMask));
 }
 
-__device__ __forceinline__ void pv_insert(uint64_t *tab, uint32_t mask, uint64_t key, uint16_t *dup, uint32_t *ndup,
-                                          uint32_t &fresh) {
-  uint32_t h = mix32((uint32_t)key * 0x9e3779b1u + (uint32_t)(key >> 32) * 0x85ebca6bu) & mask;
-  const uint64_t claim = (key << 15) | 1ull;
-  for (;;) {
-    uint64_t cur = *reinterpret_cast<volatile uint64_t *>(tab + h);
-    if (cur == 0ull) {
-      cur = atomicCAS(reinterpret_cast<unsigned long long *>(tab + h), 0ull, (unsigned long long)claim);
-      if (cur == 0ull) { ++fresh; return; }
-    }
-    if ((cur >> 15) == key) {
-      const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(tab + h), 1u);      // low word: key bits | count
-      if ((old & 0x7fffu) == 1u) { const uint32_t d = atomicAdd(ndup, 1u); if (d < (uint32_t)kDup) dup[d] = (uint16_t)h; }
-      return;
-    }
-    h = (h + 1) & mask;
-  }
-}
-
 template <bool ROWS>
 __global__ void __launch_bounds__(kCntThreads, 3)
 pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict__ fill, const PvQuery *__restrict__ pq,
-                const uint32_t *__restrict__ q_ridx0, int nq, const uint32_t *__restrict__ tot, int q_lo,
+                const uint32_t *__restrict__ reg_q, const uint32_t *__restrict__ tot, int q_lo,
                 const uint32_t *__restrict__ qover, int topn, uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_rows,
                 unsigned long long *__restrict__ n_bins) {
   extern __shared__ __align__(16) unsigned char pv_smem[];
   uint64_t *tab = reinterpret_cast<uint64_t *>(pv_smem);
   __shared__ uint16_t s_dup[kDup];
   __shared__ uint32_t s_ndup;
-  __shared__ uint64_t s_red[kCntThreads / 32];
+  __shared__ int s_nres;
   __shared__ uint64_t s_win[kPvMaxTopn];
   __shared__ uint32_t s_rows[kPvMaxTopn];
   const uint32_t r = blockIdx.x;
   if (r >= tot[0]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ql = find_segment(q_ridx0, nq, r);
+  const uint32_t n = fill[r];
+  const int ql = (int)reg_q[r];
   const PvQuery m = pq[ql];
   const uint32_t p = r - m.ridx0;
   uint64_t *__restrict__ out = cand + (int64_t)r * topn;
-  const uint32_t n = fill[r];
   if (n == 0 || qover[q_lo + ql]) {
     if (tid < topn) { out[tid] = 0ull; if (ROWS) cand_rows[(int64_t)r * topn + tid] = 0u; }
     return;
   }
-  uint32_t S = 256;
-  while (S < 2 * n && S < (uint32_t)kSlots) S <<= 1;
-  const uint32_t mask = S - 1;
+  int bits = 8;
+  while ((1u << bits) < 2 * n && bits < 13) ++bits;
+  const uint32_t S = 1u << bits, mask = S - 1;
   for (uint32_t i = tid; i < S / 2; i += kCntThreads) reinterpret_cast<ulonglong2 *>(tab)[i] = make_ulonglong2(0ull, 0ull);
   if (tid == 0) s_ndup = 0;
-  if (tid < kPvMaxTopn) s_rows[tid] = 0;
-  __syncthreads();
+  if (ROWS && tid < kPvMaxTopn) s_rows[tid] = 0;
   const uint64_t *__restrict__ reg = regions + m.reg_off + (int64_t)p * m.cap;
-  uint32_t fresh = 0;
-  for (uint32_t i0 = tid; i0 < n; i0 += 4 * kCntThreads) {
-    uint64_t t[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * kCntThreads; t[u] = i < n ? __ldcs(reg + i) : 0ull; }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) if (i0 + u * kCntThreads < n) pv_insert(tab, mask, t[u] >> 1, s_dup, &s_ndup, fresh);
+  uint32_t i = tid;
+  uint64_t nxt = i < n ? __ldcs(reg + i) : 0ull;       // the thread's next tuple, in flight while the current one probes
+  __syncthreads();
+  // Every lane inserts its tuples one probe per iteration and takes its next tuple as soon as the current one is
+  // settled, so the warp stays converged whatever the probe lengths are.  A probe is ONE compare-and-swap: it claims an
+  // empty slot (count 1) or returns the occupant.
+  uint32_t fresh = 0, h = 0;
+  uint64_t key = 0;
+  bool have = false;
+  for (;;) {
+    if (!have) {
+      if (i >= n) break;
+      key = nxt >> 1;
+      h = mix32((uint32_t)(key >> kDiffBits) * 0x9e3779b1u + (uint32_t)key) & mask;
+      have = true;
+      i += kCntThreads;
+      nxt = i < n ? __ldcs(reg + i) : 0ull;
+    }
+    const uint64_t cur = atomicCAS(reinterpret_cast<unsigned long long *>(tab + h), 0ull, (unsigned long long)((key << 15) | 1ull));
+    if (cur == 0ull) { ++fresh; have = false; }
+    else if ((cur >> 15) == key) {
+      const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(tab + h), 1u);      // low word: key bits | count
+      if ((old & 0x7fffu) == 1u) { const uint32_t d = atomicAdd(&s_ndup, 1u); if (d < (uint32_t)kDup) s_dup[d] = (uint16_t)h; }
+      have = false;
+    } else {
+      h = (h + 1) & mask;
+    }
   }
   if (n_bins) {
 #pragma unroll
@@ -395,51 +418,56 @@ pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict
     if (lane == 0 && fresh) atomicAdd(n_bins, (unsigned long long)fresh);
   }
   __syncthreads();
-  const uint32_t ndup_raw = s_ndup;
-  const uint32_t nd = min(ndup_raw, (uint32_t)kDup);
-  bool full = ndup_raw > (uint32_t)kDup;
-  int nres = 0;
-  while (nres < topn) {
-    uint64_t best = 0;
-    const uint32_t lim = full ? S : nd;
-    for (uint32_t i = tid; i < lim; i += kCntThreads) {
-      uint64_t c = pv_rank(tab[full ? i : (uint32_t)s_dup[i]]);
-      if (c > best) {
-        const uint64_t song = (c >> kDiffBits) & kM24;
-        for (int w = 0; w < nres; ++w) if (((s_win[w] >> kDiffBits) & kM24) == song) c = 0;
-        if (c > best) best = c;
+  if (warp == 0) {
+    // top-n songs of the region, by one warp: from the bins that reached count 2 (every song with a repeated bin has
+    // its best bin among them); if fewer than topn songs have one, the bins of count 1 decide and the table is scanned
+    const uint32_t ndup_raw = s_ndup;
+    const uint32_t nd = min(ndup_raw, (uint32_t)kDup);
+    bool full = ndup_raw > (uint32_t)kDup;
+    int nres = 0;
+    while (nres < topn) {
+      uint64_t best = 0;
+      const uint32_t lim = full ? S : nd;
+      for (uint32_t k = lane; k < lim; k += 32) {
+        uint64_t c = pv_rank(tab[full ? k : (uint32_t)s_dup[k]]);
+        if (c > best) {
+          const uint64_t song = (c >> kDiffBits) & kM24;
+          for (int w = 0; w < nres; ++w) if (((s_win[w] >> kDiffBits) & kM24) == song) c = 0;
+          if (c > best) best = c;
+        }
       }
-    }
 #pragma unroll
-    for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d); if (o > best) best = o; }
-    if (lane == 0) s_red[warp] = best;
-    __syncthreads();
-    best = 0;
-#pragma unroll
-    for (int w = 0; w < kCntThreads / 32; ++w) { const uint64_t o = s_red[w]; if (o > best) best = o; }
-    if (best == 0ull) {
-      if (full) break;
-      full = true;                          // fewer than topn songs with a repeated bin: the bins of count 1 decide
-      __syncthreads();
-      continue;
+      for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d); if (o > best) best = o; }
+      if (best == 0ull) {
+        if (full) break;
+        full = true;
+        continue;
+      }
+      if (lane == 0) s_win[nres] = best;
+      ++nres;
+      __syncwarp();
     }
-    if (tid == 0) s_win[nres] = best;
-    ++nres;
-    __syncthreads();
+    if (!ROWS) {
+      if (lane < topn) out[lane] = lane < nres ? s_win[lane] : 0ull;
+    } else if (lane == 0) {
+      s_nres = nres;
+    }
   }
-  if (ROWS && nres > 0) {                   // dedup_hashes of the region's winners: head tuples of their songs
-    for (uint32_t i = tid; i < n; i += kCntThreads) {
-      const uint64_t t = reg[i];
+  if (ROWS) {                               // dedup_hashes of the region's winners: head tuples of their songs
+    __syncthreads();
+    const int nres = s_nres;
+    for (uint32_t k = tid; k < n; k += kCntThreads) {
+      const uint64_t t = reg[k];
       if (t & 1ull) {
         const uint64_t isong = kM24 - (t >> (kDiffBits + 1));
         for (int w = 0; w < nres; ++w) if (((s_win[w] >> kDiffBits) & kM24) == isong) atomicAdd(&s_rows[w], 1u);
       }
     }
     __syncthreads();
-  }
-  if (tid < topn) {
-    out[tid] = tid < nres ? s_win[tid] : 0ull;
-    if (ROWS) cand_rows[(int64_t)r * topn + tid] = tid < nres ? s_rows[tid] : 0u;
+    if (tid < topn) {
+      out[tid] = tid < nres ? s_win[tid] : 0ull;
+      cand_rows[(int64_t)r * topn + tid] = tid < nres ? s_rows[tid] : 0u;
+    }
   }
 }
 
@@ -483,16 +511,16 @@ pv_merge_kernel(const uint64_t *__restrict__ cand, const uint32_t *__restrict__ 
 }
 
 struct PvScratch {
-  int64_t *seg_lo; uint32_t *seg_cnt, *seg_blk0, *q_ridx0, *tot, *fill, *cand_rows;
+  int64_t *seg_lo; uint32_t *seg_cnt, *seg_blk0, *q_ridx0, *tot, *fill, *cand_rows, *blk_seg, *reg_q;
   PvQuery *pq; uint64_t *regions, *cand;
 };
 
-size_t pv_scratch_bytes(int64_t n_seg, int64_t nq, int64_t regions, int64_t region_tuples, int topn) {
-  return (size_t)n_seg * 16 + (size_t)(n_seg + nq + 2) * 4 + (size_t)nq * sizeof(PvQuery) + (size_t)regions * (4 + 12 * (size_t)topn) +
-         (size_t)region_tuples * 8 + 16 * 256 + 64;
+size_t pv_scratch_bytes(int64_t n_seg, int64_t nq, int64_t regions, int64_t region_tuples, int64_t blocks, int topn) {
+  return (size_t)n_seg * 16 + (size_t)(n_seg + nq + 2) * 4 + (size_t)nq * sizeof(PvQuery) + (size_t)regions * (8 + 12 * (size_t)topn) +
+         (size_t)blocks * 4 + (size_t)region_tuples * 8 + 16 * 256 + 64;
 }
 
-bool pv_take(Arena &ar, PvScratch &S, int64_t n_seg, int64_t nq, int64_t regions, int64_t region_tuples, int topn) {
+bool pv_take(Arena &ar, PvScratch &S, int64_t n_seg, int64_t nq, int64_t regions, int64_t region_tuples, int64_t blocks, int topn) {
   S.seg_lo = ar.take<int64_t>(n_seg);
   S.seg_cnt = ar.take<uint32_t>(n_seg);
   S.seg_blk0 = ar.take<uint32_t>(n_seg + 1);
@@ -500,10 +528,13 @@ bool pv_take(Arena &ar, PvScratch &S, int64_t n_seg, int64_t nq, int64_t regions
   S.tot = ar.take<uint32_t>(4);
   S.pq = ar.take<PvQuery>(nq);
   S.fill = ar.take<uint32_t>(regions);
+  S.reg_q = ar.take<uint32_t>(regions);
+  S.blk_seg = ar.take<uint32_t>(blocks);
   S.cand = ar.take<uint64_t>(regions * topn);
   S.cand_rows = ar.take<uint32_t>(regions * topn);
   S.regions = ar.take<uint64_t>(region_tuples);
-  return S.seg_lo && S.seg_cnt && S.seg_blk0 && S.q_ridx0 && S.tot && S.pq && S.fill && S.cand && S.cand_rows && S.regions;
+  return S.seg_lo && S.seg_cnt && S.seg_blk0 && S.q_ridx0 && S.tot && S.pq && S.fill && S.reg_q && S.blk_seg && S.cand && S.cand_rows &&
+         S.regions;
 }
 
 int pv_attrs() {
@@ -519,26 +550,34 @@ int pv_attrs() {
   return SIA_OK;
 }
 
+// worst case over all splits of `tuples` into nq queries: a query that fits one region takes its own size (rounded to 2),
+// a larger one ceil(t / avg) <= t / avg + 1 regions of cap slots — and there are at most min(nq, tuples / cap) of those
+void pv_bounds(int64_t tuples, int64_t nq, int n_src, const PvTune &t, int64_t &regions, int64_t &region_tuples, int64_t &blocks) {
+  regions = tuples / t.avg + nq + 1;
+  region_tuples = (tuples / t.avg + 1) * (int64_t)t.cap + std::min<int64_t>(nq * (int64_t)t.cap, tuples) + 2 * nq + t.cap;
+  blocks = ceil_div(tuples, kBlk) + nq * n_src;
+}
+
 }  // namespace
 
 namespace sia {
 
-// worst case over all splits of `tuples` into nq queries: a query that fits one region takes its own size (rounded to 2),
-// a larger one ceil(t / avg) <= t / avg + 1 regions of cap slots — and there are at most min(nq, tuples / cap) of those
-static void pv_bounds(int64_t tuples, int64_t nq, const PvTune &t, int64_t &regions, int64_t &region_tuples) {
-  regions = tuples / t.avg + nq + 1;
-  region_tuples = (tuples / t.avg + 1) * (int64_t)t.cap + std::min<int64_t>(nq * (int64_t)t.cap, tuples) + 2 * nq + t.cap;
-}
-
 size_t pvote_bytes(int64_t tuples, int64_t nq, int n_src, int topn) {
-  int64_t regions, region_tuples;
-  pv_bounds(tuples, nq, pv_tune(), regions, region_tuples);
-  return pv_scratch_bytes(nq * n_src, nq, regions, region_tuples, topn);
+  int64_t regions, region_tuples, blocks;
+  pv_bounds(tuples, nq, n_src, pv_tune(), regions, region_tuples, blocks);
+  return pv_scratch_bytes(nq * n_src, nq, regions, region_tuples, blocks, topn);
 }
 
-int pvote_entries(Arena &ar, const Lookup &L, const uint64_t *post, const int64_t *d_qs, int64_t i0, const int64_t *d_goff,
-                  const int64_t *h_goff, int qa, int qb, int qid_base, int topn, const PvOut &out, uint32_t *d_qover,
-                  unsigned long long *d_nbins, cudaStream_t s) {
+int pvote_entry_info(const Lookup &L, longlong2 *d_info, uint32_t *d_qh, cudaStream_t s) {
+  if (L.n == 0) return SIA_OK;
+  pv_entry_info_kernel<<<grid_for(L.n), 256, 0, s>>>(L.ent, L.first, L.off_all, L.cnt_head, L.n, d_info, d_qh);
+  SIA_CHECK_LAUNCH();
+  return SIA_OK;
+}
+
+int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uint32_t *d_qh, const uint64_t *post, const int64_t *d_qs,
+                  int64_t i0, const int64_t *d_goff, const int64_t *h_goff, int qa, int qb, int qid_base, int topn, const PvOut &out,
+                  uint32_t *d_qover, unsigned long long *d_nbins, cudaStream_t s, double *stage_ms) {
   const int nq = qb - qa;
   if (nq <= 0) return SIA_OK;
   int rc = pv_attrs();
@@ -556,20 +595,31 @@ int pvote_entries(Arena &ar, const Lookup &L, const uint64_t *post, const int64_
   if (blocks == 0) return SIA_OK;
   SIA_REQUIRE(blocks < (1ll << 31) && regions < (1ll << 31), SIA_E_UNSUPPORTED, "vote: group too large");
   PvScratch S;
-  SIA_REQUIRE(pv_take(ar, S, nq, nq, regions, region_tuples, topn), SIA_E_NOMEM, "index scratch arena too small (partitioned vote)");
+  SIA_REQUIRE(pv_take(ar, S, nq, nq, regions, region_tuples, blocks, topn), SIA_E_NOMEM,
+              "index scratch arena too small (partitioned vote)");
+  static cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};     // SIA_QUERY_TIMING only
+  if (stage_ms) { if (!ev[0]) for (auto &e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
   SIA_CUDA(cudaMemsetAsync(S.fill, 0, sizeof(uint32_t) * regions, s));
   pv_segs_entries_kernel<<<grid_for(nq), 256, 0, s>>>(d_goff, qa, nq, S.seg_lo, S.seg_cnt);
   pv_layout_kernel<<<1, 1024, 0, s>>>(S.seg_cnt, nq, 1, tune, S.pq, S.q_ridx0, S.seg_blk0, S.tot);
+  pv_maps_kernel<<<grid_for(regions + blocks), 256, 0, s>>>(S.seg_blk0, nq, S.q_ridx0, nq, S.tot, S.blk_seg, S.reg_q);
   ScatterArgs a{};
-  a.seg_blk0 = S.seg_blk0; a.seg_lo = S.seg_lo; a.seg_cnt = S.seg_cnt; a.n_seg = nq; a.G = 1;
+  a.seg_blk0 = S.seg_blk0; a.blk_seg = S.blk_seg; a.seg_lo = S.seg_lo; a.seg_cnt = S.seg_cnt; a.G = 1;
   a.pq = S.pq; a.tot = S.tot; a.regions = S.regions; a.fill = S.fill; a.qover = d_qover; a.q_lo = qa;
-  a.ent = L.ent; a.first = L.first; a.off = L.off_all; a.cnt_head = L.cnt_head; a.post = post; a.q_ent = d_qs; a.i0 = i0;
+  a.off = L.off_all; a.info = d_info; a.qh = d_qh; a.post = post; a.q_ent = d_qs; a.i0 = i0;
+  if (stage_ms) cudaEventRecord(ev[1], s);
   pv_scatter_kernel<0><<<(unsigned)blocks, kScThreads, kScatterSmem, s>>>(a);
-  pv_count_kernel<false><<<(unsigned)regions, kCntThreads, kSlots * 8, s>>>(S.regions, S.fill, S.pq, S.q_ridx0, nq, S.tot, qa, d_qover,
-                                                                            topn, S.cand, nullptr, d_nbins);
+  if (stage_ms) cudaEventRecord(ev[2], s);
+  pv_count_kernel<false><<<(unsigned)regions, kCntThreads, kSlots * 8, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, qa, d_qover, topn,
+                                                                            S.cand, nullptr, d_nbins);
   pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, nullptr, S.pq, nq, qa, qid_base, d_qover, topn, out,
                                                                             nullptr);
   SIA_CHECK_LAUNCH();
+  if (stage_ms) {
+    cudaEventRecord(ev[3], s);
+    cudaEventSynchronize(ev[3]);
+    for (int k = 0; k < 3; ++k) { float t = 0; cudaEventElapsedTime(&t, ev[k], ev[k + 1]); stage_ms[k] += t; }
+  }
   return SIA_OK;
 }
 
@@ -580,23 +630,23 @@ int pvote_key_slots(Arena &ar, const uint64_t *d_keys, int n_slots, int64_t cap,
   if (rc) return rc;
   const PvTune tune = pv_tune();
   const int64_t T = (int64_t)n_slots * cap;                 // upper bound of the keys
-  int64_t regions, region_tuples;
-  pv_bounds(T, nq, tune, regions, region_tuples);
-  const int64_t blocks = ceil_div(T, kBlk) + (int64_t)nq * n_slots;
+  int64_t regions, region_tuples, blocks;
+  pv_bounds(T, nq, n_slots, tune, regions, region_tuples, blocks);
   SIA_REQUIRE(blocks < (1ll << 31) && regions < (1ll << 31), SIA_E_UNSUPPORTED, "vote: too many keys in one call");
   const int64_t n_seg = (int64_t)nq * n_slots;
   PvScratch S;
-  SIA_REQUIRE(pv_take(ar, S, n_seg, nq, regions, region_tuples, topn), SIA_E_NOMEM, "vote scratch too small (partitioned vote)");
+  SIA_REQUIRE(pv_take(ar, S, n_seg, nq, regions, region_tuples, blocks, topn), SIA_E_NOMEM, "vote scratch too small (partitioned vote)");
   SIA_CUDA(cudaMemsetAsync(S.fill, 0, sizeof(uint32_t) * regions, s));
   pv_segs_keys_kernel<<<grid_for(n_seg), 256, 0, s>>>(d_keys, cap, d_counts, n_slots, nq, S.seg_lo, S.seg_cnt, d_flags2);
   pv_layout_kernel<<<1, 1024, 0, s>>>(S.seg_cnt, nq, n_slots, tune, S.pq, S.q_ridx0, S.seg_blk0, S.tot);
+  pv_maps_kernel<<<grid_for(regions + blocks), 256, 0, s>>>(S.seg_blk0, (int)n_seg, S.q_ridx0, nq, S.tot, S.blk_seg, S.reg_q);
   ScatterArgs a{};
-  a.seg_blk0 = S.seg_blk0; a.seg_lo = S.seg_lo; a.seg_cnt = S.seg_cnt; a.n_seg = (int)n_seg; a.G = n_slots;
+  a.seg_blk0 = S.seg_blk0; a.blk_seg = S.blk_seg; a.seg_lo = S.seg_lo; a.seg_cnt = S.seg_cnt; a.G = n_slots;
   a.pq = S.pq; a.tot = S.tot; a.regions = S.regions; a.fill = S.fill; a.qover = d_qover; a.q_lo = 0;
   a.keys = d_keys; a.key_cap = cap; a.counts = d_counts; a.unsorted = d_flags2;
   pv_scatter_kernel<1><<<(unsigned)blocks, kScThreads, kScatterSmem, s>>>(a);
-  pv_count_kernel<true><<<(unsigned)regions, kCntThreads, kSlots * 8, s>>>(S.regions, S.fill, S.pq, S.q_ridx0, nq, S.tot, 0, d_qover, topn,
-                                                                           S.cand, S.cand_rows, nullptr);
+  pv_count_kernel<true><<<(unsigned)regions, kCntThreads, kSlots * 8, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, 0, d_qover, topn, S.cand,
+                                                                           S.cand_rows, nullptr);
   pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, S.cand_rows, S.pq, nq, 0, 0, d_qover, topn, out,
                                                                             d_flags2 + 1);
   SIA_CHECK_LAUNCH();

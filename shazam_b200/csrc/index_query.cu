@@ -1078,7 +1078,7 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     const int64_t i0 = h_query_starts[q0], n = h_query_starts[q0 + nq] - i0;
     if (h_stats) h_stats[0] += n;
     if (n == 0) continue;    // out_nres is already 0 for these queries
-    if ((rc = ix->arena.reserve((size_t)(nq + 1) * 8 * 3 + (size_t)n * 32 + lookup_bytes(n) + (1 << 20)))) return rc;
+    if ((rc = ix->arena.reserve((size_t)(nq + 1) * 8 * 3 + (size_t)n * (32 + 20) + lookup_bytes(n) + (1 << 20)))) return rc;
     int64_t *d_qs = ix->arena.take<int64_t>(nq + 1);
     int64_t *d_goff = ix->arena.take<int64_t>(2 * (size_t)(nq + 1));
     ulonglong2 *ea = ix->arena.take<ulonglong2>(n), *eb = ix->arena.take<ulonglong2>(n);
@@ -1146,11 +1146,16 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
       SIA_CUDA(cudaMemsetAsync(d_qover, 0, sizeof(uint32_t) * nq, s));
       SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long), s));
       const PvOut po{d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres};
+      double pv_ms[3] = {0, 0, 0};
+      longlong2 *d_info = ix->arena.take<longlong2>(n);
+      uint32_t *d_qh = ix->arena.take<uint32_t>(n);
+      SIA_REQUIRE(d_info && d_qh, SIA_E_NOMEM, "index scratch arena too small (entry info)");
+      if ((rc = pvote_entry_info(L, d_info, d_qh, s))) return rc;
       for (const auto &g : pg) {
         if (h_off_all[g.second] == h_off_all[g.first]) continue;
         ix->arena3.used = fixed;
-        if ((rc = pvote_entries(ix->arena3, L, ix->post, d_qs, i0, d_goff, h_off_all, g.first, g.second, (int)q0, topn, po, d_qover,
-                                h_stats ? d_nbins : nullptr, s)))
+        if ((rc = pvote_entries(ix->arena3, L, d_info, d_qh, ix->post, d_qs, i0, d_goff, h_off_all, g.first, g.second, (int)q0, topn, po, d_qover,
+                                h_stats ? d_nbins : nullptr, s, timing ? pv_ms : nullptr)))
           return rc;
         const int64_t e0 = h_query_starts[q0 + g.first] - i0, ne = h_query_starts[q0 + g.second] - i0 - e0;
         entries_rows_kernel<<<grid_for(ne * 32), 256, 0, s>>>(L.ent, e0, ne, L.first, L.cnt_head, ix->post, (int)q0, topn,
@@ -1169,7 +1174,9 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
         groups.push_back(make_group(qa, qb));
         qa = qb;
       }
-      if (timing && !groups.empty()) fprintf(stderr, "[sia]   partitioned vote: %zu group(s) of flagged queries go to the table vote\n", groups.size());
+      if (timing)
+        fprintf(stderr, "[sia]   partitioned vote, %zu group(s): layout %.2f ms, scatter %.2f, count + merge %.2f; %zu group(s) of flagged "
+                "queries go to the table vote\n", pg.size(), pv_ms[0], pv_ms[1], pv_ms[2], groups.size());
     } else {
       for (int qa = 0; qa < nq;) {
         int qb = qa + 1;

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--fan", type=int, default=15)
     ap.add_argument("--oracle-sample", type=int, default=24)
     ap.add_argument("--topn", type=int, default=3)
+    ap.add_argument("--latency-clips", type=int, default=20, help="single-clip latency section (0 = skip)")
     args = ap.parse_args()
 
     import torch
@@ -148,6 +149,46 @@ def main():
                 "hash_set_jaccard_mean": float(np.mean(jac)), "identical_ids_and_offsets_vs_oracle_hashes": same_ids,
                 "identical_ids_offsets_counts_vs_oracle_hashes": same})
             del clips, q
+    # ---- single-clip latency: the reference's main flow (recognizer.py:355-398) -----------------------------------
+    # one 5 s stereo recording -> fingerprint() per channel -> find_matches -> align_matches, through the drop-in names
+    # (shazam_b200.compat / shazam_b200.recognize: Python lists of (hex20, offset) tuples and the SELECT statement the
+    # reference builds), and through the array fast path (Fingerprinter -> recognize_batch).  The reference's own
+    # recorded run: 0.347 s per 2-channel clip (tests_csv; 0.28 s fingerprint + query + align on a 13 M-row table).
+    if args.latency_clips > 0:
+        from shazam_b200 import compat, recognize
+        compat.set_fingerprinter(fp)
+        recognize.set_database(db)
+        n = 5 * FS
+        synth_tracks_gpu(dev, 5_000_000, min(batch, args.tracks), L, [rows[i, :L] for i in range(min(batch, args.tracks))])
+        lat_ref, lat_fast, ok = [], [], 0
+        for k in range(args.latency_clips):
+            tid = k % min(batch, args.tracks)
+            s0 = (7 + 3 * k) % (args.seconds - 5) * FS
+            left = rows[tid, s0:s0 + n].cpu().numpy()
+            right = np.clip(left.astype(np.int32) + rng.integers(-40, 40, n), -32768, 32767).astype(np.int16)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res_ref = []
+            for channel in (left, right):                          # recognizer.py:369-398
+                hashes = set(compat.fingerprint(channel, Fs=FS, fan_value=args.fan))
+                matches, dedup, _ = recognize.find_matches(hashes)
+                res_ref.append(recognize.align_matches(matches, dedup, len(hashes), args.topn))
+            lat_ref.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            b = fp.fingerprint_tracks([left, right], Fs=FS, fan_value=args.fan)
+            res_fast = recognize.recognize_batch([b.track(0), b.track(1)], args.topn)
+            lat_fast.append(time.perf_counter() - t0)
+            strip = lambda rs: [(r["song_id"], r["offset"], r["hashes_matched_in_input"]) for r in rs]
+            ok += int(all(strip(a) == strip(c) for a, c in zip(res_ref, res_fast)) and res_ref[0][0]["song_id"] == tid + 1)
+        out["single_clip_latency"] = {
+            "clips": args.latency_clips, "channels": 2, "clip_seconds": 5, "index_rows": stored,
+            "drop_in_names_ms_median": 1e3 * float(np.median(lat_ref)), "drop_in_names_ms_max": 1e3 * float(np.max(lat_ref)),
+            "array_fast_path_ms_median": 1e3 * float(np.median(lat_fast)), "array_fast_path_ms_max": 1e3 * float(np.max(lat_fast)),
+            "identical_results_and_correct_song": ok,
+            "reference_recorded_seconds": 0.347,
+            "what": "fingerprint x2 channels + find_matches + align_matches per recording (recognizer.py:355-398); drop-in "
+                    "names = compat.fingerprint / recognize.find_matches / recognize.align_matches with Python tuple lists; "
+                    "fast path = Fingerprinter.fingerprint_tracks + recognize_batch"}
     print(json.dumps(out, indent=1))
 
 
