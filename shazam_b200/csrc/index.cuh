@@ -163,7 +163,7 @@ __device__ __forceinline__ const uint64_t *slot_keys(const uint64_t *__restrict_
 // sorted by partition in shared memory so that the global writes are contiguous runs), one count pass (one CTA per
 // region: bins counted in shared memory, the region's top-n songs), one merge (top-n over a query's regions: a song
 // lives in exactly one partition, so the merge of per-partition top-n lists is exact).  Queries whose partitions do
-// not fit (a bin of > 6144 matches, > 2048 * 6144 tuples) are flagged in d_qover and left to the table vote.
+// not fit (a song with > 16384 tuples, > 512 * 16384 tuples, thousands of tied bins in one partition) are flagged in d_qover and left to the table vote.
 constexpr int kPvMaxTopn = 32;
 struct PvOut { int32_t *song, *diff, *count, *rows, *nres; };
 // scratch bytes for `tuples` vote tuples of nq queries arriving from n_src sources (worst case)
@@ -174,7 +174,8 @@ int pvote_entry_info(const Lookup &L, longlong2 *d_info, uint32_t *d_qh, cudaStr
 // d_goff / h_goff: tuple offsets (off_all) at the queries' first entries, [nq_pass + 1].  Rows are NOT counted here.
 int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uint32_t *d_qh, const uint64_t *post, const int64_t *d_qs,
                   int64_t i0, const int64_t *d_goff, const int64_t *h_goff, int qa, int qb, int qid_base, int topn, const PvOut &out,
-                  uint32_t *d_qover, unsigned long long *d_nbins, cudaStream_t s,
+                  uint32_t *d_qover, uint32_t *d_qbins /* [nq_pass], zeroed: distinct bins per query */,
+                  unsigned long long *d_nbins /* NULL, or += the bins of the settled queries */, cudaStream_t s,
                   double *stage_ms /* NULL, or += {layout, scatter, count + merge} */);
 // slotted vote keys, each slot sorted by query id (else *d_unsorted is set and nothing is written); rows counted.
 // d_over_count: incremented once per flagged query.

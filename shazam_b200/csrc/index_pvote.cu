@@ -30,12 +30,14 @@ constexpr uint64_t kDiffMask = (1ull << kDiffBits) - 1;
 constexpr int kBlk = 8192;            // tuples per scatter block
 constexpr int kScThreads = 512;
 constexpr int kTpt = kBlk / kScThreads;
-constexpr int kSlots = 8192;          // slots of the count table (64 KB)
-constexpr int kCap = 6144;            // tuples a region can hold (table load <= 0.75)
-constexpr int kAvg = 3584;            // tuples per partition the layout aims at
-constexpr int kMaxParts = 2048;
-constexpr int kDup = 2048;            // repeated bins a region remembers before it scans the table instead
+constexpr int kCap = 16384;           // tuples a region can hold
+constexpr int kAvg = 10240;           // tuples per partition the layout aims at
+constexpr int kMaxParts = 512;
+constexpr int kFiltWords = 8192;      // count kernel: duplicate filter, 2 bits per bucket, 16 buckets per word (32 KB)
+constexpr int kTabSlots = 4096;       // count kernel: exact table of the tuples in twice-hit buckets (32 KB)
+constexpr int kDup = 2048;            // repeated bins a region remembers
 constexpr int kCntThreads = 512;
+constexpr size_t kCountSmem = (size_t)kFiltWords * 4 + (size_t)kTabSlots * 8;
 
 struct PvQuery {
   int64_t reg_off;                    // first tuple slot of the query's regions
@@ -293,13 +295,12 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
   if (SRC == 1 && bad) atomicOr(a.unsorted, 1u);
   __syncthreads();
 
-  // exclusive scan of the histogram (4 partitions per thread), room reserved in the regions
+  // exclusive scan of the histogram (one partition per thread), room reserved in the regions
+  static_assert(kMaxParts <= kScThreads, "one partition per thread");
   {
-    const uint32_t p0 = (uint32_t)tid * 4;
-    uint32_t v[4], sum = 0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { v[u] = p0 + u < np ? hist[p0 + u] : 0u; sum += v[u]; }
-    uint32_t inc = sum;
+    const uint32_t pme = (uint32_t)tid;
+    const uint32_t c = pme < np ? hist[pme] : 0u;
+    uint32_t inc = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
     if (lane == 31) s_warp[warp] = inc;
@@ -312,21 +313,16 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
       if (lane < kScThreads / 32) s_warp[lane] = winc - w;
     }
     __syncthreads();
-    uint32_t base = s_warp[warp] + inc - sum;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (p0 + u < np) {
-        const uint32_t c = v[u];
-        hist[p0 + u] = base;
-        int32_t d = INT32_MIN;
-        if (c) {
-          const uint32_t old = atomicAdd(&a.fill[m.ridx0 + p0 + u], c);
-          if (old + c <= m.cap) d = (int32_t)((p0 + u) * m.cap + old) - (int32_t)base;
-          else a.qover[a.q_lo + ql] = 1u;
-        }
-        gdst[p0 + u] = d;
-        base += c;
+    if (pme < np) {
+      const uint32_t base = s_warp[warp] + inc - c;
+      hist[pme] = base;
+      int32_t d = INT32_MIN;
+      if (c) {
+        const uint32_t old = atomicAdd(&a.fill[m.ridx0 + pme], c);
+        if (old + c <= m.cap) d = (int32_t)(pme * m.cap + old) - (int32_t)base;
+        else a.qover[a.q_lo + ql] = 1u;
       }
+      gdst[pme] = d;
     }
   }
   __syncthreads();
@@ -345,25 +341,41 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
 }
 
 // ---- count ----------------------------------------------------------------------------------------------------
-// slot word: (song 24 | diff 25) << 15 | count 15
+// exact-table slot word: (song 24 | diff 25) << 15 | count 15
 __device__ __forceinline__ uint64_t pv_rank(uint64_t slot) {          // count desc, song asc, diff asc as ONE maximum
   if (slot == 0ull) return 0ull;
   const uint64_t key = slot >> 15;
   return ((slot & 0x7fffull) << 49) | ((kM24 - (key >> kDiffBits)) << kDiffBits) | (kDiffMask - (key & kDiffMask));
 }
+__device__ __forceinline__ uint64_t pv_rank1(uint64_t key) {          // the same for a bin of count 1
+  return (1ull << 49) | ((kM24 - (key >> kDiffBits)) << kDiffBits) | (kDiffMask - (key & kDiffMask));
+}
+// bucket of a (song, diff) key in the duplicate filter / its slot hash in the exact table
+__device__ __forceinline__ uint32_t pv_hash(uint64_t key) { return (uint32_t)(key >> kDiffBits) * 0x85ebca6bu + (uint32_t)key * 0xc2b2ae35u; }
 
+// One CTA per region, two passes over its tuples (the second one reads them from L2):
+//   mark   every tuple sets the "seen" bit of its bucket in a 2-bit duplicate filter (one atomicOr, no probing, no
+//          divergence); an arrival in a bucket already seen sets "twice";
+//   count  tuples of twice-hit buckets — every bin of count >= 2 is among them, plus the false positives of the filter
+//          (~10 %) — are counted exactly in a small open-addressing table; all other tuples are bins of count 1 and
+//          touch nothing;
+//   top-n  by one warp from the bins that reached count 2; if fewer than topn songs have one, the bins of count 1
+//          decide: the CTA scans the tuples themselves.
 template <bool ROWS>
 __global__ void __launch_bounds__(kCntThreads, 3)
 pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict__ fill, const PvQuery *__restrict__ pq,
                 const uint32_t *__restrict__ reg_q, const uint32_t *__restrict__ tot, int q_lo,
-                const uint32_t *__restrict__ qover, int topn, uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_rows,
-                unsigned long long *__restrict__ n_bins) {
+                uint32_t *__restrict__ qover, int topn, uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_rows,
+                uint32_t *__restrict__ qbins) {
   extern __shared__ __align__(16) unsigned char pv_smem[];
-  uint64_t *tab = reinterpret_cast<uint64_t *>(pv_smem);
+  uint32_t *filt = reinterpret_cast<uint32_t *>(pv_smem);
+  uint64_t *tab = reinterpret_cast<uint64_t *>(pv_smem + (size_t)kFiltWords * 4);
   __shared__ uint16_t s_dup[kDup];
-  __shared__ uint32_t s_ndup;
+  __shared__ uint32_t s_ndup, s_over;
+  __shared__ uint64_t s_lw[kCntThreads / 32][kPvMaxTopn];
   __shared__ int s_nres;
   __shared__ uint64_t s_win[kPvMaxTopn];
+  __shared__ uint64_t s_red[kCntThreads / 32];
   __shared__ uint32_t s_rows[kPvMaxTopn];
   const uint32_t r = blockIdx.x;
   if (r >= tot[0]) return;
@@ -373,63 +385,110 @@ pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict
   const PvQuery m = pq[ql];
   const uint32_t p = r - m.ridx0;
   uint64_t *__restrict__ out = cand + (int64_t)r * topn;
-  if (n == 0 || qover[q_lo + ql]) {
+  if (n == 0 || n > m.cap || qover[q_lo + ql]) {
     if (tid < topn) { out[tid] = 0ull; if (ROWS) cand_rows[(int64_t)r * topn + tid] = 0u; }
     return;
   }
-  int bits = 8;
-  while ((1u << bits) < 2 * n && bits < 13) ++bits;
-  const uint32_t S = 1u << bits, mask = S - 1;
+  // filter: >= 8 buckets per tuple up to 2^17 buckets; table: every tuple fits while n <= 2048, else 4096 slots
+  int fb = 10;
+  while ((1u << fb) < 8 * n && fb < 17) ++fb;
+  int tb = 6;
+  while ((1u << tb) < 2 * n && tb < 12) ++tb;
+  const uint32_t nw = 1u << (fb - 4), S = 1u << tb, tmask = S - 1;
+  for (uint32_t i = tid; i < nw / 4; i += kCntThreads) reinterpret_cast<uint4 *>(filt)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (uint32_t i = tid; i < S / 2; i += kCntThreads) reinterpret_cast<ulonglong2 *>(tab)[i] = make_ulonglong2(0ull, 0ull);
-  if (tid == 0) s_ndup = 0;
+  if (tid == 0) { s_ndup = 0; s_over = 0; }
   if (ROWS && tid < kPvMaxTopn) s_rows[tid] = 0;
   const uint64_t *__restrict__ reg = regions + m.reg_off + (int64_t)p * m.cap;
-  uint32_t i = tid;
-  uint64_t nxt = i < n ? __ldcs(reg + i) : 0ull;       // the thread's next tuple, in flight while the current one probes
   __syncthreads();
-  // Every lane inserts its tuples one probe per iteration and takes its next tuple as soon as the current one is
-  // settled, so the warp stays converged whatever the probe lengths are.  A probe is ONE compare-and-swap: it claims an
-  // empty slot (count 1) or returns the occupant.
-  uint32_t fresh = 0, h = 0;
-  uint64_t key = 0;
-  bool have = false;
-  for (;;) {
-    if (!have) {
-      if (i >= n) break;
-      key = nxt >> 1;
-      h = mix32((uint32_t)(key >> kDiffBits) * 0x9e3779b1u + (uint32_t)key) & mask;
-      have = true;
-      i += kCntThreads;
-      nxt = i < n ? __ldcs(reg + i) : 0ull;
-    }
-    const uint64_t cur = atomicCAS(reinterpret_cast<unsigned long long *>(tab + h), 0ull, (unsigned long long)((key << 15) | 1ull));
-    if (cur == 0ull) { ++fresh; have = false; }
-    else if ((cur >> 15) == key) {
-      const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(tab + h), 1u);      // low word: key bits | count
-      if ((old & 0x7fffu) == 1u) { const uint32_t d = atomicAdd(&s_ndup, 1u); if (d < (uint32_t)kDup) s_dup[d] = (uint16_t)h; }
-      have = false;
-    } else {
-      h = (h + 1) & mask;
+  // ---- mark ----
+  for (uint32_t i0 = tid; i0 < n; i0 += 4 * kCntThreads) {
+    uint64_t t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * kCntThreads; t[u] = i < n ? reg[i] : 0ull; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * kCntThreads < n) {
+        const uint32_t hb = pv_hash(t[u] >> 1) >> (32 - fb);
+        const uint32_t seen = 1u << (2 * (hb & 15u));
+        uint32_t *w = filt + (hb >> 4);
+        const uint32_t old = atomicOr(w, seen);
+        if ((old & (3u * seen)) == seen) atomicOr(w, seen << 1);        // second arrival: the bucket is hit twice
+      }
     }
   }
-  if (n_bins) {
+  __syncthreads();
+  // ---- count ----
+  uint32_t fresh = 0;
+  for (uint32_t i0 = tid; i0 < n; i0 += 4 * kCntThreads) {
+    uint64_t t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * kCntThreads; t[u] = i < n ? __ldcs(reg + i) : 0ull; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * kCntThreads < n) {
+        const uint64_t key = t[u] >> 1;
+        const uint32_t hx = pv_hash(key), hb = hx >> (32 - fb);
+        if (!(filt[hb >> 4] & (2u << (2 * (hb & 15u))))) { ++fresh; continue; }      // alone in its bucket: a bin of count 1
+        uint32_t h = mix32(hx) & tmask;
+        for (uint32_t probes = 0;; ++probes) {
+          if (probes == S) { s_over = 1u; break; }                      // the table is full (tie-heavy region)
+          const uint64_t cur = atomicCAS(reinterpret_cast<unsigned long long *>(tab + h), 0ull, (unsigned long long)((key << 15) | 1ull));
+          if (cur == 0ull) { ++fresh; break; }
+          if ((cur >> 15) == key) {
+            const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(tab + h), 1u);      // low word: key bits | count
+            if ((old & 0x7fffu) == 1u) { const uint32_t d = atomicAdd(&s_ndup, 1u); if (d < (uint32_t)kDup) s_dup[d] = (uint16_t)h; }
+            break;
+          }
+          h = (h + 1) & tmask;
+        }
+      }
+    }
+  }
+  if (qbins) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
-    if (lane == 0 && fresh) atomicAdd(n_bins, (unsigned long long)fresh);
+    if (lane == 0 && fresh) atomicAdd(&qbins[q_lo + ql], fresh);
+  }
+  __syncthreads();
+  if (s_ndup > (uint32_t)kDup || s_over) {                          // cannot list / hold its repeated bins: table vote
+    if (tid == 0) qover[q_lo + ql] = 1u;
+    if (tid < topn) { out[tid] = 0ull; if (ROWS) cand_rows[(int64_t)r * topn + tid] = 0u; }
+    return;
+  }
+  // top-n songs from the bins that reached count 2: every warp ranks its share of the list (distinct songs), warp 0
+  // merges the 16 x topn survivors — the first occurrence of a song in descending order is its best bin
+  {
+    const uint32_t nd = s_ndup;
+    uint64_t *lw = s_lw[warp];
+    int nl = 0;
+    while (nl < topn) {
+      uint64_t best = 0;
+      for (uint32_t k = tid; k < nd; k += kCntThreads) {
+        uint64_t c = pv_rank(tab[s_dup[k]]);
+        if (c > best) {
+          const uint64_t song = (c >> kDiffBits) & kM24;
+          for (int w = 0; w < nl; ++w) if (((lw[w] >> kDiffBits) & kM24) == song) c = 0;
+          if (c > best) best = c;
+        }
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d); if (o > best) best = o; }
+      if (best == 0ull) break;
+      if (lane == 0) lw[nl] = best;
+      ++nl;
+      __syncwarp();
+    }
+    if (lane == 0) for (int w = nl; w < topn; ++w) lw[w] = 0ull;
   }
   __syncthreads();
   if (warp == 0) {
-    // top-n songs of the region, by one warp: from the bins that reached count 2 (every song with a repeated bin has
-    // its best bin among them); if fewer than topn songs have one, the bins of count 1 decide and the table is scanned
-    const uint32_t ndup_raw = s_ndup;
-    const uint32_t nd = min(ndup_raw, (uint32_t)kDup);
-    bool full = ndup_raw > (uint32_t)kDup;
+    const uint32_t total = (kCntThreads / 32) * (uint32_t)topn;
     int nres = 0;
     while (nres < topn) {
       uint64_t best = 0;
-      const uint32_t lim = full ? S : nd;
-      for (uint32_t k = lane; k < lim; k += 32) {
-        uint64_t c = pv_rank(tab[full ? k : (uint32_t)s_dup[k]]);
+      for (uint32_t k = lane; k < total; k += 32) {
+        uint64_t c = s_lw[k / (uint32_t)topn][k % (uint32_t)topn];
         if (c > best) {
           const uint64_t song = (c >> kDiffBits) & kM24;
           for (int w = 0; w < nres; ++w) if (((s_win[w] >> kDiffBits) & kM24) == song) c = 0;
@@ -438,24 +497,40 @@ pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict
       }
 #pragma unroll
       for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d); if (o > best) best = o; }
-      if (best == 0ull) {
-        if (full) break;
-        full = true;
-        continue;
-      }
+      if (best == 0ull) break;
       if (lane == 0) s_win[nres] = best;
       ++nres;
       __syncwarp();
     }
-    if (!ROWS) {
-      if (lane < topn) out[lane] = lane < nres ? s_win[lane] : 0ull;
-    } else if (lane == 0) {
-      s_nres = nres;
-    }
+    if (lane == 0) s_nres = nres;
   }
-  if (ROWS) {                               // dedup_hashes of the region's winners: head tuples of their songs
+  __syncthreads();
+  int nres = s_nres;
+  // fewer than topn songs with a repeated bin: the remaining songs all rank by a bin of count 1 — (song asc, diff asc)
+  // over the tuples themselves, winners' songs excluded (rare on a large index, the normal case on a tiny one)
+  while (nres < topn) {
+    uint64_t best = 0;
+    for (uint32_t k = tid; k < n; k += kCntThreads) {
+      uint64_t c = pv_rank1(reg[k] >> 1);
+      if (c > best) {
+        const uint64_t song = (c >> kDiffBits) & kM24;
+        for (int w = 0; w < nres; ++w) if (((s_win[w] >> kDiffBits) & kM24) == song) c = 0;
+        if (c > best) best = c;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d); if (o > best) best = o; }
+    if (lane == 0) s_red[warp] = best;
     __syncthreads();
-    const int nres = s_nres;
+    best = 0;
+#pragma unroll
+    for (int w = 0; w < kCntThreads / 32; ++w) { const uint64_t o = s_red[w]; if (o > best) best = o; }
+    if (best == 0ull) break;
+    if (tid == 0) s_win[nres] = best;
+    ++nres;
+    __syncthreads();
+  }
+  if (ROWS && nres > 0) {                   // dedup_hashes of the region's winners: head tuples of their songs
     for (uint32_t k = tid; k < n; k += kCntThreads) {
       const uint64_t t = reg[k];
       if (t & 1ull) {
@@ -464,22 +539,24 @@ pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict
       }
     }
     __syncthreads();
-    if (tid < topn) {
-      out[tid] = tid < nres ? s_win[tid] : 0ull;
-      cand_rows[(int64_t)r * topn + tid] = tid < nres ? s_rows[tid] : 0u;
-    }
+  }
+  if (tid < topn) {
+    out[tid] = tid < nres ? s_win[tid] : 0ull;
+    if (ROWS) cand_rows[(int64_t)r * topn + tid] = tid < nres ? s_rows[tid] : 0u;
   }
 }
 
 // ---- merge ----------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pv_merge_kernel(const uint64_t *__restrict__ cand, const uint32_t *__restrict__ cand_rows, const PvQuery *__restrict__ pq, int nq,
-                int q_lo, int qid_base, const uint32_t *__restrict__ qover, int topn, PvOut out, uint32_t *__restrict__ over_count) {
+                int q_lo, int qid_base, const uint32_t *__restrict__ qover, int topn, PvOut out, uint32_t *__restrict__ over_count,
+                const uint32_t *__restrict__ qbins, unsigned long long *__restrict__ n_bins) {
   const int lane = threadIdx.x & 31;
   const int ql = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (ql >= nq) return;
   const int q = q_lo + ql;
   if (qover[q]) { if (lane == 0 && over_count) atomicAdd(over_count, 1u); return; }
+  if (lane == 0 && n_bins && qbins[q]) atomicAdd(n_bins, (unsigned long long)qbins[q]);   // distinct bins of the settled queries
   const PvQuery m = pq[ql];
   if (m.np == 0) return;                    // no tuples: the outputs are already zero
   const uint64_t *__restrict__ c = cand + (int64_t)m.ridx0 * topn;
@@ -544,8 +621,8 @@ int pv_attrs() {
   if (dev >= 0 && dev < 64 && done[dev]) return SIA_OK;
   SIA_CUDA(cudaFuncSetAttribute(pv_scatter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
   SIA_CUDA(cudaFuncSetAttribute(pv_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
-  SIA_CUDA(cudaFuncSetAttribute(pv_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlots * 8));
-  SIA_CUDA(cudaFuncSetAttribute(pv_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlots * 8));
+  SIA_CUDA(cudaFuncSetAttribute(pv_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmem));
+  SIA_CUDA(cudaFuncSetAttribute(pv_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmem));
   if (dev >= 0 && dev < 64) done[dev] = true;
   return SIA_OK;
 }
@@ -577,7 +654,7 @@ int pvote_entry_info(const Lookup &L, longlong2 *d_info, uint32_t *d_qh, cudaStr
 
 int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uint32_t *d_qh, const uint64_t *post, const int64_t *d_qs,
                   int64_t i0, const int64_t *d_goff, const int64_t *h_goff, int qa, int qb, int qid_base, int topn, const PvOut &out,
-                  uint32_t *d_qover, unsigned long long *d_nbins, cudaStream_t s, double *stage_ms) {
+                  uint32_t *d_qover, uint32_t *d_qbins, unsigned long long *d_nbins, cudaStream_t s, double *stage_ms) {
   const int nq = qb - qa;
   if (nq <= 0) return SIA_OK;
   int rc = pv_attrs();
@@ -610,10 +687,10 @@ int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uin
   if (stage_ms) cudaEventRecord(ev[1], s);
   pv_scatter_kernel<0><<<(unsigned)blocks, kScThreads, kScatterSmem, s>>>(a);
   if (stage_ms) cudaEventRecord(ev[2], s);
-  pv_count_kernel<false><<<(unsigned)regions, kCntThreads, kSlots * 8, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, qa, d_qover, topn,
-                                                                            S.cand, nullptr, d_nbins);
+  pv_count_kernel<false><<<(unsigned)regions, kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, qa, d_qover, topn,
+                                                                            S.cand, nullptr, d_nbins ? d_qbins : nullptr);
   pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, nullptr, S.pq, nq, qa, qid_base, d_qover, topn, out,
-                                                                            nullptr);
+                                                                            nullptr, d_qbins, d_nbins);
   SIA_CHECK_LAUNCH();
   if (stage_ms) {
     cudaEventRecord(ev[3], s);
@@ -645,10 +722,10 @@ int pvote_key_slots(Arena &ar, const uint64_t *d_keys, int n_slots, int64_t cap,
   a.pq = S.pq; a.tot = S.tot; a.regions = S.regions; a.fill = S.fill; a.qover = d_qover; a.q_lo = 0;
   a.keys = d_keys; a.key_cap = cap; a.counts = d_counts; a.unsorted = d_flags2;
   pv_scatter_kernel<1><<<(unsigned)blocks, kScThreads, kScatterSmem, s>>>(a);
-  pv_count_kernel<true><<<(unsigned)regions, kCntThreads, kSlots * 8, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, 0, d_qover, topn, S.cand,
+  pv_count_kernel<true><<<(unsigned)regions, kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, 0, d_qover, topn, S.cand,
                                                                            S.cand_rows, nullptr);
   pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, S.cand_rows, S.pq, nq, 0, 0, d_qover, topn, out,
-                                                                            d_flags2 + 1);
+                                                                            d_flags2 + 1, nullptr, nullptr);
   SIA_CHECK_LAUNCH();
   return SIA_OK;
 }

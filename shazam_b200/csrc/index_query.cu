@@ -1138,12 +1138,12 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
         max_bytes = std::max(max_bytes, pvote_bytes(h_off_all[qb] - h_off_all[qa], qb - qa, 1, topn));
         qa = qb;
       }
-      if ((rc = ix->arena3.reserve(max_bytes + (size_t)nq * 4 + 65536))) return rc;
-      uint32_t *d_qover = ix->arena3.take<uint32_t>(nq);
+      if ((rc = ix->arena3.reserve(max_bytes + (size_t)nq * 8 + 65536))) return rc;
+      uint32_t *d_qover = ix->arena3.take<uint32_t>(2 * (size_t)nq), *d_qbins = d_qover + nq;
       unsigned long long *d_nbins = ix->arena3.take<unsigned long long>(1);
       SIA_REQUIRE(d_qover && d_nbins, SIA_E_NOMEM, "index scratch arena too small (vote)");
       const size_t fixed = ix->arena3.used;
-      SIA_CUDA(cudaMemsetAsync(d_qover, 0, sizeof(uint32_t) * nq, s));
+      SIA_CUDA(cudaMemsetAsync(d_qover, 0, sizeof(uint32_t) * 2 * nq, s));
       SIA_CUDA(cudaMemsetAsync(d_nbins, 0, sizeof(unsigned long long), s));
       const PvOut po{d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres};
       double pv_ms[3] = {0, 0, 0};
@@ -1155,7 +1155,7 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
         if (h_off_all[g.second] == h_off_all[g.first]) continue;
         ix->arena3.used = fixed;
         if ((rc = pvote_entries(ix->arena3, L, d_info, d_qh, ix->post, d_qs, i0, d_goff, h_off_all, g.first, g.second, (int)q0, topn, po, d_qover,
-                                h_stats ? d_nbins : nullptr, s, timing ? pv_ms : nullptr)))
+                                d_qbins, h_stats ? d_nbins : nullptr, s, timing ? pv_ms : nullptr)))
           return rc;
         const int64_t e0 = h_query_starts[q0 + g.first] - i0, ne = h_query_starts[q0 + g.second] - i0 - e0;
         entries_rows_kernel<<<grid_for(ne * 32), 256, 0, s>>>(L.ent, e0, ne, L.first, L.cnt_head, ix->post, (int)q0, topn,
