@@ -750,10 +750,21 @@ def match_leg(args, rank, world, local_rank, dev):
         peak, peak_src = measured_peak_gbs()
         algo = qstats[0] * 24 + tuples * 24
         ach = algo / (vote_ms * 1e-3) / 1e9 if vote_ms else None
-        out["roofline"] = {"bound": "hbm", "kernel": "entries_pass_kernel (mark / vote / rows passes) + topn_kernel",
+        traffic, traffic_src = None, None
+        prof = os.path.join(ROOT, "profiles", "vote_traffic.json")
+        if os.path.exists(prof):
+            try:
+                vt = json.load(open(prof))
+                traffic = vt["dram_bytes_per_tuple"] * tuples
+                traffic_src = "profiles/vote_traffic.json (ncu --set full: dram read + write of pv_scatter_kernel + pv_count_kernel per tuple) x tuples per step"
+            except Exception:
+                pass
+        out["roofline"] = {"bound": "hbm", "kernel": "pv_scatter_kernel + pv_count_kernel (partitioned vote: posting runs -> (query, song "
+                                                     "partition) regions -> shared-memory duplicate filter + exact table) + pv_merge_kernel",
                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                           "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": algo,
-                           "formula": "H*(8+16) + T*(8+16): H query (hash, offset) pairs, T vote tuples",
+                           "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_step": algo,
+                           "formula": "H*(8+16) + T*(8+16): H query (hash, offset) pairs (8 B directory + 16 B key entry), T vote tuples "
+                                      "(8 B posting read + 8 B tuple written to its region + 8 B read back by the count)",
                            "vote_ms_per_step": vote_ms, "lookup_ms_per_step": lookup_ms,
                            "vote_tuples_per_second": tuples / (vote_ms * 1e-3) if vote_ms else None}
     # ---- CPU baseline: the reference's return_matches + align_matches on a 2,714-track table (configs[2]'s size) ----
