@@ -177,7 +177,7 @@ int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uin
                   uint32_t *d_qover, uint32_t *d_qbins /* [nq_pass], zeroed: distinct bins per query */,
                   unsigned long long *d_nbins /* NULL, or += the bins of the settled queries */, cudaStream_t s,
                   double *stage_ms /* NULL, or += {layout, scatter, count + merge} */);
-// slotted vote keys, each slot sorted by query id (else *d_unsorted is set and nothing is written); rows counted.
+// slotted vote keys, each slot sorted by query id (else d_flags2[0] is set and the outputs are garbage); out.rows = 0.
 // d_over_count: incremented once per flagged query.
 int pvote_key_slots(Arena &ar, const uint64_t *d_keys, int n_slots, int64_t cap, const int64_t *d_counts, int nq, int topn,
                     const PvOut &out, uint32_t *d_qover, uint32_t *d_flags2 /* [0] unsorted, [1] flagged queries */,

@@ -30,9 +30,9 @@ constexpr uint64_t kDiffMask = (1ull << kDiffBits) - 1;
 constexpr int kBlk = 8192;            // tuples per scatter block
 constexpr int kScThreads = 512;
 constexpr int kTpt = kBlk / kScThreads;
-constexpr int kCap = 16384;           // tuples a region can hold
+constexpr int kCap = 24576;           // tuples a region can hold (a 15-bit count per bin; room for one heavy bin next to the average)
 constexpr int kAvg = 10240;           // tuples per partition the layout aims at
-constexpr int kMaxParts = 512;
+constexpr int kMaxParts = 4096;         // partitions of one query (a query of more than ~4096 * 10240 tuples goes to the table vote)
 constexpr int kFiltWords = 8192;      // count kernel: duplicate filter, 2 bits per bucket, 16 buckets per word (32 KB)
 constexpr int kTabSlots = 4096;       // count kernel: exact table of the tuples in twice-hit buckets (32 KB)
 constexpr int kDup = 2048;            // repeated bins a region remembers
@@ -68,8 +68,11 @@ __device__ __forceinline__ uint32_t mix32(uint32_t k) {
   k ^= k >> 16; k *= 0x85ebca6bu; k ^= k >> 13; k *= 0xc2b2ae35u; k ^= k >> 16;
   return k;
 }
-// partition of a song: multiplicative hash (song ids are dense integers: the top bits of id * phi are equidistributed)
-__device__ __forceinline__ uint32_t pv_part(uint32_t song, uint32_t np) { return (((song * 0x9e3779b1u) >> 16) * np) >> 16; }
+// partition of a bin (song, biased diff): multiplicative hash, top 16 bits scaled to np.  Partitioning by BIN (not by
+// song) spreads a song with tens of thousands of tuples (a long query against its own track) over all partitions.
+__device__ __forceinline__ uint32_t pv_part(uint32_t song, uint32_t dbits, uint32_t np) {
+  return (((song * 0x9e3779b1u + dbits * 0x7feb352du) >> 16) * np) >> 16;
+}
 
 // largest i in [lo, hi) with a[i] <= x, given a[lo] <= x and a non-decreasing; the 32 lanes of a warp call it with the
 // same arguments and probe 32 positions per round (3 dependent loads for 2 000 elements instead of 11)
@@ -200,6 +203,7 @@ struct ScatterArgs {
   const uint32_t *seg_blk0, *blk_seg; const int64_t *seg_lo; const uint32_t *seg_cnt; int G;
   const PvQuery *pq; const uint32_t *tot;
   uint64_t *regions; uint32_t *fill; uint32_t *qover; int q_lo;
+  int maxp;                             // partitions the shared histogram is laid out for (>= every np of the launch)
   // source 0: posting runs of the query's entries
   const int64_t *off; const longlong2 *info; const uint32_t *qh; const uint64_t *post;
   const int64_t *q_ent; int64_t i0;
@@ -207,7 +211,8 @@ struct ScatterArgs {
   const uint64_t *keys; int64_t key_cap; const int64_t *counts; uint32_t *unsorted;
 };
 
-constexpr size_t kScatterSmem = (size_t)kBlk * 8 + (size_t)kBlk * 2 + (size_t)(2 * kMaxParts + 1) * 4;
+constexpr size_t scatter_smem(int maxp) { return (size_t)kBlk * 8 + (size_t)kBlk * 2 + (size_t)(2 * maxp + 1) * 4; }
+constexpr size_t kScatterSmem = scatter_smem(kMaxParts);
 
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
   uint64_t *stage = reinterpret_cast<uint64_t *>(pv_smem);              // [kBlk] tuples in arrival order
   uint16_t *idx = reinterpret_cast<uint16_t *>(stage + kBlk);            // [kBlk] arrival index of the t-th tuple in partition order
   uint32_t *hist = reinterpret_cast<uint32_t *>(idx + kBlk);             // [np + 1] counts, then exclusive offsets
-  int32_t *gdst = reinterpret_cast<int32_t *>(hist + kMaxParts + 1);     // [np] region slot of partition order position 0
+  int32_t *gdst = reinterpret_cast<int32_t *>(hist + a.maxp + 1);        // [np] region slot of partition order position 0
   __shared__ uint32_t s_warp[kScThreads / 32];
   const uint32_t b = blockIdx.x;
   if (b >= a.tot[1]) return;
@@ -275,18 +280,19 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
     const int i = iw + k * 32 + lane;
     if (i < n) {
       const uint64_t r = stage[i];
-      uint32_t song;
+      uint32_t song, dbits;
       uint64_t tup;
       if (SRC == 0) {
         song = (uint32_t)(r >> 24) & 0xffffffu;
-        const uint32_t dbits = ((uint32_t)(r & kM24) - (pr[k] >> 1) + SIA_DIFF_BIAS) & (uint32_t)kDiffMask;
+        dbits = ((uint32_t)(r & kM24) - (pr[k] >> 1) + SIA_DIFF_BIAS) & (uint32_t)kDiffMask;
         tup = ((uint64_t)song << (kDiffBits + 1)) | ((uint64_t)dbits << 1) | (pr[k] & 1u);
       } else {
         bad = bad || ((uint32_t)(r >> (kSongBits + kDiffBits)) & ((1u << kQidBits) - 1u)) != (uint32_t)ql;
         song = (uint32_t)(r >> kDiffBits) & 0xffffffu;
-        tup = ((uint64_t)song << (kDiffBits + 1)) | ((r & kDiffMask) << 1) | (r >> 63);
+        dbits = (uint32_t)(r & kDiffMask);
+        tup = ((uint64_t)song << (kDiffBits + 1)) | ((uint64_t)dbits << 1) | (r >> 63);
       }
-      const uint32_t p = pv_part(song, np);
+      const uint32_t p = pv_part(song, dbits, np);
       const uint32_t rk = atomicAdd(&hist[p], 1u);
       stage[i] = tup;
       pr[k] = (p << 13) | rk;
@@ -295,9 +301,10 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
   if (SRC == 1 && bad) atomicOr(a.unsorted, 1u);
   __syncthreads();
 
-  // exclusive scan of the histogram (one partition per thread), room reserved in the regions
-  static_assert(kMaxParts <= kScThreads, "one partition per thread");
-  {
+  // exclusive scan of the histogram (kPpt consecutive partitions per thread), room reserved in the regions
+  constexpr int kPpt = kMaxParts / kScThreads;
+  static_assert(kPpt * kScThreads == kMaxParts && kMaxParts <= (1 << 19), "partition / rank packing");
+  if (np <= (uint32_t)kScThreads) {                    // the usual case: one partition per thread
     const uint32_t pme = (uint32_t)tid;
     const uint32_t c = pme < np ? hist[pme] : 0u;
     uint32_t inc = c;
@@ -324,6 +331,40 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
       }
       gdst[pme] = d;
     }
+  } else {
+    const uint32_t p0 = (uint32_t)tid * kPpt;
+    uint32_t v[kPpt], sum = 0;
+#pragma unroll
+    for (int u = 0; u < kPpt; ++u) { v[u] = p0 + u < np ? hist[p0 + u] : 0u; sum += v[u]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t w = lane < kScThreads / 32 ? s_warp[lane] : 0u;
+      uint32_t winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += t; }
+      if (lane < kScThreads / 32) s_warp[lane] = winc - w;
+    }
+    __syncthreads();
+    uint32_t base = s_warp[warp] + inc - sum;
+#pragma unroll
+    for (int u = 0; u < kPpt; ++u) {
+      if (p0 + u < np) {
+        const uint32_t c = v[u];
+        hist[p0 + u] = base;
+        int32_t d = INT32_MIN;
+        if (c) {
+          const uint32_t old = atomicAdd(&a.fill[m.ridx0 + p0 + u], c);
+          if (old + c <= m.cap) d = (int32_t)((p0 + u) * m.cap + old) - (int32_t)base;
+          else a.qover[a.q_lo + ql] = 1u;
+        }
+        gdst[p0 + u] = d;
+        base += c;
+      }
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -335,7 +376,7 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
   uint64_t *__restrict__ reg = a.regions + m.reg_off;
   for (int t = tid; t < n; t += kScThreads) {
     const uint64_t tup = stage[idx[t]];
-    const int32_t d = gdst[pv_part((uint32_t)(tup >> (kDiffBits + 1)), np)];
+    const int32_t d = gdst[pv_part((uint32_t)(tup >> (kDiffBits + 1)), (uint32_t)(tup >> 1) & (uint32_t)kDiffMask, np)];
     if (d != INT32_MIN) reg[(int64_t)d + t] = tup;
   }
 }
@@ -361,22 +402,19 @@ __device__ __forceinline__ uint32_t pv_hash(uint64_t key) { return (uint32_t)(ke
 //          touch nothing;
 //   top-n  by one warp from the bins that reached count 2; if fewer than topn songs have one, the bins of count 1
 //          decide: the CTA scans the tuples themselves.
-template <bool ROWS>
 __global__ void __launch_bounds__(kCntThreads, 3)
 pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict__ fill, const PvQuery *__restrict__ pq,
                 const uint32_t *__restrict__ reg_q, const uint32_t *__restrict__ tot, int q_lo,
-                uint32_t *__restrict__ qover, int topn, uint64_t *__restrict__ cand, uint32_t *__restrict__ cand_rows,
-                uint32_t *__restrict__ qbins) {
+                uint32_t *__restrict__ qover, int topn, uint64_t *__restrict__ cand, uint32_t *__restrict__ qbins) {
   extern __shared__ __align__(16) unsigned char pv_smem[];
   uint32_t *filt = reinterpret_cast<uint32_t *>(pv_smem);
   uint64_t *tab = reinterpret_cast<uint64_t *>(pv_smem + (size_t)kFiltWords * 4);
   __shared__ uint16_t s_dup[kDup];
-  __shared__ uint32_t s_ndup, s_over;
-  __shared__ uint64_t s_lw[kCntThreads / 32][kPvMaxTopn];
+  __shared__ uint32_t s_ndup, s_over, s_b2;
+  __shared__ uint64_t s_lw[kCntThreads / 32 + 1][kPvMaxTopn];       // per-warp winners; last row: the running winners
   __shared__ int s_nres;
   __shared__ uint64_t s_win[kPvMaxTopn];
   __shared__ uint64_t s_red[kCntThreads / 32];
-  __shared__ uint32_t s_rows[kPvMaxTopn];
   const uint32_t r = blockIdx.x;
   if (r >= tot[0]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -386,7 +424,7 @@ pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict
   const uint32_t p = r - m.ridx0;
   uint64_t *__restrict__ out = cand + (int64_t)r * topn;
   if (n == 0 || n > m.cap || qover[q_lo + ql]) {
-    if (tid < topn) { out[tid] = 0ull; if (ROWS) cand_rows[(int64_t)r * topn + tid] = 0u; }
+    if (tid < topn) out[tid] = 0ull;
     return;
   }
   // filter: >= 8 buckets per tuple up to 2^17 buckets; table: every tuple fits while n <= 2048, else 4096 slots
@@ -397,8 +435,7 @@ pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict
   const uint32_t nw = 1u << (fb - 4), S = 1u << tb, tmask = S - 1;
   for (uint32_t i = tid; i < nw / 4; i += kCntThreads) reinterpret_cast<uint4 *>(filt)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (uint32_t i = tid; i < S / 2; i += kCntThreads) reinterpret_cast<ulonglong2 *>(tab)[i] = make_ulonglong2(0ull, 0ull);
-  if (tid == 0) { s_ndup = 0; s_over = 0; }
-  if (ROWS && tid < kPvMaxTopn) s_rows[tid] = 0;
+  if (tid == 0) { s_ndup = 0; s_over = 0; s_b2 = 0; }
   const uint64_t *__restrict__ reg = regions + m.reg_off + (int64_t)p * m.cap;
   __syncthreads();
   // ---- mark ----
@@ -419,90 +456,123 @@ pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict
   }
   __syncthreads();
   // ---- count ----
+  // The exact table holds ~3 300 distinct candidate keys.  A tie-heavy region (a long query against a self-similar
+  // track) has more: its candidates are then counted in nsub sub-passes, each taking the keys of one residue class and
+  // re-reading the tuples from L2; the running winners ride along.  nsub starts from the number of twice-hit buckets
+  // and doubles if a sub-pass still overflows, so the kernel cannot fail for a region that fits its slots.
+  {
+    uint32_t b2 = 0;
+    for (uint32_t i = tid; i < nw; i += kCntThreads) b2 += __popc(filt[i] & 0xaaaaaaaau);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) b2 += __shfl_xor_sync(0xffffffffu, b2, d);
+    if (lane == 0 && b2) atomicAdd(&s_b2, b2);
+  }
+  __syncthreads();
+  uint32_t nsub = 1;
+  while (nsub < 16 && s_b2 * 2 > (S * 3 / 4) * nsub) nsub <<= 1;
   uint32_t fresh = 0;
-  for (uint32_t i0 = tid; i0 < n; i0 += 4 * kCntThreads) {
-    uint64_t t[4];
+  for (;;) {
+    bool ok = true;
+    fresh = 0;
+    if (tid < kPvMaxTopn) s_lw[kCntThreads / 32][tid] = 0ull;          // the running winners of this attempt
+    for (uint32_t sub = 0; sub < nsub; ++sub) {
+      if (nsub > 1 || sub > 0) {
+        __syncthreads();                                                 // the table of the previous sub-pass has been read
+        for (uint32_t i = tid; i < S / 2; i += kCntThreads) reinterpret_cast<ulonglong2 *>(tab)[i] = make_ulonglong2(0ull, 0ull);
+        if (tid == 0) { s_ndup = 0; s_over = 0; }
+        __syncthreads();
+      }
+      for (uint32_t i0 = tid; i0 < n; i0 += 4 * kCntThreads) {
+        uint64_t t[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * kCntThreads; t[u] = i < n ? __ldcs(reg + i) : 0ull; }
+        for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * kCntThreads; t[u] = i < n ? __ldcs(reg + i) : 0ull; }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (i0 + u * kCntThreads < n) {
-        const uint64_t key = t[u] >> 1;
-        const uint32_t hx = pv_hash(key), hb = hx >> (32 - fb);
-        if (!(filt[hb >> 4] & (2u << (2 * (hb & 15u))))) { ++fresh; continue; }      // alone in its bucket: a bin of count 1
-        uint32_t h = mix32(hx) & tmask;
-        for (uint32_t probes = 0;; ++probes) {
-          if (probes == S) { s_over = 1u; break; }                      // the table is full (tie-heavy region)
-          const uint64_t cur = atomicCAS(reinterpret_cast<unsigned long long *>(tab + h), 0ull, (unsigned long long)((key << 15) | 1ull));
-          if (cur == 0ull) { ++fresh; break; }
-          if ((cur >> 15) == key) {
-            const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(tab + h), 1u);      // low word: key bits | count
-            if ((old & 0x7fffu) == 1u) { const uint32_t d = atomicAdd(&s_ndup, 1u); if (d < (uint32_t)kDup) s_dup[d] = (uint16_t)h; }
-            break;
+        for (int u = 0; u < 4; ++u) {
+          if (i0 + u * kCntThreads < n) {
+            const uint64_t key = t[u] >> 1;
+            const uint32_t hx = pv_hash(key), hb = hx >> (32 - fb);
+            if (!(filt[hb >> 4] & (2u << (2 * (hb & 15u))))) { fresh += sub == 0; continue; }   // alone in its bucket: a bin of count 1
+            if (((hx >> 3) & (nsub - 1)) != sub) continue;
+            uint32_t h = mix32(hx) & tmask;
+            for (uint32_t probes = 0;; ++probes) {
+              if (probes == S) { s_over = 1u; break; }                  // the table is full
+              const uint64_t cur = atomicCAS(reinterpret_cast<unsigned long long *>(tab + h), 0ull, (unsigned long long)((key << 15) | 1ull));
+              if (cur == 0ull) { ++fresh; break; }
+              if ((cur >> 15) == key) {
+                const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(tab + h), 1u);      // low word: key bits | count
+                if ((old & 0x7fffu) == 1u) { const uint32_t d = atomicAdd(&s_ndup, 1u); if (d < (uint32_t)kDup) s_dup[d] = (uint16_t)h; }
+                break;
+              }
+              h = (h + 1) & tmask;
+            }
           }
-          h = (h + 1) & tmask;
         }
       }
+      __syncthreads();
+      if (s_ndup > (uint32_t)kDup || s_over) { ok = false; break; }
+      // top-n songs from the bins that reached count 2: every warp ranks its share of the list (distinct songs), warp 0
+      // merges the 16 x topn survivors and the running winners — the first occurrence of a song in descending order is
+      // its best bin
+      {
+        const uint32_t nd = s_ndup;
+        uint64_t *lw = s_lw[warp];
+        int nl = 0;
+        while (nl < topn) {
+          uint64_t best = 0;
+          for (uint32_t k = tid; k < nd; k += kCntThreads) {
+            uint64_t c = pv_rank(tab[s_dup[k]]);
+            if (c > best) {
+              const uint64_t song = (c >> kDiffBits) & kM24;
+              for (int w = 0; w < nl; ++w) if (((lw[w] >> kDiffBits) & kM24) == song) c = 0;
+              if (c > best) best = c;
+            }
+          }
+#pragma unroll
+          for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d); if (o > best) best = o; }
+          if (best == 0ull) break;
+          if (lane == 0) lw[nl] = best;
+          ++nl;
+          __syncwarp();
+        }
+        if (lane == 0) for (int w = nl; w < topn; ++w) lw[w] = 0ull;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t total = (kCntThreads / 32 + 1) * (uint32_t)topn;
+        int nres = 0;
+        while (nres < topn) {
+          uint64_t best = 0;
+          for (uint32_t k = lane; k < total; k += 32) {
+            uint64_t c = s_lw[k / (uint32_t)topn][k % (uint32_t)topn];
+            if (c > best) {
+              const uint64_t song = (c >> kDiffBits) & kM24;
+              for (int w = 0; w < nres; ++w) if (((s_win[w] >> kDiffBits) & kM24) == song) c = 0;
+              if (c > best) best = c;
+            }
+          }
+#pragma unroll
+          for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d); if (o > best) best = o; }
+          if (best == 0ull) break;
+          if (lane == 0) s_win[nres] = best;
+          ++nres;
+          __syncwarp();
+        }
+        if (lane < topn) s_lw[kCntThreads / 32][lane] = lane < nres ? s_win[lane] : 0ull;
+        if (lane == 0) s_nres = nres;
+      }
     }
+    if (ok) break;
+    if (nsub >= 16) {                                                    // cannot happen for n <= 16384; kept as a guard
+      if (tid == 0) qover[q_lo + ql] = 1u;
+      if (tid < topn) out[tid] = 0ull;
+      return;
+    }
+    nsub <<= 1;
   }
   if (qbins) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
     if (lane == 0 && fresh) atomicAdd(&qbins[q_lo + ql], fresh);
-  }
-  __syncthreads();
-  if (s_ndup > (uint32_t)kDup || s_over) {                          // cannot list / hold its repeated bins: table vote
-    if (tid == 0) qover[q_lo + ql] = 1u;
-    if (tid < topn) { out[tid] = 0ull; if (ROWS) cand_rows[(int64_t)r * topn + tid] = 0u; }
-    return;
-  }
-  // top-n songs from the bins that reached count 2: every warp ranks its share of the list (distinct songs), warp 0
-  // merges the 16 x topn survivors — the first occurrence of a song in descending order is its best bin
-  {
-    const uint32_t nd = s_ndup;
-    uint64_t *lw = s_lw[warp];
-    int nl = 0;
-    while (nl < topn) {
-      uint64_t best = 0;
-      for (uint32_t k = tid; k < nd; k += kCntThreads) {
-        uint64_t c = pv_rank(tab[s_dup[k]]);
-        if (c > best) {
-          const uint64_t song = (c >> kDiffBits) & kM24;
-          for (int w = 0; w < nl; ++w) if (((lw[w] >> kDiffBits) & kM24) == song) c = 0;
-          if (c > best) best = c;
-        }
-      }
-#pragma unroll
-      for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d); if (o > best) best = o; }
-      if (best == 0ull) break;
-      if (lane == 0) lw[nl] = best;
-      ++nl;
-      __syncwarp();
-    }
-    if (lane == 0) for (int w = nl; w < topn; ++w) lw[w] = 0ull;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const uint32_t total = (kCntThreads / 32) * (uint32_t)topn;
-    int nres = 0;
-    while (nres < topn) {
-      uint64_t best = 0;
-      for (uint32_t k = lane; k < total; k += 32) {
-        uint64_t c = s_lw[k / (uint32_t)topn][k % (uint32_t)topn];
-        if (c > best) {
-          const uint64_t song = (c >> kDiffBits) & kM24;
-          for (int w = 0; w < nres; ++w) if (((s_win[w] >> kDiffBits) & kM24) == song) c = 0;
-          if (c > best) best = c;
-        }
-      }
-#pragma unroll
-      for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d); if (o > best) best = o; }
-      if (best == 0ull) break;
-      if (lane == 0) s_win[nres] = best;
-      ++nres;
-      __syncwarp();
-    }
-    if (lane == 0) s_nres = nres;
   }
   __syncthreads();
   int nres = s_nres;
@@ -530,26 +600,17 @@ pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict
     ++nres;
     __syncthreads();
   }
-  if (ROWS && nres > 0) {                   // dedup_hashes of the region's winners: head tuples of their songs
-    for (uint32_t k = tid; k < n; k += kCntThreads) {
-      const uint64_t t = reg[k];
-      if (t & 1ull) {
-        const uint64_t isong = kM24 - (t >> (kDiffBits + 1));
-        for (int w = 0; w < nres; ++w) if (((s_win[w] >> kDiffBits) & kM24) == isong) atomicAdd(&s_rows[w], 1u);
-      }
-    }
-    __syncthreads();
-  }
-  if (tid < topn) {
-    out[tid] = tid < nres ? s_win[tid] : 0ull;
-    if (ROWS) cand_rows[(int64_t)r * topn + tid] = tid < nres ? s_rows[tid] : 0u;
-  }
+  if (tid < topn) out[tid] = tid < nres ? s_win[tid] : 0ull;
 }
 
 // ---- merge ----------------------------------------------------------------------------------------------------
+// one warp per query: top-n over its regions' candidates.  A song's bins are spread over the partitions, so the same
+// song can come from several regions: in descending order its first occurrence is its best bin, later ones are skipped.
+// (Exact: a song of the true top-n cannot be cut from its region's list, because the n songs ahead of it there each
+// have a bin at least that good.)  out.rows is left 0: dedup_hashes is counted by the caller.
 __global__ void __launch_bounds__(256)
-pv_merge_kernel(const uint64_t *__restrict__ cand, const uint32_t *__restrict__ cand_rows, const PvQuery *__restrict__ pq, int nq,
-                int q_lo, int qid_base, const uint32_t *__restrict__ qover, int topn, PvOut out, uint32_t *__restrict__ over_count,
+pv_merge_kernel(const uint64_t *__restrict__ cand, const PvQuery *__restrict__ pq, int nq, int q_lo, int qid_base,
+                const uint32_t *__restrict__ qover, int topn, PvOut out, uint32_t *__restrict__ over_count,
                 const uint32_t *__restrict__ qbins, unsigned long long *__restrict__ n_bins) {
   const int lane = threadIdx.x & 31;
   const int ql = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -561,39 +622,39 @@ pv_merge_kernel(const uint64_t *__restrict__ cand, const uint32_t *__restrict__ 
   if (m.np == 0) return;                    // no tuples: the outputs are already zero
   const uint64_t *__restrict__ c = cand + (int64_t)m.ridx0 * topn;
   const uint32_t total = m.np * (uint32_t)topn;
+  const int64_t obase = ((int64_t)q + qid_base) * topn;
   uint64_t prev = ~0ull;
   int nres = 0;
-  for (int r = 0; r < topn; ++r) {
+  while (nres < topn) {
     uint64_t best = 0;
-    uint32_t at = 0;
-    for (uint32_t i = lane; i < total; i += 32) { const uint64_t v = c[i]; if (v < prev && v > best) { best = v; at = i; } }
+    for (uint32_t i = lane; i < total; i += 32) { const uint64_t v = c[i]; if (v < prev && v > best) best = v; }
 #pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d);
-      const uint32_t oa = __shfl_xor_sync(0xffffffffu, at, d);
-      if (o > best) { best = o; at = oa; }
-    }
+    for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d); if (o > best) best = o; }
     if (best == 0ull) break;
-    if (lane == 0) {
-      const int64_t o = ((int64_t)q + qid_base) * topn + r;
-      out.song[o] = (int32_t)(kM24 - ((best >> kDiffBits) & kM24));
-      out.count[o] = (int32_t)(best >> 49);
-      out.diff[o] = (int32_t)(kDiffMask - (best & kDiffMask)) - SIA_DIFF_BIAS;
-      out.rows[o] = cand_rows ? (int32_t)cand_rows[(int64_t)m.ridx0 * topn + at] : 0;
-    }
     prev = best;
+    const int32_t song = (int32_t)(kM24 - ((best >> kDiffBits) & kM24));
+    bool taken = false;
+    for (int w = 0; w < nres; ++w) taken = taken || out.song[obase + w] == song;
+    if (taken) continue;                    // a lesser bin of a song that already has its place
+    if (lane == 0) {
+      out.song[obase + nres] = song;
+      out.count[obase + nres] = (int32_t)(best >> 49);
+      out.diff[obase + nres] = (int32_t)(kDiffMask - (best & kDiffMask)) - SIA_DIFF_BIAS;
+      out.rows[obase + nres] = 0;
+    }
     ++nres;
+    __syncwarp();
   }
   if (lane == 0) out.nres[q + qid_base] = nres;
 }
 
 struct PvScratch {
-  int64_t *seg_lo; uint32_t *seg_cnt, *seg_blk0, *q_ridx0, *tot, *fill, *cand_rows, *blk_seg, *reg_q;
+  int64_t *seg_lo; uint32_t *seg_cnt, *seg_blk0, *q_ridx0, *tot, *fill, *blk_seg, *reg_q;
   PvQuery *pq; uint64_t *regions, *cand;
 };
 
 size_t pv_scratch_bytes(int64_t n_seg, int64_t nq, int64_t regions, int64_t region_tuples, int64_t blocks, int topn) {
-  return (size_t)n_seg * 16 + (size_t)(n_seg + nq + 2) * 4 + (size_t)nq * sizeof(PvQuery) + (size_t)regions * (8 + 12 * (size_t)topn) +
+  return (size_t)n_seg * 16 + (size_t)(n_seg + nq + 2) * 4 + (size_t)nq * sizeof(PvQuery) + (size_t)regions * (8 + 8 * (size_t)topn) +
          (size_t)blocks * 4 + (size_t)region_tuples * 8 + 16 * 256 + 64;
 }
 
@@ -608,10 +669,8 @@ bool pv_take(Arena &ar, PvScratch &S, int64_t n_seg, int64_t nq, int64_t regions
   S.reg_q = ar.take<uint32_t>(regions);
   S.blk_seg = ar.take<uint32_t>(blocks);
   S.cand = ar.take<uint64_t>(regions * topn);
-  S.cand_rows = ar.take<uint32_t>(regions * topn);
   S.regions = ar.take<uint64_t>(region_tuples);
-  return S.seg_lo && S.seg_cnt && S.seg_blk0 && S.q_ridx0 && S.tot && S.pq && S.fill && S.reg_q && S.blk_seg && S.cand && S.cand_rows &&
-         S.regions;
+  return S.seg_lo && S.seg_cnt && S.seg_blk0 && S.q_ridx0 && S.tot && S.pq && S.fill && S.reg_q && S.blk_seg && S.cand && S.regions;
 }
 
 int pv_attrs() {
@@ -621,8 +680,7 @@ int pv_attrs() {
   if (dev >= 0 && dev < 64 && done[dev]) return SIA_OK;
   SIA_CUDA(cudaFuncSetAttribute(pv_scatter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
   SIA_CUDA(cudaFuncSetAttribute(pv_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
-  SIA_CUDA(cudaFuncSetAttribute(pv_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmem));
-  SIA_CUDA(cudaFuncSetAttribute(pv_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmem));
+  SIA_CUDA(cudaFuncSetAttribute(pv_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmem));
   if (dev >= 0 && dev < 64) done[dev] = true;
   return SIA_OK;
 }
@@ -661,10 +719,12 @@ int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uin
   if (rc) return rc;
   const PvTune tune = pv_tune();
   int64_t regions = 0, region_tuples = 0, blocks = 0;
+  uint32_t maxp = 1;
   for (int q = qa; q < qb; ++q) {
     const uint64_t t = (uint64_t)(h_goff[q + 1] - h_goff[q]);
     if (t == 0) continue;
     const uint32_t np = pv_parts(t, tune.cap, tune.avg);
+    maxp = std::max(maxp, np);
     regions += np;
     region_tuples += (int64_t)np * pv_region_cap(t, tune.cap);
     blocks += (int64_t)ceil_div((int64_t)t, kBlk);
@@ -683,14 +743,15 @@ int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uin
   ScatterArgs a{};
   a.seg_blk0 = S.seg_blk0; a.blk_seg = S.blk_seg; a.seg_lo = S.seg_lo; a.seg_cnt = S.seg_cnt; a.G = 1;
   a.pq = S.pq; a.tot = S.tot; a.regions = S.regions; a.fill = S.fill; a.qover = d_qover; a.q_lo = qa;
+  a.maxp = (int)std::min<uint32_t>(kMaxParts, (maxp + 511u) & ~511u);
   a.off = L.off_all; a.info = d_info; a.qh = d_qh; a.post = post; a.q_ent = d_qs; a.i0 = i0;
   if (stage_ms) cudaEventRecord(ev[1], s);
-  pv_scatter_kernel<0><<<(unsigned)blocks, kScThreads, kScatterSmem, s>>>(a);
+  pv_scatter_kernel<0><<<(unsigned)blocks, kScThreads, scatter_smem(a.maxp), s>>>(a);
   if (stage_ms) cudaEventRecord(ev[2], s);
-  pv_count_kernel<false><<<(unsigned)regions, kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, qa, d_qover, topn,
-                                                                            S.cand, nullptr, d_nbins ? d_qbins : nullptr);
-  pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, nullptr, S.pq, nq, qa, qid_base, d_qover, topn, out,
-                                                                            nullptr, d_qbins, d_nbins);
+  pv_count_kernel<<<(unsigned)regions, kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, qa, d_qover, topn, S.cand,
+                                                                     d_nbins ? d_qbins : nullptr);
+  pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, S.pq, nq, qa, qid_base, d_qover, topn, out, nullptr,
+                                                                            d_qbins, d_nbins);
   SIA_CHECK_LAUNCH();
   if (stage_ms) {
     cudaEventRecord(ev[3], s);
@@ -720,12 +781,13 @@ int pvote_key_slots(Arena &ar, const uint64_t *d_keys, int n_slots, int64_t cap,
   ScatterArgs a{};
   a.seg_blk0 = S.seg_blk0; a.blk_seg = S.blk_seg; a.seg_lo = S.seg_lo; a.seg_cnt = S.seg_cnt; a.G = n_slots;
   a.pq = S.pq; a.tot = S.tot; a.regions = S.regions; a.fill = S.fill; a.qover = d_qover; a.q_lo = 0;
+  a.maxp = kMaxParts;                                       // the queries' sizes are only known on the device
   a.keys = d_keys; a.key_cap = cap; a.counts = d_counts; a.unsorted = d_flags2;
   pv_scatter_kernel<1><<<(unsigned)blocks, kScThreads, kScatterSmem, s>>>(a);
-  pv_count_kernel<true><<<(unsigned)regions, kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, 0, d_qover, topn, S.cand,
-                                                                           S.cand_rows, nullptr);
-  pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, S.cand_rows, S.pq, nq, 0, 0, d_qover, topn, out,
-                                                                            d_flags2 + 1, nullptr, nullptr);
+  pv_count_kernel<<<(unsigned)regions, kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, 0, d_qover, topn, S.cand,
+                                                                     nullptr);
+  pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, S.pq, nq, 0, 0, d_qover, topn, out, d_flags2 + 1,
+                                                                            nullptr, nullptr);
   SIA_CHECK_LAUNCH();
   return SIA_OK;
 }
