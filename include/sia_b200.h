@@ -282,6 +282,37 @@ int sia_vote_key_slots(int device, const uint64_t *d_key_slots, int32_t n_slots,
                        int32_t *d_out_rows, int32_t *d_out_nres, int32_t defer, void *stream);
 int sia_vote_finish(int device);
 
+/* ---- multi-GPU: the same pass with the second exchange FUSED into the scatter kernel over NVLink peer memory ----
+ * Instead of writing vote keys, exchanging them (all-to-all #2) and partitioning them at the query's owner, the shard that
+ * owns the hashes scatters the vote tuples of its posting runs straight into the (query, partition) regions of the
+ * partitioned vote IN THE OWNER'S MEMORY (peer stores + peer atomicAdd through NVLink); the owner then only counts.
+ *   sia_peer_alloc / sia_peer_open      one allocation per rank, mapped by every other rank (CUDA IPC; the 64-byte
+ *                                       handles travel through the host layer's all-gather)
+ *   sia_index_lookup_slots              received entry slots -> sort + lookup (kept inside the handle) and, per GLOBAL
+ *                                       query (rank * queries_per_rank + local), the vote tuples this shard holds
+ *   [all-reduce (sum) of the tuple counts: every rank then derives the SAME region layout of every owner; the owner
+ *    must have zeroed its fill counters and query flags before it joins this all-reduce]
+ *   sia_index_scatter_peers             posting runs -> tuples -> the owners' regions (h_peer_*: world pointers each,
+ *                                       entry [rank] = the local buffers)
+ *   [barrier: all shards have written]
+ *   sia_vote_count_regions              the owner counts its regions: same outputs as sia_vote_key_slots.
+ * d_info (4 x int64, zeroed per pass): [0] flags (1 = an entry slot overflowed at its sender, 4 = some owner's regions do
+ * not fit region_cap tuple slots / fill_cap regions: nothing was scattered or counted), [1] low word: queries that need
+ * the key-exchange path (a bin above 24576 tuples), [2] entry slot size needed, [3] region tuple slots needed. */
+int sia_peer_alloc(int device, int64_t bytes, void **d_ptr, uint8_t *h_handle64);
+int sia_peer_open(int device, const uint8_t *h_handle64, void **d_ptr);
+int sia_peer_close(int device, void *d_ptr);
+int sia_peer_free(int device, void *d_ptr);
+int sia_index_lookup_slots(sia_index *ix, const void *d_entry_slots, int32_t world, int64_t entry_cap,
+                           int32_t queries_per_rank, int64_t *d_tuples, int64_t *d_info, void *stream);
+int sia_index_scatter_peers(sia_index *ix, int32_t world, int32_t queries_per_rank, const int64_t *d_tuples_total,
+                            void *const *h_peer_regions, void *const *h_peer_fill, void *const *h_peer_qover,
+                            int64_t region_cap, int64_t fill_cap, int64_t *d_info, void *stream);
+int sia_vote_count_regions(int device, const int64_t *d_tuples_total, int32_t n_queries, int32_t topn, uint64_t *d_regions,
+                           uint32_t *d_fill, uint32_t *d_qover, int64_t region_cap, int64_t fill_cap, int32_t *d_out_song,
+                           int32_t *d_out_diff, int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres,
+                           int64_t *d_info, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

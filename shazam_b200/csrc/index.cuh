@@ -165,6 +165,7 @@ __device__ __forceinline__ const uint64_t *slot_keys(const uint64_t *__restrict_
 // lives in exactly one partition, so the merge of per-partition top-n lists is exact).  Queries whose partitions do
 // not fit (a song with > 16384 tuples, > 512 * 16384 tuples, thousands of tied bins in one partition) are flagged in d_qover and left to the table vote.
 constexpr int kPvMaxTopn = 32;
+constexpr int kPvMaxPeers = 16;
 struct PvOut { int32_t *song, *diff, *count, *rows, *nres; };
 // scratch bytes for `tuples` vote tuples of nq queries arriving from n_src sources (worst case)
 size_t pvote_bytes(int64_t tuples, int64_t nq, int n_src, int topn);
@@ -179,6 +180,16 @@ int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uin
                   double *stage_ms /* NULL, or += {layout, scatter, count + merge} */);
 // slotted vote keys, each slot sorted by query id (else d_flags2[0] is set and the outputs are garbage); out.rows = 0.
 // d_over_count: incremented once per flagged query.
+// hash-prefix sharding over peer memory (index_dist.cu: sia_index_scatter_peers / sia_vote_count_regions)
+int pvote_scatter_peers(Arena &ar, const Lookup &L, const longlong2 *d_einfo, const uint32_t *d_qh, const uint64_t *post,
+                        const int64_t *d_q_ent, const int64_t *d_goff, int world, int qp, const int64_t *d_t_total,
+                        void *const *peer_regions, void *const *peer_fill, void *const *peer_qover, int64_t region_cap,
+                        int64_t fill_cap, int64_t *d_info, cudaStream_t s);
+int pvote_count_regions(Arena &ar, const int64_t *d_t_total, int nq, int topn, uint64_t *d_regions, uint32_t *d_fill,
+                        uint32_t *d_qover, int64_t region_cap, int64_t fill_cap, const PvOut &out, int64_t *d_info,
+                        uint32_t *d_over_count, cudaStream_t s);
+Arena &vote_arena(int device);
+int vote_scratch_finish_and_reserve(int device, size_t bytes);
 int pvote_key_slots(Arena &ar, const uint64_t *d_keys, int n_slots, int64_t cap, const int64_t *d_counts, int nq, int topn,
                     const PvOut &out, uint32_t *d_qover, uint32_t *d_flags2 /* [0] unsorted, [1] flagged queries */,
                     cudaStream_t s);
@@ -206,6 +217,12 @@ struct sia_index {
   sia::Arena arena3;                // vote tables
   cudaEvent_t ev_q[3] = {nullptr, nullptr, nullptr};   // start / after lookup / end of a query pass
   double last_lookup_ms = 0, last_vote_ms = 0;          // device time of the last sia_index_query_batch call
+  // hash-prefix sharding over peer memory: the lookup of the pass in flight (lives in `arena` until the next reserve)
+  sia::Lookup dist_L;
+  longlong2 *dist_einfo = nullptr;
+  uint32_t *dist_qh = nullptr;
+  int64_t *dist_q_ent = nullptr, *dist_goff = nullptr;
+  int dist_nq = 0;
   uint64_t *stage = nullptr;        // staging chunk of the in-place posting moves
   int64_t stage_cap = 0;
 

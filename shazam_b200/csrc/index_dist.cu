@@ -13,6 +13,8 @@
 // with larger slots.
 #include "index.cuh"
 
+#include <cstring>
+
 using namespace sia;
 
 namespace {
@@ -124,6 +126,23 @@ expand_slots_kernel(const ulonglong2 *__restrict__ ent, int64_t n, const int64_t
   }
 }
 
+// entries are sorted by global query id: entry / tuple offsets at which every query starts, and its tuple count here
+__global__ void query_bounds_kernel(const ulonglong2 *__restrict__ ent, int64_t n, const int64_t *__restrict__ off_all, int nq,
+                                    int64_t *__restrict__ q_ent, int64_t *__restrict__ goff, int64_t *__restrict__ tuples) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q <= nq; q += gridDim.x * blockDim.x) {
+    int64_t b[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int64_t lo = 0, hi = n;
+      while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if ((int64_t)(ent[mid].y >> 40) < (int64_t)q + h) lo = mid + 1; else hi = mid; }
+      b[h] = lo;
+    }
+    q_ent[q] = b[0];
+    goff[q] = off_all[b[0]];
+    if (q < nq) tuples[q] = off_all[b[1]] - off_all[b[0]];
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -189,5 +208,110 @@ int sia_vote_key_slots(int device, const uint64_t *d_key_slots, int32_t n_slots,
 }
 
 int sia_vote_finish(int device) { return vote_key_slots_finish(device); }
+
+// ---- hash-prefix sharding over peer memory (NVLink P2P) -----------------------------------------------------------
+int sia_peer_alloc(int device, int64_t bytes, void **d_ptr, uint8_t *h_handle64) {
+  SIA_REQUIRE(d_ptr && h_handle64 && bytes > 0, SIA_E_INVALID, "peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  SIA_CUDA(cudaSetDevice(device));
+  SIA_CUDA(cudaMalloc(d_ptr, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  SIA_CUDA(cudaIpcGetMemHandle(&h, *d_ptr));
+  memcpy(h_handle64, &h, 64);
+  return SIA_OK;
+}
+
+int sia_peer_open(int device, const uint8_t *h_handle64, void **d_ptr) {
+  SIA_REQUIRE(d_ptr && h_handle64, SIA_E_INVALID, "peer_open: bad argument");
+  SIA_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, h_handle64, 64);
+  SIA_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SIA_OK;
+}
+
+int sia_peer_close(int device, void *d_ptr) {
+  if (!d_ptr) return SIA_OK;
+  SIA_CUDA(cudaSetDevice(device));
+  SIA_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return SIA_OK;
+}
+
+int sia_peer_free(int device, void *d_ptr) {
+  if (!d_ptr) return SIA_OK;
+  SIA_CUDA(cudaSetDevice(device));
+  SIA_CUDA(cudaFree(d_ptr));
+  return SIA_OK;
+}
+
+int sia_index_lookup_slots(sia_index *ix, const void *d_entry_slots, int32_t world, int64_t entry_cap, int32_t queries_per_rank,
+                           int64_t *d_tuples, int64_t *d_info, void *stream) {
+  SIA_REQUIRE(ix && d_entry_slots && d_tuples && d_info, SIA_E_INVALID, "NULL argument");
+  SIA_REQUIRE(ix->n_pending == 0, SIA_E_INVALID, "index has pending rows: call sia_index_finalize first");
+  SIA_REQUIRE(world >= 1 && world <= kPvMaxPeers && entry_cap >= 2 && queries_per_rank >= 1 &&
+              (int64_t)world * queries_per_rank < (1 << 24) - 1, SIA_E_INVALID, "lookup_slots: bad sizes");
+  SIA_CUDA(cudaSetDevice(ix->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = (int64_t)world * (entry_cap - 1);
+  const int nq = world * queries_per_rank;
+  int rc = ix->arena.reserve((size_t)n * (32 + 20) + lookup_bytes(n) + (size_t)(nq + 1) * 16 + (1 << 20));
+  if (rc) return rc;
+  ulonglong2 *a = ix->arena.take<ulonglong2>(n), *b = ix->arena.take<ulonglong2>(n);
+  ix->dist_q_ent = ix->arena.take<int64_t>(nq + 1);
+  ix->dist_goff = ix->arena.take<int64_t>(nq + 1);
+  ix->dist_einfo = ix->arena.take<longlong2>(n);
+  ix->dist_qh = ix->arena.take<uint32_t>(n);
+  ix->dist_nq = 0;
+  SIA_REQUIRE(a && b && ix->dist_q_ent && ix->dist_goff && ix->dist_einfo && ix->dist_qh, SIA_E_NOMEM,
+              "index scratch arena too small (lookup_slots)");
+  gather_entries_kernel<<<grid_for(n), 256, 0, s>>>(static_cast<const ulonglong2 *>(d_entry_slots), world, entry_cap, a, d_info);
+  SIA_CHECK_LAUNCH();
+  if ((rc = lookup_sorted(ix, ix->arena, a, b, n, nullptr, 0, 0, 0, ix->dist_L, s))) return rc;
+  query_bounds_kernel<<<grid_for(nq + 1), 256, 0, s>>>(ix->dist_L.ent, n, ix->dist_L.off_all, nq, ix->dist_q_ent, ix->dist_goff, d_tuples);
+  SIA_CHECK_LAUNCH();
+  if ((rc = pvote_entry_info(ix->dist_L, ix->dist_einfo, ix->dist_qh, s))) return rc;
+  ix->dist_nq = nq;
+  return SIA_OK;
+}
+
+int sia_index_scatter_peers(sia_index *ix, int32_t world, int32_t queries_per_rank, const int64_t *d_tuples_total,
+                            void *const *h_peer_regions, void *const *h_peer_fill, void *const *h_peer_qover, int64_t region_cap,
+                            int64_t fill_cap, int64_t *d_info, void *stream) {
+  SIA_REQUIRE(ix && d_tuples_total && h_peer_regions && h_peer_fill && h_peer_qover && d_info, SIA_E_INVALID, "NULL argument");
+  SIA_REQUIRE(ix->dist_nq == world * queries_per_rank && ix->dist_nq > 0, SIA_E_INVALID,
+              "scatter_peers: call sia_index_lookup_slots for this pass first");
+  SIA_CUDA(cudaSetDevice(ix->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nq = ix->dist_nq;
+  const int64_t blocks = ceil_div(std::max<int64_t>(ix->dist_L.tuples, 1), 8192) + nq;
+  int rc = ix->arena3.reserve((size_t)nq * 80 + (size_t)blocks * 4 + (1 << 16));
+  if (rc) return rc;
+  rc = pvote_scatter_peers(ix->arena3, ix->dist_L, ix->dist_einfo, ix->dist_qh, ix->post, ix->dist_q_ent, ix->dist_goff, world,
+                           queries_per_rank, d_tuples_total, h_peer_regions, h_peer_fill, h_peer_qover, region_cap, fill_cap, d_info, s);
+  ix->dist_nq = 0;
+  return rc;
+}
+
+int sia_vote_count_regions(int device, const int64_t *d_tuples_total, int32_t n_queries, int32_t topn, uint64_t *d_regions,
+                           uint32_t *d_fill, uint32_t *d_qover, int64_t region_cap, int64_t fill_cap, int32_t *d_out_song,
+                           int32_t *d_out_diff, int32_t *d_out_count, int32_t *d_out_rows, int32_t *d_out_nres, int64_t *d_info,
+                           void *stream) {
+  SIA_REQUIRE(d_tuples_total && d_regions && d_fill && d_qover && d_info, SIA_E_INVALID, "NULL argument");
+  SIA_REQUIRE(n_queries >= 0 && topn >= 1 && topn <= kPvMaxTopn && fill_cap >= 1 && fill_cap < (1ll << 31), SIA_E_INVALID,
+              "count_regions: bad sizes (topn <= 32)");
+  if (n_queries == 0) return SIA_OK;
+  SIA_REQUIRE(d_out_song && d_out_diff && d_out_count && d_out_rows && d_out_nres, SIA_E_INVALID, "NULL output");
+  SIA_REQUIRE(device >= 0 && device < 64, SIA_E_INVALID, "device index");
+  SIA_CUDA(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  SIA_CUDA(cudaMemsetAsync(d_out_nres, 0, sizeof(int32_t) * n_queries, s));
+  for (int32_t *o : {d_out_song, d_out_diff, d_out_count, d_out_rows})
+    SIA_CUDA(cudaMemsetAsync(o, 0, sizeof(int32_t) * (size_t)n_queries * topn, s));
+  int rc = vote_scratch_finish_and_reserve(device, (size_t)n_queries * 64 + (size_t)fill_cap * (4 + 8 * (size_t)topn) + (1 << 16));
+  if (rc) return rc;
+  const PvOut po{d_out_song, d_out_diff, d_out_count, d_out_rows, d_out_nres};
+  return pvote_count_regions(vote_arena(device), d_tuples_total, n_queries, topn, d_regions, d_fill, d_qover, region_cap, fill_cap, po,
+                             d_info, reinterpret_cast<uint32_t *>(d_info + 1), s);
+}
 
 }  // extern "C"

@@ -204,6 +204,10 @@ struct ScatterArgs {
   const PvQuery *pq; const uint32_t *tot;
   uint64_t *regions; uint32_t *fill; uint32_t *qover; int q_lo;
   int maxp;                             // partitions the shared histogram is laid out for (>= every np of the launch)
+  // hash-prefix sharding over peer memory: query ql belongs to rank ql / qp_dest, whose regions / counters are written
+  // through NVLink (qp_dest = 0: everything is local)
+  int qp_dest;
+  uint64_t *regions_p[kPvMaxPeers]; uint32_t *fill_p[kPvMaxPeers]; uint32_t *qover_p[kPvMaxPeers];
   // source 0: posting runs of the query's entries
   const int64_t *off; const longlong2 *info; const uint32_t *qh; const uint64_t *post;
   const int64_t *q_ent; int64_t i0;
@@ -236,6 +240,12 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
   const int64_t j0 = lo + (int64_t)(b - a.seg_blk0[s]) * kBlk;
   const int n = (int)min((int64_t)kBlk, lo + (int64_t)a.seg_cnt[s] - j0);
   const uint32_t np = m.np;
+  uint64_t *regions_d = a.regions;
+  uint32_t *fill_d = a.fill, *qover_d = a.qover + a.q_lo + ql;
+  if (a.qp_dest > 0) {
+    const int d = ql / a.qp_dest;
+    regions_d = a.regions_p[d]; fill_d = a.fill_p[d]; qover_d = a.qover_p[d] + (ql - d * a.qp_dest);
+  }
   for (uint32_t p = tid; p <= np; p += kScThreads) hist[p] = 0;
 
   uint32_t pr[kTpt];                       // first the entry's (query offset, head), then partition << 13 | rank
@@ -325,9 +335,9 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
       hist[pme] = base;
       int32_t d = INT32_MIN;
       if (c) {
-        const uint32_t old = atomicAdd(&a.fill[m.ridx0 + pme], c);
+        const uint32_t old = atomicAdd(&fill_d[m.ridx0 + pme], c);
         if (old + c <= m.cap) d = (int32_t)(pme * m.cap + old) - (int32_t)base;
-        else a.qover[a.q_lo + ql] = 1u;
+        else *qover_d = 1u;
       }
       gdst[pme] = d;
     }
@@ -357,9 +367,9 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
         hist[p0 + u] = base;
         int32_t d = INT32_MIN;
         if (c) {
-          const uint32_t old = atomicAdd(&a.fill[m.ridx0 + p0 + u], c);
+          const uint32_t old = atomicAdd(&fill_d[m.ridx0 + p0 + u], c);
           if (old + c <= m.cap) d = (int32_t)((p0 + u) * m.cap + old) - (int32_t)base;
-          else a.qover[a.q_lo + ql] = 1u;
+          else *qover_d = 1u;
         }
         gdst[p0 + u] = d;
         base += c;
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
     if (i < n) idx[hist[pr[k] >> 13] + (pr[k] & 8191u)] = (uint16_t)i;
   }
   __syncthreads();
-  uint64_t *__restrict__ reg = a.regions + m.reg_off;
+  uint64_t *__restrict__ reg = regions_d + m.reg_off;
   for (int t = tid; t < n; t += kScThreads) {
     const uint64_t tup = stage[idx[t]];
     const int32_t d = gdst[pv_part((uint32_t)(tup >> (kDiffBits + 1)), (uint32_t)(tup >> 1) & (uint32_t)kDiffMask, np)];
@@ -648,6 +658,93 @@ pv_merge_kernel(const uint64_t *__restrict__ cand, const PvQuery *__restrict__ p
   if (lane == 0) out.nres[q + qid_base] = nres;
 }
 
+// dedup_hashes of the winners (recognizer.py:259-264) from the regions: one CTA per region counts the head tuples of
+// its query's winning songs (the tuples of a song are spread over the query's regions)
+__global__ void __launch_bounds__(256)
+pv_rows_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict__ fill, const PvQuery *__restrict__ pq,
+               const uint32_t *__restrict__ reg_q, const uint32_t *__restrict__ tot, int q_lo, int qid_base,
+               const uint32_t *__restrict__ qover, int topn, const int32_t *__restrict__ out_song,
+               const int32_t *__restrict__ out_nres, int32_t *__restrict__ out_rows) {
+  __shared__ uint32_t s_song[kPvMaxTopn], s_cnt[kPvMaxTopn];
+  const uint32_t r = blockIdx.x;
+  if (r >= tot[0]) return;
+  const int ql = (int)reg_q[r], q = q_lo + ql;
+  const uint32_t n = fill[r];
+  const int nres = out_nres[q + qid_base];
+  if (n == 0 || nres == 0 || qover[q]) return;
+  const PvQuery m = pq[ql];
+  if (n > m.cap) return;
+  const int64_t obase = ((int64_t)q + qid_base) * topn;
+  if ((int)threadIdx.x < nres) { s_song[threadIdx.x] = (uint32_t)out_song[obase + threadIdx.x]; s_cnt[threadIdx.x] = 0; }
+  __syncthreads();
+  const uint64_t *__restrict__ reg = regions + m.reg_off + (int64_t)(r - m.ridx0) * m.cap;
+  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+    const uint64_t t = __ldcs(reg + k);
+    if (t & 1ull) {
+      const uint32_t song = (uint32_t)(t >> (kDiffBits + 1));
+      for (int w = 0; w < nres; ++w) if (s_song[w] == song) atomicAdd(&s_cnt[w], 1u);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nres && s_cnt[threadIdx.x]) atomicAdd(out_rows + obase + threadIdx.x, (int32_t)s_cnt[threadIdx.x]);
+}
+
+// layout of every destination rank's queries from the TOTAL tuple counts (all shards): block d lays out the queries
+// [d * qp, (d + 1) * qp) exactly as rank d does for itself, so senders and owner agree on every region without talking.
+// dest_tot[2d] = regions, dest_tot[2d + 1] = tuple slots; an owner whose buffers are too small sets flag 4 in *info.
+__global__ void __launch_bounds__(1024)
+pv_layout_dest_kernel(const int64_t *__restrict__ t_total, int qp, PvTune tune, PvQuery *__restrict__ pq,
+                      uint32_t *__restrict__ q_ridx0, int64_t *__restrict__ dest_tot, int64_t region_cap, int64_t fill_cap,
+                      unsigned long long *__restrict__ info) {
+  __shared__ int64_t s_reg[1024];
+  __shared__ uint32_t s_idx[1024];
+  const int d = blockIdx.x;
+  const int64_t *__restrict__ tt = t_total + (int64_t)d * qp;
+  PvQuery *__restrict__ pqd = pq + (int64_t)d * qp;
+  const int per = (qp + 1023) / 1024;
+  const int a = min(qp, (int)threadIdx.x * per), b = min(qp, a + per);
+  int64_t reg = 0;
+  uint32_t idx = 0;
+  for (int q = a; q < b; ++q) {
+    const uint64_t t = (uint64_t)tt[q];
+    const uint32_t np = t ? pv_parts(t, tune.cap, tune.avg) : 0;
+    idx += np;
+    reg += (int64_t)np * pv_region_cap(t, tune.cap);
+  }
+  s_reg[threadIdx.x] = reg; s_idx[threadIdx.x] = idx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t r = 0; uint32_t i = 0;
+    for (int j = 0; j < 1024; ++j) { const int64_t x = s_reg[j]; const uint32_t y = s_idx[j]; s_reg[j] = r; s_idx[j] = i; r += x; i += y; }
+    dest_tot[2 * d] = i; dest_tot[2 * d + 1] = r;
+    if (q_ridx0) q_ridx0[(int64_t)d * (qp + 1) + qp] = i;
+    if (r > region_cap || (int64_t)i > fill_cap) atomicOr(info, 4ull);
+    atomicMax(info + 3, (unsigned long long)r);
+  }
+  __syncthreads();
+  reg = s_reg[threadIdx.x]; idx = s_idx[threadIdx.x];
+  for (int q = a; q < b; ++q) {
+    const uint64_t t = (uint64_t)tt[q];
+    PvQuery m;
+    m.np = t ? pv_parts(t, tune.cap, tune.avg) : 0;
+    m.cap = pv_region_cap(t, tune.cap);
+    m.nt = (uint32_t)min(t, (uint64_t)0xffffffffu);
+    m.reg_off = reg; m.ridx0 = idx;
+    pqd[q] = m;
+    if (q_ridx0) q_ridx0[(int64_t)d * (qp + 1) + q] = idx;
+    idx += m.np; reg += (int64_t)m.np * m.cap;
+  }
+}
+
+// a pass whose regions do not fit some owner's buffers is not scattered / counted at all (every rank sees the same flag)
+__global__ void pv_gate_kernel(const unsigned long long *__restrict__ info, uint32_t *__restrict__ tot, int which) {
+  if (*info & 4ull) tot[which] = 0;
+}
+__global__ void pv_set_regions_kernel(const int64_t *__restrict__ dest_tot, uint32_t *__restrict__ tot) {
+  tot[0] = (uint32_t)dest_tot[0]; tot[1] = 0;
+}
+__global__ void pv_blocks_only_kernel(const uint32_t *__restrict__ tot, uint32_t *__restrict__ tot2) { tot2[0] = 0; tot2[1] = tot[1]; }
+
 struct PvScratch {
   int64_t *seg_lo; uint32_t *seg_cnt, *seg_blk0, *q_ridx0, *tot, *fill, *blk_seg, *reg_q;
   PvQuery *pq; uint64_t *regions, *cand;
@@ -788,6 +885,81 @@ int pvote_key_slots(Arena &ar, const uint64_t *d_keys, int n_slots, int64_t cap,
                                                                      nullptr);
   pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, S.pq, nq, 0, 0, d_qover, topn, out, d_flags2 + 1,
                                                                             nullptr, nullptr);
+  SIA_CHECK_LAUNCH();
+  return SIA_OK;
+}
+
+// ---- hash-prefix sharding over peer memory ----------------------------------------------------------------------
+// Sender side: the posting runs of this shard's entries (queries of ALL ranks, numbered rank * qp + local) are scattered
+// straight into the owners' regions through NVLink.  d_t_total: tuples of every global query over all shards (the
+// all-reduced counts), from which every rank derives the same layout.
+int pvote_scatter_peers(Arena &ar, const Lookup &L, const longlong2 *d_einfo, const uint32_t *d_qh, const uint64_t *post,
+                        const int64_t *d_q_ent, const int64_t *d_goff, int world, int qp, const int64_t *d_t_total,
+                        void *const *peer_regions, void *const *peer_fill, void *const *peer_qover, int64_t region_cap,
+                        int64_t fill_cap, int64_t *d_info, cudaStream_t s) {
+  SIA_REQUIRE(world >= 1 && world <= kPvMaxPeers, SIA_E_UNSUPPORTED, "peer scatter: at most 16 ranks");
+  int rc = pv_attrs();
+  if (rc) return rc;
+  const PvTune tune = pv_tune();
+  const int nq = world * qp;
+  const int64_t blocks = ceil_div(std::max<int64_t>(L.tuples, 1), kBlk) + nq;
+  SIA_REQUIRE(blocks < (1ll << 31), SIA_E_UNSUPPORTED, "peer scatter: pass too large");
+  int64_t *seg_lo = ar.take<int64_t>(nq);
+  uint32_t *seg_cnt = ar.take<uint32_t>(nq), *seg_blk0 = ar.take<uint32_t>(nq + 1), *q_ridx2 = ar.take<uint32_t>(nq + 1);
+  uint32_t *tot = ar.take<uint32_t>(4), *blk_seg = ar.take<uint32_t>(blocks), *reg_q2 = ar.take<uint32_t>(1);
+  PvQuery *pq = ar.take<PvQuery>(nq), *pq2 = ar.take<PvQuery>(nq);
+  int64_t *dest_tot = ar.take<int64_t>(2 * (size_t)world);
+  SIA_REQUIRE(seg_lo && seg_cnt && seg_blk0 && q_ridx2 && tot && blk_seg && reg_q2 && pq && pq2 && dest_tot, SIA_E_NOMEM,
+              "index scratch arena too small (peer scatter)");
+  pv_segs_entries_kernel<<<grid_for(nq), 256, 0, s>>>(d_goff, 0, nq, seg_lo, seg_cnt);
+  // blocks of the LOCAL tuples (pq2 / q_ridx2 are by-products nobody reads) ...
+  pv_layout_kernel<<<1, 1024, 0, s>>>(seg_cnt, nq, 1, tune, pq2, q_ridx2, seg_blk0, tot);
+  // ... regions from the TOTAL counts, per owner
+  pv_layout_dest_kernel<<<world, 1024, 0, s>>>(d_t_total, qp, tune, pq, nullptr, dest_tot, region_cap, fill_cap,
+                                               reinterpret_cast<unsigned long long *>(d_info));
+  pv_gate_kernel<<<1, 1, 0, s>>>(reinterpret_cast<const unsigned long long *>(d_info), tot, 1);
+  pv_blocks_only_kernel<<<1, 1, 0, s>>>(tot, tot + 2);                  // the block -> query map only (no regions here)
+  pv_maps_kernel<<<grid_for(blocks), 256, 0, s>>>(seg_blk0, nq, q_ridx2, nq, tot + 2, blk_seg, reg_q2);
+  ScatterArgs a{};
+  a.seg_blk0 = seg_blk0; a.blk_seg = blk_seg; a.seg_lo = seg_lo; a.seg_cnt = seg_cnt; a.G = 1;
+  a.pq = pq; a.tot = tot; a.q_lo = 0; a.maxp = kMaxParts;
+  a.qp_dest = qp;
+  for (int d = 0; d < world; ++d) {
+    a.regions_p[d] = static_cast<uint64_t *>(peer_regions[d]);
+    a.fill_p[d] = static_cast<uint32_t *>(peer_fill[d]);
+    a.qover_p[d] = static_cast<uint32_t *>(peer_qover[d]);
+  }
+  a.off = L.off_all; a.info = d_einfo; a.qh = d_qh; a.post = post; a.q_ent = d_q_ent; a.i0 = 0;
+  pv_scatter_kernel<0><<<(unsigned)blocks, kScThreads, kScatterSmem, s>>>(a);
+  SIA_CHECK_LAUNCH();
+  return SIA_OK;
+}
+
+// Owner side: count + merge + rows over the regions the shards filled.  d_t_total: this rank's qp queries.
+int pvote_count_regions(Arena &ar, const int64_t *d_t_total, int nq, int topn, uint64_t *d_regions, uint32_t *d_fill,
+                        uint32_t *d_qover, int64_t region_cap, int64_t fill_cap, const PvOut &out, int64_t *d_info,
+                        uint32_t *d_over_count, cudaStream_t s) {
+  if (nq <= 0) return SIA_OK;
+  int rc = pv_attrs();
+  if (rc) return rc;
+  const PvTune tune = pv_tune();
+  const int64_t regions = fill_cap;                       // upper bound of the grid; the kernels stop at tot[0]
+  PvQuery *pq = ar.take<PvQuery>(nq);
+  uint32_t *q_ridx0 = ar.take<uint32_t>(nq + 1), *tot = ar.take<uint32_t>(4), *reg_q = ar.take<uint32_t>(regions);
+  uint32_t *blk_seg = ar.take<uint32_t>(1), *seg_blk0 = ar.take<uint32_t>(2);
+  int64_t *dest_tot = ar.take<int64_t>(2);
+  uint64_t *cand = ar.take<uint64_t>(regions * topn);
+  SIA_REQUIRE(pq && q_ridx0 && tot && reg_q && blk_seg && seg_blk0 && dest_tot && cand, SIA_E_NOMEM, "vote scratch too small (regions)");
+  pv_layout_dest_kernel<<<1, 1024, 0, s>>>(d_t_total, nq, tune, pq, q_ridx0, dest_tot, region_cap, fill_cap,
+                                           reinterpret_cast<unsigned long long *>(d_info));
+  pv_set_regions_kernel<<<1, 1, 0, s>>>(dest_tot, tot);
+  pv_gate_kernel<<<1, 1, 0, s>>>(reinterpret_cast<const unsigned long long *>(d_info), tot, 0);
+  SIA_CUDA(cudaMemsetAsync(seg_blk0, 0, 2 * sizeof(uint32_t), s));
+  pv_maps_kernel<<<grid_for(regions), 256, 0, s>>>(seg_blk0, 1, q_ridx0, nq, tot, blk_seg, reg_q);
+  pv_count_kernel<<<(unsigned)regions, kCntThreads, kCountSmem, s>>>(d_regions, d_fill, pq, reg_q, tot, 0, d_qover, topn, cand, nullptr);
+  pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(cand, pq, nq, 0, 0, d_qover, topn, out, d_over_count, nullptr,
+                                                                            nullptr);
+  pv_rows_kernel<<<(unsigned)regions, 256, 0, s>>>(d_regions, d_fill, pq, reg_q, tot, 0, 0, d_qover, topn, out.song, out.nres, out.rows);
   SIA_CHECK_LAUNCH();
   return SIA_OK;
 }

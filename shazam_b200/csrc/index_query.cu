@@ -796,6 +796,8 @@ static int64_t bin_slots_for(int64_t tuples, int64_t nq, int attempt) {
   return (attempt == 0 ? tuples / 2 : 2 * tuples) + 32 * nq;
 }
 
+Arena &vote_arena(int device) { return g_vote_tables[device]; }
+
 void vote_scratch_release(int device) {
   if (device >= 0 && device < 64) g_vote_tables[device].release();
 }
@@ -997,6 +999,13 @@ int vote_key_slots(int device, const uint64_t *d_keys, int n_slots, int64_t cap,
   if (rc) return rc;
   v.pending = true;
   return defer ? SIA_OK : vote_key_slots_finish(device);
+}
+
+// completes a vote left in flight on the device (it owns the arena), then sizes the arena for a new user
+int vote_scratch_finish_and_reserve(int device, size_t bytes) {
+  int rc = vote_key_slots_finish(device);
+  if (rc) return rc;
+  return g_vote_tables[device].reserve(bytes);
 }
 
 }  // namespace sia

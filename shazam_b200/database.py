@@ -229,6 +229,96 @@ class FingerprintIndex:
                                                 C.c_void_p(info.data_ptr()), self._stream()))
         return out
 
+    def lookup_slots(self, entry_slots: torch.Tensor, world: int, queries_per_rank: int, info: torch.Tensor) -> torch.Tensor:
+        """Peer-memory pass, step 1 on the shard: sort + look up the received entries (kept inside the handle) and
+        return the vote tuples this shard holds for every global query, int64[world * queries_per_rank]."""
+        self.finalize()
+        assert entry_slots.is_cuda and entry_slots.dtype == torch.int64 and entry_slots.is_contiguous()
+        t = torch.zeros(world * queries_per_rank, dtype=torch.int64, device=self.tdev)
+        N.check(self.lib.sia_index_lookup_slots(self._h, C.c_void_p(entry_slots.data_ptr()), int(world), int(entry_slots.shape[1]),
+                                                int(queries_per_rank), C.c_void_p(t.data_ptr()), C.c_void_p(info.data_ptr()),
+                                                self._stream()))
+        return t
+
+    def scatter_peers(self, world: int, queries_per_rank: int, tuples_total: torch.Tensor, peers: "PeerBuffers",
+                      info: torch.Tensor) -> None:
+        """Step 2 on the shard: posting runs -> vote tuples -> the owners' regions, through NVLink."""
+        t = tuples_total.contiguous()
+        N.check(self.lib.sia_index_scatter_peers(self._h, int(world), int(queries_per_rank), C.c_void_p(t.data_ptr()),
+                                                 peers.p_regions, peers.p_fill, peers.p_qover, peers.region_cap, peers.fill_cap,
+                                                 C.c_void_p(info.data_ptr()), self._stream()))
+
+
+class _RawCuda:
+    """A device pointer as an object torch can alias (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerBuffers:
+    """The regions of the partitioned vote of one rank, mapped by every rank of the group (CUDA IPC over NVLink):
+    ``[query flags: qp x u32][fill counters: fill_cap x u32][regions: region_cap x u64]``.  Collective: every rank
+    allocates, the 64-byte handles are all-gathered, every rank opens the others'."""
+
+    def __init__(self, device: int, rank: int, world: int, qp: int, region_cap: int, fill_cap: int, group=None):
+        import torch.distributed as dist
+        self.lib = N.lib()
+        self.device, self.rank, self.world = device, rank, world
+        self.qp, self.region_cap, self.fill_cap = int(qp), int(region_cap), int(fill_cap)
+        up = lambda x: (x + 255) // 256 * 256
+        self.off_fill = up(4 * self.qp)
+        self.off_regions = up(self.off_fill + 4 * self.fill_cap)
+        self.nbytes = self.off_regions + 8 * self.region_cap
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        N.check(self.lib.sia_peer_alloc(device, self.nbytes, C.byref(ptr), C.cast(handle, C.c_void_p)))
+        self.local = int(ptr.value)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.base = []
+        for r in range(world):
+            if r == rank:
+                self.base.append(self.local)
+                continue
+            q = C.c_void_p()
+            buf = (C.c_uint8 * 64).from_buffer_copy(handles[r])
+            N.check(self.lib.sia_peer_open(device, C.cast(buf, C.c_void_p), C.byref(q)))
+            self.base.append(int(q.value))
+        arr = lambda off: (C.c_void_p * world)(*[b + off for b in self.base])
+        self.p_qover, self.p_fill, self.p_regions = arr(0), arr(self.off_fill), arr(self.off_regions)
+        tdev = torch.device("cuda", device)
+        # local counters (query flags + fill) as one int32 tensor, for the stream-ordered zeroing before every pass
+        self.counters = torch.as_tensor(_RawCuda(self.local, self.off_regions // 4, "<i4"), device=tdev)
+
+    def close(self, group=None):
+        import torch.distributed as dist
+        if self.local is None:
+            return
+        torch.cuda.synchronize(self.device)
+        for r, b in enumerate(self.base):
+            if r != self.rank:
+                N.check(self.lib.sia_peer_close(self.device, C.c_void_p(b)))
+        dist.barrier(group=group)                 # nobody maps this rank's buffer any more
+        del self.counters
+        N.check(self.lib.sia_peer_free(self.device, C.c_void_p(self.local)))
+        self.local = None
+
+
+def vote_count_regions(device: int, tuples_total: torch.Tensor, n_queries: int, topn: int, peers: "PeerBuffers", info: torch.Tensor):
+    """The owner's half of the peer-memory pass: count the regions the shards filled (``sia_vote_count_regions``)."""
+    lib = N.lib()
+    tdev = torch.device("cuda", device)
+    outs, nres = _vote_outputs(tdev, n_queries, topn)
+    t = tuples_total.contiguous()
+    N.check(lib.sia_vote_count_regions(device, C.c_void_p(t.data_ptr()), int(n_queries), int(topn),
+                                       C.c_void_p(peers.local + peers.off_regions), C.c_void_p(peers.local + peers.off_fill),
+                                       C.c_void_p(peers.local), peers.region_cap, peers.fill_cap,
+                                       C.c_void_p(outs[0].data_ptr()), C.c_void_p(outs[1].data_ptr()), C.c_void_p(outs[2].data_ptr()),
+                                       C.c_void_p(outs[3].data_ptr()), C.c_void_p(nres.data_ptr()), C.c_void_p(info.data_ptr()),
+                                       C.c_void_p(torch.cuda.current_stream(tdev).cuda_stream)))
+    return (*outs, nres)
+
 
 def route_entries(device: int, digests: torch.Tensor, qoffsets: torch.Tensor, query_starts: torch.Tensor, qid_base: int,
                   world: int, slot_cap: int, status: torch.Tensor) -> torch.Tensor:

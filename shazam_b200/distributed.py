@@ -99,6 +99,10 @@ class ShardBackend:
         """Completes a ``vote_key_slots(..., defer=True)``."""
         raise NotImplementedError
 
+    # the peer-memory pass (CUDA only): None = this backend cannot do it
+    def make_peers(self, rank: int, world: int, qp: int, region_cap: int, fill_cap: int, group=None):
+        return None
+
     def query_batch(self, digests, qoffsets, query_starts, topn: int):
         raise NotImplementedError
 
@@ -139,6 +143,20 @@ class CudaShard(ShardBackend):
     def query_batch(self, digests, qoffsets, query_starts, topn):
         return self.index.query_batch(digests, qoffsets, query_starts, topn)
 
+    def make_peers(self, rank, world, qp, region_cap, fill_cap, group=None):
+        from .database import PeerBuffers
+        return PeerBuffers(self._dev_index, rank, world, qp, region_cap, fill_cap, group)
+
+    def lookup_slots(self, entry_slots, world, queries_per_rank, info):
+        return self.index.lookup_slots(entry_slots, world, queries_per_rank, info)
+
+    def scatter_peers(self, world, queries_per_rank, tuples_total, peers, info):
+        self.index.scatter_peers(world, queries_per_rank, tuples_total, peers, info)
+
+    def count_regions(self, tuples_total, n_queries, topn, peers, info):
+        from .database import vote_count_regions
+        return vote_count_regions(self._dev_index, tuples_total, n_queries, topn, peers, info)
+
     def close(self):
         self.index.close()
 
@@ -147,7 +165,17 @@ class ShardedIndex:
     """The hash-prefix-sharded fingerprints table over ``world`` ranks."""
 
     def __init__(self, backend: ShardBackend, rank: Optional[int] = None, world: Optional[int] = None, group=None,
-                 key_cap: int = 1 << 16):
+                 key_cap: int = 1 << 16, exchange: str = "keys", region_cap: int = 1 << 20):
+        """``exchange``: "keys" — the shards write vote keys, NCCL all-to-all #2 moves them, the query's owner
+        partitions and counts them; "peer" — the second exchange is fused into the shards' scatter kernel, which writes
+        the vote tuples straight into the owner's regions through NVLink peer memory (CUDA backends only), the owner
+        only counts.  Both give the single-index result; a pass that "peer" cannot take (a bin above the region size)
+        is redone with "keys"."""
+        assert exchange in ("keys", "peer")
+        self.exchange = exchange
+        self.region_cap = max(1 << 16, int(region_cap))   # tuple slots of this rank's regions (grown on demand)
+        self.peers = None
+        self.peer_fallbacks = 0     # passes redone with the key exchange
         self.backend = backend
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
@@ -200,6 +228,14 @@ class ShardedIndex:
         nres = torch.zeros(q_local, dtype=torch.int32, device=dev)
         qs_dev = torch.as_tensor(qs, dtype=torch.int64, device=dev)
         passes = [(min(lo, q_local), min(lo + qp, q_local)) for lo in range(0, max_q, qp)]
+        if self.exchange == "peer":
+            for a, b in passes:
+                e0, e1 = int(qs[a]), int(qs[b])
+                res = self._peer_pass(digests[e0:e1], qoffsets[e0:e1], qs_dev[a:b + 1] - e0, qp, b - a, topn)
+                for o, r in zip(outs, res[:4]):
+                    o[a:b] = r[:b - a]
+                nres[a:b] = res[4][:b - a]
+            return (*outs, nres)
         # Software pipeline over the passes: while the vote of pass i runs on the caller's stream, the routing, lookup,
         # expansion and both all-to-alls of pass i+1 run on a second (high-priority) stream.
         cuda = dev.type == "cuda"
@@ -235,6 +271,79 @@ class ShardedIndex:
             nres[a:b] = res[4]
             del keys
         return (*outs, nres)
+
+    # ---- the peer-memory pass ---------------------------------------------------------------------------------
+    def _ensure_peers(self, qp: int):
+        if self.peers is not None and (self.peers.qp != qp or self.peers.region_cap < self.region_cap):
+            self.peers.close(self.group)
+            self.peers = None
+        if self.peers is None:
+            fill_cap = qp + self.region_cap // 8192 + 64
+            self.peers = self.backend.make_peers(self.rank, self.world, qp, self.region_cap, fill_cap, self.group)
+            if self.peers is None:
+                raise RuntimeError("exchange='peer' needs a CUDA shard backend")
+
+    def close_peers(self):
+        if self.peers is not None:
+            self.peers.close(self.group)
+            self.peers = None
+
+    def _peer_pass(self, digests, qoffsets, qs_dev, qp, nq_local, topn):
+        """One pass with the vote tuples written into the owners' regions by the shards (see ``sia_b200.h``).  Collective.
+        Returns this rank's (song, diff, count, rows, nres) for its ``qp`` query slots."""
+        be, dev, G = self.backend, self.backend.device, self.world
+        timing = bool(os.environ.get("SIA_DIST_TIMING"))
+        marks = []
+
+        def mark(name):
+            if timing:
+                torch.cuda.synchronize(dev)
+                marks.append((name, time.perf_counter()))
+        while True:
+            self._ensure_peers(qp)
+            mark("start")
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+            info = torch.zeros(4, dtype=torch.int64, device=dev)
+            send_e = be.route_entries(digests, qoffsets, qs_dev, self.rank * qp, G, self.entry_cap, status)
+            mark("route")
+            recv_e = torch.empty_like(send_e)
+            dist.all_to_all_single(recv_e, send_e, group=self.group)
+            mark("all-to-all entries")
+            t = be.lookup_slots(recv_e, G, qp, info)
+            self.peers.counters.zero_()                   # before the all-reduce: every owner is clean when any shard starts
+            dist.all_reduce(t, group=self.group)          # tuples of every global query over all shards
+            mark("lookup + all-reduce of the tuple counts")
+            be.scatter_peers(G, qp, t, self.peers, info)
+            chk = torch.cat([info, status.to(torch.int64)])
+            dist.all_reduce(chk, op=dist.ReduceOp.MAX, group=self.group)      # also the barrier: all shards have written
+            mark("scatter into the owners' regions (NVLink) + barrier")
+            res = be.count_regions(t[self.rank * qp:(self.rank + 1) * qp], qp, topn, self.peers, info)
+            flagged = info[1:2].clone()
+            dist.all_reduce(flagged, op=dist.ReduceOp.MAX, group=self.group)
+            mark("count + merge + rows")
+            flags, _, need_e, need_r, st = (int(x) for x in chk.tolist())
+            n_flagged = int(flagged.item()) & 0xffffffff
+            if timing:
+                self.last_pass_ms = {n: (tm - marks[i][1]) * 1e3 for i, (n, tm) in enumerate(marks[1:])}
+            if st & 2:
+                raise ValueError("query: offset outside 0..2^24-1 or more than 2^24 queries in one pass")
+            if flags & 1:
+                self.entry_cap = int(need_e * 1.25) + 64
+                self.retries += 1
+                continue
+            if flags & 4:                                 # some owner's regions were too small: grow everywhere, redo
+                self.region_cap = int(need_r * 1.25) + (1 << 16)
+                self.retries += 1
+                continue
+            if n_flagged:                                 # a bin above the region size somewhere: the key exchange takes the pass
+                self.peer_fallbacks += 1
+                while True:
+                    keys = self._prepare_pass(digests, qoffsets, qs_dev, qp)
+                    if keys is not None:
+                        break
+                    self.retries += 1
+                res = be.vote_key_slots(keys, nq_local, topn, self._max_song)
+            return res
 
     def _prepare_pass(self, digests, qoffsets, qs_dev, qp):
         """Everything of one pass up to the vote: this rank's queries (``qs_dev``: their entry offsets into ``digests``,

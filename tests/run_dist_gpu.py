@@ -1,7 +1,8 @@
 """Multi-GPU check (launch under torchrun on N >= 2 GPUs of one node):
   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/run_dist_gpu.py
 Track-sharded fingerprinting -> hash-prefix-sharded index (NCCL all-to-all) -> routed queries with the
-exact vote over the exchanged keys; every rank's results must equal a single-GPU index built from all rows."""
+exact vote over the exchanged keys — and the same pass with the exchange fused into the scatter kernel over NVLink peer
+memory; every rank's results must equal a single-GPU index built from all rows."""
 import os
 import sys
 
@@ -48,13 +49,22 @@ def main():
     qb = fp.fingerprint_tracks([clips[i] for i in myq], fan_value=15)
     D, Oq = torch.from_numpy(qb.hash).to(dev), torch.from_numpy(qb.t1).to(dev)
     want = single.query_batch(D, Oq, qb.starts, 3)
-    for name in ("hash", "hash small passes", "track"):
+    peer = ShardedIndex(sharded.backend, exchange="peer")          # the same shards, vote tuples written through NVLink
+    peer._max_song, peer.entry_cap = sharded._max_song, sharded.entry_cap
+    for name in ("hash", "hash small passes", "track", "peer", "peer small passes", "peer, forced fallback"):
         if name == "track":
             got = by_track.query(D, Oq, qb.starts, 3)
+        elif name.startswith("peer"):
+            if "fallback" in name:
+                os.environ["SIA_PVOTE_CAP"] = "64"                 # every region overflows: the key exchange takes the pass
+            got = peer.query(D, Oq, qb.starts, 3, queries_per_pass=3 if "small" in name else 4096)
+            os.environ.pop("SIA_PVOTE_CAP", None)
         else:
             got = sharded.query(D, Oq, qb.starts, 3, queries_per_pass=4096 if name == "hash" else 3)
         for a, w in zip(got, want):
             assert torch.equal(a, w), (name, rank, a, w)
+    assert peer.peer_fallbacks >= 1
+    peer.close_peers()
     top = got[0][:, 0].cpu().tolist()
     assert top == [(i % ntracks) + 1 for i in myq], (top, myq)
     dist.barrier()
