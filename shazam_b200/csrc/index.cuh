@@ -178,7 +178,7 @@ int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uin
                   uint32_t *d_qover, uint32_t *d_qbins /* [nq_pass], zeroed: distinct bins per query */,
                   unsigned long long *d_nbins /* NULL, or += the bins of the settled queries */, cudaStream_t s,
                   double *stage_ms /* NULL, or += {layout, scatter, count + merge} */);
-// slotted vote keys, each slot sorted by query id (else d_flags2[0] is set and the outputs are garbage); out.rows = 0.
+// slotted vote keys, each slot sorted by query id (else d_flags2[0] is set and the outputs are garbage); rows counted from the regions.
 // d_over_count: incremented once per flagged query.
 // hash-prefix sharding over peer memory (index_dist.cu: sia_index_scatter_peers / sia_vote_count_regions)
 int pvote_scatter_peers(Arena &ar, const Lookup &L, const longlong2 *d_einfo, const uint32_t *d_qh, const uint64_t *post,

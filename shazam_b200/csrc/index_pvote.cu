@@ -164,7 +164,7 @@ pv_layout_kernel(const uint32_t *__restrict__ seg_cnt, int nq, int G, PvTune tun
       s_reg[j] = r; s_idx[j] = i; s_blk[j] = k;
       r += x; i += y; k += z;
     }
-    tot[0] = i; tot[1] = k;
+    tot[0] = i; tot[1] = k; tot[2] = 0; tot[3] = 0;
     q_ridx0[nq] = i; seg_blk0[nq * G] = k;
   }
   __syncthreads();
@@ -412,10 +412,10 @@ __device__ __forceinline__ uint32_t pv_hash(uint64_t key) { return (uint32_t)(ke
 //          touch nothing;
 //   top-n  by one warp from the bins that reached count 2; if fewer than topn songs have one, the bins of count 1
 //          decide: the CTA scans the tuples themselves.
-__global__ void __launch_bounds__(kCntThreads, 3)
-pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict__ fill, const PvQuery *__restrict__ pq,
-                const uint32_t *__restrict__ reg_q, const uint32_t *__restrict__ tot, int q_lo,
-                uint32_t *__restrict__ qover, int topn, uint64_t *__restrict__ cand, uint32_t *__restrict__ qbins) {
+__device__ __forceinline__ void
+pv_count_region(const uint32_t r, const uint64_t *__restrict__ regions, const uint32_t *__restrict__ fill,
+                const PvQuery *__restrict__ pq, const uint32_t *__restrict__ reg_q, int q_lo, uint32_t *__restrict__ qover, int topn,
+                uint64_t *__restrict__ cand, uint32_t *__restrict__ qbins) {
   extern __shared__ __align__(16) unsigned char pv_smem[];
   uint32_t *filt = reinterpret_cast<uint32_t *>(pv_smem);
   uint64_t *tab = reinterpret_cast<uint64_t *>(pv_smem + (size_t)kFiltWords * 4);
@@ -425,8 +425,6 @@ pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict
   __shared__ int s_nres;
   __shared__ uint64_t s_win[kPvMaxTopn];
   __shared__ uint64_t s_red[kCntThreads / 32];
-  const uint32_t r = blockIdx.x;
-  if (r >= tot[0]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n = fill[r];
   const int ql = (int)reg_q[r];
@@ -613,6 +611,24 @@ pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict
   if (tid < topn) out[tid] = tid < nres ? s_win[tid] : 0ull;
 }
 
+// CTAs take regions from a shared counter (tot[2]) until none is left: the grid is sized for the SMs, not for the
+// (device-side) number of regions
+__global__ void __launch_bounds__(kCntThreads, 3)
+pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict__ fill, const PvQuery *__restrict__ pq,
+                const uint32_t *__restrict__ reg_q, uint32_t *__restrict__ tot, int q_lo, uint32_t *__restrict__ qover, int topn,
+                uint64_t *__restrict__ cand, uint32_t *__restrict__ qbins) {
+  __shared__ uint32_t s_next;
+  const uint32_t n_regions = tot[0];
+  for (;;) {
+    __syncthreads();                          // the previous region's shared state has been read
+    if (threadIdx.x == 0) s_next = atomicAdd(&tot[2], 1u);
+    __syncthreads();
+    const uint32_t r = s_next;
+    if (r >= n_regions) return;
+    pv_count_region(r, regions, fill, pq, reg_q, q_lo, qover, topn, cand, qbins);
+  }
+}
+
 // ---- merge ----------------------------------------------------------------------------------------------------
 // one warp per query: top-n over its regions' candidates.  A song's bins are spread over the partitions, so the same
 // song can come from several regions: in descending order its first occurrence is its best bin, later ones are skipped.
@@ -666,27 +682,28 @@ pv_rows_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict_
                const uint32_t *__restrict__ qover, int topn, const int32_t *__restrict__ out_song,
                const int32_t *__restrict__ out_nres, int32_t *__restrict__ out_rows) {
   __shared__ uint32_t s_song[kPvMaxTopn], s_cnt[kPvMaxTopn];
-  const uint32_t r = blockIdx.x;
-  if (r >= tot[0]) return;
-  const int ql = (int)reg_q[r], q = q_lo + ql;
-  const uint32_t n = fill[r];
-  const int nres = out_nres[q + qid_base];
-  if (n == 0 || nres == 0 || qover[q]) return;
-  const PvQuery m = pq[ql];
-  if (n > m.cap) return;
-  const int64_t obase = ((int64_t)q + qid_base) * topn;
-  if ((int)threadIdx.x < nres) { s_song[threadIdx.x] = (uint32_t)out_song[obase + threadIdx.x]; s_cnt[threadIdx.x] = 0; }
-  __syncthreads();
-  const uint64_t *__restrict__ reg = regions + m.reg_off + (int64_t)(r - m.ridx0) * m.cap;
-  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
-    const uint64_t t = __ldcs(reg + k);
-    if (t & 1ull) {
-      const uint32_t song = (uint32_t)(t >> (kDiffBits + 1));
-      for (int w = 0; w < nres; ++w) if (s_song[w] == song) atomicAdd(&s_cnt[w], 1u);
+  const uint32_t n_regions = tot[0];
+  for (uint32_t r = blockIdx.x; r < n_regions; r += gridDim.x) {
+    const int ql = (int)reg_q[r], q = q_lo + ql;
+    const uint32_t n = fill[r];
+    const int nres = out_nres[q + qid_base];
+    const PvQuery m = pq[ql];
+    if (n == 0 || nres == 0 || qover[q] || n > m.cap) continue;       // block-uniform
+    const int64_t obase = ((int64_t)q + qid_base) * topn;
+    __syncthreads();
+    if ((int)threadIdx.x < nres) { s_song[threadIdx.x] = (uint32_t)out_song[obase + threadIdx.x]; s_cnt[threadIdx.x] = 0; }
+    __syncthreads();
+    const uint64_t *__restrict__ reg = regions + m.reg_off + (int64_t)(r - m.ridx0) * m.cap;
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+      const uint64_t t = __ldcs(reg + k);
+      if (t & 1ull) {
+        const uint32_t song = (uint32_t)(t >> (kDiffBits + 1));
+        for (int w = 0; w < nres; ++w) if (s_song[w] == song) atomicAdd(&s_cnt[w], 1u);
+      }
     }
+    __syncthreads();
+    if ((int)threadIdx.x < nres && s_cnt[threadIdx.x]) atomicAdd(out_rows + obase + threadIdx.x, (int32_t)s_cnt[threadIdx.x]);
   }
-  __syncthreads();
-  if ((int)threadIdx.x < nres && s_cnt[threadIdx.x]) atomicAdd(out_rows + obase + threadIdx.x, (int32_t)s_cnt[threadIdx.x]);
 }
 
 // layout of every destination rank's queries from the TOTAL tuple counts (all shards): block d lays out the queries
@@ -741,7 +758,7 @@ __global__ void pv_gate_kernel(const unsigned long long *__restrict__ info, uint
   if (*info & 4ull) tot[which] = 0;
 }
 __global__ void pv_set_regions_kernel(const int64_t *__restrict__ dest_tot, uint32_t *__restrict__ tot) {
-  tot[0] = (uint32_t)dest_tot[0]; tot[1] = 0;
+  tot[0] = (uint32_t)dest_tot[0]; tot[1] = 0; tot[2] = 0; tot[3] = 0;
 }
 __global__ void pv_blocks_only_kernel(const uint32_t *__restrict__ tot, uint32_t *__restrict__ tot2) { tot2[0] = 0; tot2[1] = tot[1]; }
 
@@ -845,7 +862,7 @@ int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uin
   if (stage_ms) cudaEventRecord(ev[1], s);
   pv_scatter_kernel<0><<<(unsigned)blocks, kScThreads, scatter_smem(a.maxp), s>>>(a);
   if (stage_ms) cudaEventRecord(ev[2], s);
-  pv_count_kernel<<<(unsigned)regions, kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, qa, d_qover, topn, S.cand,
+  pv_count_kernel<<<(unsigned)std::min<int64_t>(regions, kNumSMs * 3), kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, qa, d_qover, topn, S.cand,
                                                                      d_nbins ? d_qbins : nullptr);
   pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, S.pq, nq, qa, qid_base, d_qover, topn, out, nullptr,
                                                                             d_qbins, d_nbins);
@@ -881,10 +898,14 @@ int pvote_key_slots(Arena &ar, const uint64_t *d_keys, int n_slots, int64_t cap,
   a.maxp = kMaxParts;                                       // the queries' sizes are only known on the device
   a.keys = d_keys; a.key_cap = cap; a.counts = d_counts; a.unsorted = d_flags2;
   pv_scatter_kernel<1><<<(unsigned)blocks, kScThreads, kScatterSmem, s>>>(a);
-  pv_count_kernel<<<(unsigned)regions, kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, 0, d_qover, topn, S.cand,
+  pv_count_kernel<<<(unsigned)std::min<int64_t>(regions, kNumSMs * 3), kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, 0, d_qover, topn, S.cand,
                                                                      nullptr);
   pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, S.pq, nq, 0, 0, d_qover, topn, out, d_flags2 + 1,
                                                                             nullptr, nullptr);
+  // dedup_hashes of the winners: the head tuples of their songs, from the regions (queries left to the table vote have
+  // no winners yet and are skipped)
+  pv_rows_kernel<<<(unsigned)std::min<int64_t>(regions, kNumSMs * 16), 256, 0, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, 0, 0, d_qover, topn, out.song, out.nres,
+                                                   out.rows);
   SIA_CHECK_LAUNCH();
   return SIA_OK;
 }
@@ -956,10 +977,10 @@ int pvote_count_regions(Arena &ar, const int64_t *d_t_total, int nq, int topn, u
   pv_gate_kernel<<<1, 1, 0, s>>>(reinterpret_cast<const unsigned long long *>(d_info), tot, 0);
   SIA_CUDA(cudaMemsetAsync(seg_blk0, 0, 2 * sizeof(uint32_t), s));
   pv_maps_kernel<<<grid_for(regions), 256, 0, s>>>(seg_blk0, 1, q_ridx0, nq, tot, blk_seg, reg_q);
-  pv_count_kernel<<<(unsigned)regions, kCntThreads, kCountSmem, s>>>(d_regions, d_fill, pq, reg_q, tot, 0, d_qover, topn, cand, nullptr);
+  pv_count_kernel<<<(unsigned)std::min<int64_t>(regions, kNumSMs * 3), kCntThreads, kCountSmem, s>>>(d_regions, d_fill, pq, reg_q, tot, 0, d_qover, topn, cand, nullptr);
   pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(cand, pq, nq, 0, 0, d_qover, topn, out, d_over_count, nullptr,
                                                                             nullptr);
-  pv_rows_kernel<<<(unsigned)regions, 256, 0, s>>>(d_regions, d_fill, pq, reg_q, tot, 0, 0, d_qover, topn, out.song, out.nres, out.rows);
+  pv_rows_kernel<<<(unsigned)std::min<int64_t>(regions, kNumSMs * 16), 256, 0, s>>>(d_regions, d_fill, pq, reg_q, tot, 0, 0, d_qover, topn, out.song, out.nres, out.rows);
   SIA_CHECK_LAUNCH();
   return SIA_OK;
 }

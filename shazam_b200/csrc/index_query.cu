@@ -912,12 +912,6 @@ static int key_pvote_enqueue(KeyVote &v) {
   const PvOut po{v.o_song, v.o_diff, v.o_count, v.o_rows, v.o_nres};
   rc = pvote_key_slots(ar, v.d_keys, v.n_slots, v.cap, v.d_counts, v.n_queries, v.topn, po, v.d_small + 64, v.d_small, v.s);
   if (rc) return rc;
-  // dedup_hashes of the winners: the head keys of their songs (one more streaming pass over the keys; queries left
-  // to the table vote have no winners yet and are skipped)
-  const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(v.cap, 512), (kNumSMs * 32) / v.n_slots + 1)), (unsigned)v.n_slots);
-  keys_pass_kernel<true, PASS_ROWS><<<grid, 256, 0, v.s>>>(v.d_keys, v.cap, v.d_counts, v.n_queries, nullptr, Tables{}, nullptr, nullptr,
-                                                           nullptr, v.topn, v.o_song, v.o_nres, v.o_rows, reinterpret_cast<int32_t *>(v.d_small + 2));
-  SIA_CHECK_LAUNCH();
   if (v.timed) cudaEventRecord(v.ev[1], v.s);
   return SIA_OK;
 }

@@ -175,6 +175,7 @@ class ShardedIndex:
         self.exchange = exchange
         self.region_cap = max(1 << 16, int(region_cap))   # tuple slots of this rank's regions (grown on demand)
         self.peers = None
+        self._timing_fresh = True
         self.peer_fallbacks = 0     # passes redone with the key exchange
         self.backend = backend
         self.group = group
@@ -229,12 +230,27 @@ class ShardedIndex:
         qs_dev = torch.as_tensor(qs, dtype=torch.int64, device=dev)
         passes = [(min(lo, q_local), min(lo + qp, q_local)) for lo in range(0, max_q, qp)]
         if self.exchange == "peer":
+            # every pass is enqueued without a host round trip; the flags of all passes are read once at the end and a
+            # pass that raised one (slot / region capacity, a bin above the region size) is redone synchronously
+            pending = []
+            self._timing_fresh = True
             for a, b in passes:
                 e0, e1 = int(qs[a]), int(qs[b])
-                res = self._peer_pass(digests[e0:e1], qoffsets[e0:e1], qs_dev[a:b + 1] - e0, qp, b - a, topn)
+                args = (digests[e0:e1], qoffsets[e0:e1], qs_dev[a:b + 1] - e0, qp, b - a, topn)
+                self._ensure_peers(qp)
+                res, chk = self._peer_enqueue(*args)
                 for o, r in zip(outs, res[:4]):
                     o[a:b] = r[:b - a]
                 nres[a:b] = res[4][:b - a]
+                pending.append((a, b, args, chk))
+            if pending:
+                allchk = torch.stack([p[3] for p in pending]).cpu().tolist()
+                for (a, b, args, _), chk in zip(pending, allchk):
+                    if chk[0] & 5 or chk[4] & 2 or chk[5]:
+                        res = self._peer_pass(*args, first=chk)
+                        for o, r in zip(outs, res[:4]):
+                            o[a:b] = r[:b - a]
+                        nres[a:b] = res[4][:b - a]
             return (*outs, nres)
         # Software pipeline over the passes: while the vote of pass i runs on the caller's stream, the routing, lookup,
         # expansion and both all-to-alls of pass i+1 run on a second (high-priority) stream.
@@ -278,7 +294,8 @@ class ShardedIndex:
             self.peers.close(self.group)
             self.peers = None
         if self.peers is None:
-            fill_cap = qp + self.region_cap // 8192 + 64
+            cap = min(24576, max(2, int(os.environ.get("SIA_PVOTE_CAP", 24576)))) & ~1
+            fill_cap = qp + self.region_cap // cap + 64      # one region per small query + region_cap / cap full-size regions
             self.peers = self.backend.make_peers(self.rank, self.world, qp, self.region_cap, fill_cap, self.group)
             if self.peers is None:
                 raise RuntimeError("exchange='peer' needs a CUDA shard backend")
@@ -288,9 +305,11 @@ class ShardedIndex:
             self.peers.close(self.group)
             self.peers = None
 
-    def _peer_pass(self, digests, qoffsets, qs_dev, qp, nq_local, topn):
-        """One pass with the vote tuples written into the owners' regions by the shards (see ``sia_b200.h``).  Collective.
-        Returns this rank's (song, diff, count, rows, nres) for its ``qp`` query slots."""
+    def _peer_enqueue(self, digests, qoffsets, qs_dev, qp, nq_local, topn):
+        """One pass with the vote tuples written into the owners' regions by the shards (see ``sia_b200.h``), enqueued
+        without a host round trip.  Collective.  Returns this rank's (song, diff, count, rows, nres) for its ``qp`` query
+        slots and the pass's check vector on the device: [flags, -, entry slot needed, region slots needed, status,
+        queries flagged anywhere] (max over ranks)."""
         be, dev, G = self.backend, self.backend.device, self.world
         timing = bool(os.environ.get("SIA_DIST_TIMING"))
         marks = []
@@ -299,32 +318,46 @@ class ShardedIndex:
             if timing:
                 torch.cuda.synchronize(dev)
                 marks.append((name, time.perf_counter()))
+        mark("start")
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        info = torch.zeros(4, dtype=torch.int64, device=dev)
+        send_e = be.route_entries(digests, qoffsets, qs_dev, self.rank * qp, G, self.entry_cap, status)
+        mark("route")
+        recv_e = torch.empty_like(send_e)
+        dist.all_to_all_single(recv_e, send_e, group=self.group)
+        mark("all-to-all entries")
+        t = be.lookup_slots(recv_e, G, qp, info)
+        self.peers.counters.zero_()                   # before the all-reduce: every owner is clean when any shard starts
+        dist.all_reduce(t, group=self.group)          # tuples of every global query over all shards
+        mark("lookup + all-reduce of the tuple counts")
+        be.scatter_peers(G, qp, t, self.peers, info)
+        chk = torch.cat([info, status.to(torch.int64)])
+        dist.all_reduce(chk, op=dist.ReduceOp.MAX, group=self.group)      # also the barrier: all shards have written
+        mark("scatter into the owners' regions (NVLink) + barrier")
+        res = be.count_regions(t[self.rank * qp:(self.rank + 1) * qp], qp, topn, self.peers, info)
+        flagged = info[1:2] & 0xffffffff
+        dist.all_reduce(flagged, op=dist.ReduceOp.MAX, group=self.group)
+        mark("count + merge + rows")
+        if timing:                                        # keep the slowest pass of the call (the last one is usually a stub)
+            ms = {n: (tm - marks[i][1]) * 1e3 for i, (n, tm) in enumerate(marks[1:])}
+            if self._timing_fresh or sum(ms.values()) > sum((self.last_pass_ms or {}).values()):
+                self.last_pass_ms = ms
+            self._timing_fresh = False
+        return res, torch.cat([chk, flagged])
+
+    def _peer_pass(self, digests, qoffsets, qs_dev, qp, nq_local, topn, first=None):
+        """The synchronous form: enqueue, read the flags, grow what was too small and redo, or hand a pass with a bin
+        above the region size to the key exchange.  ``first``: the check vector of an attempt already made."""
+        be = self.backend
+        args = (digests, qoffsets, qs_dev, qp, nq_local, topn)
+        chk, res = first, None
         while True:
-            self._ensure_peers(qp)
-            mark("start")
-            status = torch.zeros(1, dtype=torch.int32, device=dev)
-            info = torch.zeros(4, dtype=torch.int64, device=dev)
-            send_e = be.route_entries(digests, qoffsets, qs_dev, self.rank * qp, G, self.entry_cap, status)
-            mark("route")
-            recv_e = torch.empty_like(send_e)
-            dist.all_to_all_single(recv_e, send_e, group=self.group)
-            mark("all-to-all entries")
-            t = be.lookup_slots(recv_e, G, qp, info)
-            self.peers.counters.zero_()                   # before the all-reduce: every owner is clean when any shard starts
-            dist.all_reduce(t, group=self.group)          # tuples of every global query over all shards
-            mark("lookup + all-reduce of the tuple counts")
-            be.scatter_peers(G, qp, t, self.peers, info)
-            chk = torch.cat([info, status.to(torch.int64)])
-            dist.all_reduce(chk, op=dist.ReduceOp.MAX, group=self.group)      # also the barrier: all shards have written
-            mark("scatter into the owners' regions (NVLink) + barrier")
-            res = be.count_regions(t[self.rank * qp:(self.rank + 1) * qp], qp, topn, self.peers, info)
-            flagged = info[1:2].clone()
-            dist.all_reduce(flagged, op=dist.ReduceOp.MAX, group=self.group)
-            mark("count + merge + rows")
-            flags, _, need_e, need_r, st = (int(x) for x in chk.tolist())
-            n_flagged = int(flagged.item()) & 0xffffffff
-            if timing:
-                self.last_pass_ms = {n: (tm - marks[i][1]) * 1e3 for i, (n, tm) in enumerate(marks[1:])}
+            if chk is None:
+                self._ensure_peers(qp)
+                res, c = self._peer_enqueue(*args)
+                chk = c.cpu().tolist()
+            flags, _, need_e, need_r, st, n_flagged = (int(x) for x in chk)
+            chk = None
             if st & 2:
                 raise ValueError("query: offset outside 0..2^24-1 or more than 2^24 queries in one pass")
             if flags & 1:
@@ -335,14 +368,16 @@ class ShardedIndex:
                 self.region_cap = int(need_r * 1.25) + (1 << 16)
                 self.retries += 1
                 continue
-            if n_flagged:                                 # a bin above the region size somewhere: the key exchange takes the pass
-                self.peer_fallbacks += 1
-                while True:
-                    keys = self._prepare_pass(digests, qoffsets, qs_dev, qp)
-                    if keys is not None:
-                        break
-                    self.retries += 1
-                res = be.vote_key_slots(keys, nq_local, topn, self._max_song)
+            if n_flagged or res is None:                  # a bin above the region size somewhere: the key exchange takes the pass
+                if n_flagged:
+                    self.peer_fallbacks += 1
+                    while True:
+                        keys = self._prepare_pass(digests, qoffsets, qs_dev, qp)
+                        if keys is not None:
+                            break
+                        self.retries += 1
+                    return be.vote_key_slots(keys, nq_local, topn, self._max_song)
+                continue
             return res
 
     def _prepare_pass(self, digests, qoffsets, qs_dev, qp):
