@@ -911,7 +911,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=8))
+        # NCCL on high-priority streams: its few CTAs are dispatched ahead of the pending CTAs of the big vote kernels, so
+        # the exchange of pass i+1 really overlaps the vote of pass i
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=8), pg_options=opts)
 
     out = None
     if not args.no_fingerprint:

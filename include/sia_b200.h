@@ -293,7 +293,9 @@ int sia_vote_finish(int device);
  *   [all-reduce (sum) of the tuple counts: every rank then derives the SAME region layout of every owner; the owner
  *    must have zeroed its fill counters and query flags before it joins this all-reduce]
  *   sia_index_scatter_peers             posting runs -> tuples -> the owners' regions (h_peer_*: world pointers each,
- *                                       entry [rank] = the local buffers)
+ *                                       entry [rank] = the local buffers); consecutive blocks go to different owners
+ *                                       and every shard starts with a different one (an owner's NVLink ingress is
+ *                                       never the target of all shards at once)
  *   [barrier: all shards have written]
  *   sia_vote_count_regions              the owner counts its regions: same outputs as sia_vote_key_slots.
  * d_info (4 x int64, zeroed per pass): [0] flags (1 = an entry slot overflowed at its sender, 4 = some owner's regions do
@@ -305,7 +307,7 @@ int sia_peer_close(int device, void *d_ptr);
 int sia_peer_free(int device, void *d_ptr);
 int sia_index_lookup_slots(sia_index *ix, const void *d_entry_slots, int32_t world, int64_t entry_cap,
                            int32_t queries_per_rank, int64_t *d_tuples, int64_t *d_info, void *stream);
-int sia_index_scatter_peers(sia_index *ix, int32_t world, int32_t queries_per_rank, const int64_t *d_tuples_total,
+int sia_index_scatter_peers(sia_index *ix, int32_t world, int32_t rank, int32_t queries_per_rank, const int64_t *d_tuples_total,
                             void *const *h_peer_regions, void *const *h_peer_fill, void *const *h_peer_qover,
                             int64_t region_cap, int64_t fill_cap, int64_t *d_info, void *stream);
 int sia_vote_count_regions(int device, const int64_t *d_tuples_total, int32_t n_queries, int32_t topn, uint64_t *d_regions,

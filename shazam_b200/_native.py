@@ -83,7 +83,7 @@ SIGNATURES = {
     "sia_peer_close": (C.c_int, [C.c_int, _p]),
     "sia_peer_free": (C.c_int, [C.c_int, _p]),
     "sia_index_lookup_slots": (C.c_int, [_p, _p, C.c_int32, C.c_int64, C.c_int32, _p, _p, _p]),
-    "sia_index_scatter_peers": (C.c_int, [_p, C.c_int32, C.c_int32, _p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p),
+    "sia_index_scatter_peers": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p),
                                           C.c_int64, C.c_int64, _p, _p]),
     "sia_vote_count_regions": (C.c_int, [C.c_int, _p, C.c_int32, C.c_int32, _p, _p, _p, C.c_int64, C.c_int64, _p, _p, _p, _p,
                                          _p, _p, _p]),

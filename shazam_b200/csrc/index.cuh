@@ -182,7 +182,7 @@ int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uin
 // d_over_count: incremented once per flagged query.
 // hash-prefix sharding over peer memory (index_dist.cu: sia_index_scatter_peers / sia_vote_count_regions)
 int pvote_scatter_peers(Arena &ar, const Lookup &L, const longlong2 *d_einfo, const uint32_t *d_qh, const uint64_t *post,
-                        const int64_t *d_q_ent, const int64_t *d_goff, int world, int qp, const int64_t *d_t_total,
+                        const int64_t *d_q_ent, const int64_t *d_goff, int world, int rank, int qp, const int64_t *d_t_total,
                         void *const *peer_regions, void *const *peer_fill, void *const *peer_qover, int64_t region_cap,
                         int64_t fill_cap, int64_t *d_info, cudaStream_t s);
 int pvote_count_regions(Arena &ar, const int64_t *d_t_total, int nq, int topn, uint64_t *d_regions, uint32_t *d_fill,

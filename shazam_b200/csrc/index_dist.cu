@@ -274,7 +274,7 @@ int sia_index_lookup_slots(sia_index *ix, const void *d_entry_slots, int32_t wor
   return SIA_OK;
 }
 
-int sia_index_scatter_peers(sia_index *ix, int32_t world, int32_t queries_per_rank, const int64_t *d_tuples_total,
+int sia_index_scatter_peers(sia_index *ix, int32_t world, int32_t rank, int32_t queries_per_rank, const int64_t *d_tuples_total,
                             void *const *h_peer_regions, void *const *h_peer_fill, void *const *h_peer_qover, int64_t region_cap,
                             int64_t fill_cap, int64_t *d_info, void *stream) {
   SIA_REQUIRE(ix && d_tuples_total && h_peer_regions && h_peer_fill && h_peer_qover && d_info, SIA_E_INVALID, "NULL argument");
@@ -286,7 +286,7 @@ int sia_index_scatter_peers(sia_index *ix, int32_t world, int32_t queries_per_ra
   const int64_t blocks = ceil_div(std::max<int64_t>(ix->dist_L.tuples, 1), 8192) + nq;
   int rc = ix->arena3.reserve((size_t)nq * 80 + (size_t)blocks * 4 + (1 << 16));
   if (rc) return rc;
-  rc = pvote_scatter_peers(ix->arena3, ix->dist_L, ix->dist_einfo, ix->dist_qh, ix->post, ix->dist_q_ent, ix->dist_goff, world,
+  rc = pvote_scatter_peers(ix->arena3, ix->dist_L, ix->dist_einfo, ix->dist_qh, ix->post, ix->dist_q_ent, ix->dist_goff, world, rank,
                            queries_per_rank, d_tuples_total, h_peer_regions, h_peer_fill, h_peer_qover, region_cap, fill_cap, d_info, s);
   ix->dist_nq = 0;
   return rc;

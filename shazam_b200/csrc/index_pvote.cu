@@ -37,6 +37,7 @@ constexpr int kFiltWords = 8192;      // count kernel: duplicate filter, 2 bits 
 constexpr int kTabSlots = 4096;       // count kernel: exact table of the tuples in twice-hit buckets (32 KB)
 constexpr int kDup = 2048;            // repeated bins a region remembers
 constexpr int kCntThreads = 512;
+constexpr int kRegionsPerCta = 8;
 constexpr size_t kCountSmem = (size_t)kFiltWords * 4 + (size_t)kTabSlots * 8;
 
 struct PvQuery {
@@ -91,11 +92,18 @@ __device__ __forceinline__ int64_t warp_search(const T *__restrict__ a, int64_t 
 
 // ---- layout ---------------------------------------------------------------------------------------------------
 // segments: (query, source) -> a range of tuples / keys.  Entries variant: one source, the query's slice of off_all.
+// il_world > 0 (peer scatter): segment j is the query of owner (j + il_rank) % il_world, slot j / il_world — consecutive
+// blocks go to different owners and every shard starts with a different one, so no owner's NVLink ingress is the
+// target of all shards at once
+__device__ __forceinline__ int pv_seg_query(int j, int il_world, int il_rank, int qp) {
+  return il_world > 0 ? ((j + il_rank) % il_world) * qp + j / il_world : j;
+}
 __global__ void pv_segs_entries_kernel(const int64_t *__restrict__ goff, int qa, int nq, int64_t *__restrict__ seg_lo,
-                                       uint32_t *__restrict__ seg_cnt) {
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
-    seg_lo[q] = goff[qa + q];
-    seg_cnt[q] = (uint32_t)(goff[qa + q + 1] - goff[qa + q]);
+                                       uint32_t *__restrict__ seg_cnt, int il_world, int il_rank, int qp) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += gridDim.x * blockDim.x) {
+    const int q = pv_seg_query(j, il_world, il_rank, qp);
+    seg_lo[j] = goff[qa + q];
+    seg_cnt[j] = (uint32_t)(goff[qa + q + 1] - goff[qa + q]);
   }
 }
 
@@ -206,7 +214,7 @@ struct ScatterArgs {
   int maxp;                             // partitions the shared histogram is laid out for (>= every np of the launch)
   // hash-prefix sharding over peer memory: query ql belongs to rank ql / qp_dest, whose regions / counters are written
   // through NVLink (qp_dest = 0: everything is local)
-  int qp_dest;
+  int qp_dest, il_rank, il_world;
   uint64_t *regions_p[kPvMaxPeers]; uint32_t *fill_p[kPvMaxPeers]; uint32_t *qover_p[kPvMaxPeers];
   // source 0: posting runs of the query's entries
   const int64_t *off; const longlong2 *info; const uint32_t *qh; const uint64_t *post;
@@ -234,7 +242,8 @@ __global__ void __launch_bounds__(kScThreads, 2) pv_scatter_kernel(const Scatter
   if (b >= a.tot[1]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = (int)a.blk_seg[b];
-  const int ql = s / a.G, g = s - ql * a.G;
+  const int ql = a.qp_dest > 0 ? pv_seg_query(s, a.il_world, a.il_rank, a.qp_dest) : s / a.G;
+  const int g = a.qp_dest > 0 ? 0 : s - ql * a.G;
   const PvQuery m = a.pq[ql];
   const int64_t lo = a.seg_lo[s];
   const int64_t j0 = lo + (int64_t)(b - a.seg_blk0[s]) * kBlk;
@@ -611,7 +620,7 @@ pv_count_region(const uint32_t r, const uint64_t *__restrict__ regions, const ui
   if (tid < topn) out[tid] = tid < nres ? s_win[tid] : 0ull;
 }
 
-// CTAs take regions from a shared counter (tot[2]) until none is left: the grid is sized for the SMs, not for the
+// CTAs take up to kRegionsPerCta regions each from a shared counter (tot[2]): the grid is 1/8 of the host-side bound of the
 // (device-side) number of regions
 __global__ void __launch_bounds__(kCntThreads, 3)
 pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict__ fill, const PvQuery *__restrict__ pq,
@@ -619,7 +628,7 @@ pv_count_kernel(const uint64_t *__restrict__ regions, const uint32_t *__restrict
                 uint64_t *__restrict__ cand, uint32_t *__restrict__ qbins) {
   __shared__ uint32_t s_next;
   const uint32_t n_regions = tot[0];
-  for (;;) {
+  for (int it = 0; it < kRegionsPerCta; ++it) {   // bounded: CTAs retire regularly, so kernels of other streams (NCCL) get SMs
     __syncthreads();                          // the previous region's shared state has been read
     if (threadIdx.x == 0) s_next = atomicAdd(&tot[2], 1u);
     __syncthreads();
@@ -851,7 +860,7 @@ int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uin
   static cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};     // SIA_QUERY_TIMING only
   if (stage_ms) { if (!ev[0]) for (auto &e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
   SIA_CUDA(cudaMemsetAsync(S.fill, 0, sizeof(uint32_t) * regions, s));
-  pv_segs_entries_kernel<<<grid_for(nq), 256, 0, s>>>(d_goff, qa, nq, S.seg_lo, S.seg_cnt);
+  pv_segs_entries_kernel<<<grid_for(nq), 256, 0, s>>>(d_goff, qa, nq, S.seg_lo, S.seg_cnt, 0, 0, 0);
   pv_layout_kernel<<<1, 1024, 0, s>>>(S.seg_cnt, nq, 1, tune, S.pq, S.q_ridx0, S.seg_blk0, S.tot);
   pv_maps_kernel<<<grid_for(regions + blocks), 256, 0, s>>>(S.seg_blk0, nq, S.q_ridx0, nq, S.tot, S.blk_seg, S.reg_q);
   ScatterArgs a{};
@@ -862,7 +871,7 @@ int pvote_entries(Arena &ar, const Lookup &L, const longlong2 *d_info, const uin
   if (stage_ms) cudaEventRecord(ev[1], s);
   pv_scatter_kernel<0><<<(unsigned)blocks, kScThreads, scatter_smem(a.maxp), s>>>(a);
   if (stage_ms) cudaEventRecord(ev[2], s);
-  pv_count_kernel<<<(unsigned)std::min<int64_t>(regions, kNumSMs * 3), kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, qa, d_qover, topn, S.cand,
+  pv_count_kernel<<<(unsigned)ceil_div(regions, kRegionsPerCta), kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, qa, d_qover, topn, S.cand,
                                                                      d_nbins ? d_qbins : nullptr);
   pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, S.pq, nq, qa, qid_base, d_qover, topn, out, nullptr,
                                                                             d_qbins, d_nbins);
@@ -898,7 +907,7 @@ int pvote_key_slots(Arena &ar, const uint64_t *d_keys, int n_slots, int64_t cap,
   a.maxp = kMaxParts;                                       // the queries' sizes are only known on the device
   a.keys = d_keys; a.key_cap = cap; a.counts = d_counts; a.unsorted = d_flags2;
   pv_scatter_kernel<1><<<(unsigned)blocks, kScThreads, kScatterSmem, s>>>(a);
-  pv_count_kernel<<<(unsigned)std::min<int64_t>(regions, kNumSMs * 3), kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, 0, d_qover, topn, S.cand,
+  pv_count_kernel<<<(unsigned)ceil_div(regions, kRegionsPerCta), kCntThreads, kCountSmem, s>>>(S.regions, S.fill, S.pq, S.reg_q, S.tot, 0, d_qover, topn, S.cand,
                                                                      nullptr);
   pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(S.cand, S.pq, nq, 0, 0, d_qover, topn, out, d_flags2 + 1,
                                                                             nullptr, nullptr);
@@ -915,10 +924,10 @@ int pvote_key_slots(Arena &ar, const uint64_t *d_keys, int n_slots, int64_t cap,
 // straight into the owners' regions through NVLink.  d_t_total: tuples of every global query over all shards (the
 // all-reduced counts), from which every rank derives the same layout.
 int pvote_scatter_peers(Arena &ar, const Lookup &L, const longlong2 *d_einfo, const uint32_t *d_qh, const uint64_t *post,
-                        const int64_t *d_q_ent, const int64_t *d_goff, int world, int qp, const int64_t *d_t_total,
+                        const int64_t *d_q_ent, const int64_t *d_goff, int world, int rank, int qp, const int64_t *d_t_total,
                         void *const *peer_regions, void *const *peer_fill, void *const *peer_qover, int64_t region_cap,
                         int64_t fill_cap, int64_t *d_info, cudaStream_t s) {
-  SIA_REQUIRE(world >= 1 && world <= kPvMaxPeers, SIA_E_UNSUPPORTED, "peer scatter: at most 16 ranks");
+  SIA_REQUIRE(world >= 1 && world <= kPvMaxPeers && rank >= 0 && rank < world, SIA_E_UNSUPPORTED, "peer scatter: at most 16 ranks");
   int rc = pv_attrs();
   if (rc) return rc;
   const PvTune tune = pv_tune();
@@ -932,7 +941,7 @@ int pvote_scatter_peers(Arena &ar, const Lookup &L, const longlong2 *d_einfo, co
   int64_t *dest_tot = ar.take<int64_t>(2 * (size_t)world);
   SIA_REQUIRE(seg_lo && seg_cnt && seg_blk0 && q_ridx2 && tot && blk_seg && reg_q2 && pq && pq2 && dest_tot, SIA_E_NOMEM,
               "index scratch arena too small (peer scatter)");
-  pv_segs_entries_kernel<<<grid_for(nq), 256, 0, s>>>(d_goff, 0, nq, seg_lo, seg_cnt);
+  pv_segs_entries_kernel<<<grid_for(nq), 256, 0, s>>>(d_goff, 0, nq, seg_lo, seg_cnt, world, rank, qp);
   // blocks of the LOCAL tuples (pq2 / q_ridx2 are by-products nobody reads) ...
   pv_layout_kernel<<<1, 1024, 0, s>>>(seg_cnt, nq, 1, tune, pq2, q_ridx2, seg_blk0, tot);
   // ... regions from the TOTAL counts, per owner
@@ -944,7 +953,7 @@ int pvote_scatter_peers(Arena &ar, const Lookup &L, const longlong2 *d_einfo, co
   ScatterArgs a{};
   a.seg_blk0 = seg_blk0; a.blk_seg = blk_seg; a.seg_lo = seg_lo; a.seg_cnt = seg_cnt; a.G = 1;
   a.pq = pq; a.tot = tot; a.q_lo = 0; a.maxp = kMaxParts;
-  a.qp_dest = qp;
+  a.qp_dest = qp; a.il_world = world; a.il_rank = rank;
   for (int d = 0; d < world; ++d) {
     a.regions_p[d] = static_cast<uint64_t *>(peer_regions[d]);
     a.fill_p[d] = static_cast<uint32_t *>(peer_fill[d]);
@@ -977,7 +986,7 @@ int pvote_count_regions(Arena &ar, const int64_t *d_t_total, int nq, int topn, u
   pv_gate_kernel<<<1, 1, 0, s>>>(reinterpret_cast<const unsigned long long *>(d_info), tot, 0);
   SIA_CUDA(cudaMemsetAsync(seg_blk0, 0, 2 * sizeof(uint32_t), s));
   pv_maps_kernel<<<grid_for(regions), 256, 0, s>>>(seg_blk0, 1, q_ridx0, nq, tot, blk_seg, reg_q);
-  pv_count_kernel<<<(unsigned)std::min<int64_t>(regions, kNumSMs * 3), kCntThreads, kCountSmem, s>>>(d_regions, d_fill, pq, reg_q, tot, 0, d_qover, topn, cand, nullptr);
+  pv_count_kernel<<<(unsigned)ceil_div(regions, kRegionsPerCta), kCntThreads, kCountSmem, s>>>(d_regions, d_fill, pq, reg_q, tot, 0, d_qover, topn, cand, nullptr);
   pv_merge_kernel<<<(unsigned)ceil_div((int64_t)nq * 32, 256), 256, 0, s>>>(cand, pq, nq, 0, 0, d_qover, topn, out, d_over_count, nullptr,
                                                                             nullptr);
   pv_rows_kernel<<<(unsigned)std::min<int64_t>(regions, kNumSMs * 16), 256, 0, s>>>(d_regions, d_fill, pq, reg_q, tot, 0, 0, d_qover, topn, out.song, out.nres, out.rows);

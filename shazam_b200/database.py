@@ -244,7 +244,7 @@ class FingerprintIndex:
                       info: torch.Tensor) -> None:
         """Step 2 on the shard: posting runs -> vote tuples -> the owners' regions, through NVLink."""
         t = tuples_total.contiguous()
-        N.check(self.lib.sia_index_scatter_peers(self._h, int(world), int(queries_per_rank), C.c_void_p(t.data_ptr()),
+        N.check(self.lib.sia_index_scatter_peers(self._h, int(world), int(peers.rank), int(queries_per_rank), C.c_void_p(t.data_ptr()),
                                                  peers.p_regions, peers.p_fill, peers.p_qover, peers.region_cap, peers.fill_cap,
                                                  C.c_void_p(info.data_ptr()), self._stream()))
 
