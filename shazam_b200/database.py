@@ -258,11 +258,11 @@ class _RawCuda:
 
 class PeerBuffers:
     """The regions of the partitioned vote of one rank, mapped by every rank of the group (CUDA IPC over NVLink):
-    ``[query flags: qp x u32][fill counters: fill_cap x u32][regions: region_cap x u64]``.  Collective: every rank
-    allocates, the 64-byte handles are all-gathered, every rank opens the others'."""
+    ``[query flags: qp x u32][fill counters: fill_cap x u32][regions: region_cap x u64]``.  ``PeerBuffers.create`` is the
+    collective constructor: every rank allocates, the 64-byte handles are all-gathered, every rank opens the others'.
+    (``__init__`` + ``connect`` are the two halves; a test that plays all ranks on one GPU connects local pointers.)"""
 
-    def __init__(self, device: int, rank: int, world: int, qp: int, region_cap: int, fill_cap: int, group=None):
-        import torch.distributed as dist
+    def __init__(self, device: int, rank: int, world: int, qp: int, region_cap: int, fill_cap: int):
         self.lib = N.lib()
         self.device, self.rank, self.world = device, rank, world
         self.qp, self.region_cap, self.fill_cap = int(qp), int(region_cap), int(fill_cap)
@@ -274,32 +274,46 @@ class PeerBuffers:
         handle = (C.c_uint8 * 64)()
         N.check(self.lib.sia_peer_alloc(device, self.nbytes, C.byref(ptr), C.cast(handle, C.c_void_p)))
         self.local = int(ptr.value)
+        self.handle = bytes(handle)
+        self.base, self._opened = None, []
+        # local counters (query flags + fill) as one int32 tensor, for the stream-ordered zeroing before every pass
+        self.counters = torch.as_tensor(_RawCuda(self.local, self.off_regions // 4, "<i4"), device=torch.device("cuda", device))
+
+    def connect(self, bases) -> None:
+        """``bases[r]``: rank r's buffer as a pointer valid in THIS process."""
+        self.base = [int(b) for b in bases]
+        arr = lambda off: (C.c_void_p * self.world)(*[b + off for b in self.base])
+        self.p_qover, self.p_fill, self.p_regions = arr(0), arr(self.off_fill), arr(self.off_regions)
+
+    @classmethod
+    def create(cls, device: int, rank: int, world: int, qp: int, region_cap: int, fill_cap: int, group=None) -> "PeerBuffers":
+        import torch.distributed as dist
+        self = cls(device, rank, world, qp, region_cap, fill_cap)
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle), group=group)
-        self.base = []
+        dist.all_gather_object(handles, self.handle, group=group)
+        bases = []
         for r in range(world):
             if r == rank:
-                self.base.append(self.local)
+                bases.append(self.local)
                 continue
             q = C.c_void_p()
             buf = (C.c_uint8 * 64).from_buffer_copy(handles[r])
             N.check(self.lib.sia_peer_open(device, C.cast(buf, C.c_void_p), C.byref(q)))
-            self.base.append(int(q.value))
-        arr = lambda off: (C.c_void_p * world)(*[b + off for b in self.base])
-        self.p_qover, self.p_fill, self.p_regions = arr(0), arr(self.off_fill), arr(self.off_regions)
-        tdev = torch.device("cuda", device)
-        # local counters (query flags + fill) as one int32 tensor, for the stream-ordered zeroing before every pass
-        self.counters = torch.as_tensor(_RawCuda(self.local, self.off_regions // 4, "<i4"), device=tdev)
+            bases.append(int(q.value))
+            self._opened.append(int(q.value))
+        self.connect(bases)
+        return self
 
     def close(self, group=None):
-        import torch.distributed as dist
         if self.local is None:
             return
         torch.cuda.synchronize(self.device)
-        for r, b in enumerate(self.base):
-            if r != self.rank:
-                N.check(self.lib.sia_peer_close(self.device, C.c_void_p(b)))
-        dist.barrier(group=group)                 # nobody maps this rank's buffer any more
+        for b in self._opened:
+            N.check(self.lib.sia_peer_close(self.device, C.c_void_p(b)))
+        if self._opened:
+            import torch.distributed as dist
+            dist.barrier(group=group)             # nobody maps this rank's buffer any more
+        self._opened = []
         del self.counters
         N.check(self.lib.sia_peer_free(self.device, C.c_void_p(self.local)))
         self.local = None

@@ -145,7 +145,7 @@ class CudaShard(ShardBackend):
 
     def make_peers(self, rank, world, qp, region_cap, fill_cap, group=None):
         from .database import PeerBuffers
-        return PeerBuffers(self._dev_index, rank, world, qp, region_cap, fill_cap, group)
+        return PeerBuffers.create(self._dev_index, rank, world, qp, region_cap, fill_cap, group)
 
     def lookup_slots(self, entry_slots, world, queries_per_rank, info):
         return self.index.lookup_slots(entry_slots, world, queries_per_rank, info)

@@ -2,6 +2,8 @@
 return_matches + align_matches semantics (oracle + golden vectors)."""
 import hashlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -250,7 +252,56 @@ def test_hash_prefix_slots_equal_single_index(gpudb):
                     vote_finish(0)                          # the deferred form: enqueue, then complete
                 for x, y in zip(ref, got):
                     assert torch.equal(x[a:b], y), (attempt, r)
-            if attempt == 0:                            # the same keys, unslotted, through the plain key vote
+            if attempt == 0:
+                # the same pass with the second exchange fused into the scatter kernel (csrc/index_pvote.cu): every shard
+                # looks its entries up, the per-query tuple counts are summed (the all-reduce), every shard scatters its
+                # tuples straight into the owners' regions (here: G buffers on one GPU stand in for the peers' memory),
+                # every owner counts its regions
+                from shazam_b200.database import PeerBuffers, vote_count_regions
+                for cap in (None, "64"):                # "64": tiny regions -> every query is flagged for the key exchange
+                    if cap:
+                        os.environ["SIA_PVOTE_CAP"] = cap
+                    bufs = [PeerBuffers(0, r, G, QP, 1 << 16, 4096) for r in range(G)]
+                    try:
+                        for pb in bufs:
+                            pb.connect([x.local for x in bufs])
+                            pb.counters.zero_()
+                        recvs, infos2, t_total = [], [], torch.zeros(G * QP, dtype=torch.int64, device=dev)
+                        for g in range(G):
+                            recv = torch.zeros((G, ecap, 2), dtype=torch.int64, device=dev)
+                            for r in range(len(owners)):
+                                recv[r] = sent[r][g]
+                            recvs.append(recv)
+                        for g in range(G):              # every shard keeps the lookup of its pass inside its handle
+                            info = torch.zeros(4, dtype=torch.int64, device=dev)
+                            t_total += shards[g].lookup_slots(recvs[g], G, QP, info)
+                            infos2.append(info)
+                        for g in range(G):
+                            shards[g].scatter_peers(G, QP, t_total, bufs[g], infos2[g])
+                        assert all(int(i[0].item()) == 0 for i in infos2)
+                        for r, (a, b) in enumerate(owners):
+                            info = torch.zeros(4, dtype=torch.int64, device=dev)
+                            got = vote_count_regions(0, t_total[r * QP:(r + 1) * QP], QP, 3, bufs[r], info)
+                            flagged = int(info[1].item()) & 0xffffffff
+                            if cap:
+                                assert flagged > 0      # nothing wrong is reported for a flagged query: it stays empty
+                            else:
+                                assert flagged == 0
+                                for x, y in zip(ref, got):
+                                    assert torch.equal(x[a:b], y[:b - a]), ("peer regions", r)
+                        # regions that do not fit the owner's buffer: flag 4 and the size needed, nothing scattered
+                        info = torch.zeros(4, dtype=torch.int64, device=dev)
+                        tiny = PeerBuffers(0, 0, G, QP, 64, 4096)
+                        tiny.connect([tiny.local] * G)
+                        shards[0].lookup_slots(recvs[0], G, QP, info)
+                        shards[0].scatter_peers(G, QP, t_total, tiny, info)
+                        assert int(info[0].item()) & 4 and int(info[3].item()) > 64
+                        tiny.close()
+                    finally:
+                        os.environ.pop("SIA_PVOTE_CAP", None)
+                        for pb in bufs:
+                            pb.close()
+                # the same keys, unslotted, through the plain key vote
                 allk = torch.cat([keys[g][0][1:1 + int(keys[g][0][0])] for g in range(G)])
                 got = vote_tuples(0, allk[torch.randperm(allk.numel(), device=dev)], QP, 3, max_song)
                 for x, y in zip(ref, got):
