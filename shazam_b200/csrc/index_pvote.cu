@@ -429,7 +429,7 @@ pv_count_region(const uint32_t r, const uint64_t *__restrict__ regions, const ui
   uint32_t *filt = reinterpret_cast<uint32_t *>(pv_smem);
   uint64_t *tab = reinterpret_cast<uint64_t *>(pv_smem + (size_t)kFiltWords * 4);
   __shared__ uint16_t s_dup[kDup];
-  __shared__ uint32_t s_ndup, s_over, s_b2;
+  __shared__ uint32_t s_ndup, s_over;
   __shared__ uint64_t s_lw[kCntThreads / 32 + 1][kPvMaxTopn];       // per-warp winners; last row: the running winners
   __shared__ int s_nres;
   __shared__ uint64_t s_win[kPvMaxTopn];
@@ -452,7 +452,7 @@ pv_count_region(const uint32_t r, const uint64_t *__restrict__ regions, const ui
   const uint32_t nw = 1u << (fb - 4), S = 1u << tb, tmask = S - 1;
   for (uint32_t i = tid; i < nw / 4; i += kCntThreads) reinterpret_cast<uint4 *>(filt)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (uint32_t i = tid; i < S / 2; i += kCntThreads) reinterpret_cast<ulonglong2 *>(tab)[i] = make_ulonglong2(0ull, 0ull);
-  if (tid == 0) { s_ndup = 0; s_over = 0; s_b2 = 0; }
+  if (tid == 0) { s_ndup = 0; s_over = 0; }
   const uint64_t *__restrict__ reg = regions + m.reg_off + (int64_t)p * m.cap;
   __syncthreads();
   // ---- mark ----
@@ -475,18 +475,9 @@ pv_count_region(const uint32_t r, const uint64_t *__restrict__ regions, const ui
   // ---- count ----
   // The exact table holds ~3 300 distinct candidate keys.  A tie-heavy region (a long query against a self-similar
   // track) has more: its candidates are then counted in nsub sub-passes, each taking the keys of one residue class and
-  // re-reading the tuples from L2; the running winners ride along.  nsub starts from the number of twice-hit buckets
-  // and doubles if a sub-pass still overflows, so the kernel cannot fail for a region that fits its slots.
-  {
-    uint32_t b2 = 0;
-    for (uint32_t i = tid; i < nw; i += kCntThreads) b2 += __popc(filt[i] & 0xaaaaaaaau);
-#pragma unroll
-    for (int d = 16; d; d >>= 1) b2 += __shfl_xor_sync(0xffffffffu, b2, d);
-    if (lane == 0 && b2) atomicAdd(&s_b2, b2);
-  }
-  __syncthreads();
+  // re-reading the tuples from L2; the running winners ride along.  nsub starts at 1 and doubles while a sub-pass
+  // overflows, so the kernel cannot fail for a region that fits its slots.
   uint32_t nsub = 1;
-  while (nsub < 16 && s_b2 * 2 > (S * 3 / 4) * nsub) nsub <<= 1;
   uint32_t fresh = 0;
   for (;;) {
     bool ok = true;
@@ -579,7 +570,7 @@ pv_count_region(const uint32_t r, const uint64_t *__restrict__ regions, const ui
       }
     }
     if (ok) break;
-    if (nsub >= 16) {                                                    // cannot happen for n <= 16384; kept as a guard
+    if (nsub >= 16) {                                                    // cannot happen for n <= 24576 (16 x 3328 keys); kept as a guard
       if (tid == 0) qover[q_lo + ql] = 1u;
       if (tid < topn) out[tid] = 0ull;
       return;

@@ -1069,7 +1069,7 @@ int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d
     SIA_CUDA(cudaMemsetAsync(o, 0, sizeof(int32_t) * (size_t)n_queries * topn, s));
 
   // vote tuples per group of queries (one set of launches per group): bounded by what the device has left
-  int64_t tuple_budget = getenv("SIA_VOTE_GROUP_TUPLES") ? std::max(1ll, atoll(getenv("SIA_VOTE_GROUP_TUPLES"))) : (256ll << 20);
+  int64_t tuple_budget = getenv("SIA_VOTE_GROUP_TUPLES") ? std::max(1ll, atoll(getenv("SIA_VOTE_GROUP_TUPLES"))) : (512ll << 20);
   {
     size_t free_b = 0, total_b = 0;
     SIA_CUDA(cudaMemGetInfo(&free_b, &total_b));
