@@ -619,6 +619,7 @@ def match_leg(args, rank, world, local_rank, dev):
     track_line, hash_eq_track = None, None
     pass_ms = None
     peer_line = None
+    hp = None
     if world > 1:
         retries = hashed.retries
         os.environ["SIA_DIST_TIMING"] = "1"           # stage times of one more step (synchronising: not a timed one)
@@ -651,9 +652,6 @@ def match_leg(args, rank, world, local_rank, dev):
                                      "owner's HBM (peer stores + peer atomicAdd over NVLink, CUDA IPC mappings); collectives left: "
                                      "all-to-all of the query entries, one all-reduce of the per-query tuple counts, two tiny "
                                      "all-reduces (barrier + flags)"}
-                hp.close_peers()
-                del hp
-                torch.cuda.empty_cache()
             except Exception as e:      # e.g. no peer access on this box: keep the key-exchange line
                 import traceback
                 traceback.print_exc()
@@ -670,9 +668,14 @@ def match_leg(args, rank, world, local_rank, dev):
     # ---- end to end: query hashes start in pinned host memory, results end in host memory, every step ----------
     h_qh = qh.cpu().pin_memory(); h_qt1 = qt1.cpu().pin_memory()
 
+    # N > 1: through the variant of the hash-prefix path that gives `value` (every rank takes the same branch: the
+    # comparison is made on all-reduced times)
+    use_peer = bool(world > 1 and peer_line and peer_line.get("equals_key_exchange_results") and peer_line.get("ms_per_step", 1e30) < ms_step)
+    sharded_q = hp if use_peer else hashed
+
     def step_host():
         d_h = h_qh.to(dev, non_blocking=True); d_t = h_qt1.to(dev, non_blocking=True)
-        r = single.query_batch(d_h, d_t, q_starts, topn) if world == 1 else hashed.query(d_h, d_t, q_starts, topn, queries_per_pass=qp)
+        r = single.query_batch(d_h, d_t, q_starts, topn) if world == 1 else sharded_q.query(d_h, d_t, q_starts, topn, queries_per_pass=qp)
         return [x.cpu() for x in r[:5]]
     step_host()
     barrier()
@@ -687,9 +690,14 @@ def match_leg(args, rank, world, local_rank, dev):
     io = torch.tensor([h_qh.numel() + 4 * h_qt1.numel(), sum(x.numel() * 4 for x in res_host)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(io)
+    if hp is not None:
+        hp.close_peers()
+        hp = None
+        torch.cuda.empty_cache()
     e2e = {"value": Q / e2e_s, "unit": "queries/s", "ms_per_step": e2e_s * 1e3,
            "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
-           "api": "pinned host (digest, offset) arrays -> FingerprintIndex.query_batch / ShardedIndex.query -> results in host memory"}
+           "api": "pinned host (digest, offset) arrays -> FingerprintIndex.query_batch / ShardedIndex.query -> results in host memory",
+           "variant": "one index" if world == 1 else ("hash prefix over peer memory" if use_peer else "hash prefix, key exchange")}
 
     # ---- gather every rank's results (small) for the accuracy, the checksum and the n-th-count statistics ----------
     mine = {"qids": q_ids, "res": res_np, "hashes": int(qt1.numel()), "rows": gen_rows}
@@ -772,7 +780,7 @@ def match_leg(args, rank, world, local_rank, dev):
     if world > 1:
         out["key_exchange"] = {"value": out["value"], "unit": "queries/s", "ms_per_step": ms_step, "ms_per_step_median": ms_med}
         out["peer_memory"] = peer_line
-        if peer_line and peer_line.get("equals_key_exchange_results") and peer_line.get("value", 0) > out["value"]:
+        if use_peer:
             # the headline of the hash-prefix design is its faster exact variant; both are printed
             out["value"], out["ms_per_step"], out["ms_per_step_median"] = peer_line["value"], peer_line["ms_per_step"], peer_line["ms_per_step_median"]
             out["sharding"] = ("hash prefix: query entries routed to the shard owning their hash (NCCL all-to-all), vote tuples "
