@@ -71,7 +71,7 @@ def parse():
     ap.add_argument("--match-topn", type=int, default=3)
     ap.add_argument("--match-gen-batch", type=int, default=500, help="tracks generated per batch")
     ap.add_argument("--match-flush-rows", type=int, default=250_000_000, help="pending rows per finalize (merge)")
-    ap.add_argument("--match-pass-keys", type=int, default=1_000_000_000, help="N>1: vote keys a rank receives per pass")
+    ap.add_argument("--match-pass-keys", type=int, default=600_000_000, help="N>1: vote keys a rank receives per pass")
     ap.add_argument("--match-check-queries", type=int, default=256, help="N>1: subsample checked against one full index")
     ap.add_argument("--match-cpu-tracks", type=int, default=2714, help="index size of the CPU baseline (configs[2])")
     ap.add_argument("--no-peer", action="store_true", help="N>1: skip the peer-memory (fused exchange) variant of the hash-prefix path")
@@ -629,6 +629,8 @@ def match_leg(args, rank, world, local_rank, dev):
         # ---- the same hash-prefix pass with the second exchange fused into the scatter kernel (NVLink peer memory) ----
         if not args.no_peer:
             try:
+                del res
+                hashed.backend.index.trim()       # the key path's scratch (vote tables, key buffers of the build): tens of GB
                 torch.cuda.empty_cache()
                 hp = ShardedIndex(hashed.backend, rank=rank, world=world, exchange="peer")
                 hp._max_song, hp.entry_cap = hashed._max_song, hashed.entry_cap
@@ -658,6 +660,9 @@ def match_leg(args, rank, world, local_rank, dev):
                 peer_line = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
         res_t, ms_t, ms_t_med = timed(lambda: tracked.query(qh, qt1, q_starts, topn), args.steps, max(args.warmup, 3))
         res_t_np = [t.cpu().numpy() for t in res_t]
+        del res_t
+        tracked.backend.index.trim()
+        torch.cuda.empty_cache()
         eq = torch.tensor([int(all(np.array_equal(a, b) for a, b in zip(res_np, res_t_np)))], device=dev)
         dist.all_reduce(eq, op=dist.ReduceOp.MIN)
         hash_eq_track = bool(eq.item())
