@@ -174,7 +174,8 @@ class ShardedIndex:
         assert exchange in ("keys", "peer")
         self.exchange = exchange
         self.region_cap = max(1 << 16, int(region_cap))   # tuple slots of this rank's regions (grown on demand)
-        self.peers = None
+        self.peer_sets = []         # two sets of PeerBuffers
+        self._marks = []
         self._timing_fresh = True
         self.peer_fallbacks = 0     # passes redone with the key exchange
         self.backend = backend
@@ -230,27 +231,55 @@ class ShardedIndex:
         qs_dev = torch.as_tensor(qs, dtype=torch.int64, device=dev)
         passes = [(min(lo, q_local), min(lo + qp, q_local)) for lo in range(0, max_q, qp)]
         if self.exchange == "peer":
-            # every pass is enqueued without a host round trip; the flags of all passes are read once at the end and a
-            # pass that raised one (slot / region capacity, a bin above the region size) is redone synchronously
-            pending = []
+            # Every pass is enqueued without a host round trip, and pipelined: the shard half of pass k+1 (route, lookup,
+            # scatter into the owners' regions — NVLink-bound) runs on the caller's stream while the owner half of pass k
+            # (count, merge, rows) runs on a second stream; two sets of peer buffers alternate.  The flags of all passes
+            # are read once at the end; a pass that raised one is redone synchronously.
+            cuda = dev.type == "cuda"
+            timing = bool(os.environ.get("SIA_DIST_TIMING"))
+            self._ensure_peers(qp)
+            if cuda and self._side is None:
+                self._side = torch.cuda.Stream(dev, priority=-1)
+            main = torch.cuda.current_stream(dev) if cuda else None
+            pending, done_ev, keep = [], [], []
             self._timing_fresh = True
-            for a, b in passes:
+            for k, (a, b) in enumerate(passes):
                 e0, e1 = int(qs[a]), int(qs[b])
                 args = (digests[e0:e1], qoffsets[e0:e1], qs_dev[a:b + 1] - e0, qp, b - a, topn)
-                self._ensure_peers(qp)
-                res, chk = self._peer_enqueue(*args)
-                for o, r in zip(outs, res[:4]):
-                    o[a:b] = r[:b - a]
-                nres[a:b] = res[4][:b - a]
-                pending.append((a, b, args, chk))
+                pb = self.peer_sets[k % 2]
+                if cuda and k >= 2:
+                    main.wait_event(done_ev[k - 2])          # this rank has counted the pass that used these buffers
+                t, info, chk = self._peer_send(pb, *args[:4])
+                if cuda and not timing:
+                    ev = main.record_event()
+                    with torch.cuda.stream(self._side):
+                        self._side.wait_event(ev)
+                        res = self._peer_count(pb, t, info, qp, topn)
+                        for o, r in zip(outs, res[:4]):
+                            o[a:b] = r[:b - a]
+                        nres[a:b] = res[4][:b - a]
+                        done_ev.append(self._side.record_event())
+                else:
+                    res = self._peer_count(pb, t, info, qp, topn)
+                    for o, r in zip(outs, res[:4]):
+                        o[a:b] = r[:b - a]
+                    nres[a:b] = res[4][:b - a]
+                    done_ev.append(main.record_event() if cuda else None)
+                pending.append((a, b, args, chk, info))
+                keep.append((t, res))                        # alive until both streams are done with them
+            if cuda:
+                main.wait_stream(self._side)
             if pending:
-                allchk = torch.stack([p[3] for p in pending]).cpu().tolist()
-                for (a, b, args, _), chk in zip(pending, allchk):
+                flagged = torch.stack([p[4][1] & 0xffffffff for p in pending])
+                dist.all_reduce(flagged, op=dist.ReduceOp.MAX, group=self.group)
+                allchk = torch.cat([torch.stack([p[3] for p in pending]), flagged[:, None]], 1).cpu().tolist()
+                for (a, b, args, _, _), chk in zip(pending, allchk):
                     if chk[0] & 5 or chk[4] & 2 or chk[5]:
                         res = self._peer_pass(*args, first=chk)
                         for o, r in zip(outs, res[:4]):
                             o[a:b] = r[:b - a]
                         nres[a:b] = res[4][:b - a]
+            del keep
             return (*outs, nres)
         # Software pipeline over the passes: while the vote of pass i runs on the caller's stream, the routing, lookup,
         # expansion and both all-to-alls of pass i+1 run on a second (high-priority) stream.
@@ -290,34 +319,35 @@ class ShardedIndex:
 
     # ---- the peer-memory pass ---------------------------------------------------------------------------------
     def _ensure_peers(self, qp: int):
-        if self.peers is not None and (self.peers.qp != qp or self.peers.region_cap < self.region_cap):
-            self.peers.close(self.group)
-            self.peers = None
-        if self.peers is None:
+        if self.peer_sets and (self.peer_sets[0].qp != qp or self.peer_sets[0].region_cap < self.region_cap):
+            self.close_peers()
+        if not self.peer_sets:
             cap = min(24576, max(2, int(os.environ.get("SIA_PVOTE_CAP", 24576)))) & ~1
             fill_cap = qp + self.region_cap // cap + 64      # one region per small query + region_cap / cap full-size regions
-            self.peers = self.backend.make_peers(self.rank, self.world, qp, self.region_cap, fill_cap, self.group)
-            if self.peers is None:
-                raise RuntimeError("exchange='peer' needs a CUDA shard backend")
+            for _ in range(2):                               # two sets: pass k+1 is scattered while pass k is counted
+                pb = self.backend.make_peers(self.rank, self.world, qp, self.region_cap, fill_cap, self.group)
+                if pb is None:
+                    raise RuntimeError("exchange='peer' needs a CUDA shard backend")
+                self.peer_sets.append(pb)
 
     def close_peers(self):
-        if self.peers is not None:
-            self.peers.close(self.group)
-            self.peers = None
+        for pb in self.peer_sets:
+            pb.close(self.group)
+        self.peer_sets = []
 
-    def _peer_enqueue(self, digests, qoffsets, qs_dev, qp, nq_local, topn):
-        """One pass with the vote tuples written into the owners' regions by the shards (see ``sia_b200.h``), enqueued
-        without a host round trip.  Collective.  Returns this rank's (song, diff, count, rows, nres) for its ``qp`` query
-        slots and the pass's check vector on the device: [flags, -, entry slot needed, region slots needed, status,
-        queries flagged anywhere] (max over ranks)."""
+    def _peer_send(self, pb, digests, qoffsets, qs_dev, qp):
+        """The shard half of a pass (see ``sia_b200.h``): route the entries, look them up, agree on the tuple counts, scatter
+        the vote tuples into the owners' regions ``pb``.  Collective, no host round trip.  Returns the all-reduced tuple
+        counts, the pass's info vector and its check vector [flags, -, entry slot needed, region slots needed, status]
+        (max over ranks; the all-reduce that makes it is also the barrier "all shards have written")."""
         be, dev, G = self.backend, self.backend.device, self.world
         timing = bool(os.environ.get("SIA_DIST_TIMING"))
-        marks = []
+        self._marks = []
 
         def mark(name):
             if timing:
                 torch.cuda.synchronize(dev)
-                marks.append((name, time.perf_counter()))
+                self._marks.append((name, time.perf_counter()))
         mark("start")
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         info = torch.zeros(4, dtype=torch.int64, device=dev)
@@ -327,22 +357,35 @@ class ShardedIndex:
         dist.all_to_all_single(recv_e, send_e, group=self.group)
         mark("all-to-all entries")
         t = be.lookup_slots(recv_e, G, qp, info)
-        self.peers.counters.zero_()                   # before the all-reduce: every owner is clean when any shard starts
+        pb.counters.zero_()                           # before the all-reduce: every owner is clean when any shard starts
         dist.all_reduce(t, group=self.group)          # tuples of every global query over all shards
         mark("lookup + all-reduce of the tuple counts")
-        be.scatter_peers(G, qp, t, self.peers, info)
+        be.scatter_peers(G, qp, t, pb, info)
         chk = torch.cat([info, status.to(torch.int64)])
         dist.all_reduce(chk, op=dist.ReduceOp.MAX, group=self.group)      # also the barrier: all shards have written
         mark("scatter into the owners' regions (NVLink) + barrier")
-        res = be.count_regions(t[self.rank * qp:(self.rank + 1) * qp], qp, topn, self.peers, info)
-        flagged = info[1:2] & 0xffffffff
-        dist.all_reduce(flagged, op=dist.ReduceOp.MAX, group=self.group)
-        mark("count + merge + rows")
+        return t, info, chk
+
+    def _peer_count(self, pb, t, info, qp, topn):
+        """The owner half: count + merge + rows over the regions the shards filled.  Local (no collective)."""
+        timing = bool(os.environ.get("SIA_DIST_TIMING"))
+        res = self.backend.count_regions(t[self.rank * qp:(self.rank + 1) * qp], qp, topn, pb, info)
         if timing:                                        # keep the slowest pass of the call (the last one is usually a stub)
+            torch.cuda.synchronize(self.backend.device)
+            marks = self._marks + [("count + merge + rows", time.perf_counter())]
             ms = {n: (tm - marks[i][1]) * 1e3 for i, (n, tm) in enumerate(marks[1:])}
             if self._timing_fresh or sum(ms.values()) > sum((self.last_pass_ms or {}).values()):
                 self.last_pass_ms = ms
             self._timing_fresh = False
+        return res
+
+    def _peer_enqueue(self, digests, qoffsets, qs_dev, qp, nq_local, topn):
+        """Both halves of one pass on the current stream (the synchronous retry path)."""
+        pb = self.peer_sets[0]
+        t, info, chk = self._peer_send(pb, digests, qoffsets, qs_dev, qp)
+        res = self._peer_count(pb, t, info, qp, topn)
+        flagged = info[1:2] & 0xffffffff
+        dist.all_reduce(flagged, op=dist.ReduceOp.MAX, group=self.group)
         return res, torch.cat([chk, flagged])
 
     def _peer_pass(self, digests, qoffsets, qs_dev, qp, nq_local, topn, first=None):
