@@ -14,9 +14,11 @@ A "step" is one pass of the whole path (K1 STFT->dB, K2 peaks, K3 pairs+SHA-1) o
 
 M2 ("match"): match queries per second.  Workload = configs[3]/[4]: a 100,000-track synthetic index (~8e9 fingerprints)
 and 10,000 concurrent 5 s queries, on N = 1/2/4/8 GPUs ("scaling": "strong": index and query set are fixed).  N = 1: one
-index on one GPU.  N > 1: the index is sharded by HASH PREFIX (north_star: query hashes routed to their owning GPU, vote
-keys exchanged over NCCL, exact vote at the query's owner) — `match.value` — and, next to it, by TRACK
-(`match.track_sharded`, SURVEY §8e's alternative).  Identity is checked inside the run: hash-prefix == track-sharded for
+index on one GPU.  N > 1: the index is sharded by HASH PREFIX (north_star: query hashes routed to their owning GPU over
+NCCL, every vote tuple delivered to the query's owner, exact vote there) in two exact variants — `match.peer_memory`: the
+shard scatters the tuples straight into the owner's HBM over NVLink peer memory (the exchange fused into the kernel);
+`match.key_exchange`: vote keys through a second NCCL all-to-all — `match.value` is the faster one, and, next to it, by
+TRACK (`match.track_sharded`, SURVEY §8e's alternative).  Identity is checked inside the run: hash-prefix == track-sharded for
 every query, a 256-query subsample against ONE index holding all rows on rank 0, and a checksum of all results that is
 the same number at every N.
 
