@@ -37,7 +37,7 @@ constexpr int kFiltWords = 8192;      // count kernel: duplicate filter, 2 bits 
 constexpr int kTabSlots = 4096;       // count kernel: exact table of the tuples in twice-hit buckets (32 KB)
 constexpr int kDup = 2048;            // repeated bins a region remembers
 constexpr int kCntThreads = 512;
-constexpr int kRegionsPerCta = 8;
+constexpr int kRegionsPerCta = 1;
 constexpr size_t kCountSmem = (size_t)kFiltWords * 4 + (size_t)kTabSlots * 8;
 
 struct PvQuery {
