@@ -173,7 +173,7 @@ class ShardedIndex:
         is redone with "keys"."""
         assert exchange in ("keys", "peer")
         self.exchange = exchange
-        self.region_cap = max(1 << 16, int(region_cap))   # tuple slots of this rank's regions (grown on demand)
+        self.region_cap = max(64, int(region_cap))        # tuple slots of this rank's regions (grown on demand)
         self.peer_sets = []         # two sets of PeerBuffers
         self._marks = []
         self._timing_fresh = True

@@ -32,6 +32,26 @@ def unpack_entry(x, y):
     return qid, hi.to_bytes(8, "big") + lo16.to_bytes(2, "big"), x & M24
 
 
+class _Counters:
+    def __init__(self, owner):
+        self.owner = owner
+
+    def zero_(self):
+        self.owner.tuples = []
+
+
+class CpuPeers:
+    """Stand-in for database.PeerBuffers."""
+
+    def __init__(self, rank, world, qp, region_cap, group):
+        self.rank, self.world, self.qp, self.region_cap, self.group = rank, world, qp, region_cap, group
+        self.tuples = []
+        self.counters = _Counters(self)
+
+    def close(self, group=None):
+        pass
+
+
 class CpuShard(ShardBackend):
     def __init__(self):
         self.device = torch.device("cpu")
@@ -101,6 +121,58 @@ class CpuShard(ShardBackend):
 
     def vote_finish(self):
         pass
+
+    # ---- the peer-memory pass: the "regions" of a rank are a list its peers fill through the process group ----------
+    def make_peers(self, rank, world, qp, region_cap, fill_cap, group=None):
+        return CpuPeers(rank, world, qp, region_cap, group)
+
+    def lookup_slots(self, entry_slots, world, queries_per_rank, info):
+        ent = set()
+        cap = entry_slots.shape[1]
+        for s in range(world):
+            c = int(entry_slots[s, 0, 0])
+            if c > cap - 1:
+                info[0] |= 1
+                info[2] = max(int(info[2]), c + 1)
+            for k in range(1, min(c, cap - 1) + 1):
+                ent.add(unpack_entry(int(entry_slots[s, k, 0]), int(entry_slots[s, k, 1])))
+        self._ent = sorted(ent)
+        t = torch.zeros(world * queries_per_rank, dtype=torch.int64)
+        for q, h, _ in self._ent:
+            t[q] += len(self.rows.get(h, ()))
+        return t
+
+    def scatter_peers(self, world, queries_per_rank, tuples_total, peers, info):
+        import torch.distributed as dist
+        need = max(int(tuples_total[d * queries_per_rank:(d + 1) * queries_per_rank].sum()) for d in range(world))
+        info[3] = max(int(info[3]), need)
+        out = [[] for _ in range(world)]
+        if need > peers.region_cap:
+            info[0] |= 4                                        # every rank sees the same totals: nobody scatters
+        else:
+            seen = set()
+            for q, h, qo in self._ent:
+                dest, ql = divmod(q, queries_per_rank)
+                head = (q, h) not in seen
+                seen.add((q, h))
+                for song, off in sorted(self.rows.get(h, ())):
+                    out[dest].append((int(head) << 63) | (ql << (SONG_BITS + DIFF_BITS)) | (song << DIFF_BITS) | (off - qo + BIAS))
+        got = [None] * world
+        dist.all_gather_object(got, out, group=peers.group)      # stands in for the stores into the owners' memory
+        for src in range(world):
+            peers.tuples += got[src][peers.rank]
+
+    def count_regions(self, tuples_total, n_queries, topn, peers, info):
+        import os
+        cap = int(os.environ.get("SIA_PVOTE_CAP", 24576))
+        bins = {}
+        for k in peers.tuples:
+            key = k & ((1 << 63) - 1)
+            bins[key] = bins.get(key, 0) + 1
+        flagged = {(key >> (SONG_BITS + DIFF_BITS)) & ((1 << QID_BITS) - 1) for key, c in bins.items() if c > cap}
+        info[1] += len(flagged)                                  # a bin above the region size: the key exchange takes the pass
+        keys = [k for k in peers.tuples if ((k >> (SONG_BITS + DIFF_BITS)) & ((1 << QID_BITS) - 1)) not in flagged]
+        return vote_keys(keys, n_queries, topn)
 
     def vote_key_slots(self, key_slots, n_queries, topn, max_song, defer=False):
         keys = []

@@ -1,5 +1,6 @@
 """world_size-2 gloo tests of the multi-GPU host logic (track sharding, hash-prefix routing through fixed-size slots,
-overflow retries, the exact vote over the keys of all shards) with a CPU stand-in shard.  The CUDA shard is covered by tests/test_index_gpu.py."""
+overflow retries, the exact vote over the keys of all shards, the peer-memory pass with its flag handling, region growth
+and fallback to the key exchange) with a CPU stand-in shard.  The CUDA shard is covered by tests/test_index_gpu.py."""
 import hashlib
 import os
 import socket
@@ -52,7 +53,12 @@ def _worker(rank, world, port, topn, mode="hash"):
         from tests.dist_helpers import CpuShard
         songs, queries = _world()
         want, nrows = _oracle_results(songs, queries, topn)
-        ix = TrackShardedIndex(CpuShard()) if mode == "track" else ShardedIndex(CpuShard(), key_cap=8)
+        if mode == "track":
+            ix = TrackShardedIndex(CpuShard())
+        elif mode == "peer":      # the second exchange fused into the shards' scatter (stand-in: lists filled through the group)
+            ix = ShardedIndex(CpuShard(), key_cap=8, exchange="peer", region_cap=64)
+        else:
+            ix = ShardedIndex(CpuShard(), key_cap=8)
         mine = shard_tracks(len(songs), rank, world)            # tracks fingerprinted by this rank
         assert sorted(np.concatenate([shard_tracks(len(songs), r, world) for r in range(world)]).tolist()) == list(range(len(songs)))
         sid = torch.tensor([songs[i][0] for i in mine for _ in songs[i][1]], dtype=torch.int32)
@@ -70,9 +76,17 @@ def _worker(rank, world, port, topn, mode="hash"):
         D = np.array([np.frombuffer(h, np.uint8) for qi in myq for h, _ in queries[qi]], np.uint8).reshape(-1, 10)
         Oq = np.array([o for qi in myq for _, o in queries[qi]], np.int32)
         starts = np.cumsum([0] + [len(queries[qi]) for qi in myq])
-        kw = dict(queries_per_pass=3) if mode == "hash" else {}      # forces split passes; tiny first slots force retries
+        kw = dict(queries_per_pass=3) if mode in ("hash", "peer") else {}      # forces split passes; tiny first slots force retries
         res = ix.query(torch.from_numpy(D), torch.from_numpy(Oq), starts, topn, **kw)
-        if mode == "hash":
+        if mode == "peer":
+            assert ix.retries >= 1 and ix.peer_fallbacks == 0   # the regions were grown, no pass needed the key exchange
+            os.environ["SIA_PVOTE_CAP"] = "2"                   # now every true bin is "above the region size"
+            res3 = ix.query(torch.from_numpy(D), torch.from_numpy(Oq), starts, topn, **kw)
+            os.environ.pop("SIA_PVOTE_CAP")
+            assert ix.peer_fallbacks >= 1                       # those passes were redone with the key exchange
+            for a, b in zip(res, res3):
+                assert torch.equal(a, b)
+        if mode in ("hash", "peer"):
             assert ix.retries >= 1                              # the first pass outgrew the initial key slots
             before = ix.retries
             res2 = ix.query(torch.from_numpy(D), torch.from_numpy(Oq), starts, topn, **kw)
@@ -98,7 +112,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("topn,mode", [(1, "hash"), (3, "hash"), (2, "track")])
+@pytest.mark.parametrize("topn,mode", [(1, "hash"), (3, "hash"), (2, "track"), (3, "peer")])
 def test_sharded_index_world2_gloo(topn, mode):
     mp.spawn(_worker, args=(2, _free_port(), topn, mode), nprocs=2, join=True)
 
