@@ -751,6 +751,7 @@ size_t lookup_bytes(int64_t n) {
 
 int lookup_sorted(::sia_index *ix, Arena &ar, ulonglong2 *a, ulonglong2 *b, int64_t n, const int64_t *d_query_starts,
                   int64_t i0, int n_queries, int64_t max_query_entries, Lookup &L, cudaStream_t s) {
+  ix->dist_nq = 0;                 // any new lookup reuses the arena: a pending sia_index_lookup_slots is void
   L = Lookup();
   L.n = n;
   if (n == 0) return SIA_OK;
