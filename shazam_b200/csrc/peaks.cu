@@ -76,6 +76,30 @@ __device__ __forceinline__ void sliding21_max3(float (&v)[LEN]) {
   for (int i = 0; i < OUTN; ++i) v[i] = fmaxf(fmaxf(v[i], v[i + 9]), v[i + 12]);             // [i, i+21)
 }
 
+// The same 16 windows of 21 out of 36 values, van Herk / Gil-Werman style: suffix maxima of v[0..20], prefix maxima of
+// v[21..35], out[i] = max(suffix[i], prefix[i + 20]) — 49 max operations instead of 78 (the two scans advance two
+// elements per step with a 3-input max, so the dependent chains are 10 and 7 long).
+__device__ __forceinline__ void vanherk21_36(float (&v)[36]) {
+  // suffix: v[i] = max(v[i..20]), i = 19 .. 0
+#pragma unroll
+  for (int i = 18; i >= 0; i -= 2) {
+    const float s2 = v[i + 2];
+    const float a = fmaxf(v[i + 1], s2);
+    v[i] = fmaxf(fmaxf(v[i], v[i + 1]), s2);
+    v[i + 1] = a;
+  }
+  // prefix: v[j] = max(v[21..j]), j = 22 .. 35
+#pragma unroll
+  for (int j = 22; j + 1 <= 35; j += 2) {
+    const float p2 = v[j - 1];
+    const float a = fmaxf(v[j], p2);
+    v[j + 1] = fmaxf(fmaxf(v[j + 1], v[j]), p2);
+    v[j] = a;
+  }
+#pragma unroll
+  for (int i = 1; i < 16; ++i) v[i] = fmaxf(v[i], v[i + 20]);
+}
+
 struct TileCoord {
   int trk;
   int64_t row_lo, row_hi;  // global rows of this track [row_lo, row_hi)
@@ -217,10 +241,10 @@ __device__ __forceinline__ void warp_tile_peaks(const float4 *__restrict__ A, ui
     const float4 t = A[(16 * q + i) * kW2Cols4 + col];
     vx[i] = t.x; vy[i] = t.y; vz[i] = t.z; vw[i] = t.w;
   }
-  sliding21_max3<36, 16>(vx);
-  sliding21_max3<36, 16>(vy);
-  sliding21_max3<36, 16>(vz);
-  sliding21_max3<36, 16>(vw);
+  vanherk21_36(vx);
+  vanherk21_36(vy);
+  vanherk21_36(vz);
+  vanherk21_36(vw);
 
   const unsigned FULL = 0xffffffffu;
   const float amp_up = nextafterf(amp_lo, CUDART_INF_F);
