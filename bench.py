@@ -601,6 +601,7 @@ def match_leg(args, rank, world, local_rank, dev):
             evs[i + 1].record()
         barrier()
         per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+        timed.last_per_step = [round(x, 2) for x in per]
         ms = torch.tensor([evs[0].elapsed_time(evs[-1]) / steps, float(np.median(per))], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -610,6 +611,7 @@ def match_leg(args, rank, world, local_rank, dev):
     sampler.start()
     sampler.mark()
     res, ms_step, ms_med = timed(step_main, args.steps, max(args.warmup, 3))
+    per_step_ms = timed.last_per_step
     clocks = sampler.stop()
     lookup_ms = vote_ms = None
     qstats = None
@@ -763,6 +765,7 @@ def match_leg(args, rank, world, local_rank, dev):
 
     out = {"metric": "match_queries_per_second", "value": Q / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world,
            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_step_median": ms_med,
+           "ms_of_each_step_rank0": per_step_ms,
            "higher_is_better": True, "scaling": "strong", "dtype": "u64", "data": "synthetic",
            "sharding": ("one index on one GPU" if world == 1 else
                         "hash prefix: query entries routed to the shard owning their hash, vote keys exchanged (2 equal-split "
