@@ -229,6 +229,38 @@ def bind_to_gpu_numa(gpu_index: int):
     return None
 
 
+def per_kernel_roofline(kernel_ms, audio_s, n_hashes, peak_gbs, digest_table):
+    """north_star: achieved HBM GB/s of EVERY kernel of the fingerprint path against the measured peak, from the
+    event-timed kernel times of the timed region.  Algorithmic bytes are SURVEY §8(d)'s (K1 264 684 B and K2 176 484 B per
+    audio-second, K3 14 B written per hash); K3 is not bound by its algorithmic bytes (SHA-1 mode: integer ALU; table
+    mode: one random 32-byte sector per hash), so its sector-granular rate is given next to it.  Pure arithmetic:
+    ``kernel_ms`` = {name: ms per step}, ``audio_s`` / ``n_hashes`` per step and GPU."""
+    frames = audio_s * FS / 2048.0
+    rows = [
+        ("stft_db(K1)", K1_BYTES_PER_AUDIO_S * audio_s, "fp64 pipe (float64 butterflies); bytes are streamed once"),
+        ("peaks_bitmap(K2)", 176_484 * audio_s, "latency / ALU (FMNMX on the half-rate pipe at 8 warps per SM)"),
+        ("peaks_compact(K2)", 352.0 * frames, "trivial: 88-word bitmap row per frame -> ordered peak lists"),
+        ("pairs_sha1(K3)", 14.0 * n_hashes,
+         "random 32-byte sectors of the digest table" if digest_table else "integer ALU (80 SHA-1 rounds per hash)"),
+    ]
+    out = {}
+    for name, nbytes, bound in rows:
+        ms = float(kernel_ms.get(name) or 0.0)
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
+        out[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": nbytes, "achieved_gbs": gbs,
+                     "frac_of_hbm_peak": (gbs / peak_gbs) if gbs else None, "limited_by": bound}
+    k3 = out["pairs_sha1(K3)"]
+    if k3["achieved_gbs"]:
+        ms = k3["ms_per_step"]
+        k3["hashes_per_second"] = n_hashes / (ms * 1e-3)
+        if digest_table:
+            sect = (14.0 + 32.0) * n_hashes
+            k3["sector_granular_bytes_per_step"] = sect
+            k3["sector_granular_gbs"] = sect / (ms * 1e-3) / 1e9
+            k3["sector_granular_frac_of_hbm_peak"] = k3["sector_granular_gbs"] / peak_gbs
+    return out
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -381,6 +413,7 @@ def fingerprint_leg(args, rank, world, local_rank, dev, config):
                     "algorithmic_bytes_per_launch": algo_bytes_per_launch, "launches_timed": k1_launches,
                     "avg_launch_ms": k1_ms / k1_launches, "kernel_ms_per_step": kernel_ms,
                     "share_of_step": round(k1_ms / max(sum(kms), 1e-9), 4)}
+        roofline["per_kernel"] = per_kernel_roofline(kernel_ms, audio_s, n_hashes, peak, not args.no_digest_table)
         if args.compute == "f64" and k1_ms > 0:
             # what actually bounds K1: the FP64 pipe (+ the integer pipe).  854 DP arithmetic instructions
             # per thread and frame (static SASS count: 455 DADD, 249 DFMA, 150 DMUL) x 4 warps = 3 416 DP warp
@@ -410,9 +443,12 @@ def fingerprint_leg(args, rank, world, local_rank, dev, config):
             ntr = args.cpu_sample_tracks or min(B, 4 * procs)
             tracks = [rows[i, :L].cpu().numpy() for i in range(ntr)]
             v, dt, nh = cpu_reference_run(tracks, procs)
+            v1, dt1, _ = cpu_reference_run(tracks[:2], 1)        # the one-process figure next to the Pool's
             cpu = {"value": v, "unit": "audio-s/s", "cores": procs, "kind": "port",
                    "sample": f"first {ntr} of the {B} tracks ({ntr * audio_s_per_track:.0f} audio-s, {dt:.1f} s wall), "
-                             f"oracle port of the reference CPU path, Pool({procs}) one task per track"}
+                             f"oracle port of the reference CPU path, Pool({procs}) one task per track",
+                   "one_process": {"value": v1, "unit": "audio-s/s", "cores": 1,
+                                   "sample": f"first {len(tracks[:2])} tracks, {dt1:.1f} s wall"}}
 
         out = {"metric": "fingerprint_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -911,12 +947,15 @@ def main():
         v, dt, nh = cpu_reference_run(tracks, procs, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
         sample = (f"{ntr} of the {args.tracks} tracks per step ({ntr * audio_s_per_track:.0f} audio-s), "
                   f"Pool({procs}) one task per track like fingerprint_directory (__init__.py:341,357)")
+        v1, dt1, _ = cpu_reference_run(tracks[:2], 1)            # the one-process figure, outside the timed steps
+        one = {"value": v1, "unit": "audio-s/s", "cores": 1, "sample": f"first {len(tracks[:2])} tracks, {dt1:.1f} s wall"}
         print(json.dumps({
             "impl": "reference", "metric": "fingerprint_audio_seconds_per_second", "value": v, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
-            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": procs, "kind": "port", "sample": sample,
+                             "one_process": one},
             "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "hashes_per_step_sample": nh}))
         return

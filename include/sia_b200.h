@@ -228,7 +228,8 @@ int sia_index_select_host(sia_index *ix, const uint8_t *h_hash, int64_t n, int32
  *   out_rows             — dedup_hashes[song]: DB rows matched, counted once per row,
  *   out_nres[q]          — number of valid results (<= topn).
  * Equal counts order by ascending song id (stable sort, recognizer.py:307-310).
- * The vote uses per-query hash tables (no vote tuples are written or sorted; any query size).
+ * The vote is the partitioned vote of csrc/index_pvote.cu (vote tuples written once into per-(query, partition)
+ * regions and counted in shared memory); a query it cannot take is voted by per-query hash tables in HBM (any size).
  * h_stats (optional, 4 x int64): query (hash, offset) pairs, DB rows matched (the total of
  * dedup_hashes), (song, diff) tuples voted (len(results) of return_matches), distinct bins. */
 int sia_index_query_batch(sia_index *ix, const uint8_t *d_hash, const int32_t *d_qoff,

@@ -150,13 +150,11 @@ def test_k2_other_neighbourhoods_and_float32(fpr):
             assert got == want, (amp, k)
 
 
-@pytest.mark.parametrize("kernel", ["warp", "prune"])
-def test_k2_float32_production_kernel(fpr, monkeypatch, kernel):
-    """The float32 square-footprint kernels (the full separable max filter the pipeline runs, and the
-    candidate-pruning alternative): ties, thresholds that are not float32-representable, ragged multi-track
-    layouts whose tiles end mid-way, loud tracks where every block is above the threshold, coarse plateaus."""
+def test_k2_float32_production_kernel(fpr):
+    """The float32 square-footprint kernel the pipeline runs (TMA tiles, van Herk vertical pass, shuffle horizontal
+    pass): ties, thresholds that are not float32-representable, ragged multi-track layouts whose tiles end mid-way,
+    loud tracks where every block is above the threshold, coarse plateaus."""
     import torch
-    monkeypatch.setenv("SIA_PEAKS_KERNEL", kernel)
     rng = np.random.default_rng(12)
     frames = [130, 1, 64, 65, 7, 200, 90, 75]
     arrs = []
