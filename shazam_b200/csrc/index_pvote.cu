@@ -1,23 +1,26 @@
 // K4, the partitioned vote — align_matches' histogram (recognizer.py:303-310) counted in SHARED memory.
 //
 // The table vote of index_query.cu counts every (query, song, diff) tuple with atomics on tables that live in HBM:
-// a random 32-byte sector per tuple and pass.  Here the tuples of a query are first split by a hash of the SONG id
-// into partitions of ~3 600 tuples, so that each partition's bins fit an exact open-addressing table in shared memory:
+// a random 32-byte sector per tuple and pass.  Here the tuples of a query are first split by a hash of the BIN
+// (song, diff) into partitions of ~10 240 tuples (regions of at most 24 576 slots), so that each partition's repeated
+// bins fit a duplicate filter + a small exact table in shared memory:
 //
 //   scatter  one CTA per block of 8 192 consecutive tuples of ONE query (posting runs walked entry by entry, or a slice
-//            of received vote keys): tuple -> (song 24 | diff 25 | head 1), partition = hash(song) * np >> 32, counted in
-//            a shared histogram, sorted by partition through a shared staging buffer, and written as one contiguous
-//            run per partition into the (query, partition) region (one global atomicAdd per block and partition
-//            reserves the room);
-//   count    one CTA per region: every tuple inserted into a shared-memory table (one 64-bit word per slot =
-//            key 49 | count 15; CAS to claim, 32-bit add to bump), bins that reach count 2 remembered in a list; the
+//            of received vote keys): tuple -> (song 24 | diff 25 | head 1), partition = hi16(hash(song, diff)) * np >> 16,
+//            counted in a shared histogram, sorted by partition through a shared staging buffer, and written as one
+//            contiguous run per partition into the (query, partition) region (one global atomicAdd per block and
+//            partition reserves the room; with peer memory the region lives in the query owner's HBM);
+//   count    one CTA per region, two passes over its tuples: a 2-bit duplicate filter marks the buckets hit twice, then
+//            only the tuples of those buckets go to an exact open-addressing table (one 64-bit word per slot =
+//            key 49 | count 15; CAS to claim, 32-bit add to bump); bins that reach count 2 are remembered in a list; the
 //            region's top-n songs by (count desc, song asc), per song the largest bin, smallest diff on ties, come
-//            from that list (or from a scan of the table when fewer than n songs have a repeated bin);
-//   merge    one warp per query: top-n over its regions' candidates.  A song's bins all live in ONE partition, so
-//            the per-partition winners are exact and so is their merge.
-// All traffic is streaming: 8 B read + 8 B written per tuple (scatter), 8 B read (count).  Queries that do not fit —
-// a partition above its capacity (one song with thousands of tuples), more than 2 048 partitions — are flagged and
-// voted by the table vote instead; nothing is approximated.
+//            from that list (or from a scan of the tuples when fewer than n songs have a repeated bin);
+//   merge    one warp per query: top-n over its regions' candidates.  A BIN lives in exactly one partition, so its
+//            count is exact; a song's bins are spread over the partitions, so the merge keeps a song's first (= best)
+//            occurrence in descending order and skips the later ones.
+// All traffic is streaming: 8 B read + 8 B written per tuple (scatter), 8 B read (count; the second pass hits L2).
+// Queries that do not fit — one BIN above a region's capacity, more than 4 096 partitions — are flagged and voted by
+// the table vote instead; nothing is approximated.
 #include "index.cuh"
 
 using namespace sia;

@@ -1,5 +1,7 @@
 // K4, query side — the SELECT ... WHERE hash IN (...) lookup (recognizer.py:60-64, 252-259) and the vote inside
-// align_matches (recognizer.py:303-310) for a batch of queries, without materialising or sorting vote tuples.
+// align_matches (recognizer.py:303-310) for a batch of queries.  The default vote is the partitioned vote of
+// index_pvote.cu (called from here per group of queries); this file holds the lookup, the grouping, and the TABLE vote
+// described below — the path of queries the partitioned vote flags (a bin above a region's size) and of SIA_VOTE=tables.
 //
 // Lookup: the (hash, offset) pairs of the queries are packed into 16-byte entries, sorted by (query, hash, offset)
 // — duplicates drop out, equal hashes of one query become adjacent — and each is looked up: directory -> binary

@@ -9,13 +9,18 @@
 //   peak = (A == max(window)) and not all(window == 0) and A > amp_min.
 // The all-zero term can only matter when amp_min < 0 and is compiled in only then.
 //
-// Stage 1 (this file, peaks_*_kernel): one CTA per 64-frame x 128-bin tile; writes a
-//   bitmap, 1 bit per spectrogram element, row-major [frame][65 words].  The square
-//   footprint (CONNECTIVITY_MASK = 2, the reference default) is separable: a sliding
-//   max down the frames with threads along bins, a transposed store, then a sliding max
-//   along the bins with threads along frames — every shared-memory access of both
-//   passes is conflict-free, and each thread's window lives in registers (log-doubling:
-//   8.4 max ops per output for the 21-wide window).
+// Stage 1 writes a bitmap, 1 bit per spectrogram element.  Three kernels:
+//   peaks_square_warp_tma_kernel  the pipeline's kernel (float32 dB, square 21x21 = CONNECTIVITY_MASK 2, the reference
+//     default, amp_min >= 0): persistent CTAs walk 64-frame x 96-bin tiles; the 84 x 120 halo tile arrives by one TMA
+//     tensor copy (cp.async.bulk.tensor.2d, out-of-range elements arrive as zeros), double-buffered on two mbarriers;
+//     each warp owns 16 frames, each lane a float4 column: vertical 21-max in registers (van Herk / Gil-Werman: suffix
+//     maxima of one block of rows, prefix maxima of the next, one max to combine), horizontal 21-max across lanes with
+//     shuffles; 4 ballots per frame go to a striped bitmap [frame][22 strips][4 words];
+//   peaks_square_kernel<T, N, EROSION>  float64 input (the bit-exact parity path) and amp_min < 0: one CTA per
+//     64-frame x 128-bin tile + halo in shared memory; the separable filter as a sliding max down the frames with
+//     threads along bins, a transposed store, then a sliding max along the bins with threads along frames (register
+//     windows, log-doubling); plain bitmap [frame][65 words];
+//   peaks_generic_kernel<T>  any half-width <= SIA_MAX_NBHD, square or diamond, brute force from the same tile.
 // Stage 2 (peaks_rowcount/extract): bitmap -> per-row popcounts -> scan -> ordered
 //   (t asc, f asc) peak lists per track, which is the order generate_hashes' stable
 //   sort by time produces (__init__.py:194-195).
