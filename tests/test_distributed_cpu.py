@@ -117,6 +117,13 @@ def test_sharded_index_world2_gloo(topn, mode):
     mp.spawn(_worker, args=(2, _free_port(), topn, mode), nprocs=2, join=True)
 
 
+@pytest.mark.parametrize("world,topn,mode", [(4, 3, "hash"), (4, 3, "peer"), (4, 2, "track"), (3, 2, "hash"), (3, 3, "peer")])
+def test_sharded_index_other_world_sizes_gloo(world, topn, mode):
+    """The same checks at world 4 (the N the GPU box runs between 2 and 8) and at an odd world size: 9 queries over 4 / 3
+    ranks give the ranks different numbers of queries and passes (stub passes on the ranks that have run out)."""
+    mp.spawn(_worker, args=(world, _free_port(), topn, mode), nprocs=world, join=True)
+
+
 def test_single_rank_path_matches_oracle():
     """world=1 takes no collective at all."""
     from shazam_b200.distributed import ShardedIndex, hash_owner
