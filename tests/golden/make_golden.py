@@ -147,7 +147,8 @@ def synth_clip(kind, seed):
     raise KeyError(kind)
 
 
-def main():
+def main(out_dir=HERE):
+    """Writes the four fixture files into ``out_dir`` (default: this directory, i.e. the committed fixtures)."""
     ns = ref_namespace()
     out = {}
 
@@ -171,7 +172,7 @@ def main():
     # list-of-python-ints input, as the recorder passes it (recognizer.py:361-368)
     h, t = hashes_to_arrays(ns["fingerprint"]([int(v) for v in pcm[:50000]], Fs=44100))
     out["hash_list50k"], out["t1_list50k"] = h, t
-    np.savez_compressed(f"{HERE}/wav_fixture.npz", **out)
+    np.savez_compressed(f"{out_dir}/wav_fixture.npz", **out)
     print("wav: peaks", len(out["peaks_c2"]), "hashes fan5", len(out["hash_c2_fan5_fs22050"]),
           "fan15", len(out["hash_c2_fan15_fs22050"]), "diamond peaks", len(out["peaks_c1"]))
 
@@ -187,7 +188,7 @@ def main():
             out[f"{kind}_hash_fan{fan}_amp{amp}"] = h
             out[f"{kind}_t1_fan{fan}_amp{amp}"] = t
         print(kind, len(x), "samples ->", len(out[f"{kind}_hash_fan15_amp10"]), "hashes @fan15")
-    np.savez_compressed(f"{HERE}/synth_cases.npz", **out)
+    np.savez_compressed(f"{out_dir}/synth_cases.npz", **out)
 
     # ---- raw peak cases: small float64 spectrograms ----------------------------------
     out = {}
@@ -215,7 +216,7 @@ def main():
                 pk = ns["get_2D_peaks"](arr, amp_min=amp)
                 out[f"{name}_c{conn}_amp{amp}"] = np.array(pk, np.int32).reshape(-1, 2)
     ns["CONNECTIVITY_MASK"] = 2
-    np.savez_compressed(f"{HERE}/peaks_cases.npz", **out)
+    np.savez_compressed(f"{out_dir}/peaks_cases.npz", **out)
 
     # ---- match cases ---------------------------------------------------------------
     mcases = []
@@ -265,9 +266,9 @@ def main():
                                {7: 3, 2: 4, 9: 1}, 10, 3)
     mcases.append({"case": "kat", "results": [{k: (v.decode() if isinstance(v, bytes) else v)
                                                for k, v in r.items()} for r in kat]})
-    json.dump(mcases, open(f"{HERE}/match_cases.json", "w"), indent=0)
+    json.dump(mcases, open(f"{out_dir}/match_cases.json", "w"), indent=0)
     print("match cases:", len(mcases))
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else HERE)

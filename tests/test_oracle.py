@@ -1,6 +1,7 @@
 """The oracle against the committed golden vectors (made by executing the reference's own
 functions, tests/golden/make_golden.py) and against scipy for the restated specgram."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -104,3 +105,23 @@ def test_synth_track_is_deterministic():
     s = O.mix_noise(a.astype(np.float64), np.random.default_rng(0).normal(0, 1, 50000), 10.0)
     n = s - a
     assert abs(20 * np.log10(np.sqrt(np.mean(a.astype(float) ** 2)) / np.sqrt(np.mean(n ** 2))) - 10.0) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the dev container")
+def test_committed_golden_vectors_regenerate_from_the_reference(tmp_path):
+    """The pin of the pin: tests/golden/make_golden.py executes the reference's OWN functions (AST-extracted from
+    /root/reference) and must reproduce every committed fixture bit for bit.  Dev container only — nothing that runs on
+    the GPU box reads /root/reference."""
+    import importlib.util
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    mg.main(str(tmp_path))
+    for name in ("wav_fixture.npz", "synth_cases.npz", "peaks_cases.npz"):
+        a, b = np.load(os.path.join(here, name)), np.load(tmp_path / name)
+        assert set(a.files) == set(b.files), name
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), (name, k)
+    assert json.load(open(os.path.join(here, "match_cases.json"))) == json.load(open(tmp_path / "match_cases.json"))
