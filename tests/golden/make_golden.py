@@ -21,6 +21,7 @@ Outputs (all under ``tests/golden/``):
   synth_cases.npz   seeded short clips (silence gaps, sub-frame input, ...) + reference hashes
   peaks_cases.npz   small float64 spectrograms (plateaus, zeros, negative amp_min) + reference peaks
   match_cases.json  reference return_matches + align_matches on small tables
+  noise_cases.npz   reference get_noise_from_sound (recognizer_test.py:426-435) on seeded signal / noise pairs
 """
 import ast
 import hashlib
@@ -268,6 +269,25 @@ def main(out_dir=HERE):
                                                for k, v in r.items()} for r in kat]})
     json.dump(mcases, open(f"{out_dir}/match_cases.json", "w"), indent=0)
     print("match cases:", len(mcases))
+
+    # ---- SNR mixer of the experiment script ----------------------------------------------
+    import math
+    nns = dict(np=np, math=math)
+    exec(extract(f"{REF}/recognizer_test.py", {"get_noise_from_sound"}), nns)
+    out = {"snrs": np.array([0.0, 10.0, -5.0, 3.5])}
+    rng = np.random.default_rng(2024)
+    for k, n in enumerate((2048, 8192)):
+        # the script rescales both to [-1, 1] before the call (recognizer_test.py:547-551); keep that range
+        t = np.arange(n) / 22050.0
+        signal = 0.6 * np.sin(2 * np.pi * 440 * t) + 0.2 * rng.standard_normal(n)
+        signal = np.interp(signal, (signal.min(), signal.max()), (-1, 1))
+        noise = np.cumsum(rng.standard_normal(n))                  # coloured, non-zero mean
+        noise = np.interp(noise, (noise.min(), noise.max()), (-1, 1))
+        out[f"signal_{k}"], out[f"noise_{k}"] = signal, noise
+        for j, snr in enumerate(out["snrs"]):
+            out[f"scaled_{k}_{j}"] = nns["get_noise_from_sound"](signal, noise, float(snr))
+    np.savez_compressed(f"{out_dir}/noise_cases.npz", **out)
+    print("noise cases: 2 x", len(out["snrs"]))
 
 
 if __name__ == "__main__":

@@ -126,6 +126,21 @@ def test_match_cases(match_cases):
             assert got == want
 
 
+def test_mix_noise_equals_the_reference_mixer():
+    """``get_noise_from_sound`` (recognizer_test.py:426-435, executed from the reference's source by make_golden.py)
+    + the addition of :554: the oracle's mixer — what the GPU mixer ``sia_mix_noise`` is checked against — gives the
+    reference's scaled noise to the last bit, and the mix has the requested SNR."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "noise_cases.npz"))
+    for k in range(2):
+        signal, noise = g[f"signal_{k}"], g[f"noise_{k}"]
+        for j, snr in enumerate(g["snrs"]):
+            want = g[f"scaled_{k}_{j}"]
+            mixed = O.mix_noise(signal, noise, float(snr))
+            assert np.array_equal(mixed, signal + want), (k, j)
+            got_snr = 20 * np.log10(np.sqrt(np.mean(signal ** 2)) / np.sqrt(np.mean(want ** 2)))
+            assert abs(got_snr - snr) < 1e-9
+
+
 def test_synth_track_is_deterministic():
     a = O.synth_track(5, 50000)
     b = O.synth_track(5, 50000)
@@ -147,7 +162,7 @@ def test_committed_golden_vectors_regenerate_from_the_reference(tmp_path):
     mg = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mg)
     mg.main(str(tmp_path))
-    for name in ("wav_fixture.npz", "synth_cases.npz", "peaks_cases.npz"):
+    for name in ("wav_fixture.npz", "synth_cases.npz", "peaks_cases.npz", "noise_cases.npz"):
         a, b = np.load(os.path.join(here, name)), np.load(tmp_path / name)
         assert set(a.files) == set(b.files), name
         for k in a.files:
