@@ -21,6 +21,7 @@ Outputs (all under ``tests/golden/``):
   synth_cases.npz   seeded short clips (silence gaps, sub-frame input, ...) + reference hashes
   peaks_cases.npz   small float64 spectrograms (plateaus, zeros, negative amp_min) + reference peaks
   match_cases.json  reference return_matches + align_matches on small tables
+  apriori_cases.json  reference return_matches of recognizer_apriori.py (early exit, :246-310) on small tables
   noise_cases.npz   reference get_noise_from_sound (recognizer_test.py:426-435) on seeded signal / noise pairs
 """
 import ast
@@ -111,6 +112,12 @@ class _Db:
 def match_namespace(table):
     ns = dict(np=np, groupby=groupby, db=_Db(table))
     exec(extract(f"{REF}/recognizer.py", {"return_matches", "align_matches"}), ns)
+    return ns
+
+
+def apriori_namespace(table):
+    ns = dict(np=np, groupby=groupby, db=_Db(table))
+    exec(extract(f"{REF}/recognizer_apriori.py", {"return_matches", "align_matches"}), ns)
     return ns
 
 
@@ -269,6 +276,44 @@ def main(out_dir=HERE):
                                                for k, v in r.items()} for r in kat]})
     json.dump(mcases, open(f"{out_dir}/match_cases.json", "w"), indent=0)
     print("match cases:", len(mcases))
+
+    # ---- a-priori early exit: recognizer_apriori.py's return_matches, executed from its source --------
+    import contextlib
+    import io
+    acases = []
+    rng = np.random.default_rng(23)
+    for case_id, (nsongs, per_song, universe, nquery, batch, twin) in enumerate(
+            [(6, 300, 3000, 200, 20, False), (5, 200, 150, 120, 16, True), (4, 120, 90, 60, 1000, False),
+             (8, 250, 1200, 160, 10, False), (8, 250, 600, 160, 5, False)]):
+        table = O.FingerprintTable()
+        rows = []
+        for s in range(nsongs):
+            sid = table.insert_song(f"song{s}", hashlib.sha1(f"afile{s}".encode()).hexdigest().upper(), per_song)
+            if twin and s == 2:
+                hs = [(h, o) for _, h, o in rows if _ == 2]         # song 3 = a copy of song 2: the exit never triggers
+            else:
+                hs = [(hx(int(rng.integers(0, universe))), int(rng.integers(0, 80))) for _ in range(per_song)]
+            table.insert_hashes(sid, hs)
+            table.set_song_fingerprinted(sid)
+            rows += [[sid, h, o] for h, o in hs]
+        target = [r for r in rows if r[0] == 2]
+        q = [(h, max(0, o - 5)) for _, h, o in target[: (3 * nquery) // 4]]
+        q += [(hx(int(rng.integers(0, universe))), int(rng.integers(0, 30))) for _ in range(nquery - len(q))]
+        q = sorted(set(q))                                          # the batches follow this order
+        ans = apriori_namespace(table)
+        with contextlib.redirect_stdout(io.StringIO()):
+            matches, dedup, songs_arr = ans["return_matches"](q, batch)
+        acases.append({
+            "case": case_id, "rows": rows, "query": q, "batch_size": batch,
+            "songs": {str(k): v for k, v in table.songs.items()},
+            "n_matches": len(matches),
+            "matches_sorted_sha": hashlib.sha256(repr(sorted(matches)).encode()).hexdigest(),
+            "dedup": {str(k): v for k, v in dedup.items()},
+            "songs_arr": [{k: (v.decode() if isinstance(v, bytes) else v) for k, v in r.items()} for r in songs_arr],
+        })
+        full, _ = match_namespace(table)["return_matches"](q)
+        print(f"apriori case {case_id}: {len(matches)} of {len(full)} matches read, exit={'yes' if songs_arr else 'no'}")
+    json.dump(acases, open(f"{out_dir}/apriori_cases.json", "w"), indent=0)
 
     # ---- SNR mixer of the experiment script ----------------------------------------------
     import math

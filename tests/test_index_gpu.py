@@ -72,6 +72,34 @@ def test_golden_match_cases(gpudb, match_cases):
                 assert _strip(fused) == want, ("fused", case["case"], topn)
 
 
+def test_apriori_early_exit_golden(gpudb):
+    """``return_matches(..., apriori=True)`` against the outputs of recognizer_apriori.py's own
+    return_matches (:246-310, executed from the reference's source by tests/golden/make_golden.py): the tuples read up
+    to the exit, dedup_hashes at that point and the aligned results that triggered it — lookup and vote on the GPU."""
+    import json
+    from shazam_b200 import recognize
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "apriori_cases.json")))
+    exits = 0
+    for case in cases:
+        db = gpudb()
+        for sid, s in sorted(case["songs"].items(), key=lambda kv: int(kv[0])):
+            assert db.insert_song(s["song_name"], s["file_sha1"], s["total_hashes"]) == int(sid)
+        by_song = {}
+        for sid, h, o in case["rows"]:
+            by_song.setdefault(sid, []).append((h, o))
+        for sid, hs in by_song.items():
+            db.insert_hashes(sid, hs)
+            db.set_song_fingerprinted(sid)
+        q = [tuple(x) for x in case["query"]]
+        matches, dedup, songs_arr = recognize.return_matches(q, case["batch_size"], apriori=True)
+        assert len(matches) == case["n_matches"], case["case"]
+        assert hashlib.sha256(repr(sorted(matches)).encode()).hexdigest() == case["matches_sorted_sha"]
+        assert {str(k): v for k, v in dedup.items()} == case["dedup"]
+        assert _strip(songs_arr) == case["songs_arr"], case["case"]
+        exits += bool(songs_arr)
+    assert exits >= 2
+
+
 def _random_table(rng, nsongs, per_song, universe, max_off=500):
     table = O.FingerprintTable()
     rows = []
