@@ -64,10 +64,12 @@ def classification_summary(y_true: Sequence[str], y_pred: Sequence[str]) -> Dict
     tp = np.diag(cm).astype(np.float64)
     support = cm.sum(1).astype(np.float64)
     predicted = cm.sum(0).astype(np.float64)
+    # the same arithmetic, operation for operation, as scikit-learn's precision_recall_fscore_support (the CSV files the
+    # reference writes hold repr()s of these doubles): f1 from the confusion-matrix entries, 2 tp / (support + predicted)
     with np.errstate(divide="ignore", invalid="ignore"):
         precision = np.where(predicted > 0, tp / predicted, 0.0)
         recall = np.where(support > 0, tp / support, 0.0)
-        f1 = np.where(precision + recall > 0, 2 * precision * recall / (precision + recall), 0.0)
+        f1 = np.where(support + predicted > 0, 2.0 * tp / (1.0 * support + predicted), 0.0)
     report = {l: {"precision": float(precision[i]), "recall": float(recall[i]), "f1-score": float(f1[i]),
                   "support": float(support[i])} for l, i in index.items()}
     n = float(len(y_true))
@@ -75,9 +77,8 @@ def classification_summary(y_true: Sequence[str], y_pred: Sequence[str]) -> Dict
     report["accuracy"] = accuracy
     report["macro avg"] = {"precision": float(precision.mean()), "recall": float(recall.mean()),
                            "f1-score": float(f1.mean()), "support": n}
-    w = support / n if n else support
-    report["weighted avg"] = {"precision": float((precision * w).sum()), "recall": float((recall * w).sum()),
-                              "f1-score": float((f1 * w).sum()), "support": n}
+    wavg = (lambda x: float(np.average(x, weights=support))) if n else (lambda x: 0.0)
+    report["weighted avg"] = {"precision": wavg(precision), "recall": wavg(recall), "f1-score": wavg(f1), "support": n}
     return {"labels": labels, "confusion_matrix": cm, "accuracy": accuracy, "report": report}
 
 
@@ -109,11 +110,16 @@ def generate_csv_results(songs_to_recognize: Sequence[str], recognized_song_name
         w.writerows(rows)
     summary = classification_summary(names, recognized_song_names)
     labels, cm = summary["labels"], summary["confusion_matrix"]
-    # CM_: the reference's crosstab — the diagonal cell of a correctly recognised track is its count, a miss moves
-    # a 1 to the predicted column (recognizer_test.py:494-499)
+    # CM_: the reference's crosstab (recognizer_test.py:493-499) — crosstab(actual, actual), i.e. the diagonal cell of a
+    # track is how often it was played; a miss zeroes it and puts a 1 in the predicted name's column.  A predicted name
+    # that is no played track gets a NEW column, appended in order of appearance, whose untouched cells stay empty
+    # (pandas fills an enlarged column with NaN and writes NaN as an empty field)
     actual = sorted(set(names))
-    cols = sorted(set(names) | {p for t, p in zip(names, recognized_song_names) if t != p})
-    cross = {a: {c: 0 for c in cols} for a in actual}
+    cols = list(actual)
+    for t, p in zip(names, recognized_song_names):
+        if t != p and p not in cols:
+            cols.append(p)
+    cross = {a: {c: (0 if c in actual else "") for c in cols} for a in actual}
     for a in names:
         cross[a][a] += 1
     for t, p in zip(names, recognized_song_names):

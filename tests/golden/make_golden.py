@@ -22,6 +22,7 @@ Outputs (all under ``tests/golden/``):
   peaks_cases.npz   small float64 spectrograms (plateaus, zeros, negative amp_min) + reference peaks
   match_cases.json  reference return_matches + align_matches on small tables
   apriori_cases.json  reference return_matches of recognizer_apriori.py (early exit, :246-310) on small tables
+  csv_cases.json    the five report files of the reference's generate_csv_results (recognizer_test.py:437-513)
   noise_cases.npz   reference get_noise_from_sound (recognizer_test.py:426-435) on seeded signal / noise pairs
 """
 import ast
@@ -314,6 +315,66 @@ def main(out_dir=HERE):
         full, _ = match_namespace(table)["return_matches"](q)
         print(f"apriori case {case_id}: {len(matches)} of {len(full)} matches read, exit={'yes' if songs_arr else 'no'}")
     json.dump(acases, open(f"{out_dir}/apriori_cases.json", "w"), indent=0)
+
+    # ---- the experiment script's report: generate_csv_results executed from its source ----------------
+    # Stand-ins: `datetime` (a fixed stamp), `times` (the script's module global), and `pd.crosstab` returning an
+    # object-dtype frame — the script writes str(0) / str(1) into the crosstab (:497-498), which the pandas of its era
+    # (python 3.7) upcast silently and pandas 3 refuses; nothing else is touched.
+    import csv as _csv
+    import re as _re
+    import tempfile
+    import pandas as pd
+    from sklearn.metrics import accuracy_score, classification_report, confusion_matrix
+
+    class _DT:
+        class datetime:
+            @staticmethod
+            def now():
+                class _Now:
+                    def strftime(self, fmt):
+                        return "01-01-2021_00-00-00"
+                return _Now()
+
+    class _PD:
+        Series, DataFrame = pd.Series, pd.DataFrame
+        crosstab = staticmethod(lambda a, b: pd.crosstab(a, b).astype(object))
+
+    ccases = []
+    crng = np.random.default_rng(77)
+    pool = [f"{100000 + 37 * i}" for i in range(15)]                # numeric track names like the reference's mp3 files
+    big_played = [pool[int(i)] for i in crng.integers(0, 15, 60)]
+    big_pred = [t if crng.random() < 0.75 else (pool[int(crng.integers(0, 15))] if crng.random() < 0.7 else f"other{int(crng.integers(0, 4))}")
+                for t in big_played]
+    for case_id, (played, pred, add_noise, snr, secs, it) in enumerate([
+            (["a", "b", "c", "d", "e", "f", "g", "h"], ["a", "b", "x", "d", "a", "f", "g", "b"], True, 10, 5, 3),
+            (["t1", "t2", "t3", "t2"], ["t1", "t2", "t3", "t2"], False, 0, 15, 0),
+            (["k", "a", "k", "m", "q", "b", "q"], ["zz", "a", "k", "m", "c", "a", "q"], True, 0, 5, 678),
+            (big_played, big_pred, False, 0, 15, 2713)]):
+        songs = [f"songs/{i % 3:03d}/{n}.mp3" for i, n in enumerate(played)]
+        tms = [{"song_start_time": 7 * i, "fingerprint_times": 0.25 + 0.01 * i, "query_time": 0.05 * (i + 1),
+                "align_time": 0.01, "total_time": 0.31 + 0.06 * i} for i in range(len(played))]
+        finals = [str([{"song_id": i + 1, "song_name": p}]) for i, p in enumerate(pred)]
+        cns = dict(re=_re, csv=_csv, datetime=_DT, pd=_PD, confusion_matrix=confusion_matrix,
+                   classification_report=classification_report, accuracy_score=accuracy_score, times=tms,
+                   print=lambda *a, **k: None)
+        exec(extract(f"{REF}/recognizer_test.py", {"generate_csv_results"}), cns)
+        cns.update(ADD_NOISE=add_noise, SNR=snr, RECORD_SECONDS=secs)     # the script's run-time switches (:38-40)
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as td:
+            os.chdir(td)
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    cns["generate_csv_results"](songs, pred, it, finals)
+                files = {f: open(f, newline="").read() for f in sorted(os.listdir("."))}
+            finally:
+                os.chdir(cwd)
+        assert len(files) == 5
+        ccases.append({"case": case_id, "songs_to_recognize": songs, "recognized_song_names": pred, "times": tms,
+                       "final_results_arr": finals, "add_noise": add_noise, "snr": snr, "record_seconds": secs,
+                       "iteration": it, "stamp": "01-01-2021_00-00-00", "files": files})
+    json.dump(ccases, open(f"{out_dir}/csv_cases.json", "w"), indent=0)
+    print("csv cases:", len(ccases))
 
     # ---- SNR mixer of the experiment script ----------------------------------------------
     import math

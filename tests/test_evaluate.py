@@ -43,6 +43,28 @@ def test_classification_summary_equals_sklearn(tmp_path):
     assert float(acc[1][1]) == pytest.approx(out["accuracy"])
 
 
+def test_report_files_equal_the_reference_script(tmp_path):
+    """``generate_csv_results`` (recognizer_test.py:437-513) was executed from the reference's source by
+    tests/golden/make_golden.py (csv_cases.json): the results CSV, the 0/1 crosstab (``CM_``, incl. the empty cells of
+    a column added for a predicted name that is no played track), the sklearn confusion matrix (``CMSK_``), the
+    classification report (``CRSK_``) and the accuracy score (``ASSK_``) — same file names, same bytes."""
+    import json
+    from shazam_b200 import evaluate
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "csv_cases.json")))
+    assert len(cases) >= 3
+    for case in cases:
+        out_dir = tmp_path / str(case["case"])
+        out_dir.mkdir()
+        out = evaluate.generate_csv_results(case["songs_to_recognize"], case["recognized_song_names"], case["times"],
+                                            case["final_results_arr"], case["record_seconds"],
+                                            snr=case["snr"] if case["add_noise"] else None, iteration=case["iteration"],
+                                            out_dir=str(out_dir), stamp=case["stamp"])
+        assert sorted(out["files"]) == sorted(case["files"]), case["case"]
+        for name, want in case["files"].items():
+            got = open(out_dir / name, newline="").read()
+            assert got.replace("\r\n", "\n") == want.replace("\r\n", "\n"), (case["case"], name, got, want)
+
+
 @pytest.mark.gpu
 def test_mix_noise_device_equals_oracle(native_lib):
     import torch

@@ -167,5 +167,5 @@ def test_committed_golden_vectors_regenerate_from_the_reference(tmp_path):
         assert set(a.files) == set(b.files), name
         for k in a.files:
             assert np.array_equal(a[k], b[k]), (name, k)
-    for name in ("match_cases.json", "apriori_cases.json"):
+    for name in ("match_cases.json", "apriori_cases.json", "csv_cases.json"):
         assert json.load(open(os.path.join(here, name))) == json.load(open(tmp_path / name)), name
