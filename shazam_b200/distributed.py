@@ -26,9 +26,8 @@ Everything here is host-side orchestration over a ``ShardBackend`` — the CUDA 
 from __future__ import annotations
 
 import os
-import sys
 import time
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 import numpy as np
 import torch

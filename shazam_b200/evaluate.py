@@ -11,7 +11,7 @@ import csv
 import ctypes as C
 import datetime
 import re
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import numpy as np
 import torch

@@ -15,7 +15,7 @@ import os
 import wave
 from hashlib import sha1
 from time import time
-from typing import Optional, Sequence
+from typing import Optional
 
 import numpy as np
 
